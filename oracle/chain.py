@@ -1,0 +1,492 @@
+"""ORACLE (test infrastructure, NOT product code) -- CPU restatement of the MPS hot
+path of Qrochet.jl, following `/root/reference/src/Ansatz/Chain.jl`,
+`src/Ansatz.jl`, `src/Quantum.jl`, `src/Ansatz/Dense.jl` function by function.
+
+PARITY STATUS:
+  * The reference holds NO golden vectors / fixtures / seeds.  Its property tests
+    (`test/Ansatz/Chain_test.jl:189-394`) pin truncate!, rand, canonize_site!,
+    canonize!, mixed_canonize!, normalize!, adjoint; those are restated in
+    `tests/test_oracle_properties.py` and this oracle passes them.
+  * evolve!/expect/overlap have no reference test (`Chain_test.jl:396` is a TODO):
+    PARITY UNPINNED by the reference for those; this oracle is instead checked
+    against a dense state-vector simulation (`oracle/statevector.py`).
+  * The reference (Julia) cannot run in this image; numerics use the same LAPACK
+    drivers (zgesdd / zgeqrf / zgemm via SciPy/OpenBLAS).
+
+Only `tests/`, `__graft_entry__.smoke()` and bench.py's cpu_baseline /
+`--impl reference` legs may import this module.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .tenet import Tensor, TensorNetwork, contract, gensym, nextindex
+
+
+class MissingSchmidtCoefficientsException(Exception):
+    """src/Ansatz.jl:91-99."""
+
+
+def site(i: int, dual: bool = False):
+    """`Site(i; dual)` (src/Quantum.jl:10-15)."""
+    return (int(i), bool(dual))
+
+
+class Quantum:
+    """`Quantum` = TensorNetwork + Dict{Site,Symbol} (src/Quantum.jl:54-76)."""
+
+    def __init__(self, tn: TensorNetwork, sites: dict):
+        self.tn = tn
+        self.sites = dict(sites)
+
+    def copy(self):
+        return Quantum(self.tn.copy(), self.sites)
+
+    def deepcopy(self):
+        return Quantum(self.tn.deepcopy(), self.sites)
+
+    def inputs(self):
+        return sorted(s for s in self.sites if s[1])
+
+    def outputs(self):
+        return sorted(s for s in self.sites if not s[1])
+
+    def nlanes(self):
+        return len({s[0] for s in self.sites})
+
+    def ind_at(self, s):
+        """`inds(q; at=site)` (src/Quantum.jl:253-261)."""
+        return self.sites[s]
+
+    def tensor_at(self, s) -> Tensor:
+        """`tensors(q; at=site)` (src/Quantum.jl:270-278): the tensor holding the site's index.
+        (With a Λ-free physical index there is exactly one.)"""
+        hits = self.tn.intersecting(self.sites[s])
+        assert len(hits) == 1
+        return hits[0]
+
+    def adjoint(self):
+        """src/Quantum.jl:100-115: conj + swap input/output + prime all virtual indices."""
+        sites = {(s[0], not s[1]): i for s, i in self.sites.items()}
+        tn = self.tn.conj()
+        phys = set(sites.values())
+        tn.replace_inds({i: i + "'" for i in tn.inds() if i not in phys})
+        return Quantum(tn, sites)
+
+
+class Dense(Quantum):
+    """Gate container, `Dense(Operator(), array; sites)` (src/Ansatz/Dense.jl:21-34)."""
+
+    def __init__(self, array, sites):
+        array = np.asarray(array)
+        assert array.ndim == len(sites) and all(d > 1 for d in array.shape)
+        inds = [nextindex() for _ in sites]
+        super().__init__(TensorNetwork([Tensor(array, inds)]), dict(zip(sites, inds)))
+
+    def copy(self):
+        q = Quantum(self.tn.copy(), self.sites)
+        q.__class__ = Dense
+        return q
+
+
+def gate(matrix, sites):
+    """Helper: a k-site operator from a p^k x p^k matrix acting as |out><in|, array dims
+    (o_1..o_k, i_1..i_k), first lane = fastest bit."""
+    k = len(sites)
+    matrix = np.asarray(matrix)
+    p = round(matrix.shape[0] ** (1.0 / k))
+    arr = np.reshape(matrix, (p,) * (2 * k), order="F")
+    return Dense(arr, [site(s) for s in sites] + [site(s, True) for s in sites])
+
+
+class Chain(Quantum):
+    """Open-boundary MPS (`Chain(State(), Open(), arrays)`, Chain.jl:64-100)."""
+
+    def __init__(self, arrays=None, order=("o", "l", "r"), _q: Quantum | None = None):
+        if _q is not None:
+            super().__init__(_q.tn, _q.sites)
+            return
+        n = len(arrays)
+        bonds = [nextindex() for _ in range(n - 1)]
+        phys = [nextindex() for _ in range(n)]
+        tensors = []
+        for k, a in enumerate(arrays):
+            a = np.asarray(a)
+            lab = {"o": phys[k], "l": bonds[k - 1] if k > 0 else None, "r": bonds[k] if k < n - 1 else None}
+            inds = [lab[c] for c in order if lab[c] is not None]
+            assert a.ndim == len(inds), (k, a.shape, inds)
+            tensors.append(Tensor(a, inds))
+        super().__init__(TensorNetwork(tensors), {site(k + 1): phys[k] for k in range(n)})
+
+    # -- bookkeeping ---------------------------------------------------------------------
+    def copy(self):
+        return Chain(_q=Quantum(self.tn.copy(), self.sites))
+
+    def deepcopy(self):
+        return Chain(_q=Quantum(self.tn.deepcopy(), self.sites))
+
+    def adjoint(self):
+        return Chain(_q=super().adjoint())
+
+    def nsites(self):
+        return len(self.sites)
+
+    def bond_ind(self, s1, s2):
+        """`inds(tn; bond=(s1,s2))` (Ansatz.jl:58-68)."""
+        a, b = self.tensor_at(s1), self.tensor_at(s2)
+        common = [i for i in a.inds if i in b.inds]
+        if not common:
+            return None
+        (only,) = common
+        return only
+
+    def leftindex(self, s):
+        """Chain.jl:193-196."""
+        return None if s[0] == 1 else self.bond_ind(s, (s[0] - 1, s[1]))
+
+    def rightindex(self, s):
+        """Chain.jl:198-202."""
+        return None if s[0] == self.nlanes() else self.bond_ind(s, (s[0] + 1, s[1]))
+
+    def lambda_between(self, s1, s2):
+        """`tensors(tn; between=(s1,s2))` (Ansatz.jl:78-89): `tn[bond]`, i.e. the tensor whose
+        index set is exactly {bond}; `None` if the two sites do not share an index."""
+        b = self.bond_ind(s1, s2)
+        if b is None:
+            return None
+        try:
+            return self.tn.select([b])
+        except KeyError:
+            return None
+
+    # -- Chain.jl:309-333 ----------------------------------------------------------------
+    def contract_between(self, s1, s2, direction="left", delete_lambda=True):
+        lam = self.lambda_between(s1, s2)
+        if lam is None:
+            return self
+        if direction == "right":
+            g = self.tensor_at(s2)
+            self.tn.replace_tensor(g, contract(g, lam, dims=()))
+        elif direction == "left":
+            g = self.tensor_at(s1)
+            self.tn.replace_tensor(g, contract(lam, g, dims=()))
+        else:
+            raise ValueError(f"Unknown direction=:{direction}")
+        if delete_lambda:
+            self.tn.delete(lam)
+        return self
+
+    # -- Chain.jl:335-376 ----------------------------------------------------------------
+    def canonize_site(self, s, direction, method="qr"):
+        n = self.nsites()
+        left_inds, right_inds = [], []
+        if direction == "left":
+            if s == site(1):
+                raise ValueError("Cannot right-canonize left-most tensor")
+            right_inds.append(self.leftindex(s))
+            if s != site(n):
+                left_inds.append(self.rightindex(s))
+            left_inds.append(self.sites[s])
+        elif direction == "right":
+            if s == site(n):
+                raise ValueError("Cannot left-canonize right-most tensor")
+            right_inds.append(self.rightindex(s))
+            if s != site(1):
+                left_inds.append(self.leftindex(s))
+            left_inds.append(self.sites[s])
+        else:
+            raise ValueError(f"Unknown direction=:{direction}")
+        (virtualind,) = right_inds
+        tmp = gensym("tmp")
+        if method == "svd":
+            self.tn.svd_(left_inds, right_inds, tmp)
+        elif method == "qr":
+            self.tn.qr_(left_inds, right_inds, tmp)
+        else:
+            raise ValueError(f"Unknown factorization method=:{method}")
+        self.tn.contract_index(virtualind)
+        self.tn.replace_inds({tmp: virtualind})
+        return self
+
+    # -- Chain.jl:390-422 ----------------------------------------------------------------
+    def truncate(self, bond, threshold=None, maxdim=None):
+        vind = self.rightindex(bond[0])
+        if vind != self.leftindex(bond[1]):
+            raise ValueError(f"Invalid bond {bond}")
+        if vind not in self.tn.inds("hyper"):
+            raise MissingSchmidtCoefficientsException(bond)
+        spectrum = self.tn.select([vind]).data
+        size = self.tn.size(vind)
+        extent = range(min(size, maxdim)) if maxdim is not None else range(size)
+        if threshold is None:
+            threshold = 1e-16
+        keep = [i for i in extent if abs(spectrum[i]) > threshold]
+        self.tn.slice_(vind, keep)
+        return self
+
+    # -- Chain.jl:424-458 ----------------------------------------------------------------
+    def _gram(self, s, keep_ind):
+        t = self.tensor_at(s)
+        if keep_ind is None:
+            keep_ind = gensym("dummy")
+            t = Tensor(t.data[..., None], t.inds + (keep_ind,))
+        g = contract(t, t.conj().replace({keep_ind: gensym("new")}))
+        return g.data
+
+    def isleftcanonical(self, s, atol=1e-12):
+        g = self._gram(s, self.rightindex(s))
+        return bool(np.allclose(g, np.eye(g.shape[0]), atol=atol, rtol=0))
+
+    def isrightcanonical(self, s, atol=1e-12):
+        g = self._gram(s, self.leftindex(s))
+        return bool(np.allclose(g, np.eye(g.shape[0]), atol=atol, rtol=0))
+
+    # -- Chain.jl:469-497 ----------------------------------------------------------------
+    def canonize(self):
+        n = self.nsites()
+        lams = []
+        for i in range(n, 1, -1):
+            self.canonize_site(site(i), "left", "qr")
+        for i in range(1, n):
+            self.canonize_site(site(i), "right", "svd")
+            lam = self.lambda_between(site(i), site(i + 1))
+            self.tn.pop(lam)
+            a = self.tensor_at(site(i + 1))
+            self.tn.replace_tensor(a, contract(a, lam, dims=()))
+            lams.append(lam)
+        for i in range(2, n + 1):
+            lam = lams[i - 2]
+            a = self.tensor_at(site(i))
+            inv = _pinv_diag(lam.data, 1e-64)
+            self.tn.replace_tensor(a, contract(a, Tensor(inv, lam.inds), dims=()))
+            self.tn.push(lam)
+        return self
+
+    # -- Chain.jl:509-536 ----------------------------------------------------------------
+    def mixed_canonize(self, center):
+        n = self.nsites()
+        for i in range(1, center[0]):
+            self.canonize_site(site(i), "right", "qr")
+        for i in range(n, center[0], -1):
+            self.canonize_site(site(i), "left", "qr")
+        self.canonize_site(center, "left", "svd")
+        return self
+
+    def normalize(self, root):
+        self.mixed_canonize(root)
+        lam = self.lambda_between(site(root[0] - 1), root)
+        self.tn.replace_tensor(lam, Tensor(lam.data / np.linalg.norm(lam.data), lam.inds))
+        return self
+
+    # -- Chain.jl:543-603 ----------------------------------------------------------------
+    def evolve(self, g: Dense, threshold=None, maxdim=None, iscanonical=False, renormalize=False):
+        ins, outs = g.inputs(), g.outputs()
+        if not ins or not outs:
+            raise ValueError("Gate must be an operator")
+        if {(s[0], False) for s in ins} != set(outs):
+            raise ValueError("Gate inputs and outputs must be the same")
+        if not {(s[0], False) for s in ins} <= set(self.outputs()):
+            raise ValueError("Gate inputs must be a subset of the TN sites")
+        nl = g.nlanes()
+        if nl == 1:
+            self._evolve_1site(g)
+        elif nl == 2:
+            ids = sorted(s[0] for s in ins)
+            if ids != list(range(ids[0], ids[-1] + 1)):
+                raise ValueError("Gate lanes must be contiguous")
+            self._evolve_2site(g, threshold, maxdim, iscanonical, renormalize)
+        else:
+            raise ValueError(f"Invalid number of lanes {nl}, maximum is 2")
+        return self
+
+    def _evolve_1site(self, g: Dense):
+        g = g.copy()
+        tmp = gensym("tmp")
+        (gin,) = g.inputs()
+        target = (gin[0], False)
+        phys = self.sites[target]
+        self.tn.replace_inds({phys: tmp})
+        g.tn.replace_inds({g.sites[gin]: tmp})
+        (gout,) = g.outputs()
+        g.tn.replace_inds({g.sites[gout]: phys})
+        self.tn.merge_(g.tn)
+        self.tn.contract_index(tmp)
+
+    # -- Chain.jl:606-661 ----------------------------------------------------------------
+    def _evolve_2site(self, g: Dense, threshold, maxdim, iscanonical, renormalize):
+        g = g.copy()
+        g.sites = dict(g.sites)
+        sitel, siter = sorted(g.outputs())
+        bond = (sitel, siter)
+        li, ri = self.leftindex(sitel), self.rightindex(siter)
+        left_inds = [li] if li is not None else []
+        right_inds = [ri] if ri is not None else []
+        virtualind = self.bond_ind(sitel, siter)
+        if iscanonical:
+            self.contract_2sitewf(bond)
+        else:
+            self.tn.contract_index(virtualind)
+        ren_q, ren_g = {}, {}
+        for s in g.inputs():
+            tmp = gensym("tmp")
+            ren_q[self.sites[(s[0], False)]] = tmp
+            ren_g[g.sites[s]] = tmp
+        # qtn physical indices and gate inputs become the contracting indices ...
+        self.tn.replace_inds(ren_q)
+        g.tn.replace_inds(ren_g)
+        # ... and the gate outputs take over the names in the site map
+        g.tn.replace_inds({g.sites[s]: self.sites[s] for s in g.outputs()})
+        self.tn.merge_(g.tn)
+        self.tn.contract_index(list(ren_q.values()))
+        left_inds.append(self.sites[sitel])
+        right_inds.append(self.sites[siter])
+        if iscanonical:
+            self.unpack_2sitewf(bond, left_inds, right_inds, virtualind)
+        else:
+            self.tn.svd_(left_inds, right_inds, virtualind)
+        if threshold is not None or maxdim is not None:
+            self.truncate(bond, threshold=threshold, maxdim=maxdim)
+            if renormalize and iscanonical:
+                lam = self.lambda_between(*bond)
+                self.tn.replace_tensor(lam, Tensor(lam.data / np.linalg.norm(lam.data), lam.inds))
+            elif renormalize:
+                self.normalize(bond[0])
+        return self
+
+    # -- Chain.jl:669-685 ----------------------------------------------------------------
+    def contract_2sitewf(self, bond):
+        sitel, siter = bond
+        n = self.nsites()
+        lam_l = None if sitel[0] == 1 else self.lambda_between(site(sitel[0] - 1), sitel)
+        lam_r = None if sitel[0] == n - 1 else self.lambda_between(siter, site(siter[0] + 1))
+        if lam_l is not None:
+            self.contract_between(site(sitel[0] - 1), sitel, direction="right", delete_lambda=False)
+        if lam_r is not None:
+            self.contract_between(siter, site(siter[0] + 1), direction="left", delete_lambda=False)
+        self.tn.contract_index(self.bond_ind(sitel, siter))
+        return self
+
+    # -- Chain.jl:693-722 ----------------------------------------------------------------
+    def unpack_2sitewf(self, bond, left_inds, right_inds, virtualind):
+        from .tenet import svd
+
+        sitel, siter = bond
+        n = self.nsites()
+        # NB: after contract_2sitewf both sites map to θ, so `between` must look at the index
+        lam_l = None if sitel[0] == 1 else self._lambda_on(left_inds[0])
+        lam_r = None if siter[0] == n else self._lambda_on(right_inds[0])
+        theta = self.tensor_at(sitel)
+        U, s, Vt = svd(theta, left_inds, right_inds, virtualind)
+        gl = U if lam_l is None else contract(U, Tensor(_pinv_diag(lam_l.data, 1e-32), lam_l.inds), dims=())
+        gr = Vt if lam_r is None else contract(Tensor(_pinv_diag(lam_r.data, 1e-32), lam_r.inds), Vt, dims=())
+        self.tn.delete(theta)
+        self.tn.push(gl)
+        self.tn.push(s)
+        self.tn.push(gr)
+        return self
+
+    def _lambda_on(self, ind):
+        try:
+            return self.tn.select([ind])
+        except KeyError:
+            return None
+
+    # -- Chain.jl:724-752, Ansatz.jl:101-109 -----------------------------------------------
+    def expect(self, observables):
+        phi = self.copy()
+        for o in observables:
+            phi.evolve(o)
+        tn = phi.tn.merge(self.adjoint().tn)
+        return tn.contract().data[()]
+
+    def overlap(self, other: "Chain"):
+        """<other|self>: `other` is the conjugated one (Chain.jl:740-748)."""
+        b = other.copy()
+        b.tn.replace_inds({b.sites[s]: self.sites[s] for s in self.outputs()})
+        b.sites = {s: self.sites[s] for s in self.outputs()}
+        tn = self.tn.merge(b.adjoint().tn)
+        return tn.contract().data[()]
+
+    def norm(self):
+        v = self.tn.merge(self.adjoint().tn).contract().data[()]
+        return abs(np.sqrt(v))
+
+    # -- helpers for the tests ---------------------------------------------------------------
+    def lambdas(self):
+        """Λ vector on each bond (None where absent), bond k between sites k and k+1 (1-based)."""
+        out = []
+        for k in range(1, self.nsites()):
+            lam = self.lambda_between(site(k), site(k + 1))
+            out.append(None if lam is None else lam.data)
+        return out
+
+    def to_dense(self):
+        """Full state vector with qubit 1 the fastest index (column-major over sites)."""
+        t = self.tn.contract()
+        t = t.permute([self.sites[site(k + 1)] for k in range(self.nsites())])
+        return np.reshape(t.data, -1, order="F")
+
+
+def _pinv_diag(lam, atol):
+    """`diag(pinv(Diagonal(λ), atol=atol))` (Chain.jl:491,710,713)."""
+    lam = np.asarray(lam)
+    out = np.zeros_like(lam)
+    mask = np.abs(lam) > atol
+    out[mask] = 1.0 / lam[mask]
+    return out
+
+
+def gramschmidt_rows(a):
+    """`Muscle.gramschmidt!` [ext]: orthonormalise the ROWS of `a` (classical GS, in order)."""
+    a = np.array(a)
+    for i in range(a.shape[0]):
+        for _ in range(2):
+            if i:
+                a[i] -= (a[:i].conj() @ a[i]) @ a[:i]
+        a[i] /= np.linalg.norm(a[i])
+    return a
+
+
+def rand_mps_arrays(rng, n, chi, p=2, dtype=np.complex128, fast=False):
+    """Arrays of `rand(Chain, Open, State; n, χ, p, eltype)` (Chain.jl:223-256), order (o,l,r).
+    Entries U[0,1) (+ i U[0,1)) from `rng` (Julia's Xoshiro stream cannot be reproduced).
+    `fast=True` replaces the O(χ³) Gram-Schmidt loop by a QR with the same row-space property
+    (for the big bench shapes only; untimed set-up)."""
+    arrays = []
+    for i in range(1, n + 1):
+        after_mid = i > n // 2
+        j = (n + 1 - abs(2 * i - n - 1)) // 2
+        chil, chir = min(chi, p ** (j - 1)), min(chi, p ** j)
+        if n % 2 == 1 and i == n // 2 + 1:
+            chil, chir = chil, chil
+        elif after_mid:
+            chil, chir = chir, chil
+        if i == 1:
+            chil, chir = chir, 1
+        a = rng.random((chil, chir * p))
+        if np.issubdtype(dtype, np.complexfloating):
+            a = a + 1j * rng.random((chil, chir * p))
+        a = a.astype(dtype)
+        if fast:
+            q, _ = np.linalg.qr(a.conj().T)
+            a = q.conj().T.copy()
+        else:
+            a = gramschmidt_rows(a)
+        a = np.reshape(a, (chil, chir, p), order="F")
+        arrays.append(np.transpose(a, (2, 0, 1)))
+    arrays[0] = np.reshape(arrays[0], (p, p), order="F")
+    arrays[-1] = np.reshape(arrays[-1], (p, p), order="F")
+    arrays[0] = arrays[0] / np.sqrt(p)
+    return arrays
+
+
+def rand_mps(rng, n, chi, p=2, dtype=np.complex128, fast=False) -> Chain:
+    return Chain(rand_mps_arrays(rng, n, chi, p, dtype, fast))
+
+
+def haar_unitary(rng, d=4):
+    """Haar-random d x d unitary: QR of complex Ginibre, phases fixed."""
+    z = (rng.standard_normal((d, d)) + 1j * rng.standard_normal((d, d))) / np.sqrt(2)
+    q, r = np.linalg.qr(z)
+    ph = np.diag(r) / np.abs(np.diag(r))
+    return q * ph
