@@ -1,0 +1,10 @@
+"""qrochet_b200: B200-native backend for Qrochet.jl's tensor-network hot path (host-side Python mirror of the
+Julia package extension; all numerics are hand-written sm_100a CUDA behind libqrochet_b200.so)."""
+from . import _capi
+from ._capi import MissingSchmidtCoefficientsException, QB200Error
+from .device import (Context, DeviceArray, conj, contract, norm2, permute, qr, scale, scale_mode, select_mode,
+                     slice_mode, svd)
+from .mps import B200MPS
+
+__all__ = ["Context", "DeviceArray", "B200MPS", "contract", "scale_mode", "slice_mode", "select_mode", "conj",
+           "permute", "norm2", "scale", "qr", "svd", "QB200Error", "MissingSchmidtCoefficientsException"]

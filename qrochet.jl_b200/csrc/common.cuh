@@ -1,0 +1,143 @@
+// Shared internals of libqrochet_b200: context, tensor handles, error plumbing, workspace.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/qrochet_b200.h"
+
+typedef double2 c128;
+
+struct qb200_tensor {
+    int32_t dtype;
+    int32_t rank;
+    int64_t ext[QB200_MAX_RANK];
+    void* data;
+    size_t bytes;  // capacity
+    bool owned;
+    int64_t numel() const {
+        int64_t n = 1;
+        for (int i = 0; i < rank; ++i) n *= ext[i];
+        return n;
+    }
+};
+
+struct qb200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    std::string err;
+    int64_t launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 148;
+    int last_svd_sweeps = 0;
+    void* nccl_comm = nullptr;
+    void* nccl_lib = nullptr;
+    double* scratch_host = nullptr;  // pinned, 64 KiB
+};
+
+static inline size_t dtype_size(int32_t dt) {
+    switch (dt) {
+        case QB200_C128: return 16;
+        case QB200_C64: return 8;
+        case QB200_F64: return 8;
+        case QB200_F32: return 4;
+    }
+    return 0;
+}
+
+#define QB_FAIL(ctx, code, ...)                          \
+    do {                                                 \
+        char _buf[512];                                  \
+        snprintf(_buf, sizeof(_buf), __VA_ARGS__);       \
+        if (ctx) (ctx)->err = _buf;                      \
+        return (code);                                   \
+    } while (0)
+
+#define QB_CUDA(ctx, call)                                                                         \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            QB_FAIL(ctx, QB200_E_CUDA, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+    } while (0)
+
+#define QB_TRY(call)                 \
+    do {                             \
+        int32_t _r = (call);         \
+        if (_r != QB200_OK) return _r; \
+    } while (0)
+
+#define QB_LAUNCH_CHECK(ctx)                 \
+    do {                                     \
+        (ctx)->launches++;                   \
+        QB_CUDA(ctx, cudaGetLastError());    \
+    } while (0)
+
+// stream-ordered workspace from the CUDA memory pool (cached by the driver pool; no sync on free)
+struct Workspace {
+    qb200_ctx* ctx;
+    std::vector<void*> ptrs;
+    explicit Workspace(qb200_ctx* c) : ctx(c) {}
+    ~Workspace() {
+        for (void* p : ptrs) cudaFreeAsync(p, ctx->stream);
+    }
+    template <typename T>
+    T* get(size_t n) {
+        void* p = nullptr;
+        if (n == 0) n = 1;
+        if (cudaMallocAsync(&p, n * sizeof(T), ctx->stream) != cudaSuccess) return nullptr;
+        ptrs.push_back(p);
+        return (T*)p;
+    }
+};
+
+// ---- internal entry points shared between translation units -----------------------------------
+// plain column-major complex GEMM view: C(MxN, ldc) = alpha * op(A) * op(B) + beta * C
+// opA: 0 = N, 1 = T, 2 = C (conj transpose), 3 = conj only (no transpose)
+int32_t qb_gemm(qb200_ctx* ctx, int opA, int opB, int64_t M, int64_t N, int64_t K, c128 alpha, const c128* A,
+                int64_t lda, const c128* B, int64_t ldb, c128 beta, c128* C, int64_t ldc);
+
+// thin QR of a column-major m x n matrix (ld = lda); Q: m x k (ldq), R: k x n (ldr), k = min(m,n).
+// A is not modified.
+int32_t qb_qr_matrix(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64_t lda, c128* Q, int64_t ldq,
+                     c128* R, int64_t ldr);
+
+struct SvdOut {
+    // sigma sorted descending on host (k = min(m,n)), filled by qb_svd_factor
+    std::vector<double> sigma;
+};
+// One-sided block-Jacobi SVD of a column-major m x n matrix A (not modified).
+// After the call the factorisation lives in a workspace; qb_svd_emit writes the first `kept`
+// singular triplets.  Two-phase so that the truncation decision is taken on the host in between.
+struct SvdState;
+int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64_t lda, SvdState** st,
+                      std::vector<double>& sigma);
+// U: m x kept (ldu) ; S: kept doubles (device, may be null) ; V written either as
+//   vmode 0: Vc = conj(V) n x kept (ldv)       [Tenet's third factor]
+//   vmode 1: Vh = V^H    kept x n (ldv)        [row-major-in-bond layout for the fused MPS path]
+// optional fused inverse scales: rows of U multiplied by uinv[row % uinv_len] and columns of V^H
+// (index j) multiplied by vinv[j / vinv_div] (both may be null).
+int32_t qb_svd_emit(qb200_ctx* ctx, SvdState* st, int64_t kept, c128* U, int64_t ldu, double* S, c128* V,
+                    int64_t ldv, int vmode, const double* uinv, int64_t uinv_len, const double* vinv,
+                    int64_t vinv_div, double sigma_scale);
+void qb_svd_release(qb200_ctx* ctx, SvdState* st);
+
+// (left | right) matricisation of a tensor: returns a column-major rows x cols matrix (a permuted copy in
+// `ws` unless `order` is the identity)
+int32_t qb_matricize(qb200_ctx* ctx, const qb200_tensor* A, const int32_t* order, int32_t nleft, Workspace& ws,
+                     const c128** mat, int64_t* rows, int64_t* cols);
+
+// elementwise helpers (elementwise.cu)
+int32_t qb_scale_mode_raw(qb200_ctx* ctx, const c128* in, c128* out, int64_t inner, int64_t d, int64_t outer,
+                          const double* vec, int inverse, double atol);
+int32_t qb_scale_rows_cols(qb200_ctx* ctx, const c128* in, c128* out, int64_t rows, int64_t cols,
+                           const double* rvec, int64_t rlen, const double* cvec, int64_t cdiv);
+int32_t qb_copy_matrix(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64_t lda, c128* B, int64_t ldb,
+                       int conj_transpose);
+int32_t qb_apply_gate2(qb200_ctx* ctx, c128* theta, int64_t chil, int64_t chir, const c128* gate_dev);
+int32_t qb_apply_gate1(qb200_ctx* ctx, c128* t, int64_t inner, int64_t p, int64_t outer, const c128* gate_dev);
+int32_t qb_sumsq(qb200_ctx* ctx, const double* x, int64_t n_doubles, double* result_host);

@@ -1,0 +1,312 @@
+// K1 kernel: see gemm_c128.cuh for the design.
+#include "gemm_c128.cuh"
+#include "mma.cuh"
+
+#include <algorithm>
+
+namespace qb {
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_c128_kernel(const GemmArgs p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    c128* As = reinterpret_cast<c128*>(smem_raw);  // [STAGES][BK][PA]
+    c128* Bs = As + (size_t)STAGES * BK * PA;      // [STAGES][BK][PB]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp & 3, wn = warp >> 2;
+    const int g = lane >> 2, t = lane & 3;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    // blockIdx.z is the batch entry, or the K split when split-K is on (batch == 1 then)
+    const int z = (p.ksplit > 1) ? 0 : blockIdx.z;
+    const int split = (p.ksplit > 1) ? blockIdx.z : 0;
+
+    const c128* __restrict__ A = p.A + p.ab.at(z);
+    const c128* __restrict__ B = p.B + p.bb.at(z);
+    c128* __restrict__ C = p.C + p.cb.at(z);
+
+    // ---- loader coordinates (fixed for the whole K loop) ----
+    int a_ml[4], a_kl[4];
+    int64_t a_moff[4];
+    bool a_ok[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int e = tid + GEMM_THREADS * i;
+        if (p.a_kfast) {
+            a_kl[i] = e & (BK - 1);
+            a_ml[i] = e >> 3;
+        } else {
+            a_ml[i] = e & (BM - 1);
+            a_kl[i] = e >> 7;
+        }
+        a_ok[i] = (m0 + a_ml[i]) < p.M;
+        a_moff[i] = a_ok[i] ? p.am.at(m0 + a_ml[i]) : 0;
+    }
+    int b_nl[2], b_kl[2];
+    int64_t b_noff[2];
+    bool b_ok[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        int e = tid + GEMM_THREADS * i;
+        if (p.b_kfast) {
+            b_kl[i] = e & (BK - 1);
+            b_nl[i] = e >> 3;
+        } else {
+            b_nl[i] = e & (BN - 1);
+            b_kl[i] = e >> 6;
+        }
+        b_ok[i] = (n0 + b_nl[i]) < p.N;
+        b_noff[i] = b_ok[i] ? p.bn.at(n0 + b_nl[i]) : 0;
+    }
+
+    const int KT_all = (p.K + BK - 1) / BK;
+    const int kt_per = (KT_all + p.ksplit - 1) / p.ksplit;
+    const int kt0 = split * kt_per;
+    const int KT = max(0, min(KT_all, kt0 + kt_per) - kt0);  // k tiles handled by this CTA
+
+    auto load_tile = [&](int kt, int s) {
+        c128* as = As + (size_t)s * BK * PA;
+        c128* bs = Bs + (size_t)s * BK * PB;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int kg = (kt0 + kt) * BK + a_kl[i];
+            bool ok = a_ok[i] && kg < p.K;
+            const c128* src = ok ? (A + a_moff[i] + p.ak.at(kg)) : p.A;
+            cp_async16(as + a_kl[i] * PA + a_ml[i], src, ok);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            int kg = (kt0 + kt) * BK + b_kl[i];
+            bool ok = b_ok[i] && kg < p.K;
+            const c128* src = ok ? (B + b_noff[i] + p.bk.at(kg)) : p.B;
+            cp_async16(bs + b_kl[i] * PB + b_nl[i], src, ok);
+        }
+    };
+
+    double accr[4][4][2], acci[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            accr[i][j][0] = accr[i][j][1] = 0.0;
+            acci[i][j][0] = acci[i][j][1] = 0.0;
+        }
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < KT) load_tile(s, s);
+        cp_async_commit();
+    }
+
+    const int sgnA = p.conjA ? 0x80000000 : 0, sgnB = p.conjB ? 0x80000000 : 0;
+
+    for (int kt = 0; kt < KT; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            int nk = kt + STAGES - 1;
+            if (nk < KT) load_tile(nk, nk % STAGES);
+            cp_async_commit();
+        }
+        const c128* as = As + (size_t)(kt % STAGES) * BK * PA + wm * 32 + g;
+        const c128* bs = Bs + (size_t)(kt % STAGES) * BK * PB + wn * 32 + g;
+#pragma unroll
+        for (int kk = 0; kk < BK / 4; ++kk) {
+            double ar[4], ai[4], nai[4], br[4], bi[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                c128 v = as[(kk * 4 + t) * PA + i * 8];
+                ar[i] = v.x;
+                ai[i] = flip_sign(v.y, sgnA);
+                nai[i] = flip_sign(ai[i], 0x80000000);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                c128 v = bs[(kk * 4 + t) * PB + j * 8];
+                br[j] = v.x;
+                bi[j] = flip_sign(v.y, sgnB);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    dmma884(accr[i][j], ar[i], br[j]);
+                    dmma884(acci[i][j], ar[i], bi[j]);
+                    dmma884(accr[i][j], nai[i], bi[j]);
+                    dmma884(acci[i][j], ai[i], br[j]);
+                }
+        }
+    }
+    cp_async_wait<0>();
+
+    if (p.ksplit > 1) {
+        // split-K: raw partial sums, dense M x N per split; splitk_reduce_kernel finishes the job
+        c128* part = p.partial + (size_t)split * p.M * p.N;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int m = m0 + wm * 32 + i * 8 + g;
+            if (m >= p.M) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    int n = n0 + wn * 32 + j * 8 + 2 * t + h;
+                    if (n < p.N) part[m + (size_t)p.M * n] = make_double2(accr[i][j][h], acci[i][j][h]);
+                }
+        }
+        return;
+    }
+    // ---- epilogue: C = alpha * acc + beta * C, written through the C offset tables ----
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int m = m0 + wm * 32 + i * 8 + g;
+        if (m >= p.M) continue;
+        int64_t mo = p.cm.at(m);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                int n = n0 + wn * 32 + j * 8 + 2 * t + h;
+                if (n >= p.N) continue;
+                c128* dst = C + mo + p.cn.at(n);
+                double vr = accr[i][j][h], vi = acci[i][j][h];
+                c128 o;
+                o.x = p.alpha.x * vr - p.alpha.y * vi;
+                o.y = p.alpha.x * vi + p.alpha.y * vr;
+                if (!p.beta_zero) {
+                    c128 old = *dst;
+                    o.x += p.beta.x * old.x - p.beta.y * old.y;
+                    o.y += p.beta.x * old.y + p.beta.y * old.x;
+                }
+                *dst = o;
+            }
+        }
+    }
+}
+
+// sums the split-K partials in a fixed order (deterministic) and applies alpha / beta
+__global__ void splitk_reduce_kernel(const GemmArgs p) {
+    int64_t total = (int64_t)p.M * p.N;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        int m = (int)(idx % p.M), n = (int)(idx / p.M);
+        double vr = 0.0, vi = 0.0;
+        for (int s = 0; s < p.ksplit; ++s) {
+            c128 v = p.partial[(size_t)s * total + idx];
+            vr += v.x;
+            vi += v.y;
+        }
+        c128* dst = p.C + p.cm.at(m) + p.cn.at(n) + p.cb.at(0);
+        c128 o;
+        o.x = p.alpha.x * vr - p.alpha.y * vi;
+        o.y = p.alpha.x * vi + p.alpha.y * vr;
+        if (!p.beta_zero) {
+            c128 old = *dst;
+            o.x += p.beta.x * old.x - p.beta.y * old.y;
+            o.y += p.beta.x * old.y + p.beta.y * old.x;
+        }
+        *dst = o;
+    }
+}
+
+__global__ void build_offsets_kernel(const ModeList ml, int64_t total, int64_t* __restrict__ out) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int64_t rem = idx, off = 0;
+    for (int j = 0; j < ml.n; ++j) {
+        int64_t c = rem % ml.ext[j];
+        rem /= ml.ext[j];
+        off += c * ml.stride[j];
+    }
+    out[idx] = off;
+}
+
+int32_t build_offsets(qb200_ctx* ctx, const ModeList& ml, int64_t total, int64_t* out) {
+    if (total <= 0) return QB200_OK;
+    int threads = 256;
+    int64_t blocks = (total + threads - 1) / threads;
+    build_offsets_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(ml, total, out);
+    QB_LAUNCH_CHECK(ctx);
+    return QB200_OK;
+}
+
+int32_t launch_gemm(qb200_ctx* ctx, const GemmArgs& args_in) {
+    if (args_in.M <= 0 || args_in.N <= 0 || args_in.batch <= 0) return QB200_OK;
+    GemmArgs args = args_in;
+    if (args.N > args.M) {
+        // C^T = B^T A^T: put the larger free dimension on the 128-wide side of the tile
+        std::swap(args.A, args.B);
+        std::swap(args.am, args.bn);
+        std::swap(args.ak, args.bk);
+        std::swap(args.ab, args.bb);
+        std::swap(args.cm, args.cn);
+        std::swap(args.M, args.N);
+        std::swap(args.conjA, args.conjB);
+        std::swap(args.a_kfast, args.b_kfast);
+    }
+    args.ksplit = 1;
+    args.partial = nullptr;
+    Workspace ws(ctx);
+    {
+        // split-K when the output has too few tiles to fill the machine and K is long
+        int64_t tiles = (int64_t)((args.M + BM - 1) / BM) * ((args.N + BN - 1) / BN);
+        int KT = (args.K + BK - 1) / BK;
+        if (args.batch == 1 && tiles * 2 <= ctx->sm_count && KT >= 64) {
+            int want = (int)std::min<int64_t>(ctx->sm_count / tiles, KT / 16);
+            if (want > 1) {
+                args.partial = ws.get<c128>((size_t)want * args.M * args.N);
+                if (!args.partial) QB_FAIL(ctx, QB200_E_CUDA, "gemm: split-K workspace allocation failed");
+                args.ksplit = want;
+            }
+        }
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        QB_CUDA(ctx, cudaFuncSetAttribute(gemm_c128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)GEMM_SMEM));
+        attr_set = true;
+    }
+    dim3 grid((args.M + BM - 1) / BM, (args.N + BN - 1) / BN, args.ksplit > 1 ? args.ksplit : args.batch);
+    if (grid.y > 65535 || grid.z > 65535) QB_FAIL(ctx, QB200_E_UNSUPPORTED, "gemm grid too large");
+    gemm_c128_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, ctx->stream>>>(args);
+    QB_LAUNCH_CHECK(ctx);
+    if (args.ksplit > 1) {
+        int64_t total = (int64_t)args.M * args.N;
+        unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->sm_count * 8);
+        splitk_reduce_kernel<<<blocks, 256, 0, ctx->stream>>>(args);
+        QB_LAUNCH_CHECK(ctx);
+    }
+    return QB200_OK;
+}
+
+}  // namespace qb
+
+// Plain column-major GEMM view used by QR / MPS code.  opX: 0 = N, 1 = T, 2 = C, 3 = conj (no transpose)
+int32_t qb_gemm(qb200_ctx* ctx, int opA, int opB, int64_t M, int64_t N, int64_t K, c128 alpha, const c128* A,
+                int64_t lda, const c128* B, int64_t ldb, c128 beta, c128* C, int64_t ldc) {
+    using namespace qb;
+    GemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.A = A;
+    g.B = B;
+    g.C = C;
+    bool ta = (opA == 1 || opA == 2), tb = (opB == 1 || opB == 2);
+    // A(i,k): N -> i + k*lda ; T -> k + i*lda
+    g.am = {nullptr, ta ? lda : 1};
+    g.ak = {nullptr, ta ? 1 : lda};
+    g.bk = {nullptr, tb ? ldb : 1};
+    g.bn = {nullptr, tb ? 1 : ldb};
+    g.cm = {nullptr, 1};
+    g.cn = {nullptr, ldc};
+    g.ab = g.bb = g.cb = {nullptr, 0};
+    g.M = (int)M;
+    g.N = (int)N;
+    g.K = (int)K;
+    g.batch = 1;
+    g.conjA = (opA >= 2);
+    g.conjB = (opB >= 2);
+    g.a_kfast = ta;
+    g.b_kfast = !tb;
+    g.alpha = alpha;
+    g.beta = beta;
+    g.beta_zero = (beta.x == 0.0 && beta.y == 0.0);
+    return launch_gemm(ctx, g);
+}

@@ -1,0 +1,265 @@
+// K4: thin QR of a ComplexF64 matrix (LinearAlgebra.qr(::Tensor; left_inds, right_inds, virtualind),
+// Chain.jl:367), hand-written for sm_100a.
+//
+// Panels of 32 columns.  Each panel is factorised by a communication-avoiding TSQR: the rows are cut in
+// chunks of <= 192; one CTA per chunk runs an unblocked Householder QR in shared memory (column norms and
+// reflector applications by warp-shuffle reductions), keeps its explicit Q_i in place and sends its
+// 32 x 32 R_i to a stack that is factorised recursively; a second kernel multiplies the Q_i by the
+// matching 32 x 32 block of the upper level's Q.  The trailing matrix is updated with two DMMA GEMMs
+// (C = Q_p^H T with split-K, T -= Q_p C): a right-looking block Gram-Schmidt.  The whole pass is run
+// twice (A = Q1 R1, Q1 = Q R2, R = R2 R1) -- "twice is enough" -- which restores orthogonality to
+// machine precision; Q is produced explicitly, so there is no separate "form Q" phase.
+#include <algorithm>
+
+#include "common.cuh"
+#include "mma.cuh"
+
+using namespace qb;
+
+namespace {
+
+constexpr int QW = 32;    // panel width
+constexpr int QCH = 192;  // max rows per TSQR leaf
+constexpr int QPITCH = QCH + 1;
+constexpr int QR_THREADS = 256;
+constexpr size_t LEAF_SMEM = (size_t)(QW * QPITCH + QW * QW + 4 * QW) * sizeof(c128);
+
+__device__ __forceinline__ void chunk_range(int rows, int nch, int c, int& begin, int& cnt) {
+    int base = rows / nch, rem = rows % nch;
+    begin = c * base + min(c, rem);
+    cnt = base + (c < rem ? 1 : 0);
+}
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < QR_THREADS / 32; ++i) s += red[i];
+    return s;
+}
+
+// Householder QR of one row chunk (rows x w, rows >= w) in shared memory; Q explicit in place, R to Rdst
+__global__ void __launch_bounds__(QR_THREADS, 1)
+    tsqr_leaf_kernel(c128* __restrict__ P, int64_t ld, int rows_total, int nch, int w, c128* __restrict__ Rdst,
+                     int64_t ldr, int stacked) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    c128* T = reinterpret_cast<c128*>(smem_raw);  // [w][QPITCH] column-major tile
+    c128* Rs = T + QW * QPITCH;                   // [w][w] saved R
+    c128* tau = Rs + QW * QW;                     // [w]
+    double* red = reinterpret_cast<double*>(tau + QW);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int r0, rows;
+    chunk_range(rows_total, nch, blockIdx.x, r0, rows);
+    c128* Pc = P + r0;
+    for (int e = tid; e < rows * w; e += QR_THREADS) {
+        int r = e % rows, c = e / rows;
+        T[c * QPITCH + r] = Pc[r + (int64_t)c * ld];
+    }
+    __syncthreads();
+
+    for (int j = 0; j < w; ++j) {
+        // |x(j+1:)|^2
+        double part = 0.0;
+        for (int r = j + 1 + tid; r < rows; r += QR_THREADS) {
+            c128 v = T[j * QPITCH + r];
+            part += v.x * v.x + v.y * v.y;
+        }
+        double xn2 = block_sum(part, red);
+        c128 alpha = T[j * QPITCH + j];
+        c128 tj = make_double2(0.0, 0.0), scl = make_double2(0.0, 0.0);
+        double beta = alpha.x;
+        if (xn2 != 0.0 || alpha.y != 0.0) {
+            double nrm = sqrt(alpha.x * alpha.x + alpha.y * alpha.y + xn2);
+            beta = (alpha.x >= 0.0) ? -nrm : nrm;
+            tj = make_double2((beta - alpha.x) / beta, -alpha.y / beta);
+            // 1 / (alpha - beta)
+            double dr = alpha.x - beta, di = alpha.y, den = dr * dr + di * di;
+            scl = make_double2(dr / den, -di / den);
+        }
+        __syncthreads();
+        // v = x / (alpha - beta) below the diagonal, v_j = 1 implicit; R_jj = beta
+        for (int r = j + 1 + tid; r < rows; r += QR_THREADS) T[j * QPITCH + r] = cmul(T[j * QPITCH + r], scl);
+        if (tid == 0) {
+            T[j * QPITCH + j] = make_double2(beta, 0.0);
+            tau[j] = tj;
+        }
+        __syncthreads();
+        // A(j:, c) <- (I - conj(tau) v v^H) A(j:, c) for c > j : one warp per column
+        for (int c = j + 1 + warp; c < w; c += QR_THREADS / 32) {
+            double sr = 0.0, si = 0.0;
+            for (int r = j + 1 + lane; r < rows; r += 32) {
+                c128 s = cmulc(T[c * QPITCH + r], T[j * QPITCH + r]);  // a * conj(v)
+                sr += s.x;
+                si += s.y;
+            }
+            sr = warp_sum(sr);
+            si = warp_sum(si);
+            c128 ajc = T[c * QPITCH + j];
+            c128 s = make_double2(sr + ajc.x, si + ajc.y);       // v^H a (v_j = 1)
+            c128 f = cmul(cconj(tj), s);                          // conj(tau) * s
+            for (int r = j + 1 + lane; r < rows; r += 32)
+                T[c * QPITCH + r] = csub(T[c * QPITCH + r], cmul(f, T[j * QPITCH + r]));
+            if (lane == 0) T[c * QPITCH + j] = csub(ajc, f);
+        }
+        __syncthreads();
+    }
+    // save R (upper triangle)
+    for (int e = tid; e < w * w; e += QR_THREADS) {
+        int r = e % w, c = e / w;
+        Rs[e] = (r <= c) ? T[c * QPITCH + r] : make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+    // form Q in place (LAPACK zung2r)
+    for (int j = w - 1; j >= 0; --j) {
+        c128 tj = tau[j];
+        for (int c = j + 1 + warp; c < w; c += QR_THREADS / 32) {
+            double sr = 0.0, si = 0.0;
+            for (int r = j + 1 + lane; r < rows; r += 32) {
+                c128 s = cmulc(T[c * QPITCH + r], T[j * QPITCH + r]);
+                sr += s.x;
+                si += s.y;
+            }
+            sr = warp_sum(sr);
+            si = warp_sum(si);
+            c128 ajc = T[c * QPITCH + j];  // row j of column c (0 at this point, kept general)
+            c128 s = make_double2(sr + ajc.x, si + ajc.y);
+            c128 f = cmul(tj, s);
+            for (int r = j + 1 + lane; r < rows; r += 32)
+                T[c * QPITCH + r] = csub(T[c * QPITCH + r], cmul(f, T[j * QPITCH + r]));
+            if (lane == 0) T[c * QPITCH + j] = csub(ajc, f);
+        }
+        __syncthreads();
+        for (int r = tid; r < rows; r += QR_THREADS) {
+            c128 v;
+            if (r < j)
+                v = make_double2(0.0, 0.0);
+            else if (r == j)
+                v = make_double2(1.0 - tj.x, -tj.y);
+            else {
+                c128 x = T[j * QPITCH + r];
+                v = make_double2(-(tj.x * x.x - tj.y * x.y), -(tj.x * x.y + tj.y * x.x));
+            }
+            T[j * QPITCH + r] = v;
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < rows * w; e += QR_THREADS) {
+        int r = e % rows, c = e / rows;
+        Pc[r + (int64_t)c * ld] = T[c * QPITCH + r];
+    }
+    c128* rd = stacked ? (Rdst + (int64_t)blockIdx.x * w) : Rdst;
+    for (int e = tid; e < w * w; e += QR_THREADS) {
+        int r = e % w, c = e / w;
+        rd[r + (int64_t)c * ldr] = Rs[e];
+    }
+}
+
+// P_i <- P_i * B_i with B_i = rows [i*w, (i+1)*w) of the upper-level Q (ldq)
+__global__ void __launch_bounds__(QR_THREADS)
+    tsqr_apply_kernel(c128* __restrict__ P, int64_t ld, int rows_total, int nch, int w, const c128* __restrict__ Qup,
+                      int64_t ldq) {
+    __shared__ c128 B[QW * QW];
+    int r0, rows;
+    chunk_range(rows_total, nch, blockIdx.x, r0, rows);
+    for (int e = threadIdx.x; e < w * w; e += QR_THREADS) {
+        int r = e % w, c = e / w;
+        B[e] = Qup[(int64_t)blockIdx.x * w + r + (int64_t)c * ldq];
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < rows; r += QR_THREADS) {
+        c128 row[QW];
+        c128* p = P + r0 + r;
+        for (int c = 0; c < w; ++c) row[c] = p[(int64_t)c * ld];
+        for (int c2 = 0; c2 < w; ++c2) {
+            c128 acc = make_double2(0.0, 0.0);
+            for (int c = 0; c < w; ++c) acc = cadd(acc, cmul(row[c], B[c + c2 * w]));
+            p[(int64_t)c2 * ld] = acc;
+        }
+    }
+}
+
+__global__ void zero_kernel(c128* x, int64_t rows, int64_t cols, int64_t ld) {
+    int64_t total = rows * cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        x[i % rows + (i / rows) * ld] = make_double2(0.0, 0.0);
+}
+
+}  // namespace
+
+static int32_t tsqr(qb200_ctx* ctx, c128* P, int64_t ld, int rows, int w, c128* Rout, int64_t ldr) {
+    int nch = (rows + QCH - 1) / QCH;
+    if (nch == 1) {
+        tsqr_leaf_kernel<<<1, QR_THREADS, LEAF_SMEM, ctx->stream>>>(P, ld, rows, 1, w, Rout, ldr, 0);
+        QB_LAUNCH_CHECK(ctx);
+        return QB200_OK;
+    }
+    Workspace ws(ctx);
+    int srows = nch * w;
+    c128* stack = ws.get<c128>((size_t)srows * w);
+    if (!stack) QB_FAIL(ctx, QB200_E_CUDA, "qr: workspace allocation failed");
+    tsqr_leaf_kernel<<<nch, QR_THREADS, LEAF_SMEM, ctx->stream>>>(P, ld, rows, nch, w, stack, srows, 1);
+    QB_LAUNCH_CHECK(ctx);
+    QB_TRY(tsqr(ctx, stack, srows, srows, w, Rout, ldr));
+    tsqr_apply_kernel<<<nch, QR_THREADS, 0, ctx->stream>>>(P, ld, rows, nch, w, stack, srows);
+    QB_LAUNCH_CHECK(ctx);
+    return QB200_OK;
+}
+
+// one right-looking block Gram-Schmidt pass: Q (m x k, in place) = Q' R, R k x k upper triangular (zeroed first)
+static int32_t bgs_pass(qb200_ctx* ctx, int64_t m, int64_t k, c128* Q, int64_t ldq, c128* R, int64_t ldr) {
+    const c128 one = make_double2(1.0, 0.0), zero = make_double2(0.0, 0.0), mone = make_double2(-1.0, 0.0);
+    zero_kernel<<<(unsigned)std::min<int64_t>((k * k + 255) / 256, 4096), 256, 0, ctx->stream>>>(R, k, k, ldr);
+    QB_LAUNCH_CHECK(ctx);
+    for (int64_t j0 = 0; j0 < k; j0 += QW) {
+        int w = (int)std::min<int64_t>(QW, k - j0);
+        c128* P = Q + j0 * ldq;
+        QB_TRY(tsqr(ctx, P, ldq, (int)m, w, R + j0 + j0 * ldr, ldr));
+        int64_t nt = k - j0 - w;
+        if (nt > 0) {
+            c128* T = Q + (j0 + w) * ldq;
+            c128* C = R + j0 + (j0 + w) * ldr;
+            QB_TRY(qb_gemm(ctx, 2, 0, w, nt, m, one, P, ldq, T, ldq, zero, C, ldr));   // C = P^H T
+            QB_TRY(qb_gemm(ctx, 0, 0, m, nt, w, mone, P, ldq, C, ldr, one, T, ldq));   // T -= P C
+        }
+    }
+    return QB200_OK;
+}
+
+int32_t qb_qr_matrix(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64_t lda, c128* Q, int64_t ldq,
+                     c128* R, int64_t ldr) {
+    static bool attr = false;
+    if (!attr) {
+        QB_CUDA(ctx, cudaFuncSetAttribute(tsqr_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEAF_SMEM));
+        attr = true;
+    }
+    if (m <= 0 || n <= 0) QB_FAIL(ctx, QB200_E_INVALID, "qr: empty matrix");
+    if (m > INT32_MAX / 2) QB_FAIL(ctx, QB200_E_UNSUPPORTED, "qr: too many rows");
+    const int64_t k = std::min(m, n);
+    const c128 one = make_double2(1.0, 0.0), zero = make_double2(0.0, 0.0);
+    QB_TRY(qb_copy_matrix(ctx, m, k, A, lda, Q, ldq, 0));
+    Workspace ws(ctx);
+    c128* R1 = ws.get<c128>((size_t)k * k);
+    c128* R2 = ws.get<c128>((size_t)k * k);
+    if (!R1 || !R2) QB_FAIL(ctx, QB200_E_CUDA, "qr: workspace allocation failed");
+    QB_TRY(bgs_pass(ctx, m, k, Q, ldq, R1, k));
+    QB_TRY(bgs_pass(ctx, m, k, Q, ldq, R2, k));
+    QB_TRY(qb_gemm(ctx, 0, 0, k, k, k, one, R2, k, R1, k, zero, R, ldr));
+    if (n > k) QB_TRY(qb_gemm(ctx, 2, 0, k, n - k, m, one, Q, ldq, A + k * lda, lda, zero, R + k * ldr, ldr));
+    return QB200_OK;
+}
+
+extern "C" int32_t qb200_qr(qb200_ctx* ctx, const qb200_tensor* A, const int32_t* order, int32_t nleft,
+                            qb200_tensor* Q, qb200_tensor* R) {
+    if (!ctx || !A || !order || !Q || !R) QB_FAIL(ctx, QB200_E_INVALID, "qr: null argument");
+    Workspace ws(ctx);
+    const c128* mat;
+    int64_t m, n;
+    QB_TRY(qb_matricize(ctx, A, order, nleft, ws, &mat, &m, &n));
+    int64_t k = std::min(m, n);
+    if (Q->dtype != QB200_C128 || R->dtype != QB200_C128 || Q->numel() != m * k || R->numel() != k * n)
+        QB_FAIL(ctx, QB200_E_INVALID, "qr: Q must hold rows*k and R k*cols ComplexF64 entries");
+    return qb_qr_matrix(ctx, m, n, mat, m, (c128*)Q->data, m, (c128*)R->data, k);
+}

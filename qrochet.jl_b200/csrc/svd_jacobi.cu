@@ -1,0 +1,702 @@
+// K5: one-sided block-Jacobi SVD of a ComplexF64 matrix, hand-written for sm_100a.
+//
+// Work matrix Z = [X ; V] (stacked, column-major, ld = mp + np): X starts as A (zero-padded to
+// mp x np, both multiples of 64), V as the identity.  Columns are grouped in blocks of 32; a step of
+// the round-robin tournament pairs the nb = np/32 blocks into nb/2 disjoint pairs and runs three
+// kernels over all pairs at once:
+//   gram   : G_p = P_p^H P_p (64 x 64) for the panel P_p = [X_I X_J], split along the rows over
+//            several CTAs (DMMA tiles, 3-stage cp.async pipeline), partial sums written per split;
+//   evd    : one CTA per pair sums the partials in a fixed order (deterministic), then runs a
+//            two-sided cyclic Jacobi on the 64 x 64 Hermitian G in shared memory (32 disjoint
+//            rotations per parallel step) and accumulates the rotations into the unitary W_p;
+//   update : [X;V]_p <- [X;V]_p W_p with DMMA tiles, double-buffered over 64-row chunks, in place.
+// nb-1 steps make a sweep; sweeps repeat until the largest |x_i^H x_j| / (|x_i||x_j|) seen in a sweep
+// is below tolerance.  sigma_j = |x_j|, U = X / sigma, V accumulated.  The rotations only ever come
+// from Gram entries of the columns they are applied to, and W_p is a product of exact plane
+// rotations, so singular values keep norm-wise accuracy ~ eps * sigma_1 (same class as LAPACK gesdd).
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+
+#include "common.cuh"
+#include "mma.cuh"
+
+using namespace qb;
+
+namespace {
+
+constexpr int JB = 32;   // column block width
+constexpr int JP = 64;   // panel width (two blocks)
+constexpr int GLD = 65;  // shared-memory pitch of the 64 x 64 matrices in the evd kernel
+
+// circle-method round robin: n (even) players, round `step` in [0, n-1), pair k in [0, n/2)
+__device__ __forceinline__ void rr_pair(int n, int step, int k, int& p, int& q) {
+    if (n == 2) {
+        p = 0;
+        q = 1;
+        return;
+    }
+    int a, b;
+    if (k == 0) {
+        a = n - 1;
+        b = step;
+    } else {
+        a = (step + k) % (n - 1);
+        b = (step - k + (n - 1)) % (n - 1);
+    }
+    p = min(a, b);
+    q = max(a, b);
+}
+
+__device__ __forceinline__ int64_t panel_col(int I, int J, int c) { return (c < JB) ? (I * JB + c) : (J * JB + c - JB); }
+
+// ---------------------------------------------------------------------------------------------
+// gram kernel
+constexpr int G_BKR = 32, G_NST = 3, G_PITCH = G_BKR + 4;
+constexpr size_t GRAM_SMEM = (size_t)G_NST * JP * G_PITCH * sizeof(c128);
+
+__global__ void __launch_bounds__(256, 2)
+    jacobi_gram_kernel(const c128* __restrict__ Z, int64_t ldz, int mp, int nb, int step, int ksplit,
+                       c128* __restrict__ Gpart) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    c128* Ps = reinterpret_cast<c128*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int pair = blockIdx.x, split = blockIdx.y;
+    int I, J;
+    rr_pair(nb, step, pair, I, J);
+
+    int rows_per = ((mp + ksplit - 1) / ksplit + G_BKR - 1) / G_BKR * G_BKR;
+    int r_begin = split * rows_per;
+    int r_end = min(mp, r_begin + rows_per);
+    int nchunks = (r_end > r_begin) ? (r_end - r_begin + G_BKR - 1) / G_BKR : 0;
+
+    // loader: 64 cols x 32 rows per chunk, 8 elements per thread, rows contiguous
+    const int l_row = tid & 31, l_col0 = tid >> 5;
+    auto load_chunk = [&](int c, int st) {
+        c128* ps = Ps + (size_t)st * JP * G_PITCH;
+        int row = r_begin + c * G_BKR + l_row;
+        bool ok = row < r_end;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int col = l_col0 + 8 * i;
+            const c128* src = Z + (ok ? (row + panel_col(I, J, col) * ldz) : 0);
+            cp_async16(ps + col * G_PITCH + l_row, src, ok);
+        }
+    };
+
+    const int wi = warp & 3, wj = warp >> 2;
+    double cr[2][4][2], ci[2][4][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) cr[a][b][0] = cr[a][b][1] = ci[a][b][0] = ci[a][b][1] = 0.0;
+
+#pragma unroll
+    for (int s = 0; s < G_NST - 1; ++s) {
+        if (s < nchunks) load_chunk(s, s);
+        cp_async_commit();
+    }
+    for (int c = 0; c < nchunks; ++c) {
+        cp_async_wait<G_NST - 2>();
+        __syncthreads();
+        {
+            int nc = c + G_NST - 1;
+            if (nc < nchunks) load_chunk(nc, nc % G_NST);
+            cp_async_commit();
+        }
+        const c128* ps = Ps + (size_t)(c % G_NST) * JP * G_PITCH;
+        const c128* pa = ps + (wi * 16 + g) * G_PITCH + t;
+        const c128* pb = ps + (wj * 32 + g) * G_PITCH + t;
+#pragma unroll
+        for (int kk = 0; kk < G_BKR / 4; ++kk) {
+            double ar[2], ay[2], nay[2], br[4], bi[4];
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                c128 v = pa[a * 8 * G_PITCH + kk * 4];
+                ar[a] = v.x;
+                ay[a] = v.y;
+                nay[a] = -v.y;
+            }
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                c128 v = pb[b * 8 * G_PITCH + kk * 4];
+                br[b] = v.x;
+                bi[b] = v.y;
+            }
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    dmma884(cr[a][b], ar[a], br[b]);
+                    dmma884(ci[a][b], ar[a], bi[b]);
+                    dmma884(cr[a][b], ay[a], bi[b]);
+                    dmma884(ci[a][b], nay[a], br[b]);
+                }
+        }
+    }
+    cp_async_wait<0>();
+    c128* out = Gpart + ((size_t)pair * ksplit + split) * (JP * JP);
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                int i = wi * 16 + a * 8 + g, j = wj * 32 + b * 8 + 2 * t + h;
+                out[i + JP * j] = make_double2(cr[a][b][h], ci[a][b][h]);
+            }
+}
+
+// ---------------------------------------------------------------------------------------------
+// evd kernel: two-sided Jacobi on the 64 x 64 Hermitian Gram matrix
+constexpr int EVD_THREADS = 512;
+constexpr size_t EVD_SMEM = (size_t)2 * JP * GLD * sizeof(c128) + 32 * sizeof(double) + 32 * sizeof(c128) +
+                            64 * sizeof(int) + 64 * sizeof(double);
+
+__global__ void __launch_bounds__(EVD_THREADS, 1)
+    jacobi_evd_kernel(const c128* __restrict__ Gpart, int ksplit, c128* __restrict__ Wout, int* __restrict__ flags,
+                      unsigned long long* __restrict__ sweep_stat, double rot_tol, int inner_sweeps) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    c128* G = reinterpret_cast<c128*>(smem_raw);
+    c128* W = G + JP * GLD;
+    double* rcs = reinterpret_cast<double*>(W + JP * GLD);
+    c128* rsn = reinterpret_cast<c128*>(rcs + 32);
+    int* rpq = reinterpret_cast<int*>(rsn + 32);
+    double* red = reinterpret_cast<double*>(rpq + 64);
+    __shared__ int any_rot;
+
+    const int tid = threadIdx.x, pair = blockIdx.x;
+    const c128* src = Gpart + (size_t)pair * ksplit * (JP * JP);
+    for (int e = tid; e < JP * JP; e += EVD_THREADS) {
+        double sx = 0.0, sy = 0.0;
+        for (int s = 0; s < ksplit; ++s) {
+            c128 v = src[(size_t)s * (JP * JP) + e];
+            sx += v.x;
+            sy += v.y;
+        }
+        int r = e & 63, c = e >> 6;
+        G[c * GLD + r] = make_double2(sx, sy);
+        W[c * GLD + r] = make_double2(r == c ? 1.0 : 0.0, 0.0);
+    }
+    __syncthreads();
+    // largest relative off-diagonal entry of the incoming Gram matrix
+    double mx = 0.0;
+    for (int e = tid; e < JP * JP; e += EVD_THREADS) {
+        int r = e & 63, c = e >> 6;
+        if (r < c) {
+            double a = G[r * GLD + r].x, b = G[c * GLD + c].x;
+            c128 v = G[c * GLD + r];
+            double d = a * b;
+            if (d > 0.0) mx = fmax(mx, sqrt((v.x * v.x + v.y * v.y) / d));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((tid & 31) == 0) red[tid >> 5] = mx;
+    __syncthreads();
+    if (tid < 32) {
+        double v = (tid < EVD_THREADS / 32) ? red[tid] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if (tid == 0) {
+            red[0] = v;
+            atomicMax(sweep_stat, (unsigned long long)__double_as_longlong(v));
+        }
+    }
+    __syncthreads();
+    mx = red[0];
+    if (!(mx > rot_tol)) {
+        if (tid == 0) flags[pair] = 0;
+        return;
+    }
+    if (tid == 0) flags[pair] = 1;
+
+    for (int sw = 0; sw < inner_sweeps; ++sw) {
+        if (tid == 0) any_rot = 0;
+        __syncthreads();
+        for (int st = 0; st < JP - 1; ++st) {
+            if (tid < 32) {
+                int p, q;
+                rr_pair(JP, st, tid, p, q);
+                double a = G[p * GLD + p].x, b = G[q * GLD + q].x;
+                c128 c = G[q * GLD + p];  // G[p][q] = x_p^H x_q  (row p, column q)
+                double absc = sqrt(c.x * c.x + c.y * c.y);
+                double cs = 1.0;
+                c128 sn = make_double2(0.0, 0.0);
+                if (absc > rot_tol * sqrt(a * b) && absc > 0.0) {
+                    double zeta = (b - a) / (2.0 * absc);
+                    double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                    cs = 1.0 / sqrt(1.0 + tt * tt);
+                    double s = tt * cs;
+                    sn = make_double2(s * c.x / absc, s * c.y / absc);  // sn * w, w = c/|c|
+                    any_rot = 1;
+                }
+                rcs[tid] = cs;
+                rsn[tid] = sn;
+                rpq[2 * tid] = p;
+                rpq[2 * tid + 1] = q;
+            }
+            __syncthreads();
+            // column phase on G and W: [x_p, x_q] <- [x_p, x_q] J,  J = [[cs, sn w], [-sn conj(w), cs]]
+            for (int item = tid; item < 2 * 32 * JP; item += EVD_THREADS) {
+                int r = item & 63, k = (item >> 6) & 31;
+                c128* M = (item >> 11) ? W : G;
+                int p = rpq[2 * k], q = rpq[2 * k + 1];
+                double cs = rcs[k];
+                c128 sn = rsn[k];
+                c128 xp = M[p * GLD + r], xq = M[q * GLD + r];
+                c128 np_ = csub(cscale(xp, cs), cmul(cconj(sn), xq));
+                c128 nq_ = cadd(cmul(sn, xp), cscale(xq, cs));
+                M[p * GLD + r] = np_;
+                M[q * GLD + r] = nq_;
+            }
+            __syncthreads();
+            // row phase on G: G <- J^H G
+            for (int item = tid; item < 32 * JP; item += EVD_THREADS) {
+                int c = item & 63, k = item >> 6;
+                int p = rpq[2 * k], q = rpq[2 * k + 1];
+                double cs = rcs[k];
+                c128 sn = rsn[k];
+                c128 gp = G[c * GLD + p], gq = G[c * GLD + q];
+                c128 np_ = csub(cscale(gp, cs), cmul(sn, gq));
+                c128 nq_ = cadd(cmul(cconj(sn), gp), cscale(gq, cs));
+                bool rotated = (sn.x != 0.0 || sn.y != 0.0);
+                if (rotated && c == q) np_ = make_double2(0.0, 0.0);
+                if (rotated && c == p) nq_ = make_double2(0.0, 0.0);
+                if (c == p) np_.y = 0.0;
+                if (c == q) nq_.y = 0.0;
+                G[c * GLD + p] = np_;
+                G[c * GLD + q] = nq_;
+            }
+            __syncthreads();
+        }
+        if (!any_rot) break;
+    }
+    c128* dst = Wout + (size_t)pair * (JP * JP);
+    for (int e = tid; e < JP * JP; e += EVD_THREADS) {
+        int r = e & 63, c = e >> 6;
+        dst[e] = W[c * GLD + r];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// update kernel: Z_p <- Z_p W_p, 64-row chunks double buffered
+constexpr int U_ZP = 66, U_WP = 68;
+constexpr size_t UPD_SMEM = (size_t)(JP * U_WP + 2 * JP * U_ZP) * sizeof(c128);
+
+__global__ void __launch_bounds__(256, 1)
+    jacobi_update_kernel(c128* __restrict__ Z, int64_t ldz, int nb, int step, const c128* __restrict__ Wg,
+                         const int* __restrict__ flags, int chunks_per_cta, int total_chunks) {
+    const int pair = blockIdx.x;
+    if (!flags[pair]) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    c128* Ws = reinterpret_cast<c128*>(smem_raw);  // [n][k] pitch 68
+    c128* Zs = Ws + JP * U_WP;                     // [2][col][row] pitch 66
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    int I, J;
+    rr_pair(nb, step, pair, I, J);
+    const int c_begin = blockIdx.y * chunks_per_cta;
+    const int c_end = min(total_chunks, c_begin + chunks_per_cta);
+    if (c_begin >= c_end) return;
+
+    {
+        const c128* wsrc = Wg + (size_t)pair * (JP * JP);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            int e = tid + 256 * i;
+            int k = e & 63, n = e >> 6;
+            cp_async16(Ws + n * U_WP + k, wsrc + e, true);
+        }
+    }
+    const int l_row = tid & 63, l_col0 = tid >> 6;
+    auto load_chunk = [&](int c, int st) {
+        c128* zs = Zs + (size_t)st * JP * U_ZP;
+        int64_t row = (int64_t)c * 64 + l_row;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            int col = l_col0 + 4 * i;
+            cp_async16(zs + col * U_ZP + l_row, Z + row + panel_col(I, J, col) * ldz, true);
+        }
+    };
+    load_chunk(c_begin, 0);
+    cp_async_commit();
+
+    const int wi = warp & 3, wj = warp >> 2;
+    for (int c = c_begin; c < c_end; ++c) {
+        int st = (c - c_begin) & 1;
+        if (c + 1 < c_end) load_chunk(c + 1, st ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const c128* za = Zs + (size_t)st * JP * U_ZP + wi * 16 + g;
+        const c128* wb = Ws + (wj * 32 + g) * U_WP + t;
+        double cr[2][4][2], ci[2][4][2];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) cr[a][b][0] = cr[a][b][1] = ci[a][b][0] = ci[a][b][1] = 0.0;
+#pragma unroll 4
+        for (int kk = 0; kk < JP / 4; ++kk) {
+            double ar[2], ai[2], nai[2], br[4], bi[4];
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                c128 v = za[(kk * 4 + t) * U_ZP + a * 8];
+                ar[a] = v.x;
+                ai[a] = v.y;
+                nai[a] = -v.y;
+            }
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                c128 v = wb[b * 8 * U_WP + kk * 4];
+                br[b] = v.x;
+                bi[b] = v.y;
+            }
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    dmma884(cr[a][b], ar[a], br[b]);
+                    dmma884(ci[a][b], ar[a], bi[b]);
+                    dmma884(cr[a][b], nai[a], bi[b]);
+                    dmma884(ci[a][b], ai[a], br[b]);
+                }
+        }
+        int64_t r0 = (int64_t)c * 64 + wi * 16 + g;
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    int n = wj * 32 + b * 8 + 2 * t + h;
+                    Z[r0 + a * 8 + panel_col(I, J, n) * ldz] = make_double2(cr[a][b][h], ci[a][b][h]);
+                }
+        __syncthreads();  // everyone is done with stage st before it is refilled
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// set-up / finish kernels
+// Z[:, :] = [A or A^H zero-padded ; I]
+__global__ void svd_init_kernel(c128* __restrict__ Z, int64_t ldz, int mp, int np, int64_t m, int64_t n,
+                                const c128* __restrict__ A, int64_t lda, int transposed) {
+    int64_t total = ldz * np;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = idx % ldz, c = idx / ldz;
+        c128 v = make_double2(0.0, 0.0);
+        if (r < mp) {
+            if (r < m && c < n) {
+                if (!transposed)
+                    v = A[r + c * lda];
+                else {
+                    c128 a = A[c + r * lda];
+                    v = make_double2(a.x, -a.y);
+                }
+            }
+        } else if (r - mp == c) {
+            v.x = 1.0;
+        }
+        Z[idx] = v;
+    }
+}
+
+// one warp per column: sigma_j = |X[:, j]|
+__global__ void col_norm_kernel(const c128* __restrict__ Z, int64_t ldz, int mp, int np, double* __restrict__ sigma) {
+    int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (col >= np) return;
+    int lane = threadIdx.x & 31;
+    const c128* x = Z + (int64_t)col * ldz;
+    // scaled accumulation is unnecessary here: entries are O(sigma_1); plain sum of squares in fp64
+    double acc = 0.0;
+    for (int r = lane; r < mp; r += 32) {
+        c128 v = x[r];
+        acc += v.x * v.x + v.y * v.y;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) sigma[col] = sqrt(acc);
+}
+
+// dst(i, j) or dst(j, i) = f(src(i, perm[j])) for i < rows, j < kept
+__global__ void svd_emit_kernel(const c128* __restrict__ src, int64_t ldz, int64_t rows, int64_t kept,
+                                const int* __restrict__ perm, const double* __restrict__ sigma, int normalize,
+                                int conj, int transpose_out, c128* __restrict__ dst, int64_t ldd,
+                                const double* __restrict__ sc, int64_t sc_mod, int64_t sc_div) {
+    int64_t total = rows * kept;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        int64_t i = idx % rows, j = idx / rows;
+        int pj = perm[j];
+        c128 v = src[i + (int64_t)pj * ldz];
+        double f = 1.0;
+        if (normalize) {
+            double s = sigma[pj];
+            f = (s > 0.0) ? 1.0 / s : 0.0;
+        }
+        if (sc) f *= sc[(sc_mod > 0 ? i % sc_mod : i) / sc_div];
+        v.x *= f;
+        v.y *= conj ? -f : f;
+        if (transpose_out)
+            dst[j + i * ldd] = v;
+        else
+            dst[i + j * ldd] = v;
+    }
+}
+
+__global__ void svd_emit_sigma_kernel(const double* __restrict__ sigma, const int* __restrict__ perm, int64_t kept,
+                                      double scale, double* __restrict__ S) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < kept) S[j] = sigma[perm[j]] * scale;
+}
+
+}  // namespace
+
+struct SvdState {
+    int64_t m, n;  // original problem
+    bool transposed;
+    int64_t wm, wn;  // working problem (wm >= wn)
+    int mp, np;
+    int64_t ldz;
+    c128* Z = nullptr;
+    double* sigma_dev = nullptr;
+    int* perm_dev = nullptr;
+    std::vector<int> perm;
+};
+
+static unsigned grid_cap(qb200_ctx* ctx, int64_t n, int threads) {
+    int64_t b = (n + threads - 1) / threads, cap = (int64_t)ctx->sm_count * 16;
+    return (unsigned)std::max<int64_t>(1, std::min(b, cap));
+}
+
+void qb_svd_release(qb200_ctx* ctx, SvdState* st) {
+    if (!st) return;
+    if (st->Z) cudaFreeAsync(st->Z, ctx->stream);
+    if (st->sigma_dev) cudaFreeAsync(st->sigma_dev, ctx->stream);
+    if (st->perm_dev) cudaFreeAsync(st->perm_dev, ctx->stream);
+    delete st;
+}
+
+int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64_t lda, SvdState** out,
+                      std::vector<double>& sigma) {
+    static bool attrs = false;
+    if (!attrs) {
+        QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRAM_SMEM));
+        QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_evd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EVD_SMEM));
+        QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM));
+        attrs = true;
+    }
+    if (m <= 0 || n <= 0) QB_FAIL(ctx, QB200_E_INVALID, "svd: empty matrix");
+    SvdState* st = new SvdState();
+    st->m = m;
+    st->n = n;
+    st->transposed = m < n;
+    st->wm = st->transposed ? n : m;
+    st->wn = st->transposed ? m : n;
+    if (st->wm > (1 << 30)) {
+        delete st;
+        QB_FAIL(ctx, QB200_E_UNSUPPORTED, "svd: matrix too large");
+    }
+    st->mp = (int)((st->wm + 63) / 64 * 64);
+    st->np = (int)((st->wn + 63) / 64 * 64);
+    st->ldz = (int64_t)st->mp + st->np;
+    const int nb = st->np / JB, npairs = nb / 2, nsteps = (nb == 2) ? 1 : nb - 1;
+
+    auto fail = [&](int32_t code) {
+        qb_svd_release(ctx, st);
+        return code;
+    };
+    if (cudaMallocAsync(&st->Z, sizeof(c128) * st->ldz * st->np, ctx->stream) != cudaSuccess ||
+        cudaMallocAsync(&st->sigma_dev, sizeof(double) * st->np, ctx->stream) != cudaSuccess ||
+        cudaMallocAsync(&st->perm_dev, sizeof(int) * st->np, ctx->stream) != cudaSuccess) {
+        ctx->err = "svd: out of device memory";
+        return fail(QB200_E_CUDA);
+    }
+    svd_init_kernel<<<grid_cap(ctx, st->ldz * st->np, 256), 256, 0, ctx->stream>>>(st->Z, st->ldz, st->mp, st->np,
+                                                                                  st->wm, st->wn, A, lda,
+                                                                                  st->transposed ? 1 : 0);
+    ctx->launches++;
+
+    // split the Gram rows so that there are about two CTAs per SM
+    int ksplit = std::max(1, std::min(st->mp / G_BKR, (2 * ctx->sm_count + npairs - 1) / npairs));
+    if (ksplit > 16) ksplit = 16;
+    const int total_chunks = (int)(st->ldz / 64);
+    int parts = std::max(1, std::min(total_chunks, ctx->sm_count / npairs));
+    int chunks_per_cta = (total_chunks + parts - 1) / parts;
+    parts = (total_chunks + chunks_per_cta - 1) / chunks_per_cta;
+
+    Workspace ws(ctx);
+    c128* Gpart = ws.get<c128>((size_t)npairs * ksplit * JP * JP);
+    c128* Wg = ws.get<c128>((size_t)npairs * JP * JP);
+    int* flags = ws.get<int>(npairs);
+    unsigned long long* stat = ws.get<unsigned long long>(1);
+    if (!Gpart || !Wg || !flags || !stat) {
+        ctx->err = "svd: workspace allocation failed";
+        return fail(QB200_E_CUDA);
+    }
+
+    const double eps = 1.1102230246251565e-16;
+    const double rot_tol = std::sqrt((double)st->mp) * eps;
+    const double conv_tol = 1e-10;
+    const int inner_sweeps = (nb == 2) ? 12 : 2;
+    const int max_sweeps = 40;
+    int sweep = 0;
+    bool converged = false;
+    for (; sweep < max_sweeps && !converged; ++sweep) {
+        cudaMemsetAsync(stat, 0, sizeof(unsigned long long), ctx->stream);
+        for (int step = 0; step < nsteps; ++step) {
+            jacobi_gram_kernel<<<dim3(npairs, ksplit), 256, GRAM_SMEM, ctx->stream>>>(st->Z, st->ldz, st->mp, nb, step,
+                                                                                     ksplit, Gpart);
+            jacobi_evd_kernel<<<npairs, EVD_THREADS, EVD_SMEM, ctx->stream>>>(Gpart, ksplit, Wg, flags, stat, rot_tol,
+                                                                              inner_sweeps);
+            jacobi_update_kernel<<<dim3(npairs, parts), 256, UPD_SMEM, ctx->stream>>>(st->Z, st->ldz, nb, step, Wg,
+                                                                                     flags, chunks_per_cta,
+                                                                                     total_chunks);
+            ctx->launches += 3;
+        }
+        cudaError_t e = cudaMemcpyAsync(ctx->scratch_host, stat, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            ctx->err = std::string("svd: ") + cudaGetErrorString(e);
+            return fail(QB200_E_CUDA);
+        }
+        double worst = ctx->scratch_host[0];
+        if (!(worst > conv_tol)) converged = true;
+    }
+    ctx->last_svd_sweeps = sweep;
+    if (!converged) {
+        ctx->err = "svd: Jacobi did not converge within the sweep limit";
+        return fail(QB200_E_NOCONVERGE);
+    }
+    col_norm_kernel<<<(st->np + 7) / 8, 256, 0, ctx->stream>>>(st->Z, st->ldz, st->mp, st->np, st->sigma_dev);
+    ctx->launches++;
+    std::vector<double> sig(st->np);
+    cudaError_t e = cudaMemcpyAsync(sig.data(), st->sigma_dev, sizeof(double) * st->np, cudaMemcpyDeviceToHost,
+                                    ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        ctx->err = std::string("svd: ") + cudaGetErrorString(e);
+        return fail(QB200_E_CUDA);
+    }
+    // descending, ties broken by the lower column index (first occurrence); padded columns come last
+    st->perm.resize(st->np);
+    std::iota(st->perm.begin(), st->perm.end(), 0);
+    const int64_t wn = st->wn;
+    std::stable_sort(st->perm.begin(), st->perm.end(), [&](int a, int b) {
+        bool pa = a >= wn, pb = b >= wn;
+        if (pa != pb) return pb;
+        return sig[a] > sig[b];
+    });
+    int64_t k = std::min(m, n);
+    sigma.resize(k);
+    for (int64_t i = 0; i < k; ++i) sigma[i] = sig[st->perm[i]];
+    e = cudaMemcpyAsync(st->perm_dev, st->perm.data(), sizeof(int) * st->np, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        ctx->err = std::string("svd: ") + cudaGetErrorString(e);
+        return fail(QB200_E_CUDA);
+    }
+    *out = st;
+    return QB200_OK;
+}
+
+int32_t qb_svd_emit(qb200_ctx* ctx, SvdState* st, int64_t kept, c128* U, int64_t ldu, double* S, c128* V,
+                    int64_t ldv, int vmode, const double* uinv, int64_t uinv_len, const double* vinv,
+                    int64_t vinv_div, double sigma_scale) {
+    if (kept <= 0) return QB200_OK;
+    const c128* X = st->Z;            // wm x wn, needs 1/sigma
+    const c128* Vacc = st->Z + st->mp;  // wn x wn accumulated rotations
+    // A = Uw S Vw^H for the working matrix; if transposed, A = Vw S Uw^H
+    const c128* usrc = st->transposed ? Vacc : X;
+    const c128* vsrc = st->transposed ? X : Vacc;
+    int unorm = st->transposed ? 0 : 1, vnorm = st->transposed ? 1 : 0;
+    if (U) {
+        svd_emit_kernel<<<grid_cap(ctx, st->m * kept, 256), 256, 0, ctx->stream>>>(
+            usrc, st->ldz, st->m, kept, st->perm_dev, st->sigma_dev, unorm, 0, 0, U, ldu, uinv, uinv_len, 1);
+        QB_LAUNCH_CHECK(ctx);
+    }
+    if (V) {
+        svd_emit_kernel<<<grid_cap(ctx, st->n * kept, 256), 256, 0, ctx->stream>>>(
+            vsrc, st->ldz, st->n, kept, st->perm_dev, st->sigma_dev, vnorm, 1, vmode, V, ldv, vinv, 0,
+            vinv ? vinv_div : 1);
+        QB_LAUNCH_CHECK(ctx);
+    }
+    if (S) {
+        svd_emit_sigma_kernel<<<(unsigned)((kept + 255) / 256), 256, 0, ctx->stream>>>(st->sigma_dev, st->perm_dev, kept,
+                                                                                      sigma_scale, S);
+        QB_LAUNCH_CHECK(ctx);
+    }
+    return QB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// C-ABI: svd of the (left | right) matricisation of a tensor
+extern "C" int32_t qb200_svd_last_sweeps(qb200_ctx* ctx) { return ctx ? ctx->last_svd_sweeps : -1; }
+
+int32_t qb_matricize(qb200_ctx* ctx, const qb200_tensor* A, const int32_t* order, int32_t nleft, Workspace& ws,
+                     const c128** mat, int64_t* rows, int64_t* cols) {
+    if (!A || A->dtype != QB200_C128) QB_FAIL(ctx, QB200_E_UNSUPPORTED, "factorisation: ComplexF64 tensor required");
+    if (nleft < 0 || nleft > A->rank) QB_FAIL(ctx, QB200_E_INVALID, "factorisation: bad nleft");
+    bool seen[QB200_MAX_RANK] = {false}, identity = true;
+    int64_t r = 1, c = 1;
+    for (int i = 0; i < A->rank; ++i) {
+        int p = order[i];
+        if (p < 0 || p >= A->rank || seen[p]) QB_FAIL(ctx, QB200_E_INVALID, "factorisation: order is not a permutation");
+        seen[p] = true;
+        if (p != i) identity = false;
+        (i < nleft ? r : c) *= A->ext[p];
+    }
+    *rows = r;
+    *cols = c;
+    if (identity) {
+        *mat = (const c128*)A->data;
+        return QB200_OK;
+    }
+    c128* tmp = ws.get<c128>((size_t)A->numel());
+    if (!tmp) QB_FAIL(ctx, QB200_E_CUDA, "factorisation: workspace allocation failed");
+    qb200_tensor view = *A;
+    qb200_tensor outv = *A;
+    outv.data = tmp;
+    for (int i = 0; i < A->rank; ++i) outv.ext[i] = A->ext[order[i]];
+    QB_TRY(qb200_permute(ctx, &view, order, &outv));
+    *mat = tmp;
+    return QB200_OK;
+}
+
+extern "C" int32_t qb200_svd(qb200_ctx* ctx, const qb200_tensor* A, const int32_t* order, int32_t nleft,
+                             int64_t maxdim, double threshold, qb200_tensor* U, qb200_tensor* S, qb200_tensor* Vc,
+                             int64_t* kept_out, double* discarded_weight) {
+    if (!ctx || !A || !order || !U || !S || !Vc) QB_FAIL(ctx, QB200_E_INVALID, "svd: null argument");
+    Workspace ws(ctx);
+    const c128* mat;
+    int64_t m, n;
+    QB_TRY(qb_matricize(ctx, A, order, nleft, ws, &mat, &m, &n));
+    int64_t k = std::min(m, n);
+    if (U->dtype != QB200_C128 || Vc->dtype != QB200_C128 || S->dtype != QB200_F64)
+        QB_FAIL(ctx, QB200_E_INVALID, "svd: U, Vc must be C128 and S F64");
+    if (U->numel() < m * k || Vc->numel() < n * k || S->numel() < k)
+        QB_FAIL(ctx, QB200_E_INVALID, "svd: outputs too small (need k = min(rows, cols) columns)");
+    SvdState* st = nullptr;
+    std::vector<double> sigma;
+    QB_TRY(qb_svd_factor(ctx, m, n, mat, m, &st, sigma));
+    // truncate! rule (Chain.jl:404-417): i <= min(k, maxdim) and s[i] > threshold
+    int64_t lim = (maxdim > 0) ? std::min(k, maxdim) : k;
+    int64_t kept = 0;
+    for (int64_t i = 0; i < lim; ++i)
+        if (threshold < 0.0 || std::fabs(sigma[i]) > threshold) kept++;
+        else break;
+    double dw = 0.0;
+    for (int64_t i = k - 1; i >= kept; --i) dw += sigma[i] * sigma[i];
+    int32_t r = qb_svd_emit(ctx, st, kept, (c128*)U->data, m, (double*)S->data, (c128*)Vc->data, n, 0, nullptr, 0,
+                            nullptr, 1, 1.0);
+    qb_svd_release(ctx, st);
+    QB_TRY(r);
+    // shrink the trailing (bond) extent of the outputs to `kept`
+    U->ext[U->rank - 1] = kept;
+    Vc->ext[Vc->rank - 1] = kept;
+    S->ext[S->rank - 1] = kept;
+    if (kept_out) *kept_out = kept;
+    if (discarded_weight) *discarded_weight = dw;
+    return QB200_OK;
+}

@@ -1,0 +1,179 @@
+"""`B200MPS`: the fused, device-resident open-boundary MPS (the "B200Chain wrapper" of SURVEY.md §8b) --
+canonize!/mixed_canonize!/truncate!/evolve!/overlap/expect of /root/reference/src/Ansatz/Chain.jl run as
+fused kernel chains inside libqrochet_b200.so.  Site arrays cross the boundary in the reference's
+`defaultorder` (o, l, r) (Chain.jl:33) and are re-laid out to the private (l, o, r) once, at adapt time."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi as capi
+from ._capi import check, lib
+from .device import Context
+
+
+class B200MPS:
+    def __init__(self, ctx: Context, arrays=None, order=("o", "l", "r"), _handle=None):
+        self.ctx = ctx
+        if _handle is not None:
+            self.h = _handle
+            return
+        n = len(arrays)
+        h = C.c_void_p()
+        check(ctx.h, lib.qb200_mps_create(ctx.h, n, C.byref(h)))
+        self.h = h
+        for k, a in enumerate(arrays):
+            a = np.asarray(a, dtype=np.complex128)
+            labels = [c for c in order if not ((c == "l" and k == 0) or (c == "r" and k == n - 1))]
+            assert a.ndim == len(labels), (k, a.shape, labels)
+            # -> (l, o, r) with size-1 edge bonds
+            axes = {c: i for i, c in enumerate(labels)}
+            perm = [axes[c] for c in ("l", "o", "r") if c in axes]
+            a = np.transpose(a, perm)
+            if k == 0:
+                a = a[None, ...]
+            if k == n - 1:
+                a = a[..., None]
+            buf = np.asfortranarray(a)
+            check(ctx.h, lib.qb200_mps_set_site(ctx.h, self.h, k, buf.shape[0], buf.shape[1], buf.shape[2],
+                                                buf.ctypes.data_as(C.c_void_p)))
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                lib.qb200_mps_free(self.ctx.h, self.h)
+        except Exception:
+            pass
+        self.h = None
+
+    # -- bookkeeping -------------------------------------------------------------------------
+    @property
+    def nsites(self) -> int:
+        return self._n()
+
+    def _n(self):
+        if not hasattr(self, "_nsites"):
+            n = 0
+            d = (C.c_int64 * 3)()
+            while lib.qb200_mps_site_dims(self.h, n, d) == 0:
+                n += 1
+            self._nsites = n
+        return self._nsites
+
+    def copy(self) -> "B200MPS":
+        h = C.c_void_p()
+        check(self.ctx.h, lib.qb200_mps_copy(self.ctx.h, self.h, C.byref(h)))
+        return B200MPS(self.ctx, _handle=h)
+
+    def site_dims(self, s: int):
+        d = (C.c_int64 * 3)()
+        check(self.ctx.h, lib.qb200_mps_site_dims(self.h, s, d))
+        return tuple(d)
+
+    def bond_dims(self):
+        return [self.site_dims(s)[2] for s in range(self.nsites - 1)]
+
+    def site(self, s: int) -> np.ndarray:
+        """Host copy of site s (0-based) with extents (chi_l, p, chi_r)."""
+        d = self.site_dims(s)
+        out = np.empty(d, dtype=np.complex128, order="F")
+        check(self.ctx.h, lib.qb200_mps_get_site(self.ctx.h, self.h, s, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def arrays(self):
+        """Site arrays back in the reference's (o, l, r) order (edge bonds dropped)."""
+        n = self.nsites
+        out = []
+        for s in range(n):
+            a = np.transpose(self.site(s), (1, 0, 2))
+            if s == 0:
+                a = a[:, 0, :]
+            if s == n - 1:
+                a = a[..., 0]
+            out.append(a)
+        return out
+
+    def lambdas(self):
+        """Schmidt vector on each bond (None where absent) -- `tensors(ψ; between=(i, i+1))`."""
+        out = []
+        for b in range(self.nsites - 1):
+            n = C.c_int64()
+            code = lib.qb200_mps_get_lambda(self.ctx.h, self.h, b, None, C.byref(n))
+            if code == capi.E_NOSPECTRUM:
+                out.append(None)
+                continue
+            check(self.ctx.h, code)
+            v = np.empty(n.value, dtype=np.float64)
+            check(self.ctx.h, lib.qb200_mps_get_lambda(self.ctx.h, self.h, b, v.ctypes.data_as(C.POINTER(C.c_double)),
+                                                       C.byref(n)))
+            out.append(v)
+        return out
+
+    @property
+    def form(self) -> int:
+        return int(lib.qb200_mps_form(self.h))
+
+    # -- Chain.jl algorithms -------------------------------------------------------------------
+    def canonize(self) -> "B200MPS":
+        """`canonize!` (Chain.jl:469-497)."""
+        check(self.ctx.h, lib.qb200_mps_canonize(self.ctx.h, self.h))
+        return self
+
+    def mixed_canonize(self, center: int) -> "B200MPS":
+        """`mixed_canonize!(ψ, Site(center))`, center 1-based as in the reference (Chain.jl:509-524)."""
+        check(self.ctx.h, lib.qb200_mps_mixed_canonize(self.ctx.h, self.h, center - 1))
+        return self
+
+    def truncate(self, bond, threshold=None, maxdim=None) -> int:
+        """`truncate!(ψ, [Site(i), Site(i+1)]; threshold, maxdim)`; bond = (i, i+1) 1-based (Chain.jl:390-422)."""
+        i, j = bond
+        if j != i + 1:
+            raise ValueError(f"Invalid bond {bond}")
+        kept = C.c_int64()
+        check(self.ctx.h, lib.qb200_mps_truncate(self.ctx.h, self.h, i - 1, int(maxdim or 0),
+                                                 -1.0 if threshold is None else float(threshold), C.byref(kept)))
+        return kept.value
+
+    def evolve(self, gate, sites, threshold=None, maxdim=None, renormalize=False):
+        """`evolve!(ψ, Dense(Operator(), gate; sites=[s.., s'..]); ...)` (Chain.jl:543-584).  `gate` has array
+        dims (o_1.., i_1..) as in the reference; `sites` are the 1-based lanes.  Returns (kept, discarded)."""
+        gate = np.asfortranarray(np.asarray(gate, dtype=np.complex128))
+        sites = list(sites)
+        if len(sites) == 1:
+            check(self.ctx.h, lib.qb200_mps_evolve1(self.ctx.h, self.h, sites[0] - 1, gate.ctypes.data_as(C.c_void_p)))
+            return None
+        if len(sites) != 2:
+            raise ValueError(f"Invalid number of lanes {len(sites)}, maximum is 2")
+        a, b = sites
+        if abs(a - b) != 1:
+            raise ValueError("Gate lanes must be contiguous")
+        if a > b:  # gate given with lanes in descending order: swap its qubit roles
+            gate = np.asfortranarray(np.transpose(gate.reshape((2, 2, 2, 2), order="F"), (1, 0, 3, 2)))
+            a, b = b, a
+        kept = C.c_int64()
+        dw = C.c_double()
+        check(self.ctx.h, lib.qb200_mps_evolve2(self.ctx.h, self.h, a - 1, gate.ctypes.data_as(C.c_void_p),
+                                                int(maxdim or 0), -1.0 if threshold is None else float(threshold),
+                                                int(bool(renormalize)), C.byref(kept), C.byref(dw)))
+        return kept.value, dw.value
+
+    def overlap(self, other: "B200MPS") -> complex:
+        """`overlap(a, b)` = <b|a> (Chain.jl:737-748)."""
+        r = (C.c_double * 2)()
+        check(self.ctx.h, lib.qb200_mps_overlap(self.ctx.h, self.h, other.h, r))
+        return complex(r[0], r[1])
+
+    def norm(self) -> float:
+        """`norm(ψ)` (Ansatz.jl:101-109)."""
+        return abs(np.sqrt(self.overlap(self)))
+
+    def expect(self, ops, sites) -> np.ndarray:
+        """Batch of single-site `expect(ψ, [O])` values, un-normalised (Chain.jl:724-735); sites 1-based."""
+        ops = [np.asfortranarray(np.asarray(o, dtype=np.complex128)) for o in ops]
+        flat = np.concatenate([o.reshape(-1, order="F") for o in ops]) if ops else np.zeros(0, np.complex128)
+        res = np.zeros(2 * len(ops))
+        check(self.ctx.h, lib.qb200_mps_expect1_batch(self.ctx.h, self.h, len(ops), capi.i32arr(s - 1 for s in sites),
+                                                      flat.ctypes.data_as(C.c_void_p),
+                                                      res.ctypes.data_as(C.POINTER(C.c_double))))
+        return res[0::2] + 1j * res[1::2]

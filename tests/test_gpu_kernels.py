@@ -1,0 +1,187 @@
+"""GPU parity tests (through the C-ABI) of the individual kernels against NumPy/SciPy restatements:
+K1 contraction, K2/K3 mode scale, K6 slice, K7 conj/permute, K8 norm, K4 QR, K5 SVD."""
+import numpy as np
+import pytest
+import scipy.linalg as sla
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def qb():
+    import qrochet_b200 as q
+    return q
+
+
+@pytest.fixture(scope="module")
+def ctx(qb):
+    c = qb.Context(0)
+    yield c
+    c.close()
+
+
+def crand(rng, *shape):
+    return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+
+
+def einsum_ref(a, ma, b, mb, mc, conj_a=False, conj_b=False):
+    if conj_a:
+        a = a.conj()
+    if conj_b:
+        b = b.conj()
+    return np.einsum(a, list(ma), b, list(mb), list(mc))
+
+
+CONTRACT_CASES = [
+    # (shape_a, modes_a, shape_b, modes_b, modes_c)
+    ((5, 7), (0, 1), (7, 3), (1, 2), (0, 2)),                      # plain matmul, ragged
+    ((130, 70), (0, 1), (70, 66), (1, 2), (0, 2)),                 # crosses tile boundaries
+    ((70, 130), (1, 0), (66, 70), (2, 1), (2, 0)),                 # both transposed, C transposed
+    ((4, 6, 5), (0, 1, 2), (5, 3, 6), (2, 3, 1), (3, 0)),          # two summed modes, permuted
+    ((2, 3, 4, 5), (0, 1, 2, 3), (4, 2, 6), (2, 0, 6), (3, 6, 1)),  # interleaved M/K modes
+    ((3, 4, 5), (0, 1, 2), (4, 6, 3), (1, 6, 0), (0, 2, 6)),       # batch (kept shared) mode 0
+    ((8,), (0,), (8,), (0,), ()),                                  # inner product -> scalar
+    ((6,), (0,), (7,), (1,), (1, 0)),                              # outer product (K = 1)
+    ((2,) * 10, tuple(range(10)), (2,) * 8, (1, 3, 5, 7, 9, 10, 11, 12), (0, 12, 2, 11, 4, 10, 6, 8)),  # circuit-like
+    ((1, 300000), (0, 1), (300000,), (1,), (0,)),                  # long K: split-K path
+    ((300, 20), (0, 1), (20, 200), (1, 2), (0, 2)),                # M > N
+    ((20, 200), (1, 0), (20, 300), (1, 2), (0, 2)),                # N > M -> swapped operands
+]
+
+
+@pytest.mark.parametrize("case", range(len(CONTRACT_CASES)))
+@pytest.mark.parametrize("conj", [(False, False), (True, False), (False, True)])
+def test_contract_matches_einsum(qb, ctx, case, conj):
+    sa, ma, sb, mb, mc = CONTRACT_CASES[case]
+    rng = np.random.default_rng(100 + case)
+    a, b = crand(rng, *sa), crand(rng, *sb)
+    want = einsum_ref(a, ma, b, mb, mc, *conj)
+    got = qb.contract(ctx.array(a), ma, ctx.array(b), mb, mc, conj_a=conj[0], conj_b=conj[1]).to_host()
+    scale = max(1.0, np.abs(want).max())
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= 1e-12 * scale * max(1, int(np.prod(sa)) ** 0.5 / 30)
+
+
+def test_contract_alpha_beta(qb, ctx):
+    rng = np.random.default_rng(1)
+    a, b, c = crand(rng, 40, 30), crand(rng, 30, 50), crand(rng, 40, 50)
+    out = ctx.array(c)
+    qb.contract(ctx.array(a), (0, 1), ctx.array(b), (1, 2), (0, 2), out=out, alpha=2 - 1j, beta=0.5j)
+    assert np.allclose(out.to_host(), (2 - 1j) * a @ b + 0.5j * c, atol=1e-11)
+
+
+def test_contract_errors(qb, ctx):
+    a, b = ctx.array(np.ones((2, 3), complex)), ctx.array(np.ones((4, 5), complex))
+    with pytest.raises(qb.QB200Error):
+        qb.contract(a, (0, 1), b, (1, 2), (0, 2))  # extent mismatch on mode 1
+    with pytest.raises(qb.QB200Error):
+        qb.contract(a, (0, 0), b, (1, 2), (0, 2))  # repeated mode
+
+
+def test_elementwise(qb, ctx):
+    rng = np.random.default_rng(2)
+    a = crand(rng, 6, 5, 7)
+    v = rng.random(5)
+    v[2] = 1e-40
+    d, dv = ctx.array(a), ctx.array(v)
+    assert np.allclose(qb.scale_mode(d, 1, dv).to_host(), a * v[None, :, None])
+    inv = np.where(np.abs(v) > 1e-32, 1 / v, 0.0)
+    assert np.allclose(qb.scale_mode(d, 1, dv, inverse=True, atol=1e-32).to_host(), a * inv[None, :, None])
+    assert np.array_equal(qb.slice_mode(d, 2, 3).to_host(), a[:, :, :3])
+    assert np.array_equal(qb.slice_mode(d, 0, 6).to_host(), a)
+    assert np.array_equal(qb.select_mode(d, 1, 4).to_host(), a[:, 4, :])
+    assert np.array_equal(qb.conj(d).to_host(), a.conj())
+    assert np.array_equal(qb.permute(d, (2, 0, 1)).to_host(), np.transpose(a, (2, 0, 1)))
+    assert np.isclose(qb.norm2(d), np.linalg.norm(a), rtol=1e-14)
+    assert np.allclose(qb.scale(d.copy(), 0.5 - 2j).to_host(), a * (0.5 - 2j))
+    assert np.array_equal(d.reshape((30, 7)).to_host(), a.reshape((30, 7), order="F"))
+    empty = qb.slice_mode(d, 1, 0)
+    assert empty.shape == (6, 0, 7)
+
+
+QR_SHAPES = [(4, 4), (64, 32), (33, 7), (200, 64), (500, 130), (130, 500), (2, 4), (1000, 96)]
+
+
+@pytest.mark.parametrize("shape", QR_SHAPES)
+def test_qr(qb, ctx, shape):
+    rng = np.random.default_rng(3)
+    a = crand(rng, *shape)
+    q, r = qb.qr(ctx.array(a), (0, 1), 1)
+    q, r = q.to_host(), r.to_host()
+    k = min(shape)
+    assert q.shape == (shape[0], k) and r.shape == (k, shape[1])
+    assert np.abs(q.conj().T @ q - np.eye(k)).max() < 1e-13
+    assert np.abs(q @ r - a).max() < 1e-12 * np.abs(a).max() * 10
+    assert np.abs(np.tril(r[:, :k], -1)).max() < 1e-13
+    # R is unique up to row phases: compare |R| with LAPACK (gauge-invariant)
+    r_ref = sla.qr(a, mode="economic")[1]
+    assert np.allclose(np.abs(r), np.abs(r_ref), atol=1e-11 * np.abs(a).max() * 10)
+
+
+def test_qr_rank_deficient_and_permuted(qb, ctx):
+    rng = np.random.default_rng(4)
+    base = crand(rng, 96, 10)
+    a = base @ crand(rng, 10, 40)  # rank 10
+    q, r = qb.qr(ctx.array(a), (0, 1), 1)
+    q, r = q.to_host(), r.to_host()
+    assert np.abs(q.conj().T @ q - np.eye(40)).max() < 1e-12
+    assert np.abs(q @ r - a).max() < 1e-11
+    t = crand(rng, 3, 4, 5)
+    q, r = qb.qr(ctx.array(t), (2, 0, 1), 2)  # left = (mode2, mode0), right = mode1
+    mat = np.transpose(t, (2, 0, 1)).reshape((15, 4), order="F")
+    assert np.allclose(q.to_host().reshape((15, 4), order="F") @ r.to_host(), mat)
+
+
+SVD_SHAPES = [(4, 4), (2, 8), (64, 32), (33, 70), (100, 130), (256, 256), (300, 129), (512, 512)]
+
+
+@pytest.mark.parametrize("shape", SVD_SHAPES)
+def test_svd(qb, ctx, shape):
+    rng = np.random.default_rng(5)
+    a = crand(rng, *shape)
+    u, s, vc, kept, dw = qb.svd(ctx.array(a), (0, 1), 1)
+    u, s, vc = u.to_host(), s.to_host(), vc.to_host()
+    k = min(shape)
+    s_ref = sla.svd(a, compute_uv=False, lapack_driver="gesdd")
+    assert kept == k and s.shape == (k,) and dw == 0.0
+    assert np.abs(s - s_ref).max() <= 1e-12 * s_ref[0]          # north-star tolerance on sigma
+    assert np.all(np.diff(s) <= 0)
+    assert np.abs(u.conj().T @ u - np.eye(k)).max() < 1e-12
+    assert np.abs(vc.T @ vc.conj() - np.eye(k)).max() < 1e-12
+    assert np.abs((u * s) @ vc.T - a).max() < 1e-12 * s_ref[0]
+
+
+def test_svd_graded_spectrum_and_truncation(qb, ctx):
+    rng = np.random.default_rng(6)
+    n = 96
+    q1, _ = np.linalg.qr(crand(rng, n, n))
+    q2, _ = np.linalg.qr(crand(rng, n, n))
+    sig = np.logspace(0, -14, n)
+    a = (q1 * sig) @ q2.conj().T
+    u, s, vc, kept, dw = qb.svd(ctx.array(a), (0, 1), 1, maxdim=20)
+    s_ref = sla.svd(a, compute_uv=False, lapack_driver="gesdd")
+    assert kept == 20 and s.shape == (20,) and u.shape == (n, 20) and vc.shape == (n, 20)
+    assert np.abs(s.to_host() - s_ref[:20]).max() <= 1e-12 * s_ref[0]
+    assert np.isclose(dw, np.sum(s_ref[20:] ** 2), rtol=1e-9)
+    # threshold rule of truncate! (Chain.jl:411-417): s[i] > threshold, bit-exact count
+    thr = float(s_ref[9] * 0.999)
+    _, s2, _, kept2, _ = qb.svd(ctx.array(a), (0, 1), 1, threshold=thr)
+    assert kept2 == int(np.sum(s_ref > thr)) == 10
+    # both limits apply
+    _, _, _, kept3, _ = qb.svd(ctx.array(a), (0, 1), 1, maxdim=4, threshold=thr)
+    assert kept3 == 4
+
+
+def test_svd_rank_deficient_and_tensor_modes(qb, ctx):
+    rng = np.random.default_rng(7)
+    a = crand(rng, 80, 6) @ crand(rng, 6, 50)
+    u, s, vc, kept, dw = qb.svd(ctx.array(a), (0, 1), 1, threshold=1e-10)
+    s_ref = sla.svd(a, compute_uv=False)
+    assert kept == 6
+    assert np.abs(s.to_host() - s_ref[:6]).max() <= 1e-12 * s_ref[0]
+    assert np.abs((u.to_host() * s.to_host()) @ vc.to_host().T - a).max() < 1e-11 * s_ref[0]
+    t = crand(rng, 3, 4, 5)
+    u, s, vc, kept, _ = qb.svd(ctx.array(t), (1, 2, 0), 1)  # left = mode1 ; right = (mode2, mode0)
+    mat = np.transpose(t, (1, 2, 0)).reshape((4, 15), order="F")
+    rec = (u.to_host() * s.to_host()) @ vc.to_host().reshape((15, 4), order="F").T
+    assert np.allclose(rec, mat)
