@@ -1,0 +1,203 @@
+"""GPU parity of the fused MPS path (canonize!/mixed_canonize!/truncate!/evolve!/overlap/expect through the
+C-ABI) against the CPU oracle on identical seeded inputs.  Comparisons are gauge-invariant (north star):
+Schmidt values 1e-12 relative to sigma_1, overlaps / <O> 1e-10 relative, kept counts bit-exact."""
+import numpy as np
+import pytest
+
+from oracle import chain as oc
+from oracle import statevector as sv
+from oracle.chain import site
+
+pytestmark = pytest.mark.gpu
+
+SIG_TOL = 1e-12
+OBS_TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def qb():
+    import qrochet_b200 as q
+    return q
+
+
+@pytest.fixture(scope="module")
+def ctx(qb):
+    c = qb.Context(0)
+    yield c
+    c.close()
+
+
+def make(qb, ctx, seed, n, chi):
+    arrays = oc.rand_mps_arrays(np.random.default_rng(seed), n, chi)
+    return oc.Chain(arrays), qb.B200MPS(ctx, arrays)
+
+
+def dense_from_gpu(g):
+    """Contract the device MPS (with its Schmidt vectors) on the host, qubit 1 fastest."""
+    lams = g.lambdas()
+    n = g.nsites
+    psi = np.ones((1, 1), dtype=complex)
+    for s in range(n):
+        a = g.site(s)  # (l, p, r)
+        if s < n - 1 and lams[s] is not None:
+            a = a * lams[s][None, None, :]
+        psi = np.tensordot(psi, a, axes=(1, 0)).reshape(-1, a.shape[2], order="F")
+    return psi[:, 0]
+
+
+def assert_lams(g_lams, o_lams):
+    for b, (x, y) in enumerate(zip(g_lams, o_lams)):
+        assert (x is None) == (y is None), b
+        if x is None:
+            continue
+        k = min(len(x), len(y))
+        assert np.abs(x[:k] - y[:k]).max() <= SIG_TOL * y[0], b
+        assert np.all(np.abs(x[k:]) <= SIG_TOL * y[0]) and np.all(np.abs(y[k:]) <= SIG_TOL * y[0])
+
+
+def test_roundtrip_and_norm(qb, ctx):
+    o, g = make(qb, ctx, 1, 8, 10)
+    for a, b in zip(g.arrays(), oc.rand_mps_arrays(np.random.default_rng(1), 8, 10)):
+        assert np.array_equal(a, b)
+    assert abs(g.norm() - 1.0) < 1e-13  # Chain_test.jl:219
+    assert np.allclose(dense_from_gpu(g), o.to_dense(), atol=1e-14)
+
+
+@pytest.mark.parametrize("n,chi", [(5, 20), (16, 32), (9, 6)])
+def test_canonize_matches_oracle(qb, ctx, n, chi):
+    o, g = make(qb, ctx, 2, n, chi)
+    ref = o.to_dense()
+    o = o.canonize()
+    g.canonize()
+    assert g.form == 1
+    assert_lams(g.lambdas(), o.lambdas())
+    assert np.allclose(dense_from_gpu(g), ref, atol=1e-12)
+    lams = g.lambdas()
+    # Chain_test.jl:322-323: sum lambda^2 = |psi|^2 on every bond
+    assert np.allclose([np.sum(l ** 2) for l in lams], 1.0, atol=1e-12)
+    # Chain_test.jl:325-355: Λ_{i-1}Γ_i left-canonical, Γ_iΛ_i right-canonical
+    for s in range(n):
+        a = g.site(s)
+        al = a if s == 0 else a * lams[s - 1][:, None, None]
+        m = al.reshape(-1, a.shape[2], order="F")
+        assert np.abs(m.conj().T @ m - np.eye(a.shape[2])).max() < 1e-11
+        ar = a if s == n - 1 else a * lams[s][None, None, :]
+        m = ar.reshape(a.shape[0], -1, order="F")
+        assert np.abs(m @ m.conj().T - np.eye(a.shape[0])).max() < 1e-11
+
+
+def test_mixed_canonize_and_errors(qb, ctx):
+    rng = np.random.default_rng(3)
+    arrays = [rng.random((4, 4)) + 0j, rng.random((4, 4, 4)) + 0j, rng.random((4, 4, 4)) + 0j,
+              rng.random((4, 4, 4)) + 0j, rng.random((4, 4)) + 0j]
+    o = oc.Chain(arrays)
+    g = qb.B200MPS(ctx, arrays)
+    ref = o.to_dense()
+    o.mixed_canonize(site(3))
+    g.mixed_canonize(3)
+    assert_lams(g.lambdas(), o.lambdas())
+    assert [l is not None for l in g.lambdas()] == [False, True, False, False]
+    assert np.allclose(dense_from_gpu(g), ref, atol=1e-12)
+    for s in range(5):  # Chain_test.jl:364-368
+        a = g.site(s)
+        if s < 2:
+            m = a.reshape(-1, a.shape[2], order="F")
+            assert np.abs(m.conj().T @ m - np.eye(a.shape[2])).max() < 1e-12
+        else:
+            m = a.reshape(a.shape[0], -1, order="F")
+            assert np.abs(m @ m.conj().T - np.eye(a.shape[0])).max() < 1e-12
+    with pytest.raises(qb.QB200Error):
+        qb.B200MPS(ctx, arrays).mixed_canonize(1)  # Site(1) throws in the reference too (Chain.jl:344)
+
+
+def test_truncate(qb, ctx):
+    # Chain_test.jl:189-204
+    rng = np.random.default_rng(4)
+    arrays = [rng.random((2, 2)) + 0j, rng.random((2, 2, 2)) + 0j, rng.random((2, 2)) + 0j]
+    g = qb.B200MPS(ctx, arrays)
+    with pytest.raises(qb.MissingSchmidtCoefficientsException):
+        g.truncate((1, 2), maxdim=1)
+    g.mixed_canonize(3)  # Λ on bond (2,3)
+    s = g.lambdas()[1]
+    t = g.copy()
+    assert t.truncate((2, 3), maxdim=1) == 1 and t.bond_dims()[1] == 1
+    t = g.copy()
+    assert t.truncate((2, 3), threshold=s[1] + 0.1) == 1 and t.bond_dims()[1] == 1
+    t = g.copy()
+    assert t.truncate((2, 3), maxdim=5) == 2
+
+
+@pytest.mark.parametrize("vidal", [True, False])
+def test_evolve_matches_oracle_and_statevector(qb, ctx, vidal):
+    n = 8
+    o, g = make(qb, ctx, 5, n, 8)
+    psi = o.to_dense()
+    if vidal:
+        o.canonize()
+        g.canonize()
+    rng = np.random.default_rng(6)
+    for bond in [1, 3, 5, 7, 2, 4, 6, 4]:
+        U = oc.haar_unitary(rng)
+        gate = np.reshape(U, (2, 2, 2, 2), order="F")
+        o.evolve(oc.gate(U, [bond, bond + 1]), iscanonical=vidal)
+        g.evolve(gate, [bond, bond + 1])
+        psi = sv.apply_gate(psi, U, [bond, bond + 1], n)
+    H = np.array([[1, 1], [1, -1]]) / np.sqrt(2)
+    o.evolve(oc.gate(H, [4]))
+    g.evolve(H, [4])
+    psi = sv.apply_gate(psi, H, [4], n)
+    assert np.allclose(dense_from_gpu(g), psi, atol=1e-11)
+    assert_lams(g.lambdas(), o.lambdas())
+    assert abs(g.norm() - 1.0) < 1e-12
+
+
+def test_evolve_truncation_counts_and_weights(qb, ctx):
+    n = 10
+    o, g = make(qb, ctx, 7, n, 8)
+    o.canonize()
+    g.canonize()
+    rng = np.random.default_rng(8)
+    for bond in [5, 4, 6, 5]:
+        U = oc.haar_unitary(rng)
+        full = o.copy().evolve(oc.gate(U, [bond, bond + 1]), iscanonical=True).lambdas()[bond - 1]
+        o.evolve(oc.gate(U, [bond, bond + 1]), iscanonical=True, maxdim=8, renormalize=True)
+        kept, dw = g.evolve(np.reshape(U, (2, 2, 2, 2), order="F"), [bond, bond + 1], maxdim=8, renormalize=True)
+        assert kept == len(o.lambdas()[bond - 1]) == 8            # bit-exact truncation
+        assert np.isclose(dw, np.sum(full[8:] ** 2), rtol=1e-9, atol=1e-20)
+        assert_lams(g.lambdas(), o.lambdas())
+    b = oc.rand_mps(np.random.default_rng(9), n, 4)
+    gb = qb.B200MPS(ctx, oc.rand_mps_arrays(np.random.default_rng(9), n, 4))
+    want = o.overlap(b)
+    got = g.overlap(gb)
+    assert abs(got - want) <= OBS_TOL * abs(want)
+    # threshold rule
+    U = oc.haar_unitary(rng)
+    full = o.copy().evolve(oc.gate(U, [3, 4]), iscanonical=True).lambdas()[2]
+    thr = float(full[3] * 0.99)
+    o.evolve(oc.gate(U, [3, 4]), iscanonical=True, threshold=thr)
+    kept, _ = g.evolve(np.reshape(U, (2, 2, 2, 2), order="F"), [3, 4], threshold=thr)
+    assert kept == len(o.lambdas()[2]) == int(np.sum(full > thr))
+
+
+def test_overlap_and_expect(qb, ctx):
+    n = 16
+    oa, ga = make(qb, ctx, 10, n, 32)
+    ob, gb = make(qb, ctx, 11, n, 16)
+    want = oa.overlap(ob)
+    got = ga.overlap(gb)
+    assert abs(got - want) <= OBS_TOL * abs(want)
+    assert abs(gb.overlap(ga) - np.conj(want)) <= OBS_TOL * abs(want)
+    Z = np.diag([1.0, -1.0]).astype(complex)
+    X = np.array([[0, 1], [1, 0]], dtype=complex)
+    Y = np.array([[0, -1j], [1j, 0]])
+    ops, sites = [Z, X, Y, Z, X], [8, 1, 16, 3, 12]
+    want = np.array([oa.expect([oc.gate(o, [s])]) for o, s in zip(ops, sites)])
+    got = ga.expect(ops, sites)
+    assert np.abs(got - want).max() <= OBS_TOL * max(1.0, np.abs(want).max())
+    # config 1 of BASELINE.json: canonize! + overlap + single-site expect, Vidal form keeps <O>
+    oa.canonize()
+    ga.canonize()
+    got2 = ga.expect(ops, sites)
+    assert np.abs(got2 - want).max() <= OBS_TOL
+    assert abs(ga.overlap(ga) - 1.0) < 1e-12
+    assert abs(ga.expect([np.eye(2)], [5])[0] - 1.0) < 1e-12
