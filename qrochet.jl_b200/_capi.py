@@ -45,6 +45,8 @@ _protos = {
     "qb200_launch_count": (_i64, [_p]),
     "qb200_timer_begin": (_i32, [_p]),
     "qb200_timer_end": (_i32, [_p, _pdbl]),
+    "qb200_prof_enable": (_i32, [_p, _i32]),
+    "qb200_prof_read": (_i32, [_p, _i32, _pi64, _pdbl, _pdbl]),
     "qb200_tensor_alloc": (_i32, [_p, _i32, _i32, _pi64, C.POINTER(_p)]),
     "qb200_tensor_wrap": (_i32, [_p, _i32, _i32, _pi64, _p, C.POINTER(_p)]),
     "qb200_tensor_free": (_i32, [_p, _p]),
@@ -76,6 +78,7 @@ _protos = {
     "qb200_mps_set_lambda": (_i32, [_p, _p, _i32, _i64, _pdbl]),
     "qb200_mps_get_lambda": (_i32, [_p, _p, _i32, _pdbl, _pi64]),
     "qb200_mps_form": (_i32, [_p]),
+    "qb200_mps_set_form": (_i32, [_p, _i32]),
     "qb200_mps_canonize": (_i32, [_p, _p]),
     "qb200_mps_mixed_canonize": (_i32, [_p, _p, _i32]),
     "qb200_mps_truncate": (_i32, [_p, _p, _i32, _i64, _dbl, _pi64]),

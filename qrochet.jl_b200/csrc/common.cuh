@@ -38,6 +38,55 @@ struct qb200_ctx {
     void* nccl_comm = nullptr;
     void* nccl_lib = nullptr;
     double* scratch_host = nullptr;  // pinned, 64 KiB
+    // optional phase profiler (CUDA events on the context stream; resolved lazily)
+    bool prof_on = false;
+    struct ProfRec {
+        int phase;
+        cudaEvent_t e0, e1;
+        double work;  // algorithmic flops (or bytes) of the timed region
+    };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
+};
+
+enum QbPhase {
+    QB_PH_THETA_GEMM = 0,
+    QB_PH_GATE = 1,
+    QB_PH_SVD = 2,
+    QB_PH_JGRAM = 3,
+    QB_PH_JEVD = 4,
+    QB_PH_JUPDATE = 5,
+    QB_PH_EMIT = 6,
+    QB_PH_SCALE = 7,
+    QB_PH_QR = 8,
+    QB_PH_TN_GEMM = 9,
+    QB_PH_COUNT = 10
+};
+
+// RAII phase timer: records two events on the stream when profiling is enabled, otherwise free
+struct PhaseTimer {
+    qb200_ctx* ctx;
+    int idx = -1;
+    PhaseTimer(qb200_ctx* c, int phase, double work) : ctx(c) {
+        if (!c->prof_on) return;
+        qb200_ctx::ProfRec r;
+        r.phase = phase;
+        r.work = work;
+        for (cudaEvent_t* e : {&r.e0, &r.e1}) {
+            if (!c->prof_pool.empty()) {
+                *e = c->prof_pool.back();
+                c->prof_pool.pop_back();
+            } else {
+                cudaEventCreate(e);
+            }
+        }
+        cudaEventRecord(r.e0, c->stream);
+        c->prof_recs.push_back(r);
+        idx = (int)c->prof_recs.size() - 1;
+    }
+    ~PhaseTimer() {
+        if (idx >= 0) cudaEventRecord(ctx->prof_recs[idx].e1, ctx->stream);
+    }
 };
 
 static inline size_t dtype_size(int32_t dt) {

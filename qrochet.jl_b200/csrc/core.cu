@@ -87,6 +87,35 @@ int32_t qb200_timer_end(qb200_ctx* ctx, double* ms) {
     return QB200_OK;
 }
 
+// phase profiler: enable/disable, and read back {count, total ms, total work} per phase (resets the records)
+int32_t qb200_prof_enable(qb200_ctx* ctx, int32_t on) {
+    if (!ctx) return QB200_E_INVALID;
+    ctx->prof_on = on != 0;
+    return QB200_OK;
+}
+int32_t qb200_prof_read(qb200_ctx* ctx, int32_t nphases, int64_t* counts, double* ms, double* work) {
+    if (!ctx || !counts || !ms || !work) return QB200_E_INVALID;
+    QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < nphases; ++i) {
+        counts[i] = 0;
+        ms[i] = 0.0;
+        work[i] = 0.0;
+    }
+    for (auto& r : ctx->prof_recs) {
+        float f = 0.f;
+        cudaEventElapsedTime(&f, r.e0, r.e1);
+        if (r.phase < nphases) {
+            counts[r.phase]++;
+            ms[r.phase] += f;
+            work[r.phase] += r.work;
+        }
+        ctx->prof_pool.push_back(r.e0);
+        ctx->prof_pool.push_back(r.e1);
+    }
+    ctx->prof_recs.clear();
+    return QB200_OK;
+}
+
 static int32_t make_tensor(qb200_ctx* ctx, int32_t dtype, int32_t rank, const int64_t* ext, void* ptr,
                            qb200_tensor** out) {
     if (!ctx || !out || rank < 0 || rank > QB200_MAX_RANK) QB_FAIL(ctx, QB200_E_INVALID, "bad tensor rank %d", rank);

@@ -316,6 +316,11 @@ int32_t qb200_mps_get_lambda(qb200_ctx* ctx, const qb200_mps* m, int32_t b, doub
 }
 
 int32_t qb200_mps_form(const qb200_mps* m) { return m ? m->form : -1; }
+int32_t qb200_mps_set_form(qb200_mps* m, int32_t form) {
+    if (!m || form < 0 || form > 2) return QB200_E_INVALID;
+    m->form = form;
+    return QB200_OK;
+}
 
 // canonize! (Chain.jl:469-497)
 int32_t qb200_mps_canonize(qb200_ctx* ctx, qb200_mps* m) {
@@ -429,20 +434,33 @@ int32_t qb200_mps_evolve2(qb200_ctx* ctx, qb200_mps* m, int32_t b, const void* g
     const c128* Aop = m->site[b];
     const c128* Bop = m->site[b + 1];
     if (laml || lamb) {
+        PhaseTimer pt(ctx, QB_PH_SCALE, 32.0 * rows * chib);
         QB_TRY(qb_scale_rows_cols(ctx, m->site[b], Al, rows, chib, laml, chil, lamb, 1));
         Aop = Al;
     }
     if (lamr) {
+        PhaseTimer pt(ctx, QB_PH_SCALE, 32.0 * chib * cols);
         QB_TRY(qb_scale_rows_cols(ctx, m->site[b + 1], Br, chib, cols, nullptr, 1, lamr, 2));
         Bop = Br;
     }
-    QB_TRY(qb_gemm(ctx, 0, 0, rows, cols, chib, ONE, Aop, rows, Bop, chib, ZERO, theta, rows));
+    {
+        PhaseTimer pt(ctx, QB_PH_THETA_GEMM, 8.0 * rows * cols * chib);
+        QB_TRY(qb_gemm(ctx, 0, 0, rows, cols, chib, ONE, Aop, rows, Bop, chib, ZERO, theta, rows));
+    }
     // gate on the two physical indices (Chain.jl:635-636)
-    QB_TRY(qb_apply_gate2(ctx, theta, chil, chir, g));
+    {
+        PhaseTimer pt(ctx, QB_PH_GATE, 32.0 * rows * cols);
+        QB_TRY(qb_apply_gate2(ctx, theta, chil, chir, g));
+    }
     // SVD (Chain.jl:705 / :645)
     SvdState* st = nullptr;
     std::vector<double> sigma;
-    QB_TRY(qb_svd_factor(ctx, rows, cols, theta, rows, &st, sigma));
+    {
+        // algorithmic count of a thin complex SVD with U and V: 4 (14 m n^2 + 8 n^3), m >= n
+        double mm = (double)std::max(rows, cols), nn = (double)std::min(rows, cols);
+        PhaseTimer pt(ctx, QB_PH_SVD, 4.0 * (14.0 * mm * nn * nn + 8.0 * nn * nn * nn));
+        QB_TRY(qb_svd_factor(ctx, rows, cols, theta, rows, &st, sigma));
+    }
     int64_t k = (int64_t)sigma.size();
     int64_t kept = k;
     if (maxdim > 0 || threshold >= 0.0) kept = kept_count(sigma, maxdim, threshold >= 0.0 ? threshold : 1e-16);

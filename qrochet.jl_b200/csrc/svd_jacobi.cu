@@ -546,13 +546,21 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
     for (; sweep < max_sweeps && !converged; ++sweep) {
         cudaMemsetAsync(stat, 0, sizeof(unsigned long long), ctx->stream);
         for (int step = 0; step < nsteps; ++step) {
-            jacobi_gram_kernel<<<dim3(npairs, ksplit), 256, GRAM_SMEM, ctx->stream>>>(st->Z, st->ldz, st->mp, nb, step,
-                                                                                     ksplit, Gpart);
-            jacobi_evd_kernel<<<npairs, EVD_THREADS, EVD_SMEM, ctx->stream>>>(Gpart, ksplit, Wg, flags, stat, rot_tol,
-                                                                              inner_sweeps);
-            jacobi_update_kernel<<<dim3(npairs, parts), 256, UPD_SMEM, ctx->stream>>>(st->Z, st->ldz, nb, step, Wg,
-                                                                                     flags, chunks_per_cta,
-                                                                                     total_chunks);
+            {
+                PhaseTimer pt(ctx, QB_PH_JGRAM, 8.0 * npairs * (double)st->mp * JP * JP);
+                jacobi_gram_kernel<<<dim3(npairs, ksplit), 256, GRAM_SMEM, ctx->stream>>>(st->Z, st->ldz, st->mp, nb,
+                                                                                         step, ksplit, Gpart);
+            }
+            {
+                PhaseTimer pt(ctx, QB_PH_JEVD, 0.0);
+                jacobi_evd_kernel<<<npairs, EVD_THREADS, EVD_SMEM, ctx->stream>>>(Gpart, ksplit, Wg, flags, stat,
+                                                                                  rot_tol, inner_sweeps);
+            }
+            {
+                PhaseTimer pt(ctx, QB_PH_JUPDATE, 8.0 * npairs * (double)st->ldz * JP * JP);
+                jacobi_update_kernel<<<dim3(npairs, parts), 256, UPD_SMEM, ctx->stream>>>(
+                    st->Z, st->ldz, nb, step, Wg, flags, chunks_per_cta, total_chunks);
+            }
             ctx->launches += 3;
         }
         cudaError_t e = cudaMemcpyAsync(ctx->scratch_host, stat, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);

@@ -43,6 +43,19 @@ class Context:
         check(self.h, lib.qb200_timer_end(self.h, C.byref(ms)))
         return ms.value
 
+    PHASES = ("theta_gemm", "gate", "svd", "jacobi_gram", "jacobi_evd", "jacobi_update", "svd_emit", "mode_scale",
+              "qr", "tn_gemm")
+
+    def profile(self, on: bool):
+        check(self.h, lib.qb200_prof_enable(self.h, int(on)))
+
+    def profile_read(self) -> dict:
+        """{phase: (launches, total_ms, total_algorithmic_work)} since the last read."""
+        n = len(self.PHASES)
+        cnt, ms, work = (C.c_int64 * n)(), (C.c_double * n)(), (C.c_double * n)()
+        check(self.h, lib.qb200_prof_read(self.h, n, cnt, ms, work))
+        return {name: (int(cnt[i]), float(ms[i]), float(work[i])) for i, name in enumerate(self.PHASES)}
+
     def dmma_peak_tflops(self) -> float:
         v = C.c_double()
         check(self.h, lib.qb200_bench_dmma_peak(self.h, C.byref(v)))

@@ -39,6 +39,30 @@ class B200MPS:
             check(ctx.h, lib.qb200_mps_set_site(ctx.h, self.h, k, buf.shape[0], buf.shape[1], buf.shape[2],
                                                 buf.ctypes.data_as(C.c_void_p)))
 
+    @classmethod
+    def from_sites(cls, ctx: Context, sites, lambdas=None, form: int = 0) -> "B200MPS":
+        """Adapt an MPS given in the private layout: `sites[k]` has extents (chi_l, p, chi_r) (Fortran order,
+        ideally pinned host memory), `lambdas[b]` the Schmidt vector on bond b or None."""
+        n = len(sites)
+        h = C.c_void_p()
+        check(ctx.h, lib.qb200_mps_create(ctx.h, n, C.byref(h)))
+        self = cls(ctx, _handle=h)
+        for k, a in enumerate(sites):
+            assert a.dtype == np.complex128 and a.ndim == 3 and a.flags.f_contiguous
+            check(ctx.h, lib.qb200_mps_set_site(ctx.h, h, k, a.shape[0], a.shape[1], a.shape[2],
+                                                a.ctypes.data_as(C.c_void_p)))
+        for b, lam in enumerate(lambdas or []):
+            if lam is not None:
+                lam = np.ascontiguousarray(lam, dtype=np.float64)
+                check(ctx.h, lib.qb200_mps_set_lambda(ctx.h, h, b, lam.shape[0],
+                                                      lam.ctypes.data_as(C.POINTER(C.c_double))))
+        check(ctx.h, lib.qb200_mps_set_form(h, form))
+        return self
+
+    def site_into(self, s: int, out: np.ndarray):
+        """Download site s into a caller-provided (pinned) Fortran-ordered buffer."""
+        check(self.ctx.h, lib.qb200_mps_get_site(self.ctx.h, self.h, s, out.ctypes.data_as(C.c_void_p)))
+
     def __del__(self):
         try:
             if self.h and self.ctx.h:

@@ -1,0 +1,46 @@
+"""Host-side input generators of the reference API: `rand(Chain, Open, State; n, χ, p, eltype)`
+(/root/reference/src/Ansatz/Chain.jl:223-256) and Haar-random two-site gates.  Pure set-up code (K11 in
+SURVEY.md §2.3): runs on the host, never inside a timed region."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def bond_dims(n: int, chi: int, p: int = 2):
+    """Bond dimensions of `rand` (Chain.jl:230-236): bond b (1-based) has min(χ, p^b, p^(n-b))."""
+    return [min(chi, p ** b, p ** (n - b)) for b in range(1, n)]
+
+
+def rand_mps_arrays(rng: np.random.Generator, n: int, chi: int, p: int = 2):
+    """Site arrays in the reference's default order (o, l, r): random row-orthonormal χl x (χr p) matrices
+    (the reference orthonormalises the rows with Muscle.gramschmidt!; a Householder QR of the adjoint spans
+    the same row space and is O(χ³) BLAS-3), reshaped (χl, χr, p) -> permuted (p, χl, χr); site 1 / sqrt(p)
+    => right-canonical, norm 1."""
+    arrays = []
+    for i in range(1, n + 1):
+        after_mid = i > n // 2
+        j = (n + 1 - abs(2 * i - n - 1)) // 2
+        chil, chir = min(chi, p ** (j - 1)), min(chi, p ** j)
+        if n % 2 == 1 and i == n // 2 + 1:
+            chir = chil
+        elif after_mid:
+            chil, chir = chir, chil
+        if i == 1:
+            chil, chir = chir, 1
+        a = rng.random((chil, chir * p)) + 1j * rng.random((chil, chir * p))
+        q, _ = np.linalg.qr(a.conj().T)
+        a = np.reshape(q.conj().T, (chil, chir, p), order="F")
+        arrays.append(np.transpose(a, (2, 0, 1)))
+    arrays[0] = np.reshape(arrays[0], (p, p), order="F") / np.sqrt(p)
+    arrays[-1] = np.reshape(arrays[-1], (p, p), order="F")
+    return arrays
+
+
+def haar_gate(rng: np.random.Generator, d: int = 4):
+    """Haar-random d x d unitary (QR of complex Ginibre, phases fixed) as the reference's gate array with
+    dims (o1, o2, i1, i2), column-major reshape, first lane = fastest bit."""
+    z = (rng.standard_normal((d, d)) + 1j * rng.standard_normal((d, d))) / np.sqrt(2)
+    q, r = np.linalg.qr(z)
+    u = q * (np.diag(r) / np.abs(np.diag(r)))
+    k = int(round(np.log2(d)))
+    return np.reshape(u, (2,) * (2 * k), order="F")
