@@ -5,6 +5,7 @@ from ._capi import MissingSchmidtCoefficientsException, QB200Error
 from .device import (Context, DeviceArray, conj, contract, norm2, permute, qr, scale, scale_mode, select_mode,
                      slice_mode, svd)
 from .mps import B200MPS
+from .tn import SlicedContraction, amplitude_network, fsim, random_fsim_circuit
 from .rand import bond_dims, haar_gate, rand_mps_arrays
 
 __all__ = ["Context", "DeviceArray", "B200MPS", "contract", "scale_mode", "slice_mode", "select_mode", "conj",

@@ -110,7 +110,7 @@ for _name, (_res, _args) in _protos.items():
 
 def check(ctx, code):
     if code != 0:
-        msg = lib.qb200_last_error(ctx)
+        msg = lib.qb200_last_error(ctx) if ctx is not None else b"(no context)"
         msg = msg.decode() if msg else ""
         if code == E_NOSPECTRUM:
             raise MissingSchmidtCoefficientsException(code, msg)

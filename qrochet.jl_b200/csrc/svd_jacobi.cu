@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cmath>
 #include <numeric>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "mma.cuh"
@@ -156,7 +157,9 @@ constexpr size_t EVD_SMEM = (size_t)2 * JP * GLD * sizeof(c128) + 32 * sizeof(do
 
 __global__ void __launch_bounds__(EVD_THREADS, 1)
     jacobi_evd_kernel(const c128* __restrict__ Gpart, int ksplit, c128* __restrict__ Wout, int* __restrict__ flags,
-                      unsigned long long* __restrict__ sweep_stat, double rot_tol, int inner_sweeps) {
+                      unsigned long long* __restrict__ sweep_stat, double rot_tol, int inner_sweeps,
+                      const double* __restrict__ scale_in, unsigned long long* __restrict__ scale_out, double abs_c,
+                      int nact) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     c128* G = reinterpret_cast<c128*>(smem_raw);
     c128* W = G + JP * GLD;
@@ -180,17 +183,27 @@ __global__ void __launch_bounds__(EVD_THREADS, 1)
         W[c * GLD + r] = make_double2(r == c ? 1.0 : 0.0, 0.0);
     }
     __syncthreads();
-    // largest relative off-diagonal entry of the incoming Gram matrix
-    double mx = 0.0;
+    // A pair (i, j) counts as orthogonal when |g_ij| <= rot_tol |x_i||x_j| + abs_tol max(|x_i|, |x_j|):
+    // the first term is the usual relative criterion, the second is the accuracy a GEMM-applied rotation can
+    // deliver at all (every column of an updated panel carries an absolute error ~ eps * sigma_1), without it
+    // columns whose norm is at the rounding level of sigma_1 would be rotated for ever.
+    const double abs_tol = abs_c * scale_in[0];
+    // largest relative off-diagonal entry (over the pairs that still count) and largest column norm
+    double mx = 0.0, gmax = 0.0;
     for (int e = tid; e < JP * JP; e += EVD_THREADS) {
         int r = e & 63, c = e >> 6;
+        if (r == c) gmax = fmax(gmax, G[c * GLD + c].x);
         if (r < c) {
             double a = G[r * GLD + r].x, b = G[c * GLD + c].x;
             c128 v = G[c * GLD + r];
             double d = a * b;
-            if (d > 0.0) mx = fmax(mx, sqrt((v.x * v.x + v.y * v.y) / d));
+            double av = sqrt(v.x * v.x + v.y * v.y);
+            if (d > 0.0 && av > rot_tol * sqrt(d) + abs_tol * sqrt(fmax(a, b))) mx = fmax(mx, av / sqrt(d));
         }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+    if ((tid & 31) == 0 && gmax > 0.0) atomicMax(scale_out, (unsigned long long)__double_as_longlong(sqrt(gmax)));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if ((tid & 31) == 0) red[tid >> 5] = mx;
@@ -212,19 +225,21 @@ __global__ void __launch_bounds__(EVD_THREADS, 1)
     }
     if (tid == 0) flags[pair] = 1;
 
+    // round robin over the active columns only (a lone pair of a small matrix is mostly padding)
+    const int nrr = nact, nrot = nact / 2;
     for (int sw = 0; sw < inner_sweeps; ++sw) {
         if (tid == 0) any_rot = 0;
         __syncthreads();
-        for (int st = 0; st < JP - 1; ++st) {
+        for (int st = 0; st < (nrr == 2 ? 1 : nrr - 1); ++st) {
             if (tid < 32) {
-                int p, q;
-                rr_pair(JP, st, tid, p, q);
+                int p = 0, q = 0;
+                if (tid < nrot) rr_pair(nrr, st, tid, p, q);
                 double a = G[p * GLD + p].x, b = G[q * GLD + q].x;
                 c128 c = G[q * GLD + p];  // G[p][q] = x_p^H x_q  (row p, column q)
                 double absc = sqrt(c.x * c.x + c.y * c.y);
                 double cs = 1.0;
                 c128 sn = make_double2(0.0, 0.0);
-                if (absc > rot_tol * sqrt(a * b) && absc > 0.0) {
+                if (tid < nrot && absc > rot_tol * sqrt(a * b) + abs_tol * sqrt(fmax(a, b)) && absc > 0.0) {
                     double zeta = (b - a) / (2.0 * absc);
                     double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
                     cs = 1.0 / sqrt(1.0 + tt * tt);
@@ -241,6 +256,7 @@ __global__ void __launch_bounds__(EVD_THREADS, 1)
             // column phase on G and W: [x_p, x_q] <- [x_p, x_q] J,  J = [[cs, sn w], [-sn conj(w), cs]]
             for (int item = tid; item < 2 * 32 * JP; item += EVD_THREADS) {
                 int r = item & 63, k = (item >> 6) & 31;
+                if (k >= nrot) continue;
                 c128* M = (item >> 11) ? W : G;
                 int p = rpq[2 * k], q = rpq[2 * k + 1];
                 double cs = rcs[k];
@@ -255,6 +271,7 @@ __global__ void __launch_bounds__(EVD_THREADS, 1)
             // row phase on G: G <- J^H G
             for (int item = tid; item < 32 * JP; item += EVD_THREADS) {
                 int c = item & 63, k = item >> 6;
+                if (k >= nrot) continue;
                 int p = rpq[2 * k], q = rpq[2 * k + 1];
                 double cs = rcs[k];
                 c128 sn = rsn[k];
@@ -403,6 +420,28 @@ __global__ void svd_init_kernel(c128* __restrict__ Z, int64_t ldz, int mp, int n
     }
 }
 
+// squared row and column norms of A (m x n, lda): one thread per row / per column
+__global__ void rowcol_norm2_kernel(const c128* __restrict__ A, int64_t lda, int64_t m, int64_t n,
+                                    double* __restrict__ rown, double* __restrict__ coln) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < m) {
+        double acc = 0.0;
+        for (int64_t j = 0; j < n; ++j) {
+            c128 v = A[idx + j * lda];
+            acc += v.x * v.x + v.y * v.y;
+        }
+        rown[idx] = acc;
+    } else if (idx < m + n) {
+        int64_t j = idx - m;
+        double acc = 0.0;
+        for (int64_t i = 0; i < m; ++i) {
+            c128 v = A[i + j * lda];
+            acc += v.x * v.x + v.y * v.y;
+        }
+        coln[j] = acc;
+    }
+}
+
 // one warp per column: sigma_j = |X[:, j]|
 __global__ void col_norm_kernel(const c128* __restrict__ Z, int64_t ldz, int mp, int np, double* __restrict__ sigma) {
     int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -419,17 +458,35 @@ __global__ void col_norm_kernel(const c128* __restrict__ Z, int64_t ldz, int mp,
     if (lane == 0) sigma[col] = sqrt(acc);
 }
 
+// scale[0] = scale[1] = max_j sigma[j] (bit pattern of a non-negative double orders like an integer)
+__global__ void max_reduce_kernel(const double* __restrict__ sigma, int n, double* __restrict__ scale) {
+    __shared__ double sh[32];
+    double mx = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) mx = fmax(mx, sigma[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < (int)(blockDim.x >> 5); ++i) mx = fmax(mx, sh[i]);
+        scale[0] = mx;
+        scale[1] = mx;
+    }
+}
+
 // dst(i, j) or dst(j, i) = f(src(i, perm[j])) for i < rows, j < kept
+// (output row = rowmap[i] when rowmap is given)
 __global__ void svd_emit_kernel(const c128* __restrict__ src, int64_t ldz, int64_t rows, int64_t kept,
                                 const int* __restrict__ perm, const double* __restrict__ sigma, int normalize,
-                                int conj, int transpose_out, c128* __restrict__ dst, int64_t ldd,
-                                const double* __restrict__ sc, int64_t sc_mod, int64_t sc_div) {
+                                int conj, int transpose_out, const int* __restrict__ rowmap, c128* __restrict__ dst,
+                                int64_t ldd, const double* __restrict__ sc, int64_t sc_mod, int64_t sc_div) {
     int64_t total = rows * kept;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (int64_t)gridDim.x * blockDim.x) {
         int64_t i = idx % rows, j = idx / rows;
         int pj = perm[j];
         c128 v = src[i + (int64_t)pj * ldz];
+        if (rowmap) i = rowmap[i];
         double f = 1.0;
         if (normalize) {
             double s = sigma[pj];
@@ -454,14 +511,16 @@ __global__ void svd_emit_sigma_kernel(const double* __restrict__ sigma, const in
 }  // namespace
 
 struct SvdState {
-    int64_t m, n;  // original problem
-    bool transposed;
-    int64_t wm, wn;  // working problem (wm >= wn)
-    int mp, np;
+    int64_t m, n, k;    // original problem, k = min(m, n)
+    bool tall;          // m >= n: B = A, else B = A^H; B (rb x k) P = Q R, Jacobi runs on X0 = R^H (k x k)
+    int64_t rb;         // rows of B
+    int mp, np;         // padded k (rows of X, columns)
     int64_t ldz;
-    c128* Z = nullptr;
+    c128* Z = nullptr;  // [X ; V] stacked
+    c128* Q = nullptr;  // rb x k, orthonormal columns
     double* sigma_dev = nullptr;
-    int* perm_dev = nullptr;
+    int* perm_dev = nullptr;     // sigma order (descending) -> column of Z
+    int* colperm_dev = nullptr;  // column j of the QR input was column colperm[j] of B
     std::vector<int> perm;
 };
 
@@ -473,10 +532,33 @@ static unsigned grid_cap(qb200_ctx* ctx, int64_t n, int threads) {
 void qb_svd_release(qb200_ctx* ctx, SvdState* st) {
     if (!st) return;
     if (st->Z) cudaFreeAsync(st->Z, ctx->stream);
+    if (st->Q) cudaFreeAsync(st->Q, ctx->stream);
     if (st->sigma_dev) cudaFreeAsync(st->sigma_dev, ctx->stream);
     if (st->perm_dev) cudaFreeAsync(st->perm_dev, ctx->stream);
+    if (st->colperm_dev) cudaFreeAsync(st->colperm_dev, ctx->stream);
     delete st;
 }
+
+namespace {
+// B0(:, j) = B(:, colperm[j]) with B = A (tall) or A^H (wide); B0 is rb x k, ld = rb
+__global__ void svd_gather_cols_kernel(const c128* __restrict__ A, int64_t lda, int tall, int64_t rb, int64_t k,
+                                       const int* __restrict__ colperm, c128* __restrict__ B0) {
+    int64_t total = rb * k;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        int64_t i = idx % rb, j = idx / rb;
+        int64_t c = colperm[j];
+        c128 v;
+        if (tall)
+            v = A[i + c * lda];
+        else {
+            v = A[c + i * lda];  // B(i, c) = conj(A(c, i))
+            v.y = -v.y;
+        }
+        B0[idx] = v;
+    }
+}
+}  // namespace
 
 int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64_t lda, SvdState** out,
                       std::vector<double>& sigma) {
@@ -488,50 +570,88 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
         attrs = true;
     }
     if (m <= 0 || n <= 0) QB_FAIL(ctx, QB200_E_INVALID, "svd: empty matrix");
+    if (std::max(m, n) > (1 << 30)) QB_FAIL(ctx, QB200_E_UNSUPPORTED, "svd: matrix too large");
     SvdState* st = new SvdState();
     st->m = m;
     st->n = n;
-    st->transposed = m < n;
-    st->wm = st->transposed ? n : m;
-    st->wn = st->transposed ? m : n;
-    if (st->wm > (1 << 30)) {
-        delete st;
-        QB_FAIL(ctx, QB200_E_UNSUPPORTED, "svd: matrix too large");
-    }
-    st->mp = (int)((st->wm + 63) / 64 * 64);
-    st->np = (int)((st->wn + 63) / 64 * 64);
+    st->tall = m >= n;
+    st->k = std::min(m, n);
+    st->rb = std::max(m, n);
+    const int64_t k = st->k, rb = st->rb;
+    st->mp = st->np = (int)((k + 63) / 64 * 64);
     st->ldz = (int64_t)st->mp + st->np;
     const int nb = st->np / JB, npairs = nb / 2, nsteps = (nb == 2) ? 1 : nb - 1;
-
     auto fail = [&](int32_t code) {
         qb_svd_release(ctx, st);
         return code;
     };
+    auto cuda_fail = [&](cudaError_t e) {
+        ctx->err = std::string("svd: ") + cudaGetErrorString(e);
+        return fail(QB200_E_CUDA);
+    };
     if (cudaMallocAsync(&st->Z, sizeof(c128) * st->ldz * st->np, ctx->stream) != cudaSuccess ||
+        cudaMallocAsync(&st->Q, sizeof(c128) * rb * k, ctx->stream) != cudaSuccess ||
         cudaMallocAsync(&st->sigma_dev, sizeof(double) * st->np, ctx->stream) != cudaSuccess ||
-        cudaMallocAsync(&st->perm_dev, sizeof(int) * st->np, ctx->stream) != cudaSuccess) {
+        cudaMallocAsync(&st->perm_dev, sizeof(int) * st->np, ctx->stream) != cudaSuccess ||
+        cudaMallocAsync(&st->colperm_dev, sizeof(int) * k, ctx->stream) != cudaSuccess) {
         ctx->err = "svd: out of device memory";
         return fail(QB200_E_CUDA);
     }
-    svd_init_kernel<<<grid_cap(ctx, st->ldz * st->np, 256), 256, 0, ctx->stream>>>(st->Z, st->ldz, st->mp, st->np,
-                                                                                  st->wm, st->wn, A, lda,
-                                                                                  st->transposed ? 1 : 0);
-    ctx->launches++;
+    Workspace ws(ctx);
+    // ---- preconditioner (Drmac & Veselic): B P = Q R with the columns of B = A or A^H sorted by decreasing norm,
+    //      then one-sided Jacobi on X0 = R^H.  R^H is column graded with a well-conditioned scaled part whatever
+    //      the grading of A (row, column or both, as for theta = Λl Γ Λ Γ Λr), which both halves the number of
+    //      sweeps on graded matrices and gives the small singular vectors relative accuracy. ----
+    {
+        double* nr = ws.get<double>((size_t)(m + n));
+        c128* B0 = ws.get<c128>((size_t)(rb * k));
+        c128* R = ws.get<c128>((size_t)(k * k));
+        if (!nr || !B0 || !R) {
+            ctx->err = "svd: workspace allocation failed";
+            return fail(QB200_E_CUDA);
+        }
+        rowcol_norm2_kernel<<<(unsigned)((m + n + 127) / 128), 128, 0, ctx->stream>>>(A, lda, m, n, nr, nr + m);
+        ctx->launches++;
+        std::vector<double> h((size_t)(m + n));
+        cudaError_t e = cudaMemcpyAsync(h.data(), nr, sizeof(double) * (m + n), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) return cuda_fail(e);
+        const double* cn = st->tall ? h.data() + m : h.data();  // column norms of B
+        std::vector<int> cp((size_t)k);
+        std::iota(cp.begin(), cp.end(), 0);
+        std::stable_sort(cp.begin(), cp.end(), [&](int a, int b) { return cn[a] > cn[b]; });
+        e = cudaMemcpyAsync(st->colperm_dev, cp.data(), sizeof(int) * k, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) return cuda_fail(e);
+        svd_gather_cols_kernel<<<grid_cap(ctx, rb * k, 256), 256, 0, ctx->stream>>>(A, lda, st->tall ? 1 : 0, rb, k,
+                                                                                   st->colperm_dev, B0);
+        ctx->launches++;
+        {
+            PhaseTimer pt(ctx, QB_PH_QR, 8.0 * (2.0 * rb * k * k - 2.0 / 3.0 * k * k * k));
+            int32_t r = qb_qr_matrix(ctx, rb, k, B0, rb, st->Q, rb, R, k);
+            if (r != QB200_OK) return fail(r);
+        }
+        // Z = [R^H zero-padded ; I]
+        svd_init_kernel<<<grid_cap(ctx, st->ldz * st->np, 256), 256, 0, ctx->stream>>>(st->Z, st->ldz, st->mp, st->np, k,
+                                                                                      k, R, k, 1);
+        ctx->launches++;
+    }
 
     // split the Gram rows so that there are about two CTAs per SM
     int ksplit = std::max(1, std::min(st->mp / G_BKR, (2 * ctx->sm_count + npairs - 1) / npairs));
     if (ksplit > 16) ksplit = 16;
+    while (ksplit > 1 && (st->mp / G_BKR) % ksplit != 0) --ksplit;
     const int total_chunks = (int)(st->ldz / 64);
     int parts = std::max(1, std::min(total_chunks, ctx->sm_count / npairs));
     int chunks_per_cta = (total_chunks + parts - 1) / parts;
     parts = (total_chunks + chunks_per_cta - 1) / chunks_per_cta;
 
-    Workspace ws(ctx);
     c128* Gpart = ws.get<c128>((size_t)npairs * ksplit * JP * JP);
     c128* Wg = ws.get<c128>((size_t)npairs * JP * JP);
     int* flags = ws.get<int>(npairs);
     unsigned long long* stat = ws.get<unsigned long long>(1);
-    if (!Gpart || !Wg || !flags || !stat) {
+    double* scale = ws.get<double>(2);  // [0] largest column norm seen in the previous sweep, [1] running max
+    if (!Gpart || !Wg || !flags || !stat || !scale) {
         ctx->err = "svd: workspace allocation failed";
         return fail(QB200_E_CUDA);
     }
@@ -539,7 +659,12 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
     const double eps = 1.1102230246251565e-16;
     const double rot_tol = std::sqrt((double)st->mp) * eps;
     const double conv_tol = 1e-10;
+    const double abs_c = 2.0 * eps;
     const int inner_sweeps = (nb == 2) ? 12 : 2;
+    const int nact = (nb == 2) ? (int)std::min<int64_t>(64, (k + 1) / 2 * 2) : 64;
+    col_norm_kernel<<<(st->np + 7) / 8, 256, 0, ctx->stream>>>(st->Z, st->ldz, st->mp, st->np, st->sigma_dev);
+    max_reduce_kernel<<<1, 256, 0, ctx->stream>>>(st->sigma_dev, st->np, scale);
+    ctx->launches += 2;
     const int max_sweeps = 40;
     int sweep = 0;
     bool converged = false;
@@ -553,8 +678,9 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
             }
             {
                 PhaseTimer pt(ctx, QB_PH_JEVD, 0.0);
-                jacobi_evd_kernel<<<npairs, EVD_THREADS, EVD_SMEM, ctx->stream>>>(Gpart, ksplit, Wg, flags, stat,
-                                                                                  rot_tol, inner_sweeps);
+                jacobi_evd_kernel<<<npairs, EVD_THREADS, EVD_SMEM, ctx->stream>>>(
+                    Gpart, ksplit, Wg, flags, stat, rot_tol, inner_sweeps, scale, (unsigned long long*)(scale + 1),
+                    abs_c, nact);
             }
             {
                 PhaseTimer pt(ctx, QB_PH_JUPDATE, 8.0 * npairs * (double)st->ldz * JP * JP);
@@ -563,13 +689,15 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
             }
             ctx->launches += 3;
         }
+        cudaMemcpyAsync(scale, scale + 1, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
         cudaError_t e = cudaMemcpyAsync(ctx->scratch_host, stat, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) {
-            ctx->err = std::string("svd: ") + cudaGetErrorString(e);
-            return fail(QB200_E_CUDA);
-        }
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) return cuda_fail(e);
         double worst = ctx->scratch_host[0];
+        if (getenv("QB200_DEBUG"))
+            fprintf(stderr, "[qb200 svd] %lld x %lld (jacobi on %lld^2, nb %d) sweep %d worst %.3e\n", (long long)m,
+                    (long long)n, (long long)k, nb, sweep, worst);
         if (!(worst > conv_tol)) converged = true;
     }
     ctx->last_svd_sweeps = sweep;
@@ -583,52 +711,79 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
     cudaError_t e = cudaMemcpyAsync(sig.data(), st->sigma_dev, sizeof(double) * st->np, cudaMemcpyDeviceToHost,
                                     ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) {
-        ctx->err = std::string("svd: ") + cudaGetErrorString(e);
-        return fail(QB200_E_CUDA);
-    }
+    if (e != cudaSuccess) return cuda_fail(e);
     // descending, ties broken by the lower column index (first occurrence); padded columns come last
     st->perm.resize(st->np);
     std::iota(st->perm.begin(), st->perm.end(), 0);
-    const int64_t wn = st->wn;
     std::stable_sort(st->perm.begin(), st->perm.end(), [&](int a, int b) {
-        bool pa = a >= wn, pb = b >= wn;
+        bool pa = a >= k, pb = b >= k;
         if (pa != pb) return pb;
         return sig[a] > sig[b];
     });
-    int64_t k = std::min(m, n);
     sigma.resize(k);
     for (int64_t i = 0; i < k; ++i) sigma[i] = sig[st->perm[i]];
     e = cudaMemcpyAsync(st->perm_dev, st->perm.data(), sizeof(int) * st->np, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) {
-        ctx->err = std::string("svd: ") + cudaGetErrorString(e);
-        return fail(QB200_E_CUDA);
-    }
+    if (e != cudaSuccess) return cuda_fail(e);
     *out = st;
     return QB200_OK;
 }
 
+// B P = Q R, R^H = Xn S Vs^H  =>  B = (Q Vs) S (P Xn)^H.  tall: A = B, U = Q Vs, V = P Xn.  wide: A = B^H,
+// U = P Xn, V = Q Vs.  (Xn = normalised columns of X, Vs = accumulated rotations, both in sigma order;
+// (P Xn)(colperm[j], :) = Xn(j, :).)
 int32_t qb_svd_emit(qb200_ctx* ctx, SvdState* st, int64_t kept, c128* U, int64_t ldu, double* S, c128* V,
                     int64_t ldv, int vmode, const double* uinv, int64_t uinv_len, const double* vinv,
                     int64_t vinv_div, double sigma_scale) {
     if (kept <= 0) return QB200_OK;
-    const c128* X = st->Z;            // wm x wn, needs 1/sigma
-    const c128* Vacc = st->Z + st->mp;  // wn x wn accumulated rotations
-    // A = Uw S Vw^H for the working matrix; if transposed, A = Vw S Uw^H
-    const c128* usrc = st->transposed ? Vacc : X;
-    const c128* vsrc = st->transposed ? X : Vacc;
-    int unorm = st->transposed ? 0 : 1, vnorm = st->transposed ? 1 : 0;
-    if (U) {
-        svd_emit_kernel<<<grid_cap(ctx, st->m * kept, 256), 256, 0, ctx->stream>>>(
-            usrc, st->ldz, st->m, kept, st->perm_dev, st->sigma_dev, unorm, 0, 0, U, ldu, uinv, uinv_len, 1);
+    const int64_t k = st->k;
+    const c128* X = st->Z;
+    const c128* Vacc = st->Z + st->mp;
+    const c128 ONE = make_double2(1.0, 0.0), ZERO = make_double2(0.0, 0.0);
+    Workspace ws(ctx);
+    c128* Vs = nullptr;
+    auto need_vs = [&]() -> int32_t {
+        if (Vs) return QB200_OK;
+        Vs = ws.get<c128>((size_t)(k * kept));
+        if (!Vs) QB_FAIL(ctx, QB200_E_CUDA, "svd: workspace allocation failed");
+        svd_emit_kernel<<<grid_cap(ctx, k * kept, 256), 256, 0, ctx->stream>>>(
+            Vacc, st->ldz, k, kept, st->perm_dev, st->sigma_dev, 0, 0, 0, nullptr, Vs, k, nullptr, 0, 1);
         QB_LAUNCH_CHECK(ctx);
+        return QB200_OK;
+    };
+    PhaseTimer pt(ctx, QB_PH_EMIT, 8.0 * st->rb * k * kept);
+    if (U) {
+        if (st->tall) {  // U = Q Vs, rows scaled by uinv[i % uinv_len]
+            QB_TRY(need_vs());
+            QB_TRY(qb_gemm(ctx, 0, 0, st->m, kept, k, ONE, st->Q, st->rb, Vs, k, ZERO, U, ldu));
+            if (uinv) QB_TRY(qb_scale_rows_cols(ctx, U, U, st->m, kept, uinv, uinv_len, nullptr, 1));
+        } else {  // U = P Xn
+            if (ldu != st->m && uinv) QB_FAIL(ctx, QB200_E_UNSUPPORTED, "svd: strided U with fused scaling");
+            svd_emit_kernel<<<grid_cap(ctx, st->m * kept, 256), 256, 0, ctx->stream>>>(
+                X, st->ldz, st->m, kept, st->perm_dev, st->sigma_dev, 1, 0, 0, st->colperm_dev, U, ldu, uinv, uinv_len,
+                1);
+            QB_LAUNCH_CHECK(ctx);
+        }
     }
     if (V) {
-        svd_emit_kernel<<<grid_cap(ctx, st->n * kept, 256), 256, 0, ctx->stream>>>(
-            vsrc, st->ldz, st->n, kept, st->perm_dev, st->sigma_dev, vnorm, 1, vmode, V, ldv, vinv, 0,
-            vinv ? vinv_div : 1);
-        QB_LAUNCH_CHECK(ctx);
+        if (!st->tall) {  // V = Q Vs (n x kept): Vc = conj(Q) conj(Vs) or Vh = Vs^H Q^H
+            QB_TRY(need_vs());
+            if (vmode == 0) {
+                QB_TRY(qb_gemm(ctx, 3, 3, st->n, kept, k, ONE, st->Q, st->rb, Vs, k, ZERO, V, ldv));
+                if (vinv) QB_FAIL(ctx, QB200_E_UNSUPPORTED, "svd: fused V scaling needs vmode 1");
+            } else {
+                QB_TRY(qb_gemm(ctx, 2, 2, kept, st->n, k, ONE, Vs, k, st->Q, st->rb, ZERO, V, ldv));
+                if (vinv) {
+                    if (ldv != kept) QB_FAIL(ctx, QB200_E_UNSUPPORTED, "svd: strided Vh with fused scaling");
+                    QB_TRY(qb_scale_rows_cols(ctx, V, V, kept, st->n, nullptr, 1, vinv, vinv_div));
+                }
+            }
+        } else {  // V = P Xn
+            svd_emit_kernel<<<grid_cap(ctx, st->n * kept, 256), 256, 0, ctx->stream>>>(
+                X, st->ldz, st->n, kept, st->perm_dev, st->sigma_dev, 1, 1, vmode, st->colperm_dev, V, ldv, vinv, 0,
+                vinv ? vinv_div : 1);
+            QB_LAUNCH_CHECK(ctx);
+        }
     }
     if (S) {
         svd_emit_sigma_kernel<<<(unsigned)((kept + 255) / 256), 256, 0, ctx->stream>>>(st->sigma_dev, st->perm_dev, kept,

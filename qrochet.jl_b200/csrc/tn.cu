@@ -99,7 +99,8 @@ extern "C" {
 
 int32_t qb200_tn_plan(qb200_ctx* ctx, int32_t ntensors, const int32_t* ranks, const int32_t* modes,
                       const int64_t* extents, int64_t max_elements, qb200_tnplan** out) {
-    if (!ctx || ntensors < 1 || !ranks || !modes || !extents || !out) QB_FAIL(ctx, QB200_E_INVALID, "tn_plan: bad argument");
+    // planning is pure host work: ctx may be NULL (then there is no error string, only the code)
+    if (ntensors < 1 || !ranks || !modes || !extents || !out) QB_FAIL(ctx, QB200_E_INVALID, "tn_plan: bad argument");
     qb200_tnplan* P = new qb200_tnplan();
     P->nleaves = ntensors;
     std::map<int32_t, int> count;      // live tensors holding each index
@@ -290,9 +291,9 @@ int32_t qb200_tn_plan(qb200_ctx* ctx, int32_t ntensors, const int32_t* ranks, co
 int32_t qb200_tn_plan_free(qb200_ctx* ctx, qb200_tnplan* P) {
     if (!P) return QB200_OK;
     for (auto& s : P->steps)
-        if (s.tables) cudaFreeAsync(s.tables, ctx->stream);
+        if (s.tables && ctx) cudaFreeAsync(s.tables, ctx->stream);
     for (auto p : P->cached)
-        if (p) cudaFreeAsync(p, ctx->stream);
+        if (p && ctx) cudaFreeAsync(p, ctx->stream);
     delete P;
     return QB200_OK;
 }

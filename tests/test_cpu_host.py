@@ -1,0 +1,98 @@
+"""CPU-side tests: the C-ABI library loads and exports every symbol the header declares, the host logic
+(rand MPS generator, sweep order, circuit -> network builder) and the C++ planner against the oracle's
+restatement (same path, same cut indices -- bit-exact)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import chain as oc
+from oracle import circuit as ocirc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol():
+    import qrochet_b200 as qb
+    header = open(os.path.join(ROOT, "include", "qrochet_b200.h")).read()
+    declared = set(re.findall(r"\b(qb200_[a-z0-9_]+)\s*\(", header))
+    lib = ctypes.CDLL(qb._capi.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    assert declared == set(qb._capi.EXPORTS), declared ^ set(qb._capi.EXPORTS)
+
+
+def test_no_cpu_fallback():
+    import qrochet_b200 as qb
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(qb.QB200Error):
+        qb.Context(0)
+
+
+def test_rand_mps_generator_matches_reference_properties():
+    import qrochet_b200 as qb
+    n, chi = 8, 10
+    arrays = qb.rand_mps_arrays(np.random.default_rng(0), n, chi)
+    # Chain_test.jl:206-221: norm 1, all dims <= chi; Appendix B: right-canonical on sites 2..n
+    q = oc.Chain(arrays)
+    assert np.isclose(q.norm(), 1.0)
+    assert max(max(a.shape) for a in arrays) <= chi
+    for k in range(2, n + 1):
+        assert q.isrightcanonical(oc.site(k))
+    ref = oc.rand_mps_arrays(np.random.default_rng(0), n, chi)
+    assert [a.shape for a in arrays] == [a.shape for a in ref]
+    assert qb.bond_dims(64, 1024).count(1024) == 45 and qb.bond_dims(16, 32).count(32) == 7
+
+
+def test_haar_gate_is_unitary_in_reference_layout():
+    import qrochet_b200 as qb
+    g = qb.haar_gate(np.random.default_rng(1))
+    assert g.shape == (2, 2, 2, 2)
+    u = np.reshape(g, (4, 4), order="F")
+    assert np.allclose(u.conj().T @ u, np.eye(4))
+
+
+def test_circuit_network_matches_oracle_builder():
+    import qrochet_b200 as qb
+    gates = qb.random_fsim_circuit(8, 3)
+    ogates = ocirc.random_fsim_circuit(8, 3)
+    assert [(a, b) for a, b, _ in gates] == [(a, b) for a, b, _ in ogates]
+    arrays, modes = qb.amplitude_network(8, gates)
+    oarrays, omodes = ocirc.amplitude_network(8, ogates)
+    assert modes == omodes and all(np.array_equal(x, y) for x, y in zip(arrays, oarrays))
+    assert len(arrays) == 12 + 16
+
+
+@pytest.mark.parametrize("n,depth,maxel", [(8, 3, 0), (10, 4, 2 ** 6), (12, 4, 2 ** 5), (16, 6, 2 ** 8)])
+def test_planner_matches_oracle_bit_exactly(n, depth, maxel):
+    import qrochet_b200 as qb
+    gates = qb.random_fsim_circuit(n, depth)
+    arrays, modes = qb.amplitude_network(n, gates)
+    plan = qb.SlicedContraction(None, arrays, modes, maxel)
+    extents = {x: 2 for m in modes for x in m}
+    want = ocirc.plan(modes, extents, maxel)
+    assert plan.path == want["path"]
+    assert plan.sliced_modes == want["sliced"]          # first-occurrence slice choice, bit-exact
+    assert plan.nslices == 2 ** len(want["sliced"])
+    if maxel:
+        assert plan.max_intermediate <= maxel
+
+
+def test_oracle_sliced_sum_equals_statevector():
+    n, depth = 10, 4
+    gates = ocirc.random_fsim_circuit(n, depth)
+    arrays, modes = ocirc.amplitude_network(n, gates)
+    extents = {x: 2 for m in modes for x in m}
+    exact = ocirc.statevector_amplitude(n, gates)
+    full, nsl = ocirc.contract_sliced(arrays, modes, ocirc.plan(modes, extents, 0))
+    assert nsl == 1 and abs(full - exact) < 1e-12
+    pl = ocirc.plan(modes, extents, 2 ** 5)
+    total, nsl = ocirc.contract_sliced(arrays, modes, pl)
+    assert nsl > 1 and abs(total - exact) < 1e-12
+    # every slice exactly once when dealt round-robin to 3 ranks
+    parts = [ocirc.contract_sliced(arrays, modes, pl, r, 3)[0] for r in range(3)]
+    assert abs(sum(parts) - exact) < 1e-12
