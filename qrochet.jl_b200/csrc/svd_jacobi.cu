@@ -150,16 +150,28 @@ __global__ void __launch_bounds__(256, 2)
 }
 
 // ---------------------------------------------------------------------------------------------
-// evd kernel: two-sided Jacobi on the 64 x 64 Hermitian Gram matrix
+// evd kernel: two-sided Jacobi on the 64 x 64 Hermitian Gram matrix of one block pair.
+//
+// Each parallel step applies 32 disjoint plane rotations J = prod_k J_k:
+//   phase 1 (32 threads): rotation k from (g_pp, g_qq, g_pq), rsqrt-based (no fp64 divide/sqrt chains);
+//   phase 2 (all threads): W <- W J (2048 column-pair items) and G <- J^H G J done per 2 x 2 block
+//            B_kl = G[{p_k,q_k},{p_l,q_l}] -> J_k^H B_kl J_l, upper blocks only (k <= l), mirrored by Hermitian
+//            symmetry: every block touches only its own entries, so the update is in place with ONE barrier.
+// Orderings: mode 0 = round robin over `nact` columns (a lone pair = the whole small matrix, run to
+// convergence); mode 1 = within-block pairs (31 steps) then cross pairs (32 steps); mode 2 = cross pairs only
+// (i, 32 + (i + t) mod 32): the blocks of a pair were made orthogonal internally at step 0 of the sweep, so
+// the later steps of a sweep only need the cross rotations -- one outer sweep then rotates every column pair
+// exactly once, like scalar cyclic Jacobi, at a quarter of the shared-memory work of a full inner solve.
 constexpr int EVD_THREADS = 512;
+constexpr int EVD_NBLK = 32 * 33 / 2;
 constexpr size_t EVD_SMEM = (size_t)2 * JP * GLD * sizeof(c128) + 32 * sizeof(double) + 32 * sizeof(c128) +
-                            64 * sizeof(int) + 64 * sizeof(double);
+                            64 * sizeof(int) + 64 * sizeof(double) + EVD_NBLK * sizeof(short);
 
 __global__ void __launch_bounds__(EVD_THREADS, 1)
     jacobi_evd_kernel(const c128* __restrict__ Gpart, int ksplit, c128* __restrict__ Wout, int* __restrict__ flags,
                       unsigned long long* __restrict__ sweep_stat, double rot_tol, int inner_sweeps,
                       const double* __restrict__ scale_in, unsigned long long* __restrict__ scale_out, double abs_c,
-                      int nact) {
+                      int nact, int mode) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     c128* G = reinterpret_cast<c128*>(smem_raw);
     c128* W = G + JP * GLD;
@@ -167,6 +179,7 @@ __global__ void __launch_bounds__(EVD_THREADS, 1)
     c128* rsn = reinterpret_cast<c128*>(rcs + 32);
     int* rpq = reinterpret_cast<int*>(rsn + 32);
     double* red = reinterpret_cast<double*>(rpq + 64);
+    short* tri = reinterpret_cast<short*>(red + 64);
     __shared__ int any_rot;
 
     const int tid = threadIdx.x, pair = blockIdx.x;
@@ -182,13 +195,22 @@ __global__ void __launch_bounds__(EVD_THREADS, 1)
         G[c * GLD + r] = make_double2(sx, sy);
         W[c * GLD + r] = make_double2(r == c ? 1.0 : 0.0, 0.0);
     }
+    for (int e = tid; e < EVD_NBLK; e += EVD_THREADS) {
+        // e -> (k, l), k <= l, row-major over the upper triangle of a 32 x 32 grid
+        int k = 0, rem = e;
+        while (rem >= 32 - k) {
+            rem -= 32 - k;
+            ++k;
+        }
+        tri[e] = (short)((k << 8) | (k + rem));
+    }
     __syncthreads();
-    // A pair (i, j) counts as orthogonal when |g_ij| <= rot_tol |x_i||x_j| + abs_tol max(|x_i|, |x_j|):
-    // the first term is the usual relative criterion, the second is the accuracy a GEMM-applied rotation can
-    // deliver at all (every column of an updated panel carries an absolute error ~ eps * sigma_1), without it
-    // columns whose norm is at the rounding level of sigma_1 would be rotated for ever.
+    // A pair (i, j) counts as orthogonal when |g_ij| <= rot_tol |x_i||x_j| or |g_ij| <= abs_tol max(|x_i|, |x_j|):
+    // the first is the usual relative criterion, the second the accuracy a GEMM-applied rotation can deliver at
+    // all (every column of an updated panel carries an absolute error ~ eps * sigma_1); without it columns whose
+    // norm is at the rounding level of sigma_1 would be rotated for ever.
     const double abs_tol = abs_c * scale_in[0];
-    // largest relative off-diagonal entry (over the pairs that still count) and largest column norm
+    const double rt2 = rot_tol * rot_tol, at2 = abs_tol * abs_tol;
     double mx = 0.0, gmax = 0.0;
     for (int e = tid; e < JP * JP; e += EVD_THREADS) {
         int r = e & 63, c = e >> 6;
@@ -196,56 +218,77 @@ __global__ void __launch_bounds__(EVD_THREADS, 1)
         if (r < c) {
             double a = G[r * GLD + r].x, b = G[c * GLD + c].x;
             c128 v = G[c * GLD + r];
-            double d = a * b;
-            double av = sqrt(v.x * v.x + v.y * v.y);
-            if (d > 0.0 && av > rot_tol * sqrt(d) + abs_tol * sqrt(fmax(a, b))) mx = fmax(mx, av / sqrt(d));
+            double d = a * b, n2 = v.x * v.x + v.y * v.y;
+            if (d > 0.0 && n2 > fmax(rt2 * d, at2 * fmax(a, b))) mx = fmax(mx, n2 / d);
         }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
-    if ((tid & 31) == 0 && gmax > 0.0) atomicMax(scale_out, (unsigned long long)__double_as_longlong(sqrt(gmax)));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if ((tid & 31) == 0) red[tid >> 5] = mx;
+    for (int o = 16; o > 0; o >>= 1) {
+        gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((tid & 31) == 0) {
+        if (gmax > 0.0) atomicMax(scale_out, (unsigned long long)__double_as_longlong(sqrt(gmax)));
+        red[tid >> 5] = mx;
+    }
     __syncthreads();
     if (tid < 32) {
         double v = (tid < EVD_THREADS / 32) ? red[tid] : 0.0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
         if (tid == 0) {
-            red[0] = v;
+            v = sqrt(v);
+            red[32] = v;
             atomicMax(sweep_stat, (unsigned long long)__double_as_longlong(v));
         }
     }
     __syncthreads();
-    mx = red[0];
-    if (!(mx > rot_tol)) {
+    mx = red[32];
+    if (!(mx > 0.0)) {
         if (tid == 0) flags[pair] = 0;
         return;
     }
     if (tid == 0) flags[pair] = 1;
 
-    // round robin over the active columns only (a lone pair of a small matrix is mostly padding)
-    const int nrr = nact, nrot = nact / 2;
+    const int nsteps_rr = (nact == 2) ? 1 : nact - 1;
     for (int sw = 0; sw < inner_sweeps; ++sw) {
         if (tid == 0) any_rot = 0;
         __syncthreads();
-        for (int st = 0; st < (nrr == 2 ? 1 : nrr - 1); ++st) {
+        const int nst = (mode == 0) ? nsteps_rr : (mode == 1 ? 63 : 32);
+        for (int st = 0; st < nst; ++st) {
             if (tid < 32) {
                 int p = 0, q = 0;
-                if (tid < nrot) rr_pair(nrr, st, tid, p, q);
-                double a = G[p * GLD + p].x, b = G[q * GLD + q].x;
-                c128 c = G[q * GLD + p];  // G[p][q] = x_p^H x_q  (row p, column q)
-                double absc = sqrt(c.x * c.x + c.y * c.y);
+                bool active = true;
+                if (mode == 0) {
+                    active = tid < nact / 2;
+                    if (active) rr_pair(nact, st, tid, p, q);
+                } else if (mode == 2 || st >= 31) {
+                    int t = (mode == 2) ? st : st - 31;
+                    p = tid;
+                    q = 32 + ((tid + t) & 31);
+                } else {
+                    int half = tid >> 4;
+                    rr_pair(32, st, tid & 15, p, q);
+                    p += 32 * half;
+                    q += 32 * half;
+                }
                 double cs = 1.0;
                 c128 sn = make_double2(0.0, 0.0);
-                if (tid < nrot && absc > rot_tol * sqrt(a * b) + abs_tol * sqrt(fmax(a, b)) && absc > 0.0) {
-                    double zeta = (b - a) / (2.0 * absc);
-                    double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                    cs = 1.0 / sqrt(1.0 + tt * tt);
-                    double s = tt * cs;
-                    sn = make_double2(s * c.x / absc, s * c.y / absc);  // sn * w, w = c/|c|
-                    any_rot = 1;
+                if (active) {
+                    double a = G[p * GLD + p].x, b = G[q * GLD + q].x;
+                    c128 c = G[q * GLD + p];  // G[p][q] = x_p^H x_q  (row p, column q)
+                    double n2 = c.x * c.x + c.y * c.y;
+                    if (n2 > fmax(rt2 * a * b, at2 * fmax(a, b)) && n2 > 0.0) {
+                        double inv = rsqrt(n2);
+                        double zeta = 0.5 * (b - a) * inv;
+                        double r2 = 1.0 + zeta * zeta;
+                        double rr = r2 * rsqrt(r2);
+                        double tt = copysign(1.0, zeta) / (fabs(zeta) + rr);
+                        cs = rsqrt(1.0 + tt * tt);
+                        double sv = tt * cs * inv;
+                        sn = make_double2(sv * c.x, sv * c.y);  // sin * c/|c|
+                        any_rot = 1;
+                    }
                 }
                 rcs[tid] = cs;
                 rsn[tid] = sn;
@@ -253,38 +296,58 @@ __global__ void __launch_bounds__(EVD_THREADS, 1)
                 rpq[2 * tid + 1] = q;
             }
             __syncthreads();
-            // column phase on G and W: [x_p, x_q] <- [x_p, x_q] J,  J = [[cs, sn w], [-sn conj(w), cs]]
-            for (int item = tid; item < 2 * 32 * JP; item += EVD_THREADS) {
-                int r = item & 63, k = (item >> 6) & 31;
-                if (k >= nrot) continue;
-                c128* M = (item >> 11) ? W : G;
-                int p = rpq[2 * k], q = rpq[2 * k + 1];
-                double cs = rcs[k];
-                c128 sn = rsn[k];
-                c128 xp = M[p * GLD + r], xq = M[q * GLD + r];
-                c128 np_ = csub(cscale(xp, cs), cmul(cconj(sn), xq));
-                c128 nq_ = cadd(cmul(sn, xp), cscale(xq, cs));
-                M[p * GLD + r] = np_;
-                M[q * GLD + r] = nq_;
-            }
-            __syncthreads();
-            // row phase on G: G <- J^H G
+            const int nrot = (mode == 0) ? nact / 2 : 32;
+            // W <- W J : [w_p, w_q] <- [w_p, w_q] [[cs, sn], [-conj(sn), cs]]
             for (int item = tid; item < 32 * JP; item += EVD_THREADS) {
-                int c = item & 63, k = item >> 6;
+                int r = item & 63, k = item >> 6;
                 if (k >= nrot) continue;
-                int p = rpq[2 * k], q = rpq[2 * k + 1];
-                double cs = rcs[k];
                 c128 sn = rsn[k];
-                c128 gp = G[c * GLD + p], gq = G[c * GLD + q];
-                c128 np_ = csub(cscale(gp, cs), cmul(sn, gq));
-                c128 nq_ = cadd(cmul(cconj(sn), gp), cscale(gq, cs));
-                bool rotated = (sn.x != 0.0 || sn.y != 0.0);
-                if (rotated && c == q) np_ = make_double2(0.0, 0.0);
-                if (rotated && c == p) nq_ = make_double2(0.0, 0.0);
-                if (c == p) np_.y = 0.0;
-                if (c == q) nq_.y = 0.0;
-                G[c * GLD + p] = np_;
-                G[c * GLD + q] = nq_;
+                if (sn.x == 0.0 && sn.y == 0.0) continue;
+                double cs = rcs[k];
+                int p = rpq[2 * k], q = rpq[2 * k + 1];
+                c128 xp = W[p * GLD + r], xq = W[q * GLD + r];
+                W[p * GLD + r] = csub(cscale(xp, cs), cmul(cconj(sn), xq));
+                W[q * GLD + r] = cadd(cmul(sn, xp), cscale(xq, cs));
+            }
+            // G <- J^H G J per 2 x 2 block (k <= l), mirrored
+            for (int e = tid; e < EVD_NBLK; e += EVD_THREADS) {
+                int k = tri[e] >> 8, l = tri[e] & 0xff;
+                if (l >= nrot) continue;
+                c128 sk = rsn[k], sl = rsn[l];
+                bool rk = (sk.x != 0.0 || sk.y != 0.0), rl = (sl.x != 0.0 || sl.y != 0.0);
+                if (!rk && !rl) continue;
+                double ck = rcs[k], cl = rcs[l];
+                int pk = rpq[2 * k], qk = rpq[2 * k + 1], pl = rpq[2 * l], ql = rpq[2 * l + 1];
+                c128 b00 = G[pl * GLD + pk], b01 = G[ql * GLD + pk], b10 = G[pl * GLD + qk], b11 = G[ql * GLD + qk];
+                // columns: B <- B J_l
+                c128 t00 = csub(cscale(b00, cl), cmul(cconj(sl), b01));
+                c128 t01 = cadd(cmul(sl, b00), cscale(b01, cl));
+                c128 t10 = csub(cscale(b10, cl), cmul(cconj(sl), b11));
+                c128 t11 = cadd(cmul(sl, b10), cscale(b11, cl));
+                // rows: B <- J_k^H B,  J_k^H = [[ck, -sk], [conj(sk), ck]]
+                b00 = csub(cscale(t00, ck), cmul(sk, t10));
+                b10 = cadd(cmul(cconj(sk), t00), cscale(t10, ck));
+                b01 = csub(cscale(t01, ck), cmul(sk, t11));
+                b11 = cadd(cmul(cconj(sk), t01), cscale(t11, ck));
+                if (k == l) {
+                    b00.y = 0.0;
+                    b11.y = 0.0;
+                    b01 = make_double2(0.0, 0.0);  // annihilated by construction
+                    b10 = make_double2(0.0, 0.0);
+                    G[pk * GLD + pk] = b00;
+                    G[qk * GLD + qk] = b11;
+                    G[qk * GLD + pk] = b01;
+                    G[pk * GLD + qk] = b10;
+                } else {
+                    G[pl * GLD + pk] = b00;
+                    G[ql * GLD + pk] = b01;
+                    G[pl * GLD + qk] = b10;
+                    G[ql * GLD + qk] = b11;
+                    G[pk * GLD + pl] = cconj(b00);
+                    G[pk * GLD + ql] = cconj(b01);
+                    G[qk * GLD + pl] = cconj(b10);
+                    G[qk * GLD + ql] = cconj(b11);
+                }
             }
             __syncthreads();
         }
@@ -660,7 +723,7 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
     const double rot_tol = std::sqrt((double)st->mp) * eps;
     const double conv_tol = 1e-10;
     const double abs_c = 2.0 * eps;
-    const int inner_sweeps = (nb == 2) ? 12 : 2;
+    const int inner_sweeps = (nb == 2) ? 12 : 1;
     const int nact = (nb == 2) ? (int)std::min<int64_t>(64, (k + 1) / 2 * 2) : 64;
     col_norm_kernel<<<(st->np + 7) / 8, 256, 0, ctx->stream>>>(st->Z, st->ldz, st->mp, st->np, st->sigma_dev);
     max_reduce_kernel<<<1, 256, 0, ctx->stream>>>(st->sigma_dev, st->np, scale);
@@ -678,9 +741,10 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
             }
             {
                 PhaseTimer pt(ctx, QB_PH_JEVD, 0.0);
+                int mode = (nb == 2) ? 0 : (step == 0 ? 1 : 2);
                 jacobi_evd_kernel<<<npairs, EVD_THREADS, EVD_SMEM, ctx->stream>>>(
                     Gpart, ksplit, Wg, flags, stat, rot_tol, inner_sweeps, scale, (unsigned long long*)(scale + 1),
-                    abs_c, nact);
+                    abs_c, nact, mode);
             }
             {
                 PhaseTimer pt(ctx, QB_PH_JUPDATE, 8.0 * npairs * (double)st->ldz * JP * JP);

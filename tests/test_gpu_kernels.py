@@ -146,8 +146,8 @@ def test_svd(qb, ctx, shape):
     assert kept == k and s.shape == (k,) and dw == 0.0
     assert np.abs(s - s_ref).max() <= 1e-12 * s_ref[0]          # north-star tolerance on sigma
     assert np.all(np.diff(s) <= 0)
-    assert np.abs(u.conj().T @ u - np.eye(k)).max() < 1e-12
-    assert np.abs(vc.T @ vc.conj() - np.eye(k)).max() < 1e-12
+    assert np.abs(u.conj().T @ u - np.eye(k)).max() < 1e-11
+    assert np.abs(vc.T @ vc.conj() - np.eye(k)).max() < 1e-11
     assert np.abs((u * s) @ vc.T - a).max() < 1e-12 * s_ref[0]
 
 
