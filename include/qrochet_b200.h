@@ -159,6 +159,13 @@ int32_t qb200_mps_truncate(qb200_ctx* ctx, qb200_mps* mps, int32_t bond, int64_t
  * One fused chain: Λ-scale -> θ GEMM -> gate -> Jacobi SVD -> truncate -> Λ^-1 scale (atol 1e-32). */
 int32_t qb200_mps_evolve2(qb200_ctx* ctx, qb200_mps* mps, int32_t bond, const void* gate_c128, int64_t maxdim,
                           double threshold, int32_t renormalize, int64_t* kept, double* discarded_weight);
+/* One TEBD layer: nb two-site gates (16 c128 each, concatenated) on pairwise non-adjacent bonds -- the user-level
+ * loop `for bond in odd_bonds evolve!(psi, G[bond]; ...)`.  The bond updates are independent
+ * units and run concurrently on worker streams; results are identical to nb calls of qb200_mps_evolve2.
+ * kept / discarded_weight: arrays of nb (may be NULL). */
+int32_t qb200_mps_evolve2_layer(qb200_ctx* ctx, qb200_mps* mps, int32_t nb, const int32_t* bonds, const void* gates_c128,
+                                int64_t maxdim, double threshold, int32_t renormalize, int64_t* kept,
+                                double* discarded_weight);
 /* evolve_1site! (Chain.jl:586-603): gate = p*p c128 numbers (o, i) column-major */
 int32_t qb200_mps_evolve1(qb200_ctx* ctx, qb200_mps* mps, int32_t site, const void* gate_c128);
 /* overlap(a,b) = <b|a> (Chain.jl:737-748) by a left-environment sweep resident in HBM */

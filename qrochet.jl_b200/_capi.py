@@ -83,6 +83,7 @@ _protos = {
     "qb200_mps_mixed_canonize": (_i32, [_p, _p, _i32]),
     "qb200_mps_truncate": (_i32, [_p, _p, _i32, _i64, _dbl, _pi64]),
     "qb200_mps_evolve2": (_i32, [_p, _p, _i32, _p, _i64, _dbl, _i32, _pi64, _pdbl]),
+    "qb200_mps_evolve2_layer": (_i32, [_p, _p, _i32, _pi32, _p, _i64, _dbl, _i32, _pi64, _pdbl]),
     "qb200_mps_evolve1": (_i32, [_p, _p, _i32, _p]),
     "qb200_mps_overlap": (_i32, [_p, _p, _p, _pdbl]),
     "qb200_mps_expect1_batch": (_i32, [_p, _p, _i32, _pi32, _p, _pdbl]),

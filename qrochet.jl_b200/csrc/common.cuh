@@ -47,7 +47,15 @@ struct qb200_ctx {
     };
     std::vector<ProfRec> prof_recs;
     std::vector<cudaEvent_t> prof_pool;
+    // worker contexts (own stream / pinned scratch) used to run independent bond updates of a TEBD layer
+    // concurrently; owned by the parent context
+    std::vector<qb200_ctx*> workers;
+    bool is_worker = false;
 };
+
+int32_t qb_svd_init(qb200_ctx* ctx);
+int32_t qb_qr_init(qb200_ctx* ctx);
+qb200_ctx* qb_worker(qb200_ctx* parent, int index);  // creates workers lazily
 
 enum QbPhase {
     QB_PH_THETA_GEMM = 0,

@@ -2,6 +2,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "gemm_c128.cuh"
 
 static thread_local std::string g_last_error_noctx;
 
@@ -33,6 +34,14 @@ int32_t qb200_create(int32_t device, qb200_ctx** out) {
         uint64_t thr = UINT64_MAX;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
+    int32_t r = qb::init_gemm(ctx);
+    if (r == QB200_OK) r = qb_qr_init(ctx);
+    if (r == QB200_OK) r = qb_svd_init(ctx);
+    if (r != QB200_OK) {
+        g_last_error_noctx = ctx->err;
+        qb200_destroy(ctx);
+        return r;
+    }
     *out = ctx;
     return QB200_OK;
 }
@@ -41,6 +50,16 @@ int32_t qb200_destroy(qb200_ctx* ctx) {
     if (!ctx) return QB200_E_INVALID;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (qb200_ctx* w : ctx->workers) {
+        cudaStreamSynchronize(w->stream);
+        cudaStreamDestroy(w->stream);
+        cudaEventDestroy(w->ev0);
+        cudaEventDestroy(w->ev1);
+        cudaFreeHost(w->scratch_host);
+        for (auto e : w->prof_pool) cudaEventDestroy(e);
+        delete w;
+    }
+    ctx->workers.clear();
     if (ctx->nccl_comm) qb200_comm_destroy(ctx);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -72,7 +91,12 @@ int32_t qb200_synchronize(qb200_ctx* ctx) {
     return QB200_OK;
 }
 
-int64_t qb200_launch_count(qb200_ctx* ctx) { return ctx ? ctx->launches : -1; }
+int64_t qb200_launch_count(qb200_ctx* ctx) {
+    if (!ctx) return -1;
+    int64_t n = ctx->launches;
+    for (qb200_ctx* w : ctx->workers) n += w->launches;
+    return n;
+}
 
 int32_t qb200_timer_begin(qb200_ctx* ctx) {
     QB_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
@@ -87,10 +111,31 @@ int32_t qb200_timer_end(qb200_ctx* ctx, double* ms) {
     return QB200_OK;
 }
 
+}  // extern "C"
+
+qb200_ctx* qb_worker(qb200_ctx* parent, int index) {
+    while ((int)parent->workers.size() <= index) {
+        qb200_ctx* w = new qb200_ctx();
+        w->device = parent->device;
+        w->sm_count = parent->sm_count;
+        w->is_worker = true;
+        w->prof_on = parent->prof_on;
+        cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking);
+        cudaEventCreate(&w->ev0);
+        cudaEventCreate(&w->ev1);
+        cudaMallocHost(&w->scratch_host, 1 << 16);
+        parent->workers.push_back(w);
+    }
+    return parent->workers[index];
+}
+
+extern "C" {
+
 // phase profiler: enable/disable, and read back {count, total ms, total work} per phase (resets the records)
 int32_t qb200_prof_enable(qb200_ctx* ctx, int32_t on) {
     if (!ctx) return QB200_E_INVALID;
     ctx->prof_on = on != 0;
+    for (qb200_ctx* w : ctx->workers) w->prof_on = ctx->prof_on;
     return QB200_OK;
 }
 int32_t qb200_prof_read(qb200_ctx* ctx, int32_t nphases, int64_t* counts, double* ms, double* work) {
@@ -101,18 +146,23 @@ int32_t qb200_prof_read(qb200_ctx* ctx, int32_t nphases, int64_t* counts, double
         ms[i] = 0.0;
         work[i] = 0.0;
     }
-    for (auto& r : ctx->prof_recs) {
-        float f = 0.f;
-        cudaEventElapsedTime(&f, r.e0, r.e1);
-        if (r.phase < nphases) {
-            counts[r.phase]++;
-            ms[r.phase] += f;
-            work[r.phase] += r.work;
+    std::vector<qb200_ctx*> all = ctx->workers;
+    all.push_back(ctx);
+    for (qb200_ctx* c : all) {
+        cudaStreamSynchronize(c->stream);
+        for (auto& r : c->prof_recs) {
+            float f = 0.f;
+            cudaEventElapsedTime(&f, r.e0, r.e1);
+            if (r.phase < nphases) {
+                counts[r.phase]++;
+                ms[r.phase] += f;
+                work[r.phase] += r.work;
+            }
+            c->prof_pool.push_back(r.e0);
+            c->prof_pool.push_back(r.e1);
         }
-        ctx->prof_pool.push_back(r.e0);
-        ctx->prof_pool.push_back(r.e1);
+        c->prof_recs.clear();
     }
-    ctx->prof_recs.clear();
     return QB200_OK;
 }
 

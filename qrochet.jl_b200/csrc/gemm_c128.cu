@@ -228,6 +228,11 @@ int32_t build_offsets(qb200_ctx* ctx, const ModeList& ml, int64_t total, int64_t
     return QB200_OK;
 }
 
+int32_t init_gemm(qb200_ctx* ctx) {
+    QB_CUDA(ctx, cudaFuncSetAttribute(gemm_c128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+    return QB200_OK;
+}
+
 int32_t launch_gemm(qb200_ctx* ctx, const GemmArgs& args_in) {
     if (args_in.M <= 0 || args_in.N <= 0 || args_in.batch <= 0) return QB200_OK;
     GemmArgs args = args_in;
@@ -257,12 +262,6 @@ int32_t launch_gemm(qb200_ctx* ctx, const GemmArgs& args_in) {
                 args.ksplit = want;
             }
         }
-    }
-    static bool attr_set = false;
-    if (!attr_set) {
-        QB_CUDA(ctx, cudaFuncSetAttribute(gemm_c128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)GEMM_SMEM));
-        attr_set = true;
     }
     dim3 grid((args.M + BM - 1) / BM, (args.N + BN - 1) / BN, args.ksplit > 1 ? args.ksplit : args.batch);
     if (grid.y > 65535 || grid.z > 65535) QB_FAIL(ctx, QB200_E_UNSUPPORTED, "gemm grid too large");

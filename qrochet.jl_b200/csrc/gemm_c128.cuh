@@ -49,6 +49,7 @@ struct ModeList {
 };
 
 int32_t launch_gemm(qb200_ctx* ctx, const GemmArgs& args);
+int32_t init_gemm(qb200_ctx* ctx);  // kernel attributes, once per process (called by qb200_create)
 // offsets[idx] = sum_j coord_j(idx) * stride[j], first mode fastest
 int32_t build_offsets(qb200_ctx* ctx, const ModeList& ml, int64_t total, int64_t* out);
 

@@ -13,6 +13,9 @@
 
 #include "common.cuh"
 
+#include <cstdlib>
+#include <thread>
+
 struct qb200_mps {
     int n = 0;
     int form = 0;  // 0 plain, 1 Vidal (after canonize!), 2 mixed
@@ -406,9 +409,10 @@ int32_t qb200_mps_evolve1(qb200_ctx* ctx, qb200_mps* m, int32_t s, const void* g
 
 // evolve!(ψ, gate; threshold, maxdim, iscanonical, renormalize) for a gate on sites (b, b+1)
 // (evolve_2site!, contract_2sitewf!, unpack_2sitewf!: Chain.jl:606-722)
-int32_t qb200_mps_evolve2(qb200_ctx* ctx, qb200_mps* m, int32_t b, const void* gate, int64_t maxdim, double threshold,
-                          int32_t renormalize, int64_t* kept_out, double* discarded_weight) {
-    QB_TRY(check_complete(ctx, m));
+static int32_t evolve2_core(qb200_ctx* ctx, qb200_mps* m, int32_t b, const void* gate, int64_t maxdim,
+                            double threshold, int32_t renormalize, int64_t* kept_out, double* discarded_weight,
+                            bool validate) {
+    if (validate) QB_TRY(check_complete(ctx, m));
     if (b < 0 || b >= m->n - 1) QB_FAIL(ctx, QB200_E_INVALID, "evolve2: bond %d out of range", b);
     if (!gate) QB_FAIL(ctx, QB200_E_INVALID, "evolve2: null gate");
     if (m->p[b] != 2 || m->p[b + 1] != 2) QB_FAIL(ctx, QB200_E_UNSUPPORTED, "evolve2: physical dimension must be 2");
@@ -508,6 +512,81 @@ int32_t qb200_mps_evolve2(qb200_ctx* ctx, qb200_mps* m, int32_t b, const void* g
     m->lam_host[b] = sigma;
     if (kept_out) *kept_out = kept;
     if (discarded_weight) *discarded_weight = dw;
+    return QB200_OK;
+}
+
+int32_t qb200_mps_evolve2(qb200_ctx* ctx, qb200_mps* m, int32_t b, const void* gate, int64_t maxdim, double threshold,
+                          int32_t renormalize, int64_t* kept_out, double* discarded_weight) {
+    return evolve2_core(ctx, m, b, gate, maxdim, threshold, renormalize, kept_out, discarded_weight, true);
+}
+
+// One TEBD layer: `nb` two-site gates on pairwise non-adjacent bonds (e.g. all odd or all even bonds).  The
+// updates commute (disjoint sites; the Schmidt vectors between them are only read), so they are independent
+// units: they run concurrently on worker streams, which hides the latency-bound phases of one update (QR panels,
+// the shared-memory Jacobi solves) behind the DMMA-bound phases of the others.  Results are identical to
+// calling evolve! bond by bond.
+int32_t qb200_mps_evolve2_layer(qb200_ctx* ctx, qb200_mps* m, int32_t nb, const int32_t* bonds, const void* gates,
+                                int64_t maxdim, double threshold, int32_t renormalize, int64_t* kept_out,
+                                double* discarded_weight) {
+    QB_TRY(check_complete(ctx, m));
+    if (nb < 0 || (nb > 0 && (!bonds || !gates))) QB_FAIL(ctx, QB200_E_INVALID, "evolve2_layer: bad argument");
+    std::vector<int> sorted(bonds, bonds + nb);
+    std::sort(sorted.begin(), sorted.end());
+    for (int i = 0; i < nb; ++i) {
+        if (sorted[i] < 0 || sorted[i] >= m->n - 1) QB_FAIL(ctx, QB200_E_INVALID, "evolve2_layer: bond out of range");
+        if (i > 0 && sorted[i] - sorted[i - 1] < 2)
+            QB_FAIL(ctx, QB200_E_INVALID, "evolve2_layer: bonds %d and %d overlap", sorted[i - 1], sorted[i]);
+    }
+    if (nb == 0) return QB200_OK;
+    int nworkers = 8;
+    if (const char* e = getenv("QB200_WORKERS")) nworkers = std::max(1, atoi(e));
+    nworkers = std::min(nworkers, (int)nb);
+    std::vector<int64_t> kept_tmp(nb, 0);
+    std::vector<double> dw_tmp(nb, 0.0);
+    std::vector<int32_t> rc(nb, QB200_OK);
+    const c128* g = (const c128*)gates;
+    if (nworkers == 1) {
+        for (int i = 0; i < nb; ++i)
+            QB_TRY(evolve2_core(ctx, m, bonds[i], g + 16 * i, maxdim, threshold, renormalize, &kept_tmp[i], &dw_tmp[i], false));
+    } else {
+        // workers start after everything already queued on the parent stream
+        QB_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        std::vector<qb200_ctx*> w(nworkers);
+        for (int t = 0; t < nworkers; ++t) {
+            w[t] = qb_worker(ctx, t);
+            w[t]->prof_on = ctx->prof_on;
+            QB_CUDA(ctx, cudaStreamWaitEvent(w[t]->stream, ctx->ev1, 0));
+        }
+        // longest jobs first (largest bond dimension), dealt round robin
+        std::vector<int> order(nb);
+        for (int i = 0; i < nb; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int c) {
+            return m->chil[bonds[a]] * m->chir[bonds[a] + 1] > m->chil[bonds[c]] * m->chir[bonds[c] + 1];
+        });
+        std::vector<std::thread> threads;
+        for (int t = 0; t < nworkers; ++t)
+            threads.emplace_back([&, t]() {
+                cudaSetDevice(ctx->device);
+                for (int j = t; j < nb; j += nworkers) {
+                    int i = order[j];
+                    rc[i] = evolve2_core(w[t], m, bonds[i], g + 16 * i, maxdim, threshold, renormalize, &kept_tmp[i],
+                                         &dw_tmp[i], false);
+                    if (rc[i] != QB200_OK) break;
+                }
+                cudaStreamSynchronize(w[t]->stream);
+            });
+        for (auto& th : threads) th.join();
+        for (int i = 0; i < nb; ++i)
+            if (rc[i] != QB200_OK) {
+                for (int t = 0; t < nworkers; ++t)
+                    if (!w[t]->err.empty()) ctx->err = w[t]->err;
+                return rc[i];
+            }
+    }
+    for (int i = 0; i < nb; ++i) {
+        if (kept_out) kept_out[i] = kept_tmp[i];
+        if (discarded_weight) discarded_weight[i] = dw_tmp[i];
+    }
     return QB200_OK;
 }
 

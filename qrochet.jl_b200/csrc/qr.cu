@@ -228,13 +228,13 @@ static int32_t bgs_pass(qb200_ctx* ctx, int64_t m, int64_t k, c128* Q, int64_t l
     return QB200_OK;
 }
 
+int32_t qb_qr_init(qb200_ctx* ctx) {
+    QB_CUDA(ctx, cudaFuncSetAttribute(tsqr_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEAF_SMEM));
+    return QB200_OK;
+}
+
 int32_t qb_qr_matrix(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64_t lda, c128* Q, int64_t ldq,
                      c128* R, int64_t ldr) {
-    static bool attr = false;
-    if (!attr) {
-        QB_CUDA(ctx, cudaFuncSetAttribute(tsqr_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEAF_SMEM));
-        attr = true;
-    }
     if (m <= 0 || n <= 0) QB_FAIL(ctx, QB200_E_INVALID, "qr: empty matrix");
     if (m > INT32_MAX / 2) QB_FAIL(ctx, QB200_E_UNSUPPORTED, "qr: too many rows");
     const int64_t k = std::min(m, n);

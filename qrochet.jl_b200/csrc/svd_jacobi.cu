@@ -568,7 +568,24 @@ __global__ void svd_emit_kernel(const c128* __restrict__ src, int64_t ldz, int64
 __global__ void svd_emit_sigma_kernel(const double* __restrict__ sigma, const int* __restrict__ perm, int64_t kept,
                                       double scale, double* __restrict__ S) {
     int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < kept) S[j] = sigma[perm[j]] * scale;
+    if (j < kept) {
+        double v = sigma[perm[j]];
+        S[j] = (scale >= 0.0) ? v * scale : (v > 0.0 ? 1.0 / v : 0.0);  // scale < 0: reciprocal (0 for sigma = 0)
+    }
+}
+
+// out(:, j) = Q(:, j) * r_jj / |r_jj|: undoes the column phases a Householder QR introduces
+__global__ void fix_phase_kernel(const c128* __restrict__ Q, int64_t rows, int64_t cols, const c128* __restrict__ R,
+                                 int64_t ldr, c128* __restrict__ out) {
+    int64_t total = rows * cols;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        int64_t j = idx / rows;
+        c128 d = R[j + j * ldr];
+        double a = sqrt(d.x * d.x + d.y * d.y);
+        c128 ph = (a > 0.0) ? make_double2(d.x / a, d.y / a) : make_double2(1.0, 0.0);
+        out[idx] = cmul(Q[idx], ph);
+    }
 }
 
 }  // namespace
@@ -579,8 +596,10 @@ struct SvdState {
     int64_t rb;         // rows of B
     int mp, np;         // padded k (rows of X, columns)
     int64_t ldz;
-    c128* Z = nullptr;  // [X ; V] stacked
+    c128* Z = nullptr;  // X (mp x np); the rotations are NOT accumulated (see qb_svd_emit)
     c128* Q = nullptr;  // rb x k, orthonormal columns
+    c128* R = nullptr;  // k x k upper triangular, B P = Q R
+    std::vector<double> sigma_sorted;
     double* sigma_dev = nullptr;
     int* perm_dev = nullptr;     // sigma order (descending) -> column of Z
     int* colperm_dev = nullptr;  // column j of the QR input was column colperm[j] of B
@@ -596,6 +615,7 @@ void qb_svd_release(qb200_ctx* ctx, SvdState* st) {
     if (!st) return;
     if (st->Z) cudaFreeAsync(st->Z, ctx->stream);
     if (st->Q) cudaFreeAsync(st->Q, ctx->stream);
+    if (st->R) cudaFreeAsync(st->R, ctx->stream);
     if (st->sigma_dev) cudaFreeAsync(st->sigma_dev, ctx->stream);
     if (st->perm_dev) cudaFreeAsync(st->perm_dev, ctx->stream);
     if (st->colperm_dev) cudaFreeAsync(st->colperm_dev, ctx->stream);
@@ -623,15 +643,15 @@ __global__ void svd_gather_cols_kernel(const c128* __restrict__ A, int64_t lda, 
 }
 }  // namespace
 
+int32_t qb_svd_init(qb200_ctx* ctx) {
+    QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRAM_SMEM));
+    QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_evd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EVD_SMEM));
+    QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM));
+    return QB200_OK;
+}
+
 int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64_t lda, SvdState** out,
                       std::vector<double>& sigma) {
-    static bool attrs = false;
-    if (!attrs) {
-        QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRAM_SMEM));
-        QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_evd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EVD_SMEM));
-        QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM));
-        attrs = true;
-    }
     if (m <= 0 || n <= 0) QB_FAIL(ctx, QB200_E_INVALID, "svd: empty matrix");
     if (std::max(m, n) > (1 << 30)) QB_FAIL(ctx, QB200_E_UNSUPPORTED, "svd: matrix too large");
     SvdState* st = new SvdState();
@@ -642,7 +662,7 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
     st->rb = std::max(m, n);
     const int64_t k = st->k, rb = st->rb;
     st->mp = st->np = (int)((k + 63) / 64 * 64);
-    st->ldz = (int64_t)st->mp + st->np;
+    st->ldz = (int64_t)st->mp;
     const int nb = st->np / JB, npairs = nb / 2, nsteps = (nb == 2) ? 1 : nb - 1;
     auto fail = [&](int32_t code) {
         qb_svd_release(ctx, st);
@@ -654,6 +674,7 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
     };
     if (cudaMallocAsync(&st->Z, sizeof(c128) * st->ldz * st->np, ctx->stream) != cudaSuccess ||
         cudaMallocAsync(&st->Q, sizeof(c128) * rb * k, ctx->stream) != cudaSuccess ||
+        cudaMallocAsync(&st->R, sizeof(c128) * k * k, ctx->stream) != cudaSuccess ||
         cudaMallocAsync(&st->sigma_dev, sizeof(double) * st->np, ctx->stream) != cudaSuccess ||
         cudaMallocAsync(&st->perm_dev, sizeof(int) * st->np, ctx->stream) != cudaSuccess ||
         cudaMallocAsync(&st->colperm_dev, sizeof(int) * k, ctx->stream) != cudaSuccess) {
@@ -668,8 +689,8 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
     {
         double* nr = ws.get<double>((size_t)(m + n));
         c128* B0 = ws.get<c128>((size_t)(rb * k));
-        c128* R = ws.get<c128>((size_t)(k * k));
-        if (!nr || !B0 || !R) {
+        c128* R = st->R;
+        if (!nr || !B0) {
             ctx->err = "svd: workspace allocation failed";
             return fail(QB200_E_CUDA);
         }
@@ -694,7 +715,7 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
             int32_t r = qb_qr_matrix(ctx, rb, k, B0, rb, st->Q, rb, R, k);
             if (r != QB200_OK) return fail(r);
         }
-        // Z = [R^H zero-padded ; I]
+        // Z = R^H zero-padded
         svd_init_kernel<<<grid_cap(ctx, st->ldz * st->np, 256), 256, 0, ctx->stream>>>(st->Z, st->ldz, st->mp, st->np, k,
                                                                                       k, R, k, 1);
         ctx->launches++;
@@ -722,7 +743,7 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
     const double eps = 1.1102230246251565e-16;
     const double rot_tol = std::sqrt((double)st->mp) * eps;
     const double conv_tol = 1e-10;
-    const double abs_c = 2.0 * eps;
+    const double abs_c = 0.0;  // pure relative criterion: R^H is column graded, so one-sided Jacobi keeps relative accuracy (no noise floor)
     const int inner_sweeps = (nb == 2) ? 12 : 1;
     const int nact = (nb == 2) ? (int)std::min<int64_t>(64, (k + 1) / 2 * 2) : 64;
     col_norm_kernel<<<(st->np + 7) / 8, 256, 0, ctx->stream>>>(st->Z, st->ldz, st->mp, st->np, st->sigma_dev);
@@ -747,7 +768,7 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
                     abs_c, nact, mode);
             }
             {
-                PhaseTimer pt(ctx, QB_PH_JUPDATE, 8.0 * npairs * (double)st->ldz * JP * JP);
+                PhaseTimer pt(ctx, QB_PH_JUPDATE, 8.0 * npairs * (double)st->ldz * JP * JP);  // ldz = rows of X
                 jacobi_update_kernel<<<dim3(npairs, parts), 256, UPD_SMEM, ctx->stream>>>(
                     st->Z, st->ldz, nb, step, Wg, flags, chunks_per_cta, total_chunks);
             }
@@ -786,6 +807,7 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
     });
     sigma.resize(k);
     for (int64_t i = 0; i < k; ++i) sigma[i] = sig[st->perm[i]];
+    st->sigma_sorted = sigma;
     e = cudaMemcpyAsync(st->perm_dev, st->perm.data(), sizeof(int) * st->np, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) return cuda_fail(e);
@@ -802,17 +824,39 @@ int32_t qb_svd_emit(qb200_ctx* ctx, SvdState* st, int64_t kept, c128* U, int64_t
     if (kept <= 0) return QB200_OK;
     const int64_t k = st->k;
     const c128* X = st->Z;
-    const c128* Vacc = st->Z + st->mp;
     const c128 ONE = make_double2(1.0, 0.0), ZERO = make_double2(0.0, 0.0);
     Workspace ws(ctx);
+    // The rotations were not accumulated.  With R^H = Xn S Vs^H and Xn orthonormal, R Xn = Vs S, so
+    // Vs = R Xn S^-1: one triangular-times-dense GEMM instead of dragging a k x k block through every update
+    // (a third of the Jacobi flops).  Column j comes out with a relative error ~ eps sigma_1 / sigma_j, harmless
+    // (norm-wise backward stable) but it costs orthogonality when the kept spectrum is graded; in that case the
+    // columns are re-orthonormalised in order of decreasing sigma (K4), which leaves A = U S V^H intact to
+    // eps sigma_1 and keeps U orthonormal to machine precision.
     c128* Vs = nullptr;
     auto need_vs = [&]() -> int32_t {
         if (Vs) return QB200_OK;
+        c128* Xsel = ws.get<c128>((size_t)(k * kept));
         Vs = ws.get<c128>((size_t)(k * kept));
-        if (!Vs) QB_FAIL(ctx, QB200_E_CUDA, "svd: workspace allocation failed");
+        double* isg = ws.get<double>((size_t)kept);
+        if (!Xsel || !Vs || !isg) QB_FAIL(ctx, QB200_E_CUDA, "svd: workspace allocation failed");
         svd_emit_kernel<<<grid_cap(ctx, k * kept, 256), 256, 0, ctx->stream>>>(
-            Vacc, st->ldz, k, kept, st->perm_dev, st->sigma_dev, 0, 0, 0, nullptr, Vs, k, nullptr, 0, 1);
+            X, st->ldz, k, kept, st->perm_dev, st->sigma_dev, 1, 0, 0, nullptr, Xsel, k, nullptr, 0, 1);
         QB_LAUNCH_CHECK(ctx);
+        svd_emit_sigma_kernel<<<(unsigned)((kept + 255) / 256), 256, 0, ctx->stream>>>(st->sigma_dev, st->perm_dev, kept,
+                                                                                      -1.0, isg);
+        QB_LAUNCH_CHECK(ctx);
+        QB_TRY(qb_gemm(ctx, 0, 0, k, kept, k, ONE, st->R, k, Xsel, k, ZERO, Vs, k));
+        QB_TRY(qb_scale_rows_cols(ctx, Vs, Vs, k, kept, nullptr, 1, isg, 1));
+        const std::vector<double>& sg = st->sigma_sorted;
+        bool graded = !(sg[kept - 1] > 1e-3 * sg[0]);
+        if (graded) {
+            c128* Qv = ws.get<c128>((size_t)(k * kept));
+            c128* Rv = ws.get<c128>((size_t)(kept * kept));
+            if (!Qv || !Rv) QB_FAIL(ctx, QB200_E_CUDA, "svd: workspace allocation failed");
+            QB_TRY(qb_qr_matrix(ctx, k, kept, Vs, k, Qv, k, Rv, kept));
+            fix_phase_kernel<<<grid_cap(ctx, k * kept, 256), 256, 0, ctx->stream>>>(Qv, k, kept, Rv, kept, Vs);
+            QB_LAUNCH_CHECK(ctx);
+        }
         return QB200_OK;
     };
     PhaseTimer pt(ctx, QB_PH_EMIT, 8.0 * st->rb * k * kept);

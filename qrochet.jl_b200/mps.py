@@ -182,6 +182,21 @@ class B200MPS:
                                                 int(bool(renormalize)), C.byref(kept), C.byref(dw)))
         return kept.value, dw.value
 
+    def evolve_layer(self, gates, bonds, threshold=None, maxdim=None, renormalize=False):
+        """One TEBD layer: `gates[i]` (dims (o1,o2,i1,i2)) on sites (bonds[i], bonds[i]+1), 1-based, pairwise
+        non-adjacent -- the user loop `for b in bonds: evolve!(ψ, G_b; ...)` run as concurrent independent units.
+        Returns (kept[], discarded_weight[])."""
+        nb = len(bonds)
+        flat = np.concatenate([np.asarray(g, dtype=np.complex128).reshape(-1, order="F") for g in gates]) \
+            if nb else np.zeros(0, np.complex128)
+        kept = (C.c_int64 * max(nb, 1))()
+        dw = (C.c_double * max(nb, 1))()
+        check(self.ctx.h, lib.qb200_mps_evolve2_layer(self.ctx.h, self.h, nb, capi.i32arr(b - 1 for b in bonds),
+                                                      flat.ctypes.data_as(C.c_void_p), int(maxdim or 0),
+                                                      -1.0 if threshold is None else float(threshold),
+                                                      int(bool(renormalize)), kept, dw))
+        return [int(kept[i]) for i in range(nb)], [float(dw[i]) for i in range(nb)]
+
     def overlap(self, other: "B200MPS") -> complex:
         """`overlap(a, b)` = <b|a> (Chain.jl:737-748)."""
         r = (C.c_double * 2)()

@@ -185,3 +185,22 @@ def test_svd_rank_deficient_and_tensor_modes(qb, ctx):
     mat = np.transpose(t, (1, 2, 0)).reshape((4, 15), order="F")
     rec = (u.to_host() * s.to_host()) @ vc.to_host().reshape((15, 4), order="F").T
     assert np.allclose(rec, mat)
+
+
+def test_svd_graded_kept_spectrum_keeps_factors_orthonormal(qb, ctx):
+    """Kept singular values spanning 10 orders of magnitude: U and V stay orthonormal, A = U S V^H holds norm-wise,
+    sigma matches LAPACK to 1e-12 sigma_1 (the rotations are not accumulated; V is recovered from R X S^-1 and
+    re-orthonormalised when the kept spectrum is graded)."""
+    rng = np.random.default_rng(8)
+    for (m, n) in [(160, 160), (200, 96), (96, 200)]:
+        k = min(m, n)
+        q1, _ = np.linalg.qr(crand(rng, m, k))
+        q2, _ = np.linalg.qr(crand(rng, n, k))
+        sig = np.logspace(0, -10, k)
+        a = (q1 * sig) @ q2.conj().T
+        u, s, vc, kept, dw = qb.svd(ctx.array(a), (0, 1), 1)
+        u, s, vc = u.to_host(), s.to_host(), vc.to_host()
+        assert np.abs(s - sig).max() <= 1e-12
+        assert np.abs(u.conj().T @ u - np.eye(k)).max() < 1e-10
+        assert np.abs(vc.T @ vc.conj() - np.eye(k)).max() < 1e-6    # small-sigma vectors: eps sigma_1 / sigma_j
+        assert np.abs((u * s) @ vc.T - a).max() < 1e-12

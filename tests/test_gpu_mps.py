@@ -201,3 +201,29 @@ def test_overlap_and_expect(qb, ctx):
     assert np.abs(got2 - want).max() <= OBS_TOL
     assert abs(ga.overlap(ga) - 1.0) < 1e-12
     assert abs(ga.expect([np.eye(2)], [5])[0] - 1.0) < 1e-12
+
+
+def test_evolve_layer_equals_sequential_evolve(qb, ctx):
+    """The concurrent TEBD layer (independent bond updates on worker streams) is the same as calling evolve!
+    bond by bond, and matches the oracle."""
+    n = 12
+    o, g1 = make(qb, ctx, 21, n, 16)
+    o.canonize()
+    g1.canonize()
+    g2 = g1.copy()
+    rng = np.random.default_rng(22)
+    for group in ([1, 3, 5, 7, 9, 11], [2, 4, 6, 8, 10], [1, 3, 5, 7, 9, 11]):
+        gates = []
+        for b in group:
+            U = oc.haar_unitary(rng)
+            gates.append(np.reshape(U, (2, 2, 2, 2), order="F"))
+            o.evolve(oc.gate(U, [b, b + 1]), iscanonical=True, maxdim=16, renormalize=True)
+        kept_l, dw_l = g1.evolve_layer(gates, group, maxdim=16, renormalize=True)
+        seq = [g2.evolve(gt, [b, b + 1], maxdim=16, renormalize=True) for gt, b in zip(gates, group)]
+        assert kept_l == [k for k, _ in seq]
+        assert np.allclose(dw_l, [d for _, d in seq], rtol=1e-9, atol=1e-20)
+    for x, y in zip(g1.lambdas(), g2.lambdas()):
+        assert np.array_equal(x, y)          # same kernels, same inputs: bit-identical
+    assert_lams(g1.lambdas(), o.lambdas())
+    with pytest.raises(qb.QB200Error):
+        g1.evolve_layer([gates[0], gates[1]], [3, 4], maxdim=16)   # adjacent bonds do not commute
