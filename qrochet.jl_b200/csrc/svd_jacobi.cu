@@ -52,101 +52,149 @@ __device__ __forceinline__ void rr_pair(int n, int step, int k, int& p, int& q) 
 __device__ __forceinline__ int64_t panel_col(int I, int J, int c) { return (c < JB) ? (I * JB + c) : (J * JB + c - JB); }
 
 // ---------------------------------------------------------------------------------------------
-// gram kernel
+// gram kernel: G_p = P_p^H P_p for every pair of the step.
+//
+// Work items are (pair, 32-row chunk), flattened pair-major and cut into equal contiguous ranges, one per CTA of
+// a persistent grid of 2 x #SM CTAs (no tail wave: 2048 items over 296 CTAs at chi = 1024).  A CTA accumulates
+// over its items and flushes a partial Gram whenever the pair changes (at most twice: a range is shorter than a
+// pair); the evd kernel sums the partials of its pair in CTA order (deterministic).
+// Only the 36 upper 8 x 8 tiles of the 8 x 8 tile grid are computed (G is Hermitian) -- dealt to the 8 warps as
+// <= 5 tiles each by a compile-time table -- and mirrored on the way out: 5/8 of the DMMA work of the full product.
 constexpr int G_BKR = 32, G_NST = 3, G_PITCH = G_BKR + 4;
 constexpr size_t GRAM_SMEM = (size_t)G_NST * JP * G_PITCH * sizeof(c128);
 
+struct GramTiles {
+    int n;
+    int r[5], c[5];
+};
+__host__ __device__ constexpr GramTiles gram_tiles(int w) {
+    switch (w) {
+        case 0: return {5, {0, 0, 0, 0, 0}, {0, 1, 2, 3, 4}};
+        case 1: return {5, {0, 0, 0, 1, 1}, {5, 6, 7, 1, 2}};
+        case 2: return {5, {1, 1, 1, 1, 1}, {3, 4, 5, 6, 7}};
+        case 3: return {5, {2, 2, 2, 2, 2}, {2, 3, 4, 5, 6}};
+        case 4: return {5, {2, 3, 3, 3, 3}, {7, 3, 4, 5, 6}};
+        case 5: return {5, {3, 4, 4, 4, 4}, {7, 4, 5, 6, 7}};
+        case 6: return {5, {5, 5, 5, 6, 6}, {5, 6, 7, 6, 7}};
+        default: return {1, {7, 0, 0, 0, 0}, {7, 0, 0, 0, 0}};
+    }
+}
+
+__device__ __forceinline__ void gram_item_range(int cta, int ncta, int total, int& lo, int& hi) {
+    lo = (int)(((long long)cta * total) / ncta);
+    hi = (int)(((long long)(cta + 1) * total) / ncta);
+}
+
+template <int W>
+__device__ __forceinline__ void gram_mma_chunk(const c128* __restrict__ ps, int g, int t, double (&cr)[5][2],
+                                               double (&ci)[5][2]) {
+    constexpr GramTiles T = gram_tiles(W);
+#pragma unroll
+    for (int kk = 0; kk < G_BKR / 4; ++kk) {
+#pragma unroll
+        for (int i = 0; i < T.n; ++i) {
+            c128 a = ps[(T.r[i] * 8 + g) * G_PITCH + t + kk * 4];
+            c128 b = ps[(T.c[i] * 8 + g) * G_PITCH + t + kk * 4];
+            // G = P^H P: A operand is conj(P)
+            dmma884(cr[i], a.x, b.x);
+            dmma884(ci[i], a.x, b.y);
+            dmma884(cr[i], a.y, b.y);
+            dmma884(ci[i], -a.y, b.x);
+        }
+    }
+}
+
+template <int W>
+__device__ __forceinline__ void gram_flush(c128* __restrict__ out, int g, int t, double (&cr)[5][2],
+                                           double (&ci)[5][2]) {
+    constexpr GramTiles T = gram_tiles(W);
+#pragma unroll
+    for (int i = 0; i < T.n; ++i) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            int row = T.r[i] * 8 + g, col = T.c[i] * 8 + 2 * t + h;
+            c128 v = make_double2(cr[i][h], ci[i][h]);
+            out[row + JP * col] = v;
+            if (T.r[i] != T.c[i]) out[col + JP * row] = make_double2(v.x, -v.y);
+            cr[i][h] = 0.0;
+            ci[i][h] = 0.0;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256, 2)
-    jacobi_gram_kernel(const c128* __restrict__ Z, int64_t ldz, int mp, int nb, int step, int ksplit,
+    jacobi_gram_kernel(const c128* __restrict__ Z, int64_t ldz, int mp, int nb, int step, int npairs,
                        c128* __restrict__ Gpart) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     c128* Ps = reinterpret_cast<c128*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int pair = blockIdx.x, split = blockIdx.y;
-    int I, J;
-    rr_pair(nb, step, pair, I, J);
+    const int nchunk = mp / G_BKR, total = npairs * nchunk;
+    int lo, hi;
+    gram_item_range(blockIdx.x, gridDim.x, total, lo, hi);
+    const int nitems = hi - lo;
 
-    int rows_per = ((mp + ksplit - 1) / ksplit + G_BKR - 1) / G_BKR * G_BKR;
-    int r_begin = split * rows_per;
-    int r_end = min(mp, r_begin + rows_per);
-    int nchunks = (r_end > r_begin) ? (r_end - r_begin + G_BKR - 1) / G_BKR : 0;
-
-    // loader: 64 cols x 32 rows per chunk, 8 elements per thread, rows contiguous
     const int l_row = tid & 31, l_col0 = tid >> 5;
-    auto load_chunk = [&](int c, int st) {
+    auto load_item = [&](int it, int st) {
         c128* ps = Ps + (size_t)st * JP * G_PITCH;
-        int row = r_begin + c * G_BKR + l_row;
-        bool ok = row < r_end;
+        int item = lo + it;
+        int pair = item / nchunk, chunk = item - pair * nchunk;
+        int I, J;
+        rr_pair(nb, step, pair, I, J);
+        int row = chunk * G_BKR + l_row;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             int col = l_col0 + 8 * i;
-            const c128* src = Z + (ok ? (row + panel_col(I, J, col) * ldz) : 0);
-            cp_async16(ps + col * G_PITCH + l_row, src, ok);
+            cp_async16(ps + col * G_PITCH + l_row, Z + row + panel_col(I, J, col) * ldz, true);
         }
     };
 
-    const int wi = warp & 3, wj = warp >> 2;
-    double cr[2][4][2], ci[2][4][2];
+    double cr[5][2], ci[5][2];
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) cr[a][b][0] = cr[a][b][1] = ci[a][b][0] = ci[a][b][1] = 0.0;
+    for (int i = 0; i < 5; ++i) cr[i][0] = cr[i][1] = ci[i][0] = ci[i][1] = 0.0;
 
 #pragma unroll
     for (int s = 0; s < G_NST - 1; ++s) {
-        if (s < nchunks) load_chunk(s, s);
+        if (s < nitems) load_item(s, s);
         cp_async_commit();
     }
-    for (int c = 0; c < nchunks; ++c) {
+    const int first_pair = (nitems > 0) ? lo / nchunk : 0;
+    for (int it = 0; it < nitems; ++it) {
         cp_async_wait<G_NST - 2>();
         __syncthreads();
         {
-            int nc = c + G_NST - 1;
-            if (nc < nchunks) load_chunk(nc, nc % G_NST);
+            int nx = it + G_NST - 1;
+            if (nx < nitems) load_item(nx, nx % G_NST);
             cp_async_commit();
         }
-        const c128* ps = Ps + (size_t)(c % G_NST) * JP * G_PITCH;
-        const c128* pa = ps + (wi * 16 + g) * G_PITCH + t;
-        const c128* pb = ps + (wj * 32 + g) * G_PITCH + t;
-#pragma unroll
-        for (int kk = 0; kk < G_BKR / 4; ++kk) {
-            double ar[2], ay[2], nay[2], br[4], bi[4];
-#pragma unroll
-            for (int a = 0; a < 2; ++a) {
-                c128 v = pa[a * 8 * G_PITCH + kk * 4];
-                ar[a] = v.x;
-                ay[a] = v.y;
-                nay[a] = -v.y;
+        const c128* ps = Ps + (size_t)(it % G_NST) * JP * G_PITCH;
+        switch (warp) {
+            case 0: gram_mma_chunk<0>(ps, g, t, cr, ci); break;
+            case 1: gram_mma_chunk<1>(ps, g, t, cr, ci); break;
+            case 2: gram_mma_chunk<2>(ps, g, t, cr, ci); break;
+            case 3: gram_mma_chunk<3>(ps, g, t, cr, ci); break;
+            case 4: gram_mma_chunk<4>(ps, g, t, cr, ci); break;
+            case 5: gram_mma_chunk<5>(ps, g, t, cr, ci); break;
+            case 6: gram_mma_chunk<6>(ps, g, t, cr, ci); break;
+            default: gram_mma_chunk<7>(ps, g, t, cr, ci); break;
+        }
+        int pair = (lo + it) / nchunk;
+        bool last_of_pair = (it + 1 == nitems) || ((lo + it + 1) / nchunk != pair);
+        if (last_of_pair) {
+            c128* out = Gpart + ((size_t)2 * blockIdx.x + (pair != first_pair ? 1 : 0)) * (JP * JP);
+            switch (warp) {
+                case 0: gram_flush<0>(out, g, t, cr, ci); break;
+                case 1: gram_flush<1>(out, g, t, cr, ci); break;
+                case 2: gram_flush<2>(out, g, t, cr, ci); break;
+                case 3: gram_flush<3>(out, g, t, cr, ci); break;
+                case 4: gram_flush<4>(out, g, t, cr, ci); break;
+                case 5: gram_flush<5>(out, g, t, cr, ci); break;
+                case 6: gram_flush<6>(out, g, t, cr, ci); break;
+                default: gram_flush<7>(out, g, t, cr, ci); break;
             }
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                c128 v = pb[b * 8 * G_PITCH + kk * 4];
-                br[b] = v.x;
-                bi[b] = v.y;
-            }
-#pragma unroll
-            for (int a = 0; a < 2; ++a)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    dmma884(cr[a][b], ar[a], br[b]);
-                    dmma884(ci[a][b], ar[a], bi[b]);
-                    dmma884(cr[a][b], ay[a], bi[b]);
-                    dmma884(ci[a][b], nay[a], br[b]);
-                }
         }
     }
     cp_async_wait<0>();
-    c128* out = Gpart + ((size_t)pair * ksplit + split) * (JP * JP);
-#pragma unroll
-    for (int a = 0; a < 2; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                int i = wi * 16 + a * 8 + g, j = wj * 32 + b * 8 + 2 * t + h;
-                out[i + JP * j] = make_double2(cr[a][b][h], ci[a][b][h]);
-            }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -168,7 +216,8 @@ constexpr size_t EVD_SMEM = (size_t)2 * JP * GLD * sizeof(c128) + 32 * sizeof(do
                             64 * sizeof(int) + 64 * sizeof(double) + EVD_NBLK * sizeof(short);
 
 __global__ void __launch_bounds__(EVD_THREADS, 1)
-    jacobi_evd_kernel(const c128* __restrict__ Gpart, int ksplit, c128* __restrict__ Wout, int* __restrict__ flags,
+    jacobi_evd_kernel(const c128* __restrict__ Gpart, int gram_ctas, int nchunk, int npairs_total,
+                      c128* __restrict__ Wout, int* __restrict__ flags,
                       unsigned long long* __restrict__ sweep_stat, double rot_tol, int inner_sweeps,
                       const double* __restrict__ scale_in, unsigned long long* __restrict__ scale_out, double abs_c,
                       int nact, int mode) {
@@ -183,11 +232,29 @@ __global__ void __launch_bounds__(EVD_THREADS, 1)
     __shared__ int any_rot;
 
     const int tid = threadIdx.x, pair = blockIdx.x;
-    const c128* src = Gpart + (size_t)pair * ksplit * (JP * JP);
+    // partial Grams of this pair: the gram CTAs whose item range overlaps [pair*nchunk, (pair+1)*nchunk), in order
+    __shared__ int slots[64];
+    __shared__ int nslots;
+    if (tid == 0) {
+        const int total_items = npairs_total * nchunk;
+        const int p_lo = pair * nchunk, p_hi = p_lo + nchunk;
+        int c = (int)(((long long)p_lo * gram_ctas) / total_items) - 1;
+        if (c < 0) c = 0;
+        int ns = 0;
+        for (; c < gram_ctas && ns < 64; ++c) {
+            int lo, hi;
+            gram_item_range(c, gram_ctas, total_items, lo, hi);
+            if (lo >= p_hi) break;
+            if (hi <= p_lo || hi == lo) continue;
+            slots[ns++] = 2 * c + ((lo / nchunk) != pair ? 1 : 0);
+        }
+        nslots = ns;
+    }
+    __syncthreads();
     for (int e = tid; e < JP * JP; e += EVD_THREADS) {
         double sx = 0.0, sy = 0.0;
-        for (int s = 0; s < ksplit; ++s) {
-            c128 v = src[(size_t)s * (JP * JP) + e];
+        for (int i = 0; i < nslots; ++i) {
+            c128 v = Gpart[(size_t)slots[i] * (JP * JP) + e];
             sx += v.x;
             sy += v.y;
         }
@@ -361,56 +428,71 @@ __global__ void __launch_bounds__(EVD_THREADS, 1)
 }
 
 // ---------------------------------------------------------------------------------------------
-// update kernel: Z_p <- Z_p W_p, 64-row chunks double buffered
+// update kernel: X_p <- X_p W_p in place.  Work items are (pair, 64-row chunk), flattened pair-major and cut into
+// equal contiguous ranges over a persistent grid of #SM CTAs (1024 items over 148 CTAs at chi = 1024: no tail
+// wave).  W_p stays in shared memory while the CTA walks the chunks of a pair (reloaded at most once), chunks
+// are double buffered with cp.async, results go straight from the DMMA accumulators to global memory.
 constexpr int U_ZP = 66, U_WP = 68;
 constexpr size_t UPD_SMEM = (size_t)(JP * U_WP + 2 * JP * U_ZP) * sizeof(c128);
 
 __global__ void __launch_bounds__(256, 1)
     jacobi_update_kernel(c128* __restrict__ Z, int64_t ldz, int nb, int step, const c128* __restrict__ Wg,
-                         const int* __restrict__ flags, int chunks_per_cta, int total_chunks) {
-    const int pair = blockIdx.x;
-    if (!flags[pair]) return;
+                         const int* __restrict__ flags, int npairs, int nchunk) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     c128* Ws = reinterpret_cast<c128*>(smem_raw);  // [n][k] pitch 68
     c128* Zs = Ws + JP * U_WP;                     // [2][col][row] pitch 66
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    int I, J;
-    rr_pair(nb, step, pair, I, J);
-    const int c_begin = blockIdx.y * chunks_per_cta;
-    const int c_end = min(total_chunks, c_begin + chunks_per_cta);
-    if (c_begin >= c_end) return;
+    const int total = npairs * nchunk;
+    int lo, hi;
+    gram_item_range(blockIdx.x, gridDim.x, total, lo, hi);
 
-    {
-        const c128* wsrc = Wg + (size_t)pair * (JP * JP);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            int e = tid + 256 * i;
-            int k = e & 63, n = e >> 6;
-            cp_async16(Ws + n * U_WP + k, wsrc + e, true);
-        }
-    }
     const int l_row = tid & 63, l_col0 = tid >> 6;
-    auto load_chunk = [&](int c, int st) {
+    auto load_chunk = [&](int item, int st) {
         c128* zs = Zs + (size_t)st * JP * U_ZP;
-        int64_t row = (int64_t)c * 64 + l_row;
+        int pair = item / nchunk, chunk = item - pair * nchunk;
+        int I, J;
+        rr_pair(nb, step, pair, I, J);
+        int64_t row = (int64_t)chunk * 64 + l_row;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             int col = l_col0 + 4 * i;
             cp_async16(zs + col * U_ZP + l_row, Z + row + panel_col(I, J, col) * ldz, true);
         }
     };
-    load_chunk(c_begin, 0);
-    cp_async_commit();
+    // skip the items of pairs that are already orthogonal (W = I)
+    auto next_active = [&](int item) {
+        while (item < hi && !flags[item / nchunk]) item = (item / nchunk + 1) * nchunk;
+        return min(item, hi);
+    };
 
     const int wi = warp & 3, wj = warp >> 2;
-    for (int c = c_begin; c < c_end; ++c) {
-        int st = (c - c_begin) & 1;
-        if (c + 1 < c_end) load_chunk(c + 1, st ^ 1);
+    int cur_pair = -1, stage = 0;
+    int item = next_active(lo);
+    if (item < hi) load_chunk(item, 0);
+    cp_async_commit();
+    while (item < hi) {
+        const int pair = item / nchunk, chunk = item - pair * nchunk;
+        if (pair != cur_pair) {
+            __syncthreads();  // every warp is done with the previous W
+            const c128* wsrc = Wg + (size_t)pair * (JP * JP);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                int e = tid + 256 * i;
+                cp_async16(Ws + (e >> 6) * U_WP + (e & 63), wsrc + e, true);
+            }
+            cp_async_commit();
+            cp_async_wait<0>();  // W (and the current chunk) have landed
+            cur_pair = pair;
+        }
+        const int nxt = next_active(item + 1);
+        if (nxt < hi) load_chunk(nxt, stage ^ 1);
         cp_async_commit();
         cp_async_wait<1>();
         __syncthreads();
-        const c128* za = Zs + (size_t)st * JP * U_ZP + wi * 16 + g;
+        int I, J;
+        rr_pair(nb, step, pair, I, J);
+        const c128* za = Zs + (size_t)stage * JP * U_ZP + wi * 16 + g;
         const c128* wb = Ws + (wj * 32 + g) * U_WP + t;
         double cr[2][4][2], ci[2][4][2];
 #pragma unroll
@@ -443,7 +525,7 @@ __global__ void __launch_bounds__(256, 1)
                     dmma884(ci[a][b], ai[a], br[b]);
                 }
         }
-        int64_t r0 = (int64_t)c * 64 + wi * 16 + g;
+        int64_t r0 = (int64_t)chunk * 64 + wi * 16 + g;
 #pragma unroll
         for (int a = 0; a < 2; ++a)
 #pragma unroll
@@ -453,8 +535,11 @@ __global__ void __launch_bounds__(256, 1)
                     int n = wj * 32 + b * 8 + 2 * t + h;
                     Z[r0 + a * 8 + panel_col(I, J, n) * ldz] = make_double2(cr[a][b][h], ci[a][b][h]);
                 }
-        __syncthreads();  // everyone is done with stage st before it is refilled
+        __syncthreads();  // stage is free again before the next iteration refills it
+        stage ^= 1;
+        item = nxt;
     }
+    cp_async_wait<0>();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -653,7 +738,8 @@ int32_t qb_svd_init(qb200_ctx* ctx) {
 int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64_t lda, SvdState** out,
                       std::vector<double>& sigma) {
     if (m <= 0 || n <= 0) QB_FAIL(ctx, QB200_E_INVALID, "svd: empty matrix");
-    if (std::max(m, n) > (1 << 30)) QB_FAIL(ctx, QB200_E_UNSUPPORTED, "svd: matrix too large");
+    if (std::max(m, n) > (1 << 30) || std::min(m, n) > 16384)
+        QB_FAIL(ctx, QB200_E_UNSUPPORTED, "svd: matrix too large (min(m, n) <= 16384)");
     SvdState* st = new SvdState();
     st->m = m;
     st->n = n;
@@ -721,16 +807,12 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
         ctx->launches++;
     }
 
-    // split the Gram rows so that there are about two CTAs per SM
-    int ksplit = std::max(1, std::min(st->mp / G_BKR, (2 * ctx->sm_count + npairs - 1) / npairs));
-    if (ksplit > 16) ksplit = 16;
-    while (ksplit > 1 && (st->mp / G_BKR) % ksplit != 0) --ksplit;
-    const int total_chunks = (int)(st->ldz / 64);
-    int parts = std::max(1, std::min(total_chunks, ctx->sm_count / npairs));
-    int chunks_per_cta = (total_chunks + parts - 1) / parts;
-    parts = (total_chunks + chunks_per_cta - 1) / chunks_per_cta;
+    // persistent grids: gram 2 CTAs per SM, update 1 per SM, never more CTAs than work items
+    const int g_nchunk = st->mp / G_BKR, u_nchunk = (int)(st->ldz / 64);
+    const int gram_ctas = std::max(1, std::min(2 * ctx->sm_count, npairs * g_nchunk));
+    const int upd_ctas = std::max(1, std::min(ctx->sm_count, npairs * u_nchunk));
 
-    c128* Gpart = ws.get<c128>((size_t)npairs * ksplit * JP * JP);
+    c128* Gpart = ws.get<c128>((size_t)2 * gram_ctas * JP * JP);
     c128* Wg = ws.get<c128>((size_t)npairs * JP * JP);
     int* flags = ws.get<int>(npairs);
     unsigned long long* stat = ws.get<unsigned long long>(1);
@@ -742,7 +824,7 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
 
     const double eps = 1.1102230246251565e-16;
     const double rot_tol = std::sqrt((double)st->mp) * eps;
-    const double conv_tol = 1e-10;
+    const double conv_tol = 1e-8;  // quadratic convergence: what is left after such a sweep is ~ worst^2
     const double abs_c = 0.0;  // pure relative criterion: R^H is column graded, so one-sided Jacobi keeps relative accuracy (no noise floor)
     const int inner_sweeps = (nb == 2) ? 12 : 1;
     const int nact = (nb == 2) ? (int)std::min<int64_t>(64, (k + 1) / 2 * 2) : 64;
@@ -756,21 +838,21 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
         cudaMemsetAsync(stat, 0, sizeof(unsigned long long), ctx->stream);
         for (int step = 0; step < nsteps; ++step) {
             {
-                PhaseTimer pt(ctx, QB_PH_JGRAM, 8.0 * npairs * (double)st->mp * JP * JP);
-                jacobi_gram_kernel<<<dim3(npairs, ksplit), 256, GRAM_SMEM, ctx->stream>>>(st->Z, st->ldz, st->mp, nb,
-                                                                                         step, ksplit, Gpart);
+                PhaseTimer pt(ctx, QB_PH_JGRAM, 8.0 * npairs * (double)st->mp * JP * JP);  // full-product count
+                jacobi_gram_kernel<<<gram_ctas, 256, GRAM_SMEM, ctx->stream>>>(st->Z, st->ldz, st->mp, nb, step,
+                                                                              npairs, Gpart);
             }
             {
                 PhaseTimer pt(ctx, QB_PH_JEVD, 0.0);
                 int mode = (nb == 2) ? 0 : (step == 0 ? 1 : 2);
                 jacobi_evd_kernel<<<npairs, EVD_THREADS, EVD_SMEM, ctx->stream>>>(
-                    Gpart, ksplit, Wg, flags, stat, rot_tol, inner_sweeps, scale, (unsigned long long*)(scale + 1),
-                    abs_c, nact, mode);
+                    Gpart, gram_ctas, g_nchunk, npairs, Wg, flags, stat, rot_tol, inner_sweeps, scale,
+                    (unsigned long long*)(scale + 1), abs_c, nact, mode);
             }
             {
                 PhaseTimer pt(ctx, QB_PH_JUPDATE, 8.0 * npairs * (double)st->ldz * JP * JP);  // ldz = rows of X
-                jacobi_update_kernel<<<dim3(npairs, parts), 256, UPD_SMEM, ctx->stream>>>(
-                    st->Z, st->ldz, nb, step, Wg, flags, chunks_per_cta, total_chunks);
+                jacobi_update_kernel<<<upd_ctas, 256, UPD_SMEM, ctx->stream>>>(st->Z, st->ldz, nb, step, Wg, flags,
+                                                                              npairs, u_nchunk);
             }
             ctx->launches += 3;
         }
