@@ -7,7 +7,7 @@ sequential along the chain, so at N > 1 GPUs the TEBD line is N independent repl
 DESIGN.md §multi-GPU); the path that genuinely shards -- the sliced circuit-TN contraction with one NCCL sum --
 is reported in the same JSON line under "sliced_contraction".
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--n 64] [--chi 1024]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--sites 64] [--bond-dim 1024]
 
 `--impl reference` times the CPU oracle (the restated reference path, NumPy/SciPy -> OpenBLAS zgesdd/zgemm;
 the Julia reference itself cannot run in this image) on a bounded sample of the same workload.
@@ -317,6 +317,9 @@ def run_b200(args):
                     "d2h_bytes_per_step": mps_bytes + lam_bytes, "steps": e2e_steps},
             "roofline": roof}
 
+    if not args.no_sliced:
+        line["sliced_contraction"] = run_sliced(ctx, qb, rank, world, peak_tf, barrier)
+
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sec, desc = cpu_tebd_sample(n, chi, 3 if chi >= 512 else 1)
         line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "sweeps/s", "cores": os.cpu_count(), "kind": "port",
@@ -327,15 +330,60 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_sliced(ctx, qb, rank, world, peak_tf, barrier, qubits=40, depth=6, target=2 ** 24, reps=3):
+    """Second half of BASELINE.json's metric: sliced contraction of the <0..0|U|0..0> network of a 40-qubit, depth-6
+    random FSim circuit (examples/distributed.jl:11-53 pattern; slice target 2^24 elements, :46).  Slices are dealt
+    s mod W to the ranks (no data-path communication), each rank accumulates on its device, ONE NCCL sum (:101)."""
+    import torch.distributed as dist
+
+    gates = qb.random_fsim_circuit(qubits, depth)
+    arrays, modes = qb.amplitude_network(qubits, gates)
+    sc = qb.SlicedContraction(ctx, arrays, modes, target)
+    if world > 1:
+        uid = [qb.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        qb.comm_init(ctx, world, rank, uid[0])
+        reducer = lambda v: qb.comm_allreduce_sum(ctx, v)  # noqa: E731
+    else:
+        reducer = lambda v: v  # noqa: E731
+    # warm-up: one slice per rank (builds the offset tables, contracts the slice-invariant sub-trees once)
+    sc.contract(first_slice=rank % sc.nslices, stride=sc.nslices)
+    reducer(0j)
+    best, amp = None, None
+    for _ in range(reps):
+        barrier()
+        ctx.timer_begin()
+        amp = qb.contract_sliced_distributed(sc, rank, world, reducer)
+        ms = ctx.timer_end()
+        if world > 1:
+            import torch
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        best = ms if best is None else min(best, ms)
+    flops = sc.nslices * sc.flops_per_slice
+    tf = flops / (best * 1e-3) / 1e12
+    return {"metric": "sliced TN contraction TFLOP/s", "value": tf, "unit": "TFLOP/s", "n_gpus": world,
+            "ms": best, "scaling": "strong",
+            "config": {"workload": f"{qubits}-qubit depth-{depth} random FSim circuit amplitude <0|U|0>, greedy path, "
+                                   f"slice target 2^{int(np.log2(target))} elements (BASELINE configs[4])",
+                       "nslices": sc.nslices, "cut_indices": len(sc.sliced_modes),
+                       "flops_per_slice": sc.flops_per_slice, "max_intermediate_elements": sc.max_intermediate,
+                       "flop_count": "8 x complex MACs over all tree nodes x slices (EinExprs flops x 8)"},
+            "amplitude": [amp.real, amp.imag], "frac_of_dmma_peak": tf / (peak_tf * world),
+            "collective": "one ncclAllReduce(sum) of 2 doubles" if world > 1 else "none"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=64)
-    ap.add_argument("--chi", type=int, default=1024)
+    ap.add_argument("--sites", dest="n", type=int, default=64)
+    ap.add_argument("--bond-dim", dest="chi", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sliced", action="store_true", help="skip the sliced circuit-TN contraction part")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

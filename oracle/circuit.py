@@ -35,8 +35,9 @@ def random_fsim_circuit(n, depth, seed=3000):
     return gates
 
 
-def amplitude_network(n, gates):
-    """Closed network <0..0| U |0..0> as (arrays, modes): modes are integer labels."""
+def amplitude_network(n, gates, ket=None, bra=None):
+    """Closed network <bra| U |ket> (product states as lists of local vectors; default |0..0>) as (arrays, modes):
+    modes are integer labels."""
     counter = [0]
 
     def fresh():
@@ -55,20 +56,36 @@ def amplitude_network(n, gates):
         modes.append((fi, fj, ti, tj))  # [in_1, in_2, out_1, out_2] (QrochetYaoExt.jl:30-36)
     zero = np.array([1.0, 0.0], dtype=np.complex128)
     for q in range(n):
-        arrays.append(zero.copy())
+        arrays.append(zero.copy() if ket is None else np.asarray(ket[q], dtype=np.complex128))
         modes.append((first[q],))
     for q in range(n):
-        arrays.append(zero.copy())  # conj of a real vector
+        arrays.append(zero.copy() if bra is None else np.conj(np.asarray(bra[q], dtype=np.complex128)))
         modes.append((wire[q],))
     return arrays, modes
 
 
-def statevector_amplitude(n, gates):
-    psi = sv.zero_state(n)
+def product_vector(vectors):
+    """Dense vector of a product state, site 1 the fastest index."""
+    psi = np.ones(1, dtype=np.complex128)
+    for v in vectors:
+        psi = np.kron(np.asarray(v, dtype=np.complex128), psi)
+    return psi
+
+
+def statevector_amplitude(n, gates, ket=None, bra=None):
+    psi = sv.zero_state(n) if ket is None else product_vector(ket)
     for (i, j, mat) in gates:
         # the Yao extension labels array dims 1..k as the incoming wires (= transposed gate); FSim is symmetric
         psi = sv.apply_gate(psi, np.asarray(mat).T, [i + 1, j + 1], n)
-    return psi[0]
+    return psi[0] if bra is None else np.vdot(product_vector(bra), psi)
+
+
+def random_product_state(n, seed):
+    """n normalised random local vectors (FSim circuits act trivially on |0..0>, so <0|U|0> = 1 is a weak known
+    answer: the tests use random product states on both sides)."""
+    rng = np.random.default_rng(seed)
+    v = rng.standard_normal((n, 2)) + 1j * rng.standard_normal((n, 2))
+    return list(v / np.linalg.norm(v, axis=1, keepdims=True))
 
 
 # ---- deterministic planner (same rule as qrochet.jl_b200/csrc/tn.cu) -----------------------------------

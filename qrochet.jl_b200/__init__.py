@@ -6,6 +6,8 @@ from .device import (Context, DeviceArray, conj, contract, norm2, permute, qr, s
                      slice_mode, svd)
 from .mps import B200MPS
 from .tn import SlicedContraction, amplitude_network, fsim, random_fsim_circuit
+from .parallel import (comm_allreduce_sum, comm_init, comm_unique_id, contract_sliced_distributed, my_slices,
+                       torch_allreduce_sum)
 from .rand import bond_dims, haar_gate, rand_mps_arrays
 
 __all__ = ["Context", "DeviceArray", "B200MPS", "contract", "scale_mode", "slice_mode", "select_mode", "conj",

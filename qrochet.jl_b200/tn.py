@@ -37,8 +37,10 @@ def random_fsim_circuit(n, depth, seed=3000):
     return gates
 
 
-def amplitude_network(n, gates):
-    """Leaves (arrays, modes) of the closed network <0..0|U|0..0>."""
+def amplitude_network(n, gates, ket=None, bra=None):
+    """Leaves (arrays, modes) of the closed network <bra|U|ket>; `ket` / `bra` are product states given as lists of
+    n local vectors (default `zeros(Product, n)`, i.e. <0..0|U|0..0> as in examples/distributed.jl:26-28; the bra
+    enters conjugated, as `Quantum(ψ)'` does)."""
     nxt = [0]
 
     def fresh():
@@ -55,10 +57,10 @@ def amplitude_network(n, gates):
         modes.append((fi, fj, wire[i], wire[j]))
     zero = np.array([1.0, 0.0], dtype=np.complex128)
     for q in range(n):
-        arrays.append(zero.copy())
+        arrays.append(zero.copy() if ket is None else np.asarray(ket[q], dtype=np.complex128))
         modes.append((first[q],))
     for q in range(n):
-        arrays.append(zero.copy())
+        arrays.append(zero.copy() if bra is None else np.conj(np.asarray(bra[q], dtype=np.complex128)))
         modes.append((wire[q],))
     return arrays, modes
 

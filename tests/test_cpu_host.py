@@ -85,9 +85,11 @@ def test_planner_matches_oracle_bit_exactly(n, depth, maxel):
 def test_oracle_sliced_sum_equals_statevector():
     n, depth = 10, 4
     gates = ocirc.random_fsim_circuit(n, depth)
-    arrays, modes = ocirc.amplitude_network(n, gates)
+    assert abs(ocirc.statevector_amplitude(n, gates) - 1.0) < 1e-12   # FSim leaves |0..0> alone (the example's case)
+    ket, bra = ocirc.random_product_state(n, 1), ocirc.random_product_state(n, 2)
+    arrays, modes = ocirc.amplitude_network(n, gates, ket, bra)
     extents = {x: 2 for m in modes for x in m}
-    exact = ocirc.statevector_amplitude(n, gates)
+    exact = ocirc.statevector_amplitude(n, gates, ket, bra)
     full, nsl = ocirc.contract_sliced(arrays, modes, ocirc.plan(modes, extents, 0))
     assert nsl == 1 and abs(full - exact) < 1e-12
     pl = ocirc.plan(modes, extents, 2 ** 5)

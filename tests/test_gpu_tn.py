@@ -25,9 +25,11 @@ def ctx(qb):
 @pytest.mark.parametrize("n,depth,maxel", [(6, 2, 0), (10, 4, 0), (10, 4, 2 ** 5), (14, 5, 2 ** 7), (18, 6, 2 ** 10)])
 def test_sliced_amplitude_matches_statevector_and_oracle(qb, ctx, n, depth, maxel):
     gates = qb.random_fsim_circuit(n, depth)
-    arrays, modes = qb.amplitude_network(n, gates)
+    ket, bra = ocirc.random_product_state(n, 1), ocirc.random_product_state(n, 2)
+    arrays, modes = qb.amplitude_network(n, gates, ket, bra)
     sc = qb.SlicedContraction(ctx, arrays, modes, maxel)
-    exact = ocirc.statevector_amplitude(n, ocirc.random_fsim_circuit(n, depth))
+    exact = ocirc.statevector_amplitude(n, ocirc.random_fsim_circuit(n, depth), ket, bra)
+    assert 1e-6 < abs(exact) < 0.99          # a non-trivial amplitude (<0|U|0> of an FSim circuit is exactly 1)
     extents = {x: 2 for m in modes for x in m}
     want_plan = ocirc.plan(modes, extents, maxel)
     assert sc.path == want_plan["path"] and sc.sliced_modes == want_plan["sliced"]
