@@ -284,24 +284,40 @@ def run_b200(args):
     lam_bytes = sum(0 if l is None else l.size * 8 for l in host_lams)
     gate_bytes = len(bonds) * 256
 
-    # ---- roofline of the dominant kernel (Jacobi update: [X;V]_p <- [X;V]_p W_p, complex GEMM 8MNK) ----
-    cnt, pms, work = prof["jacobi_update"]
+    # ---- roofline of the dominant kernel (Jacobi update: X_p <- X_p W_p, complex GEMM 8MNK per pair).  Inside the
+    # timed region up to 8 bond updates run concurrently, so event pairs on one stream also see the other streams'
+    # kernels; the per-launch duration is therefore measured live right after the timed region on ONE bulk bond
+    # update issued on a single stream (same kernels, same shapes, CUDA events on the launching stream). ----
     roof = None
-    if cnt:
-        ach = work / (pms * 1e-3) / 1e12
-        svd_cnt, svd_ms, svd_work = prof["svd"]
-        roof = {"bound": "tensor", "kernel": "jacobi_update_kernel (FP64 DMMA)", "achieved": ach, "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
-                "peak_source": "measured here: DMMA m8n8k4 issue-bound micro-benchmark (qb200_bench_dmma_peak); "
-                               "MEASURED_PEAKS.json has no FP64 figure",
-                "launches": cnt, "avg_launch_ms": pms / cnt,
-                "share_of_step": pms / sum(v[1] for k, v in prof.items() if k not in ("svd",)) if world == 1 else None,
-                "share_note": "share of the summed kernel time of all concurrent streams (bond updates of a layer "
-                              "overlap, so phase sums exceed wall time)",
-                "phases_ms_per_step": {k: v[1] / args.steps for k, v in prof.items() if v[0]},
-                "svd_algorithmic": {"flops_per_step": svd_work / args.steps,
-                                    "achieved_tflops": svd_work / (svd_ms * 1e-3) / 1e12 if svd_ms else None,
-                                    "frac_of_peak": (svd_work / (svd_ms * 1e-3) / 1e12) / peak_tf if svd_ms else None}}
+    bulk = [b for b in bonds if psi.site_dims(b - 1)[0] == chi and psi.site_dims(b)[2] == chi]
+    if bulk:
+        probe = psi.copy()
+        ctx.profile(True)
+        ctx.profile_read()
+        probe.evolve(gate_for(layer, bulk[len(bulk) // 2]), [bulk[len(bulk) // 2]] * 1 + [bulk[len(bulk) // 2] + 1],
+                     maxdim=chi, renormalize=True)
+        pp = ctx.profile_read()
+        ctx.profile(False)
+        del probe
+        cnt, pms, work = pp["jacobi_update"]
+        tot_ms = sum(v[1] for k, v in pp.items() if k != "svd")
+        if cnt:
+            ach = work / (pms * 1e-3) / 1e12
+            svd_cnt, svd_ms, svd_work = pp["svd"]
+            roof = {"bound": "tensor", "kernel": "jacobi_update_kernel (FP64 DMMA)", "achieved": ach, "peak": peak_tf,
+                    "unit": "TFLOP/s", "frac": ach / peak_tf,
+                    "traffic": 71.3e6, "traffic_note": "dram read+write bytes per launch from the ncu --set full capture "
+                                                      "profiles/r1_update_full_summary.txt (algorithmic: 2 x 32 MiB of X "
+                                                      "+ 2 MiB of W per launch)",
+                    "peak_source": "measured here: DMMA m8n8k4 issue-bound micro-benchmark (qb200_bench_dmma_peak); "
+                                   "MEASURED_PEAKS.json has no FP64 figure",
+                    "launches": cnt, "avg_launch_ms": pms / cnt, "share_of_step": pms / tot_ms,
+                    "share_note": "share of the kernel time of one bulk bond update run alone on one stream",
+                    "phases_ms_one_bulk_bond": {k: v[1] for k, v in pp.items() if v[0]},
+                    "phases_ms_per_step_all_streams": {k: v[1] / args.steps for k, v in prof.items() if v[0]},
+                    "svd_algorithmic": {"flops": svd_work, "ms": svd_ms,
+                                        "achieved_tflops": svd_work / (svd_ms * 1e-3) / 1e12 if svd_ms else None,
+                                        "frac_of_peak": (svd_work / (svd_ms * 1e-3) / 1e12) / peak_tf if svd_ms else None}}
 
     line = {"metric": METRIC, "value": value, "unit": "sweeps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",

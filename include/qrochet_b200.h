@@ -168,6 +168,18 @@ int32_t qb200_mps_evolve2_layer(qb200_ctx* ctx, qb200_mps* mps, int32_t nb, cons
                                 double* discarded_weight);
 /* evolve_1site! (Chain.jl:586-603): gate = p*p c128 numbers (o, i) column-major */
 int32_t qb200_mps_evolve1(qb200_ctx* ctx, qb200_mps* mps, int32_t site, const void* gate_c128);
+/* ---- MPO x MPS (no function exists in the reference: composed from MPO(arrays) Chain.jl:133-172,
+ *      merge Quantum.jl:330-348 and contract).  The MPO is passed as host arrays, one per site, in the reference's
+ *      default order (o, i, l, r) column-major (Chain.jl:34), concatenated; dl/dr = bond dimensions per site
+ *      (dl[0] = dr[n-1] = 1). */
+/* B_s[(la,lw), o, (ra,rw)] = sum_i W_s[o,i,lw,rw] A_s[la,i,ra]; result is a plain chain with bonds chi*D */
+int32_t qb200_mps_apply_mpo(qb200_ctx* ctx, qb200_mps* mps, const int64_t* dl, const int64_t* dr,
+                            const void* sites_c128);
+/* canonize! with truncate!(maxdim, threshold) applied to each bond right after its SVD (Vidal form result) */
+int32_t qb200_mps_compress(qb200_ctx* ctx, qb200_mps* mps, int64_t maxdim, double threshold);
+/* <psi|H|psi> = contract(merge(psi, H, psi')), un-normalised; left-environment sweep resident in HBM */
+int32_t qb200_mps_expect_mpo(qb200_ctx* ctx, const qb200_mps* mps, const int64_t* dl, const int64_t* dr,
+                             const void* sites_c128, double result[2]);
 /* overlap(a,b) = <b|a> (Chain.jl:737-748) by a left-environment sweep resident in HBM */
 int32_t qb200_mps_overlap(qb200_ctx* ctx, const qb200_mps* a, const qb200_mps* b, double result[2]);
 /* expect(ψ, [O]) for a batch of single-site observables (Chain.jl:724-735), un-normalised;

@@ -490,3 +490,129 @@ def haar_unitary(rng, d=4):
     q, r = np.linalg.qr(z)
     ph = np.diag(r) / np.abs(np.diag(r))
     return q * ph
+
+
+# ---- MPO x MPS: no function exists in the reference ------------------------------------
+# Only `MPO(arrays)` (Chain.jl:133-172, default order (o, i, l, r), :34), `rand` MPO (:260-297) and the generic
+# `merge(::Quantum, ::Quantum)` + `contract` exist; "MPO application with truncation" and "expect with an MPO" must
+# be COMPOSED from them.  PARITY UNPINNED by the reference: the composition below is our definition, checked
+# against dense linear algebra (tests/test_oracle_properties.py).
+def heisenberg_mpo_arrays(n, J=1.0, h=0.0):
+    """Spin-1/2 Heisenberg chain H = J sum S_k.S_{k+1} + h sum Sz_k as an MPO with D = 5, arrays (o, i, l, r);
+    first site (o, i, r), last site (o, i, l)."""
+    sz = np.diag([0.5, -0.5]).astype(np.complex128)
+    sp = np.array([[0, 1], [0, 0]], dtype=np.complex128)
+    sm = sp.T.copy()
+    one = np.eye(2, dtype=np.complex128)
+    w = np.zeros((5, 5, 2, 2), dtype=np.complex128)  # (l, r, o, i)
+    w[0, 0] = one
+    w[1, 0] = sp
+    w[2, 0] = sm
+    w[3, 0] = sz
+    w[4, 0] = h * sz
+    w[4, 1] = 0.5 * J * sm
+    w[4, 2] = 0.5 * J * sp
+    w[4, 3] = J * sz
+    w[4, 4] = one
+    bulk = np.transpose(w, (2, 3, 0, 1))  # (o, i, l, r)
+    arrays = []
+    for k in range(n):
+        if k == 0:
+            arrays.append(bulk[:, :, 4, :].copy())      # (o, i, r): last row
+        elif k == n - 1:
+            arrays.append(bulk[:, :, :, 0].copy())      # (o, i, l): first column
+        else:
+            arrays.append(bulk.copy())
+    return arrays
+
+
+def mpo_to_dense(arrays):
+    """Dense operator of an open MPO given as (o, i, l, r) arrays; site 1 = fastest index."""
+    n = len(arrays)
+    t = arrays[0][:, :, None, :]  # (o, i, l=1, r)
+    cur = np.transpose(t, (2, 0, 1, 3))[0]  # (o, i, r)
+    cur = cur.reshape(2, 2, -1)
+    for k in range(1, n):
+        a = arrays[k] if k < n - 1 else arrays[k][:, :, :, None]
+        # cur (O, I, r) x a (o, i, l=r, r') -> (O o, I i, r') with the new site slower
+        cur = np.einsum("OIr,oirs->OoIis", cur, a)
+        s = cur.shape
+        cur = cur.reshape(s[0], s[1], s[2], s[3], s[4])
+        cur = np.reshape(np.transpose(cur, (0, 1, 2, 3, 4)), (s[0], s[1], s[2], s[3], s[4]))
+        cur = np.reshape(cur, (s[0] * s[1], s[2] * s[3], s[4]), order="C")
+        # row index (O, o) in C order has o fastest -> we want the OLD sites fastest: swap
+        cur = np.reshape(np.transpose(np.reshape(cur, (s[0], s[1], s[2], s[3], s[4])), (1, 0, 3, 2, 4)),
+                         (s[1] * s[0], s[3] * s[2], s[4]), order="C")
+    return cur[:, :, 0]
+
+
+def apply_mpo_arrays(mps_arrays, mpo_arrays):
+    """Site-wise `contract(merge(Quantum(ψ), Quantum(H)))` over the physical index: new MPS arrays (o, l, r) with
+    fused bonds (ψ bond fastest, MPO bond slower)."""
+    n = len(mps_arrays)
+    out = []
+    for k in range(n):
+        a = np.asarray(mps_arrays[k])
+        w = np.asarray(mpo_arrays[k])
+        if k == 0:
+            a = a[:, None, :]
+            w = w[:, :, None, :]
+        if k == n - 1:
+            a = a[:, :, None] if a.ndim == 2 else a
+            w = w[:, :, :, None] if w.ndim == 3 else w
+        if k == 0 and a.ndim == 2:
+            a = a[:, None, :]
+        t = np.einsum("oiwx,ilr->olwrx", w, a)  # (o, l, w, r, x)
+        o, l, wl, r, wr = t.shape
+        t = np.reshape(t, (o, l * wl, r * wr), order="F")
+        if k == 0:
+            t = t[:, 0, :]
+        if k == n - 1:
+            t = t[:, :, 0] if t.ndim == 3 else t
+        out.append(t)
+    return out
+
+
+def compress(chain: "Chain", maxdim=None, threshold=None):
+    """`canonize!` (Chain.jl:469-497) with `truncate!` (:390-422) applied to each bond right after its SVD: the
+    composition the reference's user writes to truncate an MPO-applied state."""
+    n = chain.nsites()
+    lams = []
+    for i in range(n, 1, -1):
+        chain.canonize_site(site(i), "left", "qr")
+    for i in range(1, n):
+        chain.canonize_site(site(i), "right", "svd")
+        if maxdim is not None or threshold is not None:
+            chain.truncate((site(i), site(i + 1)), threshold=threshold, maxdim=maxdim)
+        lam = chain.lambda_between(site(i), site(i + 1))
+        chain.tn.pop(lam)
+        a = chain.tensor_at(site(i + 1))
+        chain.tn.replace_tensor(a, contract(a, lam, dims=()))
+        lams.append(lam)
+    for i in range(2, n + 1):
+        lam = lams[i - 2]
+        a = chain.tensor_at(site(i))
+        chain.tn.replace_tensor(a, contract(a, Tensor(_pinv_diag(lam.data, 1e-64), lam.inds), dims=()))
+        chain.tn.push(lam)
+    return chain
+
+
+def expect_mpo(chain: "Chain", mpo_arrays):
+    """<ψ|H|ψ> = contract(merge(ψ, H, ψ')) (un-normalised), composed as overlap(Hψ, ψ)."""
+    dense_arrays = []
+    # bring ψ to plain (o, l, r) arrays by absorbing any Λ to the right
+    c = chain.copy()
+    n = c.nsites()
+    for k in range(1, n):
+        if c.lambda_between(site(k), site(k + 1)) is not None:
+            c.contract_between(site(k), site(k + 1), direction="left")
+    for k in range(1, n + 1):
+        t = c.tensor_at(site(k))
+        order = [c.sites[site(k)]]
+        if k > 1:
+            order.append(c.leftindex(site(k)))
+        if k < n:
+            order.append(c.rightindex(site(k)))
+        dense_arrays.append(t.permute(order).data)
+    hpsi = Chain(apply_mpo_arrays(dense_arrays, mpo_arrays))
+    return hpsi.overlap(Chain(dense_arrays))

@@ -8,7 +8,7 @@ from .mps import B200MPS
 from .tn import SlicedContraction, amplitude_network, fsim, random_fsim_circuit
 from .parallel import (comm_allreduce_sum, comm_init, comm_unique_id, contract_sliced_distributed, my_slices,
                        torch_allreduce_sum)
-from .rand import bond_dims, haar_gate, rand_mps_arrays
+from .rand import bond_dims, haar_gate, heisenberg_mpo_arrays, rand_mps_arrays
 
 __all__ = ["Context", "DeviceArray", "B200MPS", "contract", "scale_mode", "slice_mode", "select_mode", "conj",
            "permute", "norm2", "scale", "qr", "svd", "QB200Error", "MissingSchmidtCoefficientsException"]

@@ -85,6 +85,9 @@ _protos = {
     "qb200_mps_evolve2": (_i32, [_p, _p, _i32, _p, _i64, _dbl, _i32, _pi64, _pdbl]),
     "qb200_mps_evolve2_layer": (_i32, [_p, _p, _i32, _pi32, _p, _i64, _dbl, _i32, _pi64, _pdbl]),
     "qb200_mps_evolve1": (_i32, [_p, _p, _i32, _p]),
+    "qb200_mps_apply_mpo": (_i32, [_p, _p, _pi64, _pi64, _p]),
+    "qb200_mps_compress": (_i32, [_p, _p, _i64, _dbl]),
+    "qb200_mps_expect_mpo": (_i32, [_p, _p, _pi64, _pi64, _p, _pdbl]),
     "qb200_mps_overlap": (_i32, [_p, _p, _p, _pdbl]),
     "qb200_mps_expect1_batch": (_i32, [_p, _p, _i32, _pi32, _p, _pdbl]),
     "qb200_tn_plan": (_i32, [_p, _i32, _pi32, _pi32, _pi64, _i64, C.POINTER(_p)]),

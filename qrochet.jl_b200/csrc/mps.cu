@@ -121,11 +121,19 @@ int32_t right_canonize_qr(qb200_ctx* ctx, qb200_mps* m, int s) {
 }
 
 // site s (chil*p x chir) = U S V^H; site s <- U, Λ_s <- S, site s+1 <- V^H * site s+1  (S left on the bond)
-int32_t left_canonize_svd(qb200_ctx* ctx, qb200_mps* m, int s) {
+int32_t left_canonize_svd(qb200_ctx* ctx, qb200_mps* m, int s, int64_t maxdim = 0, double threshold = -1.0) {
     int64_t rows = m->chil[s] * m->p[s], cols = m->chir[s], k = std::min(rows, cols);
     SvdState* st = nullptr;
     std::vector<double> sigma;
     QB_TRY(qb_svd_factor(ctx, rows, cols, m->site[s], rows, &st, sigma));
+    if (maxdim > 0 || threshold >= 0.0) {  // truncate! right after the SVD (Chain.jl:404-417)
+        k = kept_count(sigma, maxdim, threshold >= 0.0 ? threshold : 1e-16);
+        if (k == 0) {
+            qb_svd_release(ctx, st);
+            QB_FAIL(ctx, QB200_E_INVALID, "compress: every Schmidt coefficient is below the threshold");
+        }
+        sigma.resize(k);
+    }
     c128* U = dev_alloc(ctx, rows * k);
     Workspace ws(ctx);
     c128* Vh = ws.get<c128>((size_t)(k * cols));
@@ -587,6 +595,169 @@ int32_t qb200_mps_evolve2_layer(qb200_ctx* ctx, qb200_mps* m, int32_t nb, const 
         if (kept_out) kept_out[i] = kept_tmp[i];
         if (discarded_weight) discarded_weight[i] = dw_tmp[i];
     }
+    return QB200_OK;
+}
+
+// canonize! with truncate! applied to each bond right after its SVD: the composition a user of the reference
+// writes to compress a state (e.g. after an MPO application).  maxdim <= 0 and threshold < 0:
+// plain canonize!.
+int32_t qb200_mps_compress(qb200_ctx* ctx, qb200_mps* m, int64_t maxdim, double threshold) {
+    QB_TRY(check_complete(ctx, m));
+    for (int b = 0; b < m->n - 1; ++b)
+        if (m->lam[b]) {  // absorb Schmidt vectors: the sweeps below start from a plain chain
+            int64_t l = m->chil[b + 1], rest = m->p[b + 1] * m->chir[b + 1];
+            QB_TRY(qb_scale_mode_raw(ctx, m->site[b + 1], m->site[b + 1], 1, l, rest, m->lam[b], 0, 0.0));
+            drop_lambda(ctx, m, b);
+        }
+    for (int s = m->n - 1; s >= 1; --s) QB_TRY(right_canonize_qr(ctx, m, s));
+    for (int s = 0; s < m->n - 1; ++s) {
+        QB_TRY(left_canonize_svd(ctx, m, s, maxdim, threshold));
+        int64_t l = m->chil[s + 1], rest = m->p[s + 1] * m->chir[s + 1];
+        QB_TRY(qb_scale_mode_raw(ctx, m->site[s + 1], m->site[s + 1], 1, l, rest, m->lam[s], 0, 0.0));
+    }
+    for (int s = 1; s < m->n; ++s) {
+        int64_t l = m->chil[s], rest = m->p[s] * m->chir[s];
+        QB_TRY(qb_scale_mode_raw(ctx, m->site[s], m->site[s], 1, l, rest, m->lam[s - 1], 1, 1e-64));
+    }
+    m->form = 1;
+    return QB200_OK;
+}
+
+namespace {
+// wrap raw device memory as a tensor view for qb200_contract
+qb200_tensor view3(c128* p, int64_t a, int64_t b, int64_t c) {
+    qb200_tensor t;
+    t.dtype = QB200_C128;
+    t.rank = 3;
+    t.ext[0] = a;
+    t.ext[1] = b;
+    t.ext[2] = c;
+    t.data = p;
+    t.bytes = 0;
+    t.owned = false;
+    return t;
+}
+qb200_tensor view4(c128* p, int64_t a, int64_t b, int64_t c, int64_t d) {
+    qb200_tensor t = view3(p, a, b, c);
+    t.rank = 4;
+    t.ext[3] = d;
+    return t;
+}
+qb200_tensor view5(c128* p, int64_t a, int64_t b, int64_t c, int64_t d, int64_t e) {
+    qb200_tensor t = view4(p, a, b, c, d);
+    t.rank = 5;
+    t.ext[4] = e;
+    return t;
+}
+
+// upload the MPO sites (host, (o, i, l, r) column-major each, concatenated) to one device buffer
+int32_t upload_mpo(qb200_ctx* ctx, const qb200_mps* m, const int64_t* dl, const int64_t* dr, const void* sites,
+                   Workspace& ws, std::vector<c128*>* dev) {
+    int64_t total = 0;
+    for (int s = 0; s < m->n; ++s) {
+        if (dl[s] < 1 || dr[s] < 1) QB_FAIL(ctx, QB200_E_INVALID, "mpo: bad bond dimension at site %d", s);
+        if (s > 0 && dl[s] != dr[s - 1]) QB_FAIL(ctx, QB200_E_INVALID, "mpo: bond %d dimension mismatch", s - 1);
+        total += m->p[s] * m->p[s] * dl[s] * dr[s];
+    }
+    if (dl[0] != 1 || dr[m->n - 1] != 1) QB_FAIL(ctx, QB200_E_INVALID, "mpo: open boundary needs edge bonds of 1");
+    c128* buf = ws.get<c128>((size_t)total);
+    if (!buf) QB_FAIL(ctx, QB200_E_CUDA, "mpo: workspace allocation failed");
+    QB_CUDA(ctx, cudaMemcpyAsync(buf, sites, sizeof(c128) * total, cudaMemcpyHostToDevice, ctx->stream));
+    QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int64_t off = 0;
+    dev->clear();
+    for (int s = 0; s < m->n; ++s) {
+        dev->push_back(buf + off);
+        off += m->p[s] * m->p[s] * dl[s] * dr[s];
+    }
+    return QB200_OK;
+}
+}  // namespace
+
+// MPO application, site by site: B_s[(la,lw), o, (ra,rw)] = sum_i W_s[o,i,lw,rw] A_s[la,i,ra]
+// (= contract(merge(Quantum(ψ), Quantum(H))) over the physical indices; bonds fuse with the ψ bond fastest).
+// Schmidt vectors are absorbed first; the result is a plain chain with bonds chi*D -- call qb200_mps_compress.
+int32_t qb200_mps_apply_mpo(qb200_ctx* ctx, qb200_mps* m, const int64_t* dl, const int64_t* dr, const void* sites) {
+    QB_TRY(check_complete(ctx, m));
+    if (!dl || !dr || !sites) QB_FAIL(ctx, QB200_E_INVALID, "apply_mpo: null argument");
+    Workspace ws(ctx);
+    std::vector<c128*> W;
+    QB_TRY(upload_mpo(ctx, m, dl, dr, sites, ws, &W));
+    for (int b = 0; b < m->n - 1; ++b)
+        if (m->lam[b]) {
+            int64_t l = m->chil[b + 1], rest = m->p[b + 1] * m->chir[b + 1];
+            QB_TRY(qb_scale_mode_raw(ctx, m->site[b + 1], m->site[b + 1], 1, l, rest, m->lam[b], 0, 0.0));
+            drop_lambda(ctx, m, b);
+        }
+    const int32_t mA[3] = {0, 1, 2};        // la, i, ra
+    const int32_t mW[4] = {3, 1, 4, 5};     // o, i, lw, rw
+    const int32_t mC[5] = {0, 4, 3, 2, 5};  // la, lw, o, ra, rw
+    for (int s = 0; s < m->n; ++s) {
+        int64_t la = m->chil[s], p = m->p[s], ra = m->chir[s];
+        c128* out = dev_alloc(ctx, la * dl[s] * p * ra * dr[s]);
+        if (!out) QB_FAIL(ctx, QB200_E_CUDA, "apply_mpo: out of device memory");
+        qb200_tensor A = view3(m->site[s], la, p, ra), Wt = view4(W[s], p, p, dl[s], dr[s]);
+        qb200_tensor C = view5(out, la, dl[s], p, ra, dr[s]);
+        int32_t r = qb200_contract(ctx, &A, mA, 0, &Wt, mW, 0, &C, mC, nullptr, nullptr);
+        if (r != QB200_OK) {
+            cudaFreeAsync(out, ctx->stream);
+            return r;
+        }
+        set_site_dev(ctx, m, s, out, la * dl[s], p, ra * dr[s]);
+    }
+    m->form = 0;
+    return QB200_OK;
+}
+
+// <ψ|H|ψ> = contract(merge(ψ, H, ψ')), un-normalised, by a left-environment sweep L[a, w, b] resident in HBM
+int32_t qb200_mps_expect_mpo(qb200_ctx* ctx, const qb200_mps* m, const int64_t* dl, const int64_t* dr,
+                             const void* sites, double result[2]) {
+    QB_TRY(check_complete(ctx, m));
+    if (!dl || !dr || !sites || !result) QB_FAIL(ctx, QB200_E_INVALID, "expect_mpo: null argument");
+    Workspace ws(ctx);
+    std::vector<c128*> W;
+    QB_TRY(upload_mpo(ctx, m, dl, dr, sites, ws, &W));
+    int64_t chimax = 1, dmax = 1, pmax = 1;
+    for (int s = 0; s < m->n; ++s) {
+        chimax = std::max(chimax, std::max(m->chil[s], m->chir[s]));
+        dmax = std::max(dmax, std::max(dl[s], dr[s]));
+        pmax = std::max(pmax, m->p[s]);
+    }
+    c128* L0 = ws.get<c128>((size_t)(chimax * dmax * chimax));
+    c128* L1 = ws.get<c128>((size_t)(chimax * dmax * chimax));
+    c128* T1 = ws.get<c128>((size_t)(dmax * chimax * pmax * chimax));
+    c128* T2 = ws.get<c128>((size_t)(chimax * chimax * pmax * dmax));
+    c128* As = ws.get<c128>((size_t)(chimax * pmax * chimax));
+    if (!L0 || !L1 || !T1 || !T2 || !As) QB_FAIL(ctx, QB200_E_CUDA, "expect_mpo: workspace allocation failed");
+    ctx->scratch_host[0] = 1.0;
+    ctx->scratch_host[1] = 0.0;
+    QB_CUDA(ctx, cudaMemcpyAsync(L0, ctx->scratch_host, sizeof(c128), cudaMemcpyHostToDevice, ctx->stream));
+    QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // modes: a=0 (ket left), w=1 (mpo left), b=2 (bra left), i=3, ra=4, o=5, rw=6, rb=7
+    const int32_t mL[3] = {0, 1, 2}, mA[3] = {0, 3, 4}, mT1[4] = {1, 2, 3, 4};
+    const int32_t mW[4] = {5, 3, 1, 6}, mT2[4] = {2, 4, 5, 6};
+    const int32_t mB[3] = {2, 5, 7}, mLn[3] = {4, 6, 7};
+    for (int s = 0; s < m->n; ++s) {
+        int64_t la = m->chil[s], p = m->p[s], ra = m->chir[s];
+        // effective site: the Schmidt vector of the bond to the right (if any) absorbed
+        const c128* site = m->site[s];
+        if (s < m->n - 1 && m->lam[s]) {
+            QB_TRY(qb_scale_mode_raw(ctx, m->site[s], As, la * p, ra, 1, m->lam[s], 0, 0.0));
+            site = As;
+        }
+        qb200_tensor L = view3(L0, la, dl[s], la), A = view3((c128*)site, la, p, ra);
+        qb200_tensor t1 = view4(T1, dl[s], la, p, ra);
+        QB_TRY(qb200_contract(ctx, &L, mL, 0, &A, mA, 0, &t1, mT1, nullptr, nullptr));
+        qb200_tensor Wt = view4(W[s], p, p, dl[s], dr[s]), t2 = view4(T2, la, ra, p, dr[s]);
+        QB_TRY(qb200_contract(ctx, &t1, mT1, 0, &Wt, mW, 0, &t2, mT2, nullptr, nullptr));
+        qb200_tensor Ln = view3(L1, ra, dr[s], ra);
+        QB_TRY(qb200_contract(ctx, &t2, mT2, 0, &A, mB, 1, &Ln, mLn, nullptr, nullptr));
+        std::swap(L0, L1);
+    }
+    QB_CUDA(ctx, cudaMemcpyAsync(ctx->scratch_host, L0, sizeof(c128), cudaMemcpyDeviceToHost, ctx->stream));
+    QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    result[0] = ctx->scratch_host[0];
+    result[1] = ctx->scratch_host[1];
     return QB200_OK;
 }
 

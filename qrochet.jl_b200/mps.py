@@ -197,6 +197,44 @@ class B200MPS:
                                                       int(bool(renormalize)), kept, dw))
         return [int(kept[i]) for i in range(nb)], [float(dw[i]) for i in range(nb)]
 
+    @staticmethod
+    def _pack_mpo(mpo_arrays):
+        """MPO arrays in the reference's default order (o, i, l, r) (first (o, i, r), last (o, i, l); Chain.jl:34,
+        133-172) -> (dl, dr, flat column-major buffer)."""
+        n = len(mpo_arrays)
+        dl, dr, parts = [], [], []
+        for k, w in enumerate(mpo_arrays):
+            w = np.asarray(w, dtype=np.complex128)
+            if k == 0:
+                w = w[:, :, None, :] if w.ndim == 3 else w
+            if k == n - 1:
+                w = w[:, :, :, None] if w.ndim == 3 else w
+            assert w.ndim == 4, (k, w.shape)
+            dl.append(w.shape[2])
+            dr.append(w.shape[3])
+            parts.append(np.reshape(w, -1, order="F"))
+        return capi.i64arr(dl), capi.i64arr(dr), np.ascontiguousarray(np.concatenate(parts))
+
+    def apply_mpo(self, mpo_arrays) -> "B200MPS":
+        """ψ <- H ψ site by site (`contract(merge(Quantum(ψ), Quantum(H)))` over the physical indices); bonds
+        become χ·D.  Follow with `compress` to truncate."""
+        dl, dr, flat = self._pack_mpo(mpo_arrays)
+        check(self.ctx.h, lib.qb200_mps_apply_mpo(self.ctx.h, self.h, dl, dr, flat.ctypes.data_as(C.c_void_p)))
+        return self
+
+    def compress(self, maxdim=None, threshold=None) -> "B200MPS":
+        """`canonize!` with `truncate!(…; maxdim, threshold)` applied to each bond right after its SVD."""
+        check(self.ctx.h, lib.qb200_mps_compress(self.ctx.h, self.h, int(maxdim or 0),
+                                                 -1.0 if threshold is None else float(threshold)))
+        return self
+
+    def expect_mpo(self, mpo_arrays) -> complex:
+        """<ψ|H|ψ> = contract(merge(ψ, H, ψ')), un-normalised."""
+        dl, dr, flat = self._pack_mpo(mpo_arrays)
+        r = (C.c_double * 2)()
+        check(self.ctx.h, lib.qb200_mps_expect_mpo(self.ctx.h, self.h, dl, dr, flat.ctypes.data_as(C.c_void_p), r))
+        return complex(r[0], r[1])
+
     def overlap(self, other: "B200MPS") -> complex:
         """`overlap(a, b)` = <b|a> (Chain.jl:737-748)."""
         r = (C.c_double * 2)()

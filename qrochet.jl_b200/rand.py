@@ -44,3 +44,18 @@ def haar_gate(rng: np.random.Generator, d: int = 4):
     u = q * (np.diag(r) / np.abs(np.diag(r)))
     k = int(round(np.log2(d)))
     return np.reshape(u, (2,) * (2 * k), order="F")
+
+
+def heisenberg_mpo_arrays(n: int, J: float = 1.0, h: float = 0.0):
+    """Spin-1/2 Heisenberg chain H = J sum S_k.S_{k+1} + h sum Sz_k as an MPO with D = 5 in the reference's default
+    MPO order (o, i, l, r) (Chain.jl:34); first site (o, i, r), last site (o, i, l) (BASELINE config 3)."""
+    sz = np.diag([0.5, -0.5]).astype(np.complex128)
+    sp = np.array([[0, 1], [0, 0]], dtype=np.complex128)
+    sm = sp.T.copy()
+    one = np.eye(2, dtype=np.complex128)
+    w = np.zeros((5, 5, 2, 2), dtype=np.complex128)  # operator-valued (l, r) matrix
+    w[0, 0], w[1, 0], w[2, 0], w[3, 0], w[4, 0] = one, sp, sm, sz, h * sz
+    w[4, 1], w[4, 2], w[4, 3], w[4, 4] = 0.5 * J * sm, 0.5 * J * sp, J * sz, one
+    bulk = np.transpose(w, (2, 3, 0, 1))
+    return [bulk[:, :, 4, :].copy() if k == 0 else (bulk[:, :, :, 0].copy() if k == n - 1 else bulk.copy())
+            for k in range(n)]

@@ -227,3 +227,40 @@ def test_evolve_layer_equals_sequential_evolve(qb, ctx):
     assert_lams(g1.lambdas(), o.lambdas())
     with pytest.raises(qb.QB200Error):
         g1.evolve_layer([gates[0], gates[1]], [3, 4], maxdim=16)   # adjacent bonds do not commute
+
+
+def test_mpo_expect_apply_compress_match_oracle(qb, ctx):
+    """SURVEY §8 a14 / BASELINE config 3 at test size: <ψ|H|ψ> with the Heisenberg MPO (D = 5), MPO application and
+    truncation.  No function exists in the reference for this (parity unpinned there): the composition is defined in
+    the oracle and checked against dense linear algebra in tests/test_oracle_properties.py."""
+    n, chi = 8, 8
+    arrays = oc.rand_mps_arrays(np.random.default_rng(31), n, chi)
+    mpo = qb.heisenberg_mpo_arrays(n)
+    assert all(np.array_equal(a, b) for a, b in zip(mpo, oc.heisenberg_mpo_arrays(n)))
+    o = oc.Chain(arrays)
+    g = qb.B200MPS(ctx, arrays)
+    want = oc.expect_mpo(o, mpo)
+    got = g.expect_mpo(mpo)
+    assert abs(got - want) <= OBS_TOL * abs(want)
+    # Vidal form and mixed form give the same <H>
+    gv = g.copy().canonize()
+    assert abs(gv.expect_mpo(mpo) - want) <= OBS_TOL * abs(want)
+    gm = g.copy().mixed_canonize(4)
+    assert abs(gm.expect_mpo(mpo) - want) <= OBS_TOL * abs(want)
+    # H|ψ>: bonds fuse to chi*D, dense vector equals the oracle's
+    hg = g.copy().apply_mpo(mpo)
+    ho = oc.Chain(oc.apply_mpo_arrays(arrays, mpo))
+    assert hg.bond_dims() == [min(2 ** (b + 1), 2 ** (n - b - 1), chi) * 5 for b in range(n - 1)]
+    assert np.allclose(dense_from_gpu(hg), ho.to_dense(), atol=1e-12)
+    # compress without truncation: same state, Vidal form, Schmidt values as the oracle's
+    cg = hg.copy().compress()
+    co = oc.compress(ho.copy())
+    assert np.allclose(dense_from_gpu(cg), ho.to_dense(), atol=1e-11)
+    assert_lams([l[: len(m)] for l, m in zip(cg.lambdas(), co.lambdas())], co.lambdas())
+    # compress with truncation: bit-exact kept counts, Schmidt values to 1e-12
+    cg = hg.copy().compress(maxdim=6)
+    co = oc.compress(ho.copy(), maxdim=6)
+    assert cg.bond_dims() == [len(l) for l in co.lambdas()]
+    assert_lams(cg.lambdas(), co.lambdas())
+    ov = cg.overlap(g)
+    assert abs(ov - co.overlap(o)) <= OBS_TOL * abs(ov)

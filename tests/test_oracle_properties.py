@@ -194,3 +194,30 @@ def test_truncation_weight():
     same = q.copy().evolve(oc.gate(np.eye(4), [5, 6]), iscanonical=True)
     for x, y in zip(same.lambdas(), q.lambdas()):
         assert np.allclose(x[: len(y)], y) and np.allclose(x[len(y):], 0, atol=1e-13)
+
+
+def test_mpo_composition_against_dense():
+    """MPO x MPS has no function in the reference: the oracle's composition vs dense algebra."""
+    n = 6
+    mpo = oc.heisenberg_mpo_arrays(n)
+    H = oc.mpo_to_dense(mpo)
+    sz, sp = np.diag([.5, -.5]), np.array([[0, 1], [0, 0]])
+
+    def op(o, k):
+        m = np.eye(1)
+        for j in range(n):
+            m = np.kron(o if j == k else np.eye(2), m)
+        return m
+    Hd = sum(op(sz, k) @ op(sz, k + 1) + 0.5 * (op(sp, k) @ op(sp.T, k + 1) + op(sp.T, k) @ op(sp, k + 1))
+             for k in range(n - 1))
+    assert np.allclose(H, Hd)
+    arrays = oc.rand_mps_arrays(np.random.default_rng(0), n, 8)
+    psi = oc.Chain(arrays)
+    v = psi.to_dense()
+    assert np.isclose(oc.expect_mpo(psi, mpo), np.vdot(v, Hd @ v))
+    assert np.isclose(oc.expect_mpo(psi.copy().canonize(), mpo), np.vdot(v, Hd @ v))
+    hp = oc.Chain(oc.apply_mpo_arrays(arrays, mpo))
+    assert np.allclose(hp.to_dense(), Hd @ v)
+    assert np.allclose(oc.compress(hp.copy()).to_dense(), Hd @ v)
+    c = oc.compress(hp.copy(), maxdim=6)
+    assert max(len(l) for l in c.lambdas()) == 6
