@@ -4,6 +4,7 @@ from . import _capi
 from ._capi import MissingSchmidtCoefficientsException, QB200Error
 from .device import (Context, DeviceArray, conj, contract, norm2, permute, qr, scale, scale_mode, select_mode,
                      slice_mode, svd)
+from . import chain
 from .mps import B200MPS
 from .tn import SlicedContraction, amplitude_network, fsim, random_fsim_circuit
 from .parallel import (comm_allreduce_sum, comm_init, comm_unique_id, contract_sliced_distributed, my_slices,
