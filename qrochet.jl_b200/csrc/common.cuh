@@ -183,6 +183,11 @@ int32_t qb_svd_emit(qb200_ctx* ctx, SvdState* st, int64_t kept, c128* U, int64_t
                     int64_t vinv_div, double sigma_scale);
 void qb_svd_release(qb200_ctx* ctx, SvdState* st);
 
+// Cholesky-QR step on a 64-column panel with the Jacobi gram / update kernels (svd_jacobi.cu), used by K4
+int32_t qb_cholqr_panel_step(qb200_ctx* ctx, c128* P, int64_t ld, int64_t m, c128* R, int64_t ldr, c128* Gpart,
+                             c128* Wbuf, int* flags_dev, int* fail_dev);
+size_t qb_cholqr_gpart_elems(qb200_ctx* ctx);
+
 // (left | right) matricisation of a tensor: returns a column-major rows x cols matrix (a permuted copy in
 // `ws` unless `order` is the identity)
 int32_t qb_matricize(qb200_ctx* ctx, const qb200_tensor* A, const int32_t* order, int32_t nleft, Workspace& ws,

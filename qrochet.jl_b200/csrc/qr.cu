@@ -10,6 +10,7 @@
 // twice (A = Q1 R1, Q1 = Q R2, R = R2 R1) -- "twice is enough" -- which restores orthogonality to
 // machine precision; Q is produced explicitly, so there is no separate "form Q" phase.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "mma.cuh"
@@ -208,15 +209,68 @@ static int32_t tsqr(qb200_ctx* ctx, c128* P, int64_t ld, int rows, int w, c128* 
     return QB200_OK;
 }
 
-// one right-looking block Gram-Schmidt pass: Q (m x k, in place) = Q' R, R k x k upper triangular (zeroed first)
+// TSQR + Gram-Schmidt on a panel of width <= 64 made of <= 2 sub-panels of 32 (the robust path)
+static int32_t tsqr_panel(qb200_ctx* ctx, int64_t m, int w, c128* P, int64_t ld, c128* R, int64_t ldr) {
+    const c128 one = make_double2(1.0, 0.0), zero = make_double2(0.0, 0.0), mone = make_double2(-1.0, 0.0);
+    for (int j0 = 0; j0 < w; j0 += QW) {
+        int ww = std::min(QW, w - j0);
+        c128* Pj = P + (int64_t)j0 * ld;
+        QB_TRY(tsqr(ctx, Pj, ld, (int)m, ww, R + j0 + (int64_t)j0 * ldr, ldr));
+        int nt = w - j0 - ww;
+        if (nt > 0) {
+            c128* T = P + (int64_t)(j0 + ww) * ld;
+            c128* C = R + j0 + (int64_t)(j0 + ww) * ldr;
+            QB_TRY(qb_gemm(ctx, 2, 0, ww, nt, m, one, Pj, ld, T, ld, zero, C, ldr));
+            QB_TRY(qb_gemm(ctx, 0, 0, m, nt, ww, mone, Pj, ld, C, ldr, one, T, ld));
+        }
+    }
+    return QB200_OK;
+}
+
+// one right-looking block Gram-Schmidt pass: Q (m x k, in place) = Q' R, R k x k upper triangular (zeroed first).
+// Panels of 64 columns.  Fast path (m % 64 == 0, full panels): Cholesky-QR2 on the panel with the Jacobi gram /
+// update kernels (Gram 64 x 64 -> scaled Cholesky in shared memory -> P <- P R^-1, twice); when a scaled pivot says
+// the panel is too ill conditioned for a Gram-based step, the saved panel is restored and factorised by the
+// Householder TSQR instead.  Trailing updates: C = Q_p^H T (split-K GEMM), T -= Q_p C.
 static int32_t bgs_pass(qb200_ctx* ctx, int64_t m, int64_t k, c128* Q, int64_t ldq, c128* R, int64_t ldr) {
     const c128 one = make_double2(1.0, 0.0), zero = make_double2(0.0, 0.0), mone = make_double2(-1.0, 0.0);
     zero_kernel<<<(unsigned)std::min<int64_t>((k * k + 255) / 256, 4096), 256, 0, ctx->stream>>>(R, k, k, ldr);
     QB_LAUNCH_CHECK(ctx);
-    for (int64_t j0 = 0; j0 < k; j0 += QW) {
-        int w = (int)std::min<int64_t>(QW, k - j0);
+    const int PW = 64;
+    const bool fast_ok = (m % 64 == 0) && m >= 64 && !getenv("QB200_NO_CHOLQR");
+    Workspace ws(ctx);
+    c128 *Gpart = nullptr, *Wbuf = nullptr, *save = nullptr, *R1 = nullptr, *R2 = nullptr;
+    int* flags = nullptr;
+    if (fast_ok) {
+        Gpart = ws.get<c128>(qb_cholqr_gpart_elems(ctx));
+        Wbuf = ws.get<c128>(64 * 64);
+        save = ws.get<c128>((size_t)(m * PW));
+        R1 = ws.get<c128>(64 * 64);
+        R2 = ws.get<c128>(64 * 64);
+        flags = ws.get<int>(2);
+        if (!Gpart || !Wbuf || !save || !R1 || !R2 || !flags) QB_FAIL(ctx, QB200_E_CUDA, "qr: workspace allocation failed");
+    }
+    for (int64_t j0 = 0; j0 < k; j0 += PW) {
+        int w = (int)std::min<int64_t>(PW, k - j0);
         c128* P = Q + j0 * ldq;
-        QB_TRY(tsqr(ctx, P, ldq, (int)m, w, R + j0 + j0 * ldr, ldr));
+        c128* Rpp = R + j0 + j0 * ldr;
+        bool done = false;
+        if (fast_ok && w == PW) {
+            QB_TRY(qb_copy_matrix(ctx, m, PW, P, ldq, save, m, 0));
+            QB_CUDA(ctx, cudaMemsetAsync(flags, 0, 2 * sizeof(int), ctx->stream));
+            QB_TRY(qb_cholqr_panel_step(ctx, P, ldq, m, R1, 64, Gpart, Wbuf, flags, flags + 1));
+            QB_TRY(qb_cholqr_panel_step(ctx, P, ldq, m, R2, 64, Gpart, Wbuf, flags, flags + 1));
+            QB_CUDA(ctx, cudaMemcpyAsync(ctx->scratch_host, flags + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            int failed = *reinterpret_cast<int*>(ctx->scratch_host);
+            if (!failed) {
+                QB_TRY(qb_gemm(ctx, 0, 0, PW, PW, PW, one, R2, 64, R1, 64, zero, Rpp, ldr));
+                done = true;
+            } else {
+                QB_TRY(qb_copy_matrix(ctx, m, PW, save, m, P, ldq, 0));
+            }
+        }
+        if (!done) QB_TRY(tsqr_panel(ctx, m, w, P, ldq, Rpp, ldr));
         int64_t nt = k - j0 - w;
         if (nt > 0) {
             c128* T = Q + (j0 + w) * ldq;

@@ -32,6 +32,11 @@ constexpr int GLD = 65;  // shared-memory pitch of the 64 x 64 matrices in the e
 
 // circle-method round robin: n (even) players, round `step` in [0, n-1), pair k in [0, n/2)
 __device__ __forceinline__ void rr_pair(int n, int step, int k, int& p, int& q) {
+    if (step < 0) {  // consecutive blocks (2k, 2k+1): a 64-column panel addressed directly (QR panels)
+        p = 2 * k;
+        q = 2 * k + 1;
+        return;
+    }
     if (n == 2) {
         p = 0;
         q = 1;
@@ -543,6 +548,109 @@ __global__ void __launch_bounds__(256, 1)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Cholesky-QR step of a 64-column panel (used by K4): sums the partial Grams, factors the diagonally scaled
+// G = R^H R in shared memory, writes R (upper triangular) and W = R^-1, which the update kernel applies (P <- P W).
+// `fail` is raised when a scaled pivot drops below `piv_tol` (panel numerically rank deficient for a Gram-based
+// factorisation): the caller then falls back to the Householder TSQR for that panel.
+__global__ void __launch_bounds__(256, 1)
+    panel_chol_kernel(const c128* __restrict__ Gpart, int gram_ctas, int nchunk, c128* __restrict__ Wout,
+                      c128* __restrict__ Rout, int64_t ldr, int* __restrict__ flags, int* __restrict__ fail,
+                      double piv_tol) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    c128* G = reinterpret_cast<c128*>(smem_raw);
+    c128* Wm = G + JP * GLD;
+    __shared__ double d[JP];
+    __shared__ int bad;
+    const int tid = threadIdx.x;
+    if (tid == 0) bad = 0;
+    // every gram CTA holds one partial of this single pair in slot 2c
+    for (int e = tid; e < JP * JP; e += 256) {
+        double sx = 0.0, sy = 0.0;
+        for (int c = 0; c < gram_ctas; ++c) {
+            c128 v = Gpart[(size_t)(2 * c) * (JP * JP) + e];
+            sx += v.x;
+            sy += v.y;
+        }
+        G[(e >> 6) * GLD + (e & 63)] = make_double2(sx, sy);
+    }
+    __syncthreads();
+    if (tid < JP) {
+        double g = G[tid * GLD + tid].x;
+        if (!(g > 0.0)) {
+            bad = 1;
+            g = 1.0;
+        }
+        d[tid] = sqrt(g);
+    }
+    __syncthreads();
+    for (int e = tid; e < JP * JP; e += 256) {
+        int r = e & 63, c = e >> 6;
+        double sc = 1.0 / (d[r] * d[c]);
+        c128 v = G[c * GLD + r];
+        G[c * GLD + r] = make_double2(v.x * sc, v.y * sc);
+    }
+    __syncthreads();
+    // right-looking Cholesky, upper factor stored in the upper triangle: G[j][c] (row j, col c >= j)
+    for (int j = 0; j < JP; ++j) {
+        double piv = G[j * GLD + j].x;
+        if (!(piv > piv_tol)) {
+            if (tid == 0) bad = 1;
+            piv = fmax(piv, piv_tol);
+        }
+        double rj = sqrt(piv), inv = 1.0 / rj;
+        __syncthreads();
+        for (int c = j + tid; c < JP; c += 256) {
+            c128 v = G[c * GLD + j];
+            G[c * GLD + j] = (c == j) ? make_double2(rj, 0.0) : make_double2(v.x * inv, v.y * inv);
+        }
+        __syncthreads();
+        // trailing update g_ic -= conj(r_ji) r_jc for j < i <= c
+        int nt = JP - j - 1;
+        for (int e = tid; e < nt * nt; e += 256) {
+            int i = j + 1 + e % nt, c = j + 1 + e / nt;
+            if (i > c) continue;
+            c128 rji = G[i * GLD + j], rjc = G[c * GLD + j];
+            c128 v = G[c * GLD + i];
+            G[c * GLD + i] = csub(v, cmul(cconj(rji), rjc));
+        }
+        __syncthreads();
+    }
+    // undo the scaling: R = Rs D  (r_jc *= d_c); zero the strict lower triangle
+    for (int e = tid; e < JP * JP; e += 256) {
+        int r = e & 63, c = e >> 6;
+        c128 v = G[c * GLD + r];
+        G[c * GLD + r] = (r <= c) ? make_double2(v.x * d[c], v.y * d[c]) : make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+    for (int e = tid; e < JP * JP; e += 256) {
+        int r = e & 63, c = e >> 6;
+        Rout[r + (int64_t)c * ldr] = G[c * GLD + r];
+    }
+    // W = R^-1 by back substitution, one thread per column (upper triangular result)
+    if (tid < JP) {
+        const int c = tid;
+        c128* w = Wm + c * GLD;  // column c of W
+        for (int i = JP - 1; i >= 0; --i) {
+            if (i > c) {
+                w[i] = make_double2(0.0, 0.0);
+                continue;
+            }
+            c128 acc = (i == c) ? make_double2(1.0, 0.0) : make_double2(0.0, 0.0);
+            for (int k = i + 1; k <= c; ++k) acc = csub(acc, cmul(G[k * GLD + i], w[k]));
+            double rii = G[i * GLD + i].x;  // real positive diagonal
+            w[i] = make_double2(acc.x / rii, acc.y / rii);
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < JP * JP; e += 256) Wout[e] = Wm[(e >> 6) * GLD + (e & 63)];
+    __syncthreads();
+    if (tid == 0) {
+        flags[0] = 1;
+        if (bad) *fail = 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // set-up / finish kernels
 // Z[:, :] = [A or A^H zero-padded ; I]
 __global__ void svd_init_kernel(c128* __restrict__ Z, int64_t ldz, int mp, int np, int64_t m, int64_t n,
@@ -732,6 +840,8 @@ int32_t qb_svd_init(qb200_ctx* ctx) {
     QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRAM_SMEM));
     QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_evd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EVD_SMEM));
     QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM));
+    QB_CUDA(ctx, cudaFuncSetAttribute(panel_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)((size_t)2 * JP * GLD * sizeof(c128))));
     return QB200_OK;
 }
 
@@ -1053,3 +1163,24 @@ extern "C" int32_t qb200_svd(qb200_ctx* ctx, const qb200_tensor* A, const int32_
     if (discarded_weight) *discarded_weight = dw;
     return QB200_OK;
 }
+
+
+constexpr size_t CHOL_SMEM = (size_t)2 * JP * GLD * sizeof(c128);
+
+// One Cholesky-QR step on the 64-column panel P (m x 64, ld, m % 64 == 0): P <- P R^-1, R (64 x 64, ldr) written.
+// Raises *fail_dev when the panel is too ill conditioned for a Gram-based step (caller falls back to TSQR).
+int32_t qb_cholqr_panel_step(qb200_ctx* ctx, c128* P, int64_t ld, int64_t m, c128* R, int64_t ldr, c128* Gpart,
+                             c128* Wbuf, int* flags_dev, int* fail_dev) {
+    const int mp = (int)m, nchunk = mp / G_BKR;
+    const int gram_ctas = std::max(1, std::min(2 * ctx->sm_count, nchunk));
+    jacobi_gram_kernel<<<gram_ctas, 256, GRAM_SMEM, ctx->stream>>>(P, ld, mp, 2, -1, 1, Gpart);
+    QB_LAUNCH_CHECK(ctx);
+    panel_chol_kernel<<<1, 256, CHOL_SMEM, ctx->stream>>>(Gpart, gram_ctas, nchunk, Wbuf, R, ldr, flags_dev, fail_dev, 1e-11);
+    QB_LAUNCH_CHECK(ctx);
+    const int u_nchunk = mp / 64;
+    const int upd_ctas = std::max(1, std::min(ctx->sm_count, u_nchunk));
+    jacobi_update_kernel<<<upd_ctas, 256, UPD_SMEM, ctx->stream>>>(P, ld, 2, -1, Wbuf, flags_dev, 1, u_nchunk);
+    QB_LAUNCH_CHECK(ctx);
+    return QB200_OK;
+}
+size_t qb_cholqr_gpart_elems(qb200_ctx* ctx) { return (size_t)2 * 2 * ctx->sm_count * JP * JP; }
