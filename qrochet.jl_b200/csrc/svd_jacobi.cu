@@ -590,55 +590,66 @@ __global__ void __launch_bounds__(256, 1)
         G[c * GLD + r] = make_double2(v.x * sc, v.y * sc);
     }
     __syncthreads();
-    // right-looking Cholesky, upper factor stored in the upper triangle: G[j][c] (row j, col c >= j)
+    // right-looking Cholesky G = R^H R, one barrier per column: the scaled row j of R goes to Wm (scratch) while the
+    // trailing update reads the unscaled row j of G
     for (int j = 0; j < JP; ++j) {
         double piv = G[j * GLD + j].x;
         if (!(piv > piv_tol)) {
             if (tid == 0) bad = 1;
             piv = fmax(piv, piv_tol);
         }
-        double rj = sqrt(piv), inv = 1.0 / rj;
-        __syncthreads();
-        for (int c = j + tid; c < JP; c += 256) {
-            c128 v = G[c * GLD + j];
-            G[c * GLD + j] = (c == j) ? make_double2(rj, 0.0) : make_double2(v.x * inv, v.y * inv);
-        }
-        __syncthreads();
-        // trailing update g_ic -= conj(r_ji) r_jc for j < i <= c
-        int nt = JP - j - 1;
-        for (int e = tid; e < nt * nt; e += 256) {
-            int i = j + 1 + e % nt, c = j + 1 + e / nt;
-            if (i > c) continue;
-            c128 rji = G[i * GLD + j], rjc = G[c * GLD + j];
-            c128 v = G[c * GLD + i];
-            G[c * GLD + i] = csub(v, cmul(cconj(rji), rjc));
+        const double inv = 1.0 / piv, rs = rsqrt(piv);
+        const int nt = JP - j - 1;
+        for (int e = tid; e < nt * nt + JP; e += 256) {
+            if (e < JP) {  // row j of R
+                int c = e;
+                c128 v = G[c * GLD + j];
+                Wm[c * GLD + j] = (c < j) ? make_double2(0.0, 0.0)
+                                          : (c == j ? make_double2(piv * rs, 0.0) : make_double2(v.x * rs, v.y * rs));
+            } else {
+                int ee = e - JP;
+                int i = j + 1 + ee % nt, c = j + 1 + ee / nt;
+                if (i > c) continue;
+                c128 gji = G[i * GLD + j], gjc = G[c * GLD + j];
+                c128 pr = cmul(cconj(gji), gjc);
+                c128 v = G[c * GLD + i];
+                G[c * GLD + i] = make_double2(v.x - pr.x * inv, v.y - pr.y * inv);
+            }
         }
         __syncthreads();
     }
-    // undo the scaling: R = Rs D  (r_jc *= d_c); zero the strict lower triangle
+    // R = Rs D (undo the scaling), kept in G; written out
     for (int e = tid; e < JP * JP; e += 256) {
         int r = e & 63, c = e >> 6;
-        c128 v = G[c * GLD + r];
-        G[c * GLD + r] = (r <= c) ? make_double2(v.x * d[c], v.y * d[c]) : make_double2(0.0, 0.0);
+        c128 v = Wm[c * GLD + r];
+        v = (r <= c) ? make_double2(v.x * d[c], v.y * d[c]) : make_double2(0.0, 0.0);
+        G[c * GLD + r] = v;
+        Rout[r + (int64_t)c * ldr] = v;
     }
     __syncthreads();
-    for (int e = tid; e < JP * JP; e += 256) {
-        int r = e & 63, c = e >> 6;
-        Rout[r + (int64_t)c * ldr] = G[c * GLD + r];
-    }
-    // W = R^-1 by back substitution, one thread per column (upper triangular result)
-    if (tid < JP) {
-        const int c = tid;
-        c128* w = Wm + c * GLD;  // column c of W
+    // W = R^-1 by back substitution: 4 threads per column split the inner sums (lanes 4c..4c+3 of one warp)
+    {
+        const int c = tid >> 2, part = tid & 3;
+        c128* w = Wm + c * GLD;  // column c of W (overwrites the scratch copy of R, which now lives in G)
         for (int i = JP - 1; i >= 0; --i) {
-            if (i > c) {
-                w[i] = make_double2(0.0, 0.0);
-                continue;
+            c128 acc = make_double2(0.0, 0.0);
+            if (i < c)
+                for (int k = i + 1 + part; k <= c; k += 4) acc = cadd(acc, cmul(G[k * GLD + i], w[k]));
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 1);
+            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 1);
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 2);
+            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 2);
+            if (part == 0) {
+                c128 v;
+                if (i > c)
+                    v = make_double2(0.0, 0.0);
+                else {
+                    double rii = 1.0 / G[i * GLD + i].x;  // real positive diagonal
+                    v = (i == c) ? make_double2(rii, 0.0) : make_double2(-acc.x * rii, -acc.y * rii);
+                }
+                w[i] = v;
             }
-            c128 acc = (i == c) ? make_double2(1.0, 0.0) : make_double2(0.0, 0.0);
-            for (int k = i + 1; k <= c; ++k) acc = csub(acc, cmul(G[k * GLD + i], w[k]));
-            double rii = G[i * GLD + i].x;  // real positive diagonal
-            w[i] = make_double2(acc.x / rii, acc.y / rii);
+            __syncwarp();
         }
     }
     __syncthreads();
@@ -1172,7 +1183,8 @@ constexpr size_t CHOL_SMEM = (size_t)2 * JP * GLD * sizeof(c128);
 int32_t qb_cholqr_panel_step(qb200_ctx* ctx, c128* P, int64_t ld, int64_t m, c128* R, int64_t ldr, c128* Gpart,
                              c128* Wbuf, int* flags_dev, int* fail_dev) {
     const int mp = (int)m, nchunk = mp / G_BKR;
-    const int gram_ctas = std::max(1, std::min(2 * ctx->sm_count, nchunk));
+    // few, fat CTAs: the single-CTA Cholesky kernel has to sum every partial Gram
+    const int gram_ctas = std::max(1, std::min(16, nchunk));
     jacobi_gram_kernel<<<gram_ctas, 256, GRAM_SMEM, ctx->stream>>>(P, ld, mp, 2, -1, 1, Gpart);
     QB_LAUNCH_CHECK(ctx);
     panel_chol_kernel<<<1, 256, CHOL_SMEM, ctx->stream>>>(Gpart, gram_ctas, nchunk, Wbuf, R, ldr, flags_dev, fail_dev, 1e-11);
