@@ -264,3 +264,63 @@ def test_mpo_expect_apply_compress_match_oracle(qb, ctx):
     assert_lams(cg.lambdas(), co.lambdas())
     ov = cg.overlap(g)
     assert abs(ov - co.overlap(o)) <= OBS_TOL * abs(ov)
+
+
+def test_product_state_and_rank_deficient_theta(qb, ctx):
+    """Edge case: bond dimension 1 everywhere (|0...0>, `zeros(Product, n)` converted to a Chain, Chain.jl:174-183):
+    theta has rank 1 before the gate and rank <= 4 after it.  With an explicit threshold the kept count is
+    well-defined and must match the oracle bit-exactly (the reference's default absolute 1e-16 threshold is
+    numerically fragile for exactly rank-deficient theta, SURVEY.md §7.3(2), so it is not asserted here)."""
+    n = 6
+    arrays = [np.array([[1.0], [0.0]], dtype=complex)] + [np.array([[[1.0]], [[0.0]]], dtype=complex)] * (n - 2) + \
+             [np.array([[1.0], [0.0]], dtype=complex)]
+    o = oc.Chain(arrays).canonize()
+    g = qb.B200MPS(ctx, arrays).canonize()
+    assert g.bond_dims() == [1] * (n - 1)
+    rng = np.random.default_rng(41)
+    psi = sv.zero_state(n)
+    for bond in [1, 3, 5, 2, 4, 3]:
+        U = oc.haar_unitary(rng)
+        o.evolve(oc.gate(U, [bond, bond + 1]), iscanonical=True, threshold=1e-12)
+        kept, _ = g.evolve(np.reshape(U, (2, 2, 2, 2), order="F"), [bond, bond + 1], threshold=1e-12)
+        assert kept == len(o.lambdas()[bond - 1])
+        psi = sv.apply_gate(psi, U, [bond, bond + 1], n)
+    assert np.allclose(dense_from_gpu(g), psi, atol=1e-12)
+    assert_lams(g.lambdas(), o.lambdas())
+
+
+def test_config2_shape_properties(qb, ctx):
+    """BASELINE config 2 at full width (n = 64, chi = 256): one brickwork layer of Haar two-site gates with
+    truncation to 256.  The oracle needs minutes at this size, so the checks are the size-independent properties
+    of the domain: bit-exact kept counts (= maxdim on bulk bonds), sum lambda^2 = 1 after renormalize, discarded
+    weight = 1 - kept weight, isometry of the new Gamma*Lambda pairs, and layer == bond-by-bond evolve."""
+    n, chi = 64, 256
+    arrays = qb.rand_mps_arrays(np.random.default_rng(1002), n, chi)
+    g = qb.B200MPS(ctx, arrays).canonize()
+    assert abs(g.norm() - 1.0) < 1e-10
+    dims = qb.bond_dims(n, chi)
+    assert g.bond_dims() == dims
+    odd = list(range(1, n, 2))
+    gates = [qb.haar_gate(np.random.default_rng(2000 + b)) for b in odd]
+    ref = g.copy()
+    kept, dw = g.evolve_layer(gates, odd, maxdim=chi, renormalize=True)
+    d = [1] + dims + [1]
+    assert kept == [min(chi, 2 * d[b - 1], 2 * d[b + 1]) for b in odd]      # bit-exact truncation
+    lams = g.lambdas()
+    for b, w in zip(odd, dw):
+        lam = lams[b - 1]
+        assert abs(np.sum(lam ** 2) - 1.0) < 1e-12 and np.all(np.diff(lam) <= 0) and 0.0 <= w < 1.0
+    # Gamma_l scaled by its left Lambda is an isometry (left-canonical), Gamma_r by its right Lambda right-canonical
+    for b in (1, 31, 63):
+        a = g.site(b - 1)
+        al = a if b == 1 else a * lams[b - 2][:, None, None]
+        m = al.reshape(-1, a.shape[2], order="F")
+        assert np.abs(m.conj().T @ m - np.eye(m.shape[1])).max() < 1e-10
+        c = g.site(b)
+        cr = c if b + 1 == n else c * lams[b][None, None, :]
+        m = cr.reshape(c.shape[0], -1, order="F")
+        assert np.abs(m @ m.conj().T - np.eye(m.shape[0])).max() < 1e-10
+    # same as three bond-by-bond calls
+    for b, gt, k in list(zip(odd, gates, kept))[14:17]:
+        kk, _ = ref.evolve(gt, [b, b + 1], maxdim=chi, renormalize=True)
+        assert kk == k and np.array_equal(ref.lambdas()[b - 1], lams[b - 1])
