@@ -40,6 +40,7 @@ struct GemmArgs {
     int beta_zero;
     int ksplit;      // set by launch_gemm
     c128* partial;   // split-K partial sums (ksplit x M x N), set by launch_gemm
+    int acc_init;    // C += (+-1) A B folded into the accumulators, set by launch_gemm
 };
 
 struct ModeList {

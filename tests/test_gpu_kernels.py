@@ -70,6 +70,16 @@ def test_contract_alpha_beta(qb, ctx):
     assert np.allclose(out.to_host(), (2 - 1j) * a @ b + 0.5j * c, atol=1e-11)
 
 
+@pytest.mark.parametrize("alpha", [1.0, -1.0])
+def test_contract_accumulate_in_place(qb, ctx, alpha):
+    """C += (+-1) A B (beta = 1): the accumulators start from +-C (the QR trailing update T -= P C)."""
+    rng = np.random.default_rng(11)
+    a, b, c = crand(rng, 200, 64), crand(rng, 64, 150), crand(rng, 200, 150)
+    out = ctx.array(c)
+    qb.contract(ctx.array(a), (0, 1), ctx.array(b), (1, 2), (0, 2), out=out, alpha=alpha, beta=1.0)
+    assert np.allclose(out.to_host(), c + alpha * (a @ b), atol=1e-11)
+
+
 def test_contract_errors(qb, ctx):
     a, b = ctx.array(np.ones((2, 3), complex)), ctx.array(np.ones((4, 5), complex))
     with pytest.raises(qb.QB200Error):
