@@ -24,34 +24,35 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_c128_kernel(const GemmAr
     c128* __restrict__ C = p.C + p.cb.at(z);
 
     // ---- loader coordinates (fixed for the whole K loop) ----
-    int a_ml[4], a_kl[4];
-    int64_t a_moff[4];
-    bool a_ok[4];
+    constexpr int A_PER = BM * BK / GEMM_THREADS, B_PER = BN * BK / GEMM_THREADS;
+    int a_ml[A_PER], a_kl[A_PER];
+    int64_t a_moff[A_PER];
+    bool a_ok[A_PER];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < A_PER; ++i) {
         int e = tid + GEMM_THREADS * i;
         if (p.a_kfast) {
-            a_kl[i] = e & (BK - 1);
-            a_ml[i] = e >> 3;
+            a_kl[i] = e % BK;
+            a_ml[i] = e / BK;
         } else {
-            a_ml[i] = e & (BM - 1);
-            a_kl[i] = e >> 7;
+            a_ml[i] = e % BM;
+            a_kl[i] = e / BM;
         }
         a_ok[i] = (m0 + a_ml[i]) < p.M;
         a_moff[i] = a_ok[i] ? p.am.at(m0 + a_ml[i]) : 0;
     }
-    int b_nl[2], b_kl[2];
-    int64_t b_noff[2];
-    bool b_ok[2];
+    int b_nl[B_PER], b_kl[B_PER];
+    int64_t b_noff[B_PER];
+    bool b_ok[B_PER];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < B_PER; ++i) {
         int e = tid + GEMM_THREADS * i;
         if (p.b_kfast) {
-            b_kl[i] = e & (BK - 1);
-            b_nl[i] = e >> 3;
+            b_kl[i] = e % BK;
+            b_nl[i] = e / BK;
         } else {
-            b_nl[i] = e & (BN - 1);
-            b_kl[i] = e >> 6;
+            b_nl[i] = e % BN;
+            b_kl[i] = e / BN;
         }
         b_ok[i] = (n0 + b_nl[i]) < p.N;
         b_noff[i] = b_ok[i] ? p.bn.at(n0 + b_nl[i]) : 0;
@@ -66,14 +67,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_c128_kernel(const GemmAr
         c128* as = As + (size_t)s * BK * PA;
         c128* bs = Bs + (size_t)s * BK * PB;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < A_PER; ++i) {
             int kg = (kt0 + kt) * BK + a_kl[i];
             bool ok = a_ok[i] && kg < p.K;
             const c128* src = ok ? (A + a_moff[i] + p.ak.at(kg)) : p.A;
             cp_async16(as + a_kl[i] * PA + a_ml[i], src, ok);
         }
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < B_PER; ++i) {
             int kg = (kt0 + kt) * BK + b_kl[i];
             bool ok = b_ok[i] && kg < p.K;
             const c128* src = ok ? (B + b_noff[i] + p.bk.at(kg)) : p.B;

@@ -13,6 +13,7 @@
 // once per plan and kept on the device), sub-trees that hold no cut index are contracted once and
 // reused by every slice, and the final rank-0 node is accumulated on the device (beta = 1).
 #include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <set>
 
@@ -433,7 +434,25 @@ int32_t qb200_tn_contract_sliced(qb200_ctx* ctx, qb200_tnplan* P, qb200_tensor* 
             g.alpha = ONE;
             g.beta = last ? ONE : ZERO;
             g.beta_zero = last ? 0 : 1;
-            QB_TRY(launch_gemm(ctx, g));
+            if (getenv("QB200_DEBUG_TN") && s == first_slice) {
+                cudaEvent_t e0, e1;
+                cudaEventCreate(&e0);
+                cudaEventCreate(&e1);
+                cudaEventRecord(e0, ctx->stream);
+                QB_TRY(launch_gemm(ctx, g));
+                cudaEventRecord(e1, ctx->stream);
+                cudaEventSynchronize(e1);
+                float msf = 0;
+                cudaEventElapsedTime(&msf, e0, e1);
+                double fl = 8.0 * g.M * (double)g.N * g.K * g.batch;
+                fprintf(stderr, "[tn] step %d M %d N %d K %d batch %d akfast %d bkfast %d tabs %d%d%d%d%d%d  %.3f ms %.2f TF/s inv %d\n",
+                        id - nl, g.M, g.N, g.K, g.batch, g.a_kfast, g.b_kfast, g.am.tab != nullptr, g.ak.tab != nullptr,
+                        g.bk.tab != nullptr, g.bn.tab != nullptr, g.cm.tab != nullptr, g.cn.tab != nullptr, msf,
+                        fl / msf / 1e9, (int)n.invariant);
+                cudaEventDestroy(e0);
+                cudaEventDestroy(e1);
+            } else
+                QB_TRY(launch_gemm(ctx, g));
             // children are consumed exactly once in a tree
             for (int ch : {n.left, n.right}) {
                 if (owned[ch] && buf[ch]) cudaFreeAsync(buf[ch], ctx->stream);
