@@ -12,7 +12,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_c128_kernel(const GemmAr
     c128* Bs = As + (size_t)STAGES * BK * PA;      // [STAGES][BK][PB]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp & 3, wn = warp >> 2;
+    const int wm = warp & 3, wn = warp >> 2;  // wn in 0..3: 16 columns each
     const int g = lane >> 2, t = lane & 3;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
     // blockIdx.z is the batch entry, or the K split when split-K is on (batch == 1 then)
@@ -82,11 +82,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_c128_kernel(const GemmAr
         }
     };
 
-    double accr[4][4][2], acci[4][4][2];
+    constexpr int NJ = 2;  // 8-column tiles per warp
+    double accr[4][NJ][2], acci[4][NJ][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < NJ; ++j) {
             accr[i][j][0] = accr[i][j][1] = 0.0;
             acci[i][j][0] = acci[i][j][1] = 0.0;
         }
@@ -100,10 +101,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_c128_kernel(const GemmAr
             if (m >= p.M) continue;
             int64_t mo = p.cm.at(m);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < NJ; ++j)
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    int n = n0 + wn * 32 + j * 8 + 2 * t + h;
+                    int n = n0 + wn * 16 + j * 8 + 2 * t + h;
                     if (n >= p.N) continue;
                     c128 v = C[mo + p.cn.at(n)];
                     accr[i][j][h] = sgn * v.x;
@@ -129,10 +130,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_c128_kernel(const GemmAr
             cp_async_commit();
         }
         const c128* as = As + (size_t)(kt % STAGES) * BK * PA + wm * 32 + g;
-        const c128* bs = Bs + (size_t)(kt % STAGES) * BK * PB + wn * 32 + g;
+        const c128* bs = Bs + (size_t)(kt % STAGES) * BK * PB + wn * 16 + g;
 #pragma unroll
         for (int kk = 0; kk < BK / 4; ++kk) {
-            double ar[4], ai[4], nai[4], br[4], bi[4];
+            double ar[4], ai[4], nai[4], br[NJ], bi[NJ];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 c128 v = as[(kk * 4 + t) * PA + i * 8];
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_c128_kernel(const GemmAr
                 nai[i] = flip_sign(ai[i], 0x80000000);
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < NJ; ++j) {
                 c128 v = bs[(kk * 4 + t) * PB + j * 8];
                 br[j] = v.x;
                 bi[j] = flip_sign(v.y, sgnB);
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_c128_kernel(const GemmAr
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < NJ; ++j) {
                     dmma884(accr[i][j], ar[i], br[j]);
                     dmma884(acci[i][j], ar[i], bi[j]);
                     dmma884(accr[i][j], nai[i], bi[j]);
@@ -167,10 +168,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_c128_kernel(const GemmAr
             int m = m0 + wm * 32 + i * 8 + g;
             if (m >= p.M) continue;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < NJ; ++j)
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    int n = n0 + wn * 32 + j * 8 + 2 * t + h;
+                    int n = n0 + wn * 16 + j * 8 + 2 * t + h;
                     if (n < p.N) part[m + (size_t)p.M * n] = make_double2(accr[i][j][h], acci[i][j][h]);
                 }
         }
@@ -183,10 +184,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_c128_kernel(const GemmAr
         if (m >= p.M) continue;
         int64_t mo = p.cm.at(m);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < NJ; ++j) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                int n = n0 + wn * 32 + j * 8 + 2 * t + h;
+                int n = n0 + wn * 16 + j * 8 + 2 * t + h;
                 if (n >= p.N) continue;
                 c128* dst = C + mo + p.cn.at(n);
                 double vr = accr[i][j][h], vi = acci[i][j][h];

@@ -8,8 +8,8 @@
 // 16-byte cp.async (= one ComplexF64) per element straight from the permuted location into shared
 // memory, so there is no TTGT copy of the operands and no output permute.
 //
-// CTA tile 128 x 64 x 8 complex, 256 threads = 8 warps as 4(M) x 2(N), warp tile 32 x 32 complex =
-// 4 x 4 DMMA tiles x (re, im): 128 accumulator registers.  4 real DMMAs per complex 8x8x4 step.
+// CTA tile 128 x 64 x 8 complex, 512 threads = 16 warps as 4(M) x 4(N), warp tile 32 x 16 complex =
+// 4 x 2 DMMA tiles x (re, im): 64 accumulator registers.  4 real DMMAs per complex 8x8x4 step.
 // 4-stage cp.async pipeline; shared tiles are k-major with pitch +2 so that the 16-byte fragment loads
 // of a quarter warp hit 8 distinct 16-byte bank groups.
 #pragma once
@@ -19,7 +19,7 @@ namespace qb {
 
 constexpr int BM = 128, BN = 64, BK = 8, STAGES = 4;
 constexpr int PA = BM + 2, PB = BN + 2;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 512;  // 16 warps as 4(M) x 4(N), warp tile 32 x 16: 4 warps per SMSP hide LDS / barrier stalls
 constexpr size_t GEMM_SMEM = (size_t)STAGES * BK * (PA + PB) * sizeof(c128);
 
 struct Operand {
