@@ -473,7 +473,9 @@ __global__ void __launch_bounds__(EVD_THREADS, 1)
 constexpr int U_ZP = 66, U_WP = 68;
 constexpr size_t UPD_SMEM = (size_t)(JP * U_WP + 2 * JP * U_ZP) * sizeof(c128);
 
-__global__ void __launch_bounds__(256, 1)
+constexpr int UPD_THREADS = 512;  // 16 warps = 4 per SMSP: enough to hide the fragment loads and the barriers
+
+__global__ void __launch_bounds__(UPD_THREADS, 1)
     jacobi_update_kernel(c128* __restrict__ Z, int64_t ldz, int nb, int step, const c128* __restrict__ Wg,
                          const int* __restrict__ flags, int npairs, int nchunk) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -493,8 +495,8 @@ __global__ void __launch_bounds__(256, 1)
         rr_pair(nb, step, pair, I, J);
         int64_t row = (int64_t)chunk * 64 + l_row;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            int col = l_col0 + 4 * i;
+        for (int i = 0; i < 8; ++i) {
+            int col = l_col0 + 8 * i;
             cp_async16(zs + col * U_ZP + l_row, Z + row + panel_col(I, J, col) * ldz, true);
         }
     };
@@ -504,7 +506,7 @@ __global__ void __launch_bounds__(256, 1)
         return min(item, hi);
     };
 
-    const int wi = warp & 3, wj = warp >> 2;
+    const int wi = warp & 3, wj = warp >> 2;  // 16 rows x 16 columns per warp
     int cur_pair = -1, stage = 0;
     int item = next_active(lo);
     if (item < hi) load_chunk(item, 0);
@@ -515,8 +517,8 @@ __global__ void __launch_bounds__(256, 1)
             __syncthreads();  // every warp is done with the previous W
             const c128* wsrc = Wg + (size_t)pair * (JP * JP);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                int e = tid + 256 * i;
+            for (int i = 0; i < 8; ++i) {
+                int e = tid + UPD_THREADS * i;
                 cp_async16(Ws + (e >> 6) * U_WP + (e & 63), wsrc + e, true);
             }
             cp_async_commit();
@@ -531,15 +533,15 @@ __global__ void __launch_bounds__(256, 1)
         int I, J;
         rr_pair(nb, step, pair, I, J);
         const c128* za = Zs + (size_t)stage * JP * U_ZP + wi * 16 + g;
-        const c128* wb = Ws + (wj * 32 + g) * U_WP + t;
-        double cr[2][4][2], ci[2][4][2];
+        const c128* wb = Ws + (wj * 16 + g) * U_WP + t;
+        double cr[2][2][2], ci[2][2][2];
 #pragma unroll
         for (int a = 0; a < 2; ++a)
 #pragma unroll
-            for (int b = 0; b < 4; ++b) cr[a][b][0] = cr[a][b][1] = ci[a][b][0] = ci[a][b][1] = 0.0;
+            for (int b = 0; b < 2; ++b) cr[a][b][0] = cr[a][b][1] = ci[a][b][0] = ci[a][b][1] = 0.0;
 #pragma unroll 4
         for (int kk = 0; kk < JP / 4; ++kk) {
-            double ar[2], ai[2], nai[2], br[4], bi[4];
+            double ar[2], ai[2], nai[2], br[2], bi[2];
 #pragma unroll
             for (int a = 0; a < 2; ++a) {
                 c128 v = za[(kk * 4 + t) * U_ZP + a * 8];
@@ -548,7 +550,7 @@ __global__ void __launch_bounds__(256, 1)
                 nai[a] = -v.y;
             }
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
+            for (int b = 0; b < 2; ++b) {
                 c128 v = wb[b * 8 * U_WP + kk * 4];
                 br[b] = v.x;
                 bi[b] = v.y;
@@ -556,7 +558,7 @@ __global__ void __launch_bounds__(256, 1)
 #pragma unroll
             for (int a = 0; a < 2; ++a)
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
+                for (int b = 0; b < 2; ++b) {
                     dmma884(cr[a][b], ar[a], br[b]);
                     dmma884(ci[a][b], ar[a], bi[b]);
                     dmma884(cr[a][b], nai[a], bi[b]);
@@ -567,10 +569,10 @@ __global__ void __launch_bounds__(256, 1)
 #pragma unroll
         for (int a = 0; a < 2; ++a)
 #pragma unroll
-            for (int b = 0; b < 4; ++b)
+            for (int b = 0; b < 2; ++b)
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    int n = wj * 32 + b * 8 + 2 * t + h;
+                    int n = wj * 16 + b * 8 + 2 * t + h;
                     Z[r0 + a * 8 + panel_col(I, J, n) * ldz] = make_double2(cr[a][b][h], ci[a][b][h]);
                 }
         __syncthreads();  // stage is free again before the next iteration refills it
@@ -1011,7 +1013,7 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
             }
             {
                 PhaseTimer pt(ctx, QB_PH_JUPDATE, 8.0 * npairs * (double)st->ldz * JP * JP);  // ldz = rows of X
-                jacobi_update_kernel<<<upd_ctas, 256, UPD_SMEM, ctx->stream>>>(st->Z, st->ldz, nb, step, Wg, flags,
+                jacobi_update_kernel<<<upd_ctas, UPD_THREADS, UPD_SMEM, ctx->stream>>>(st->Z, st->ldz, nb, step, Wg, flags,
                                                                               npairs, u_nchunk);
             }
             ctx->launches += 3;
@@ -1230,7 +1232,7 @@ int32_t qb_cholqr_panel_step(qb200_ctx* ctx, c128* P, int64_t ld, int64_t m, c12
     QB_LAUNCH_CHECK(ctx);
     const int u_nchunk = mp / 64;
     const int upd_ctas = std::max(1, std::min(ctx->sm_count, u_nchunk));
-    jacobi_update_kernel<<<upd_ctas, 256, UPD_SMEM, ctx->stream>>>(P, ld, 2, -1, Wbuf, flags_dev, 1, u_nchunk);
+    jacobi_update_kernel<<<upd_ctas, UPD_THREADS, UPD_SMEM, ctx->stream>>>(P, ld, 2, -1, Wbuf, flags_dev, 1, u_nchunk);
     QB_LAUNCH_CHECK(ctx);
     return QB200_OK;
 }
