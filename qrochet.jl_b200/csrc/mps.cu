@@ -546,7 +546,7 @@ int32_t qb200_mps_evolve2_layer(qb200_ctx* ctx, qb200_mps* m, int32_t nb, const 
             QB_FAIL(ctx, QB200_E_INVALID, "evolve2_layer: bonds %d and %d overlap", sorted[i - 1], sorted[i]);
     }
     if (nb == 0) return QB200_OK;
-    int nworkers = 8;
+    int nworkers = 12;
     if (const char* e = getenv("QB200_WORKERS")) nworkers = std::max(1, atoi(e));
     nworkers = std::min(nworkers, (int)nb);
     std::vector<int64_t> kept_tmp(nb, 0);
