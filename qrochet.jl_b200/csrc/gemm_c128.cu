@@ -14,7 +14,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_c128_kernel(const GemmAr
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp & 3, wn = warp >> 2;  // wn in 0..3: 16 columns each
     const int g = lane >> 2, t = lane & 3;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    // grouped rasterisation: consecutive CTAs walk 8 M-tiles x all N-tiles, so the tiles resident at any time share
+    // A and B panels that fit in L2 (a plain M-fastest order streams all of A from HBM once per wave)
+    int tile_m = blockIdx.x, tile_n = blockIdx.y;
+    {
+        const int gm = gridDim.x, gn = gridDim.y, GROUP = 8;
+        const int id = blockIdx.x + gm * blockIdx.y;
+        const int per_group = GROUP * gn;
+        const int first_m = (id / per_group) * GROUP;
+        const int gsz = min(gm - first_m, GROUP);
+        tile_m = first_m + (id % per_group) % gsz;
+        tile_n = (id % per_group) / gsz;
+    }
+    const int m0 = tile_m * BM, n0 = tile_n * BN;
     // blockIdx.z is the batch entry, or the K split when split-K is on (batch == 1 then)
     const int z = (p.ksplit > 1) ? 0 : blockIdx.z;
     const int split = (p.ksplit > 1) ? blockIdx.z : 0;

@@ -250,33 +250,47 @@ static int32_t bgs_pass(qb200_ctx* ctx, int64_t m, int64_t k, c128* Q, int64_t l
         flags = ws.get<int>(2);
         if (!Gpart || !Wbuf || !save || !R1 || !R2 || !flags) QB_FAIL(ctx, QB200_E_CUDA, "qr: workspace allocation failed");
     }
-    for (int64_t j0 = 0; j0 < k; j0 += PW) {
-        int w = (int)std::min<int64_t>(PW, k - j0);
-        c128* P = Q + j0 * ldq;
-        c128* Rpp = R + j0 + j0 * ldr;
-        bool done = false;
-        if (fast_ok && w == PW) {
-            QB_TRY(qb_copy_matrix(ctx, m, PW, P, ldq, save, m, 0));
-            QB_CUDA(ctx, cudaMemsetAsync(flags, 0, 2 * sizeof(int), ctx->stream));
-            QB_TRY(qb_cholqr_panel_step(ctx, P, ldq, m, R1, 64, Gpart, Wbuf, flags, flags + 1));
-            QB_TRY(qb_cholqr_panel_step(ctx, P, ldq, m, R2, 64, Gpart, Wbuf, flags, flags + 1));
-            QB_CUDA(ctx, cudaMemcpyAsync(ctx->scratch_host, flags + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-            QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            int failed = *reinterpret_cast<int*>(ctx->scratch_host);
-            if (!failed) {
-                QB_TRY(qb_gemm(ctx, 0, 0, PW, PW, PW, one, R2, 64, R1, 64, zero, Rpp, ldr));
-                done = true;
-            } else {
-                QB_TRY(qb_copy_matrix(ctx, m, PW, save, m, P, ldq, 0));
+    // super-panels of 128 columns = two Cholesky-QR sub-panels of 64; the trailing matrix is updated once per
+    // super-panel (K = 128 GEMMs: half the launches, twice the depth)
+    const int SW = 128;
+    for (int64_t s0 = 0; s0 < k; s0 += SW) {
+        int sw = (int)std::min<int64_t>(SW, k - s0);
+        for (int64_t j0 = s0; j0 < s0 + sw; j0 += PW) {
+            int w = (int)std::min<int64_t>(PW, s0 + sw - j0);
+            c128* P = Q + j0 * ldq;
+            c128* Rpp = R + j0 + j0 * ldr;
+            bool done = false;
+            if (fast_ok && w == PW) {
+                QB_TRY(qb_copy_matrix(ctx, m, PW, P, ldq, save, m, 0));
+                QB_CUDA(ctx, cudaMemsetAsync(flags, 0, 2 * sizeof(int), ctx->stream));
+                QB_TRY(qb_cholqr_panel_step(ctx, P, ldq, m, R1, 64, Gpart, Wbuf, flags, flags + 1));
+                QB_TRY(qb_cholqr_panel_step(ctx, P, ldq, m, R2, 64, Gpart, Wbuf, flags, flags + 1));
+                QB_CUDA(ctx, cudaMemcpyAsync(ctx->scratch_host, flags + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+                QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                int failed = *reinterpret_cast<int*>(ctx->scratch_host);
+                if (!failed) {
+                    QB_TRY(qb_gemm(ctx, 0, 0, PW, PW, PW, one, R2, 64, R1, 64, zero, Rpp, ldr));
+                    done = true;
+                } else {
+                    QB_TRY(qb_copy_matrix(ctx, m, PW, save, m, P, ldq, 0));
+                }
+            }
+            if (!done) QB_TRY(tsqr_panel(ctx, m, w, P, ldq, Rpp, ldr));
+            int64_t nin = s0 + sw - j0 - w;  // rest of the super-panel
+            if (nin > 0) {
+                c128* T = Q + (j0 + w) * ldq;
+                c128* C = R + j0 + (j0 + w) * ldr;
+                QB_TRY(qb_gemm(ctx, 2, 0, w, nin, m, one, P, ldq, T, ldq, zero, C, ldr));
+                QB_TRY(qb_gemm(ctx, 0, 0, m, nin, w, mone, P, ldq, C, ldr, one, T, ldq));
             }
         }
-        if (!done) QB_TRY(tsqr_panel(ctx, m, w, P, ldq, Rpp, ldr));
-        int64_t nt = k - j0 - w;
+        int64_t nt = k - s0 - sw;
         if (nt > 0) {
-            c128* T = Q + (j0 + w) * ldq;
-            c128* C = R + j0 + (j0 + w) * ldr;
-            QB_TRY(qb_gemm(ctx, 2, 0, w, nt, m, one, P, ldq, T, ldq, zero, C, ldr));   // C = P^H T
-            QB_TRY(qb_gemm(ctx, 0, 0, m, nt, w, mone, P, ldq, C, ldr, one, T, ldq));   // T -= P C
+            c128* P = Q + s0 * ldq;
+            c128* T = Q + (s0 + sw) * ldq;
+            c128* C = R + s0 + (s0 + sw) * ldr;
+            QB_TRY(qb_gemm(ctx, 2, 0, sw, nt, m, one, P, ldq, T, ldq, zero, C, ldr));   // C = P^H T
+            QB_TRY(qb_gemm(ctx, 0, 0, m, nt, sw, mone, P, ldq, C, ldr, one, T, ldq));   // T -= P C
         }
     }
     return QB200_OK;
