@@ -7,8 +7,9 @@ from .device import (Context, DeviceArray, conj, contract, norm2, permute, qr, s
 from . import chain
 from .mps import B200MPS
 from .tn import SlicedContraction, amplitude_network, fsim, random_fsim_circuit
-from .parallel import (comm_allreduce_sum, comm_init, comm_unique_id, contract_sliced_distributed, my_slices,
-                       torch_allreduce_sum)
+from .parallel import (comm_allreduce_sum, comm_allreduce_sum_vec, comm_init, comm_unique_id,
+                       contract_sliced_distributed, expect_batch_distributed, my_slices, torch_allreduce_sum,
+                       torch_allreduce_sum_vec)
 from .rand import bond_dims, haar_gate, heisenberg_mpo_arrays, rand_mps_arrays
 
 __all__ = ["Context", "DeviceArray", "B200MPS", "contract", "scale_mode", "slice_mode", "select_mode", "conj",

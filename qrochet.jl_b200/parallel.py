@@ -53,3 +53,40 @@ def contract_sliced_distributed(sc, rank: int, world: int, reducer) -> complex:
     per-rank partial amplitudes (comm_allreduce_sum / torch_allreduce_sum)."""
     partial = sc.contract(first_slice=rank, stride=world) if rank < sc.nslices else 0j
     return reducer(partial)
+
+
+def expect_batch_distributed(mps, ops, sites, rank: int, world: int, reducer_vec):
+    """Batched independent expectation values, the second path of the north star that shards: the MPS is replicated
+    on every rank (each builds / loads the same state), observable i goes to rank i mod W, every rank reuses its own
+    left/right environments for its share (`qb200_mps_expect1_batch`), and ONE sum-reduction of a zero-initialised
+    vector (2 doubles per observable) gathers the results -- `reducer_vec(list_of_floats) -> list_of_floats`
+    (comm_allreduce_sum_vec on GPUs, torch_allreduce_sum_vec for any torch.distributed group)."""
+    import numpy as np
+
+    n = len(ops)
+    mine = list(range(rank, n, world))
+    buf = [0.0] * (2 * n)
+    if mine:
+        vals = mps.expect([ops[i] for i in mine], [sites[i] for i in mine])
+        for i, v in zip(mine, vals):
+            buf[2 * i], buf[2 * i + 1] = float(np.real(v)), float(np.imag(v))
+    out = reducer_vec(buf)
+    return np.array(out[0::2]) + 1j * np.array(out[1::2])
+
+
+def comm_allreduce_sum_vec(ctx, values):
+    """NCCL sum of a short vector of doubles (<= 4096) through libqrochet_b200's communicator."""
+    n = len(values)
+    v = (C.c_double * n)(*values)
+    check(ctx.h, lib.qb200_comm_allreduce_sum(ctx.h, v, n))
+    return [float(v[i]) for i in range(n)]
+
+
+def torch_allreduce_sum_vec(values, group=None):
+    import torch
+    import torch.distributed as dist
+
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.tensor(values, dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return [float(x) for x in t.cpu()]

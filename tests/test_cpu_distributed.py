@@ -55,3 +55,34 @@ def test_slices_dealt_round_robin_and_summed(world):
         assert abs(total - exact) < 1e-12           # every rank holds the full amplitude after the reduce
         seen += mine
     assert sorted(seen) == list(range(len(seen))) and len(seen) > world   # every slice exactly once
+
+
+def _worker_expect(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import qrochet_b200 as qb
+    from oracle import chain as oc
+    n = 8
+    arrays = oc.rand_mps_arrays(np.random.default_rng(3), n, 8)
+    psi = oc.Chain(arrays)
+    Z = np.diag([1.0, -1.0]).astype(complex)
+    X = np.array([[0, 1], [1, 0]], dtype=complex)
+    ops = [Z, X, Z, X, Z, X, Z]
+    sites = [1, 2, 3, 4, 5, 6, 8]
+
+    class OracleMPS:                                   # stands in for the device MPS on a box without GPU
+        def expect(self, ops_, sites_):
+            return np.array([psi.expect([oc.gate(o, [s])]) for o, s in zip(ops_, sites_)])
+
+    vals = qb.expect_batch_distributed(OracleMPS(), ops, sites, rank, world, qb.torch_allreduce_sum_vec)
+    want = np.array([psi.expect([oc.gate(o, [s])]) for o, s in zip(ops, sites)])
+    out[rank] = float(np.abs(vals - want).max())
+    dist.destroy_process_group()
+
+
+def test_batched_expectation_values_dealt_and_gathered():
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_expect, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert out[0] < 1e-12 and out[1] < 1e-12
