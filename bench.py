@@ -122,6 +122,11 @@ def cpu_tebd_sample(n, chi, bulk_reps):
     from oracle.tenet import Tensor
     import qrochet_b200 as qb
 
+    try:  # torchrun exports OMP_NUM_THREADS=1: give OpenBLAS every host core back (BLAS threads = core count)
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
     d = [1] + qb.bond_dims(n, chi) + [1]
     classes = Counter((d[b - 1], d[b], d[b + 1]) for b in range(1, n))
     rng = np.random.default_rng(4242)
