@@ -51,7 +51,17 @@ struct qb200_ctx {
     // concurrently; owned by the parent context
     std::vector<qb200_ctx*> workers;
     bool is_worker = false;
+    cudaEvent_t ev_block = nullptr;  // cudaEventBlockingSync: worker threads sleep instead of spinning
 };
+
+// host waits for the context's stream.  Worker contexts (one host thread each, up to 12 per process and one process
+// per GPU) wait on a blocking event so that idle threads do not burn the host cores the other ranks need.
+static inline cudaError_t qb_stream_sync(qb200_ctx* ctx) {
+    if (!ctx->is_worker || !ctx->ev_block) return cudaStreamSynchronize(ctx->stream);
+    cudaError_t e = cudaEventRecord(ctx->ev_block, ctx->stream);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(ctx->ev_block);
+}
 
 int32_t qb_svd_init(qb200_ctx* ctx);
 int32_t qb_qr_init(qb200_ctx* ctx);

@@ -56,6 +56,7 @@ int32_t qb200_destroy(qb200_ctx* ctx) {
         cudaEventDestroy(w->ev0);
         cudaEventDestroy(w->ev1);
         cudaFreeHost(w->scratch_host);
+        if (w->ev_block) cudaEventDestroy(w->ev_block);
         for (auto e : w->prof_pool) cudaEventDestroy(e);
         delete w;
     }
@@ -124,6 +125,7 @@ qb200_ctx* qb_worker(qb200_ctx* parent, int index) {
         cudaEventCreate(&w->ev0);
         cudaEventCreate(&w->ev1);
         cudaMallocHost(&w->scratch_host, 1 << 16);
+        cudaEventCreateWithFlags(&w->ev_block, cudaEventBlockingSync | cudaEventDisableTiming);
         parent->workers.push_back(w);
     }
     return parent->workers[index];

@@ -205,7 +205,7 @@ int32_t qb_sumsq(qb200_ctx* ctx, const double* x, int64_t n, double* result_host
     QB_LAUNCH_CHECK(ctx);
     QB_CUDA(ctx, cudaMemcpyAsync(ctx->scratch_host, partial + blocks, sizeof(double), cudaMemcpyDeviceToHost,
                                  ctx->stream));
-    QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    QB_CUDA(ctx, qb_stream_sync(ctx));
     *result_host = ctx->scratch_host[0];
     return QB200_OK;
 }

@@ -60,7 +60,7 @@ int32_t set_lambda_host(qb200_ctx* ctx, qb200_mps* m, int b, const double* host,
     m->lam[b] = (double*)d;
     m->lam_host[b].assign(host, host + n);
     QB_CUDA(ctx, cudaMemcpyAsync(d, m->lam_host[b].data(), sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
-    QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    QB_CUDA(ctx, qb_stream_sync(ctx));
     return QB200_OK;
 }
 
@@ -290,7 +290,7 @@ int32_t qb200_mps_set_site(qb200_ctx* ctx, qb200_mps* m, int32_t s, int64_t chil
     c128* d = dev_alloc(ctx, cnt);
     if (!d) QB_FAIL(ctx, QB200_E_CUDA, "mps_set_site: out of device memory");
     QB_CUDA(ctx, cudaMemcpyAsync(d, host, sizeof(c128) * cnt, cudaMemcpyHostToDevice, ctx->stream));
-    QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    QB_CUDA(ctx, qb_stream_sync(ctx));
     return set_site_dev(ctx, m, s, d, chil, p, chir);
 }
 
@@ -306,7 +306,7 @@ int32_t qb200_mps_get_site(qb200_ctx* ctx, const qb200_mps* m, int32_t s, void* 
     QB_TRY(check_site(ctx, m, s));
     int64_t cnt = m->chil[s] * m->p[s] * m->chir[s];
     QB_CUDA(ctx, cudaMemcpyAsync(host, m->site[s], sizeof(c128) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
-    QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    QB_CUDA(ctx, qb_stream_sync(ctx));
     return QB200_OK;
 }
 
@@ -411,7 +411,7 @@ int32_t qb200_mps_evolve1(qb200_ctx* ctx, qb200_mps* m, int32_t s, const void* g
     memcpy(ctx->scratch_host, gate, sizeof(c128) * p * p);
     QB_CUDA(ctx, cudaMemcpyAsync(g, ctx->scratch_host, sizeof(c128) * p * p, cudaMemcpyHostToDevice, ctx->stream));
     QB_TRY(qb_apply_gate1(ctx, m->site[s], m->chil[s], p, m->chir[s], g));
-    QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // scratch_host is reused by later calls
+    QB_CUDA(ctx, qb_stream_sync(ctx));  // scratch_host is reused by later calls
     return QB200_OK;
 }
 
@@ -510,7 +510,7 @@ static int32_t evolve2_core(qb200_ctx* ctx, qb200_mps* m, int32_t b, const void*
                             lamr ? rinv : nullptr, 2, sscale);
     qb_svd_release(ctx, st);
     QB_TRY(r);
-    QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // scratch_host (gate) is free again
+    QB_CUDA(ctx, qb_stream_sync(ctx));  // scratch_host (gate) is free again
     set_site_dev(ctx, m, b, U, chil, 2, kept);
     set_site_dev(ctx, m, b + 1, Vh, kept, 2, chir);
     drop_lambda(ctx, m, b);
@@ -581,7 +581,7 @@ int32_t qb200_mps_evolve2_layer(qb200_ctx* ctx, qb200_mps* m, int32_t nb, const 
                                          &dw_tmp[i], false);
                     if (rc[i] != QB200_OK) break;
                 }
-                cudaStreamSynchronize(w[t]->stream);
+                qb_stream_sync(w[t]);
             });
         for (auto& th : threads) th.join();
         for (int i = 0; i < nb; ++i)
@@ -663,7 +663,7 @@ int32_t upload_mpo(qb200_ctx* ctx, const qb200_mps* m, const int64_t* dl, const 
     c128* buf = ws.get<c128>((size_t)total);
     if (!buf) QB_FAIL(ctx, QB200_E_CUDA, "mpo: workspace allocation failed");
     QB_CUDA(ctx, cudaMemcpyAsync(buf, sites, sizeof(c128) * total, cudaMemcpyHostToDevice, ctx->stream));
-    QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    QB_CUDA(ctx, qb_stream_sync(ctx));
     int64_t off = 0;
     dev->clear();
     for (int s = 0; s < m->n; ++s) {
@@ -732,7 +732,7 @@ int32_t qb200_mps_expect_mpo(qb200_ctx* ctx, const qb200_mps* m, const int64_t* 
     ctx->scratch_host[0] = 1.0;
     ctx->scratch_host[1] = 0.0;
     QB_CUDA(ctx, cudaMemcpyAsync(L0, ctx->scratch_host, sizeof(c128), cudaMemcpyHostToDevice, ctx->stream));
-    QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    QB_CUDA(ctx, qb_stream_sync(ctx));
     // modes: a=0 (ket left), w=1 (mpo left), b=2 (bra left), i=3, ra=4, o=5, rw=6, rb=7
     const int32_t mL[3] = {0, 1, 2}, mA[3] = {0, 3, 4}, mT1[4] = {1, 2, 3, 4};
     const int32_t mW[4] = {5, 3, 1, 6}, mT2[4] = {2, 4, 5, 6};
@@ -755,7 +755,7 @@ int32_t qb200_mps_expect_mpo(qb200_ctx* ctx, const qb200_mps* m, const int64_t* 
         std::swap(L0, L1);
     }
     QB_CUDA(ctx, cudaMemcpyAsync(ctx->scratch_host, L0, sizeof(c128), cudaMemcpyDeviceToHost, ctx->stream));
-    QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    QB_CUDA(ctx, qb_stream_sync(ctx));
     result[0] = ctx->scratch_host[0];
     result[1] = ctx->scratch_host[1];
     return QB200_OK;
@@ -781,7 +781,7 @@ int32_t qb200_mps_overlap(qb200_ctx* ctx, const qb200_mps* a, const qb200_mps* b
     ctx->scratch_host[0] = 1.0;
     ctx->scratch_host[1] = 0.0;
     QB_CUDA(ctx, cudaMemcpyAsync(E0, ctx->scratch_host, sizeof(c128), cudaMemcpyHostToDevice, ctx->stream));
-    QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    QB_CUDA(ctx, qb_stream_sync(ctx));
     for (int s = 0; s < a->n; ++s) {
         const double* la = (s < a->n - 1) ? a->lam[s] : nullptr;
         const double* lb = (s < b->n - 1) ? b->lam[s] : nullptr;
@@ -790,7 +790,7 @@ int32_t qb200_mps_overlap(qb200_ctx* ctx, const qb200_mps* a, const qb200_mps* b
         std::swap(E0, E1);
     }
     QB_CUDA(ctx, cudaMemcpyAsync(ctx->scratch_host, E0, sizeof(c128), cudaMemcpyDeviceToHost, ctx->stream));
-    QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    QB_CUDA(ctx, qb_stream_sync(ctx));
     result[0] = ctx->scratch_host[0];
     result[1] = ctx->scratch_host[1];
     return QB200_OK;
@@ -836,7 +836,7 @@ int32_t qb200_mps_expect1_batch(qb200_ctx* ctx, const qb200_mps* m, int32_t nobs
     ctx->scratch_host[1] = 0.0;
     QB_CUDA(ctx, cudaMemcpyAsync(L[0], ctx->scratch_host, sizeof(c128), cudaMemcpyHostToDevice, ctx->stream));
     QB_CUDA(ctx, cudaMemcpyAsync(R[n - 1], ctx->scratch_host, sizeof(c128), cudaMemcpyHostToDevice, ctx->stream));
-    QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    QB_CUDA(ctx, qb_stream_sync(ctx));
     for (int s = 0; s < smax; ++s) {
         const double* l = m->lam[s];
         QB_TRY(transfer_left(ctx, L[s], m->chil[s], m->chil[s], m->site[s], m->p[s], m->chir[s], m->site[s], m->chir[s],
@@ -858,7 +858,7 @@ int32_t qb200_mps_expect1_batch(qb200_ctx* ctx, const qb200_mps* m, int32_t nobs
             memcpy(ctx->scratch_host, src + off, sizeof(c128) * p * p);
             QB_CUDA(ctx, cudaMemcpyAsync(gates + (size_t)i * pmax * pmax, ctx->scratch_host, sizeof(c128) * p * p,
                                          cudaMemcpyHostToDevice, ctx->stream));
-            QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            QB_CUDA(ctx, qb_stream_sync(ctx));
             off += p * p;
         }
     }
@@ -877,7 +877,7 @@ int32_t qb200_mps_expect1_batch(qb200_ctx* ctx, const qb200_mps* m, int32_t nobs
     }
     std::vector<c128> host(nobs);
     QB_CUDA(ctx, cudaMemcpyAsync(host.data(), res, sizeof(c128) * nobs, cudaMemcpyDeviceToHost, ctx->stream));
-    QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    QB_CUDA(ctx, qb_stream_sync(ctx));
     for (int i = 0; i < nobs; ++i) {
         results[2 * i] = host[i].x;
         results[2 * i + 1] = host[i].y;

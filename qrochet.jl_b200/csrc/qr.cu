@@ -266,7 +266,7 @@ static int32_t bgs_pass(qb200_ctx* ctx, int64_t m, int64_t k, c128* Q, int64_t l
                 QB_TRY(qb_cholqr_panel_step(ctx, P, ldq, m, R1, 64, Gpart, Wbuf, flags, flags + 1));
                 QB_TRY(qb_cholqr_panel_step(ctx, P, ldq, m, R2, 64, Gpart, Wbuf, flags, flags + 1));
                 QB_CUDA(ctx, cudaMemcpyAsync(ctx->scratch_host, flags + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-                QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                QB_CUDA(ctx, qb_stream_sync(ctx));
                 int failed = *reinterpret_cast<int*>(ctx->scratch_host);
                 if (!failed) {
                     QB_TRY(qb_gemm(ctx, 0, 0, PW, PW, PW, one, R2, 64, R1, 64, zero, Rpp, ldr));

@@ -244,7 +244,6 @@ __global__ void __launch_bounds__(EVD_THREADS, 1)
     int* rpq = reinterpret_cast<int*>(rsn + 32);
     double* red = reinterpret_cast<double*>(rpq + 64);
     short* tri = reinterpret_cast<short*>(red + 64);
-    __shared__ int any_rot;
 
     const int tid = threadIdx.x, pair = blockIdx.x;
     // partial Grams of this pair: the gram CTAs whose item range overlaps [pair*nchunk, (pair+1)*nchunk), in order
@@ -271,24 +270,40 @@ __global__ void __launch_bounds__(EVD_THREADS, 1)
     // carried along exactly by the two-sided update; refreshed from a full Gram at step 0 of every sweep).
     int blkI = 0, blkJ = 0;
     if (Dstore) rr_pair(nb, step, pair, blkI, blkJ);
-    for (int e = tid; e < JP * JP; e += EVD_THREADS) {
-        double sx = 0.0, sy = 0.0;
-        const int er = e & 63, ec = e >> 6;
-        if (mode == 2 && ((er < JB) == (ec < JB))) {
-            const c128* dsrc = Dstore + (size_t)(er < JB ? blkI : blkJ) * (JB * JB);
-            c128 v = dsrc[(er & 31) + JB * (ec & 31)];
-            sx = v.x;
-            sy = v.y;
-        } else {
-            for (int i = 0; i < nslots; ++i) {
-                c128 v = Gpart[(size_t)slots[i] * (JP * JP) + e];
-                sx += v.x;
-                sy += v.y;
+    {
+        // 8 elements per thread; the loads of one slot are issued together (memory-level parallelism), slots in order
+        constexpr int PER = JP * JP / EVD_THREADS;
+        double sx[PER], sy[PER];
+        bool from_d[PER];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const int e = tid + EVD_THREADS * j, er = e & 63, ec = e >> 6;
+            from_d[j] = (mode == 2) && ((er < JB) == (ec < JB));
+            sx[j] = sy[j] = 0.0;
+            if (from_d[j]) {
+                c128 v = Dstore[(size_t)(er < JB ? blkI : blkJ) * (JB * JB) + (er & 31) + JB * (ec & 31)];
+                sx[j] = v.x;
+                sy[j] = v.y;
             }
         }
-        int r = e & 63, c = e >> 6;
-        G[c * GLD + r] = make_double2(sx, sy);
-        W[c * GLD + r] = make_double2(r == c ? 1.0 : 0.0, 0.0);
+        for (int i = 0; i < nslots; ++i) {
+            const c128* src = Gpart + (size_t)slots[i] * (JP * JP);
+            c128 v[PER];
+#pragma unroll
+            for (int j = 0; j < PER; ++j)
+                v[j] = from_d[j] ? make_double2(0.0, 0.0) : src[tid + EVD_THREADS * j];
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                sx[j] += v[j].x;
+                sy[j] += v[j].y;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const int e = tid + EVD_THREADS * j, r = e & 63, c = e >> 6;
+            G[c * GLD + r] = make_double2(sx[j], sy[j]);
+            W[c * GLD + r] = make_double2(r == c ? 1.0 : 0.0, 0.0);
+        }
     }
     for (int e = tid; e < EVD_NBLK; e += EVD_THREADS) {
         // e -> (k, l), k <= l, row-major over the upper triangle of a 32 x 32 grid
@@ -350,108 +365,126 @@ __global__ void __launch_bounds__(EVD_THREADS, 1)
     }
     if (tid == 0) flags[pair] = 1;
 
+    // Software pipeline over the flattened steps g = (inner sweep, step): the rotations of step g+1 only need the
+    // UPDATED G, not W, so once G <- J^H G J is done (all threads) warp 0 computes the next rotations -- a long
+    // dependent FP64 chain -- while the other 15 warps apply the current rotations to W.
     const int nsteps_rr = (nact == 2) ? 1 : nact - 1;
-    for (int sw = 0; sw < inner_sweeps; ++sw) {
-        if (tid == 0) any_rot = 0;
-        __syncthreads();
-        const int nst = (mode == 0) ? nsteps_rr : (mode == 1 ? 63 : 32);
-        for (int st = 0; st < nst; ++st) {
-            if (tid < 32) {
-                int p = 0, q = 0;
-                bool active = true;
-                if (mode == 0) {
-                    active = tid < nact / 2;
-                    if (active) rr_pair(nact, st, tid, p, q);
-                } else if (mode == 2 || st >= 31) {
-                    int t = (mode == 2) ? st : st - 31;
-                    p = tid;
-                    q = 32 + ((tid + t) & 31);
-                } else {
-                    int half = tid >> 4;
-                    rr_pair(32, st, tid & 15, p, q);
-                    p += 32 * half;
-                    q += 32 * half;
-                }
-                double cs = 1.0;
-                c128 sn = make_double2(0.0, 0.0);
-                if (active) {
-                    double a = G[p * GLD + p].x, b = G[q * GLD + q].x;
-                    c128 c = G[q * GLD + p];  // G[p][q] = x_p^H x_q  (row p, column q)
-                    double n2 = c.x * c.x + c.y * c.y;
-                    if (n2 > fmax(rt2 * a * b, at2 * fmax(a, b)) && n2 > 0.0) {
-                        double inv = rsqrt(n2);
-                        double zeta = 0.5 * (b - a) * inv;
-                        double r2 = 1.0 + zeta * zeta;
-                        double rr = r2 * rsqrt(r2);
-                        double tt = copysign(1.0, zeta) / (fabs(zeta) + rr);
-                        cs = rsqrt(1.0 + tt * tt);
-                        double sv = tt * cs * inv;
-                        sn = make_double2(sv * c.x, sv * c.y);  // sin * c/|c|
-                        any_rot = 1;
-                    }
-                }
-                rcs[tid] = cs;
-                rsn[tid] = sn;
-                rpq[2 * tid] = p;
-                rpq[2 * tid + 1] = q;
+    const int nst = (mode == 0) ? nsteps_rr : (mode == 1 ? 63 : 32);
+    const int nrot = (mode == 0) ? nact / 2 : 32;
+    const int total_steps = inner_sweeps * nst;
+    __shared__ int rot_in_sweep[16];
+    if (tid < 16) rot_in_sweep[tid] = 0;
+    // rotation buffers: [2][32]
+    double* rcs2 = rcs;             // reuse: rcs[0..31] buffer 0, red[0..31] is free after the reduction -> buffer 1
+    double* rcsb[2] = {rcs2, red};
+    __shared__ c128 rsn_buf[2][32];
+    __shared__ int rpq_buf[2][64];
+    auto compute_rotations = [&](int gstep, int buf) {
+        // executed by warp 0 only (tid < 32)
+        const int st = gstep % nst;
+        int p = 0, q = 0;
+        bool active = true;
+        if (mode == 0) {
+            active = tid < nact / 2;
+            if (active) rr_pair(nact, st, tid, p, q);
+        } else if (mode == 2 || st >= 31) {
+            int t = (mode == 2) ? st : st - 31;
+            p = tid;
+            q = 32 + ((tid + t) & 31);
+        } else {
+            int half = tid >> 4;
+            rr_pair(32, st, tid & 15, p, q);
+            p += 32 * half;
+            q += 32 * half;
+        }
+        double cs = 1.0;
+        c128 sn = make_double2(0.0, 0.0);
+        if (active) {
+            double a = G[p * GLD + p].x, b = G[q * GLD + q].x;
+            c128 c = G[q * GLD + p];  // G[p][q] = x_p^H x_q  (row p, column q)
+            double n2 = c.x * c.x + c.y * c.y;
+            if (n2 > fmax(rt2 * a * b, at2 * fmax(a, b)) && n2 > 0.0) {
+                double inv = rsqrt(n2);
+                double zeta = 0.5 * (b - a) * inv;
+                double r2 = 1.0 + zeta * zeta;
+                double rr = r2 * rsqrt(r2);
+                double tt = copysign(1.0, zeta) / (fabs(zeta) + rr);
+                cs = rsqrt(1.0 + tt * tt);
+                double sv = tt * cs * inv;
+                sn = make_double2(sv * c.x, sv * c.y);  // sin * c/|c|
+                rot_in_sweep[gstep / nst] = 1;
             }
-            __syncthreads();
-            const int nrot = (mode == 0) ? nact / 2 : 32;
-            // W <- W J : [w_p, w_q] <- [w_p, w_q] [[cs, sn], [-conj(sn), cs]]
-            for (int item = tid; item < 32 * JP; item += EVD_THREADS) {
+        }
+        rcsb[buf][tid] = cs;
+        rsn_buf[buf][tid] = sn;
+        rpq_buf[buf][2 * tid] = p;
+        rpq_buf[buf][2 * tid + 1] = q;
+    };
+    __syncthreads();
+    if (tid < 32) compute_rotations(0, 0);
+    __syncthreads();
+    for (int gs = 0; gs < total_steps; ++gs) {
+        const int buf = gs & 1;
+        if (gs > 0 && gs % nst == 0 && !rot_in_sweep[gs / nst - 1]) break;  // previous inner sweep was all identity
+        const double* rc = rcsb[buf];
+        const c128* rs = rsn_buf[buf];
+        const int* rp = rpq_buf[buf];
+        // phase A: G <- J^H G J per 2 x 2 block (k <= l), mirrored
+        for (int e = tid; e < EVD_NBLK; e += EVD_THREADS) {
+            int k = tri[e] >> 8, l = tri[e] & 0xff;
+            if (l >= nrot) continue;
+            c128 sk = rs[k], sl = rs[l];
+            bool rk = (sk.x != 0.0 || sk.y != 0.0), rl = (sl.x != 0.0 || sl.y != 0.0);
+            if (!rk && !rl) continue;
+            double ck = rc[k], cl = rc[l];
+            int pk = rp[2 * k], qk = rp[2 * k + 1], pl = rp[2 * l], ql = rp[2 * l + 1];
+            c128 b00 = G[pl * GLD + pk], b01 = G[ql * GLD + pk], b10 = G[pl * GLD + qk], b11 = G[ql * GLD + qk];
+            c128 t00 = csub(cscale(b00, cl), cmul(cconj(sl), b01));
+            c128 t01 = cadd(cmul(sl, b00), cscale(b01, cl));
+            c128 t10 = csub(cscale(b10, cl), cmul(cconj(sl), b11));
+            c128 t11 = cadd(cmul(sl, b10), cscale(b11, cl));
+            b00 = csub(cscale(t00, ck), cmul(sk, t10));
+            b10 = cadd(cmul(cconj(sk), t00), cscale(t10, ck));
+            b01 = csub(cscale(t01, ck), cmul(sk, t11));
+            b11 = cadd(cmul(cconj(sk), t01), cscale(t11, ck));
+            if (k == l) {
+                b00.y = 0.0;
+                b11.y = 0.0;
+                b01 = make_double2(0.0, 0.0);  // annihilated by construction
+                b10 = make_double2(0.0, 0.0);
+                G[pk * GLD + pk] = b00;
+                G[qk * GLD + qk] = b11;
+                G[qk * GLD + pk] = b01;
+                G[pk * GLD + qk] = b10;
+            } else {
+                G[pl * GLD + pk] = b00;
+                G[ql * GLD + pk] = b01;
+                G[pl * GLD + qk] = b10;
+                G[ql * GLD + qk] = b11;
+                G[pk * GLD + pl] = cconj(b00);
+                G[pk * GLD + ql] = cconj(b01);
+                G[qk * GLD + pl] = cconj(b10);
+                G[qk * GLD + ql] = cconj(b11);
+            }
+        }
+        __syncthreads();
+        // phase B: warp 0 prepares the next step's rotations, warps 1..15 apply the current ones to W
+        if (tid < 32) {
+            if (gs + 1 < total_steps) compute_rotations(gs + 1, buf ^ 1);
+        } else {
+            for (int item = tid - 32; item < 32 * JP; item += EVD_THREADS - 32) {
                 int r = item & 63, k = item >> 6;
                 if (k >= nrot) continue;
-                c128 sn = rsn[k];
+                c128 sn = rs[k];
                 if (sn.x == 0.0 && sn.y == 0.0) continue;
-                double cs = rcs[k];
-                int p = rpq[2 * k], q = rpq[2 * k + 1];
+                double cs = rc[k];
+                int p = rp[2 * k], q = rp[2 * k + 1];
                 c128 xp = W[p * GLD + r], xq = W[q * GLD + r];
                 W[p * GLD + r] = csub(cscale(xp, cs), cmul(cconj(sn), xq));
                 W[q * GLD + r] = cadd(cmul(sn, xp), cscale(xq, cs));
             }
-            // G <- J^H G J per 2 x 2 block (k <= l), mirrored
-            for (int e = tid; e < EVD_NBLK; e += EVD_THREADS) {
-                int k = tri[e] >> 8, l = tri[e] & 0xff;
-                if (l >= nrot) continue;
-                c128 sk = rsn[k], sl = rsn[l];
-                bool rk = (sk.x != 0.0 || sk.y != 0.0), rl = (sl.x != 0.0 || sl.y != 0.0);
-                if (!rk && !rl) continue;
-                double ck = rcs[k], cl = rcs[l];
-                int pk = rpq[2 * k], qk = rpq[2 * k + 1], pl = rpq[2 * l], ql = rpq[2 * l + 1];
-                c128 b00 = G[pl * GLD + pk], b01 = G[ql * GLD + pk], b10 = G[pl * GLD + qk], b11 = G[ql * GLD + qk];
-                // columns: B <- B J_l
-                c128 t00 = csub(cscale(b00, cl), cmul(cconj(sl), b01));
-                c128 t01 = cadd(cmul(sl, b00), cscale(b01, cl));
-                c128 t10 = csub(cscale(b10, cl), cmul(cconj(sl), b11));
-                c128 t11 = cadd(cmul(sl, b10), cscale(b11, cl));
-                // rows: B <- J_k^H B,  J_k^H = [[ck, -sk], [conj(sk), ck]]
-                b00 = csub(cscale(t00, ck), cmul(sk, t10));
-                b10 = cadd(cmul(cconj(sk), t00), cscale(t10, ck));
-                b01 = csub(cscale(t01, ck), cmul(sk, t11));
-                b11 = cadd(cmul(cconj(sk), t01), cscale(t11, ck));
-                if (k == l) {
-                    b00.y = 0.0;
-                    b11.y = 0.0;
-                    b01 = make_double2(0.0, 0.0);  // annihilated by construction
-                    b10 = make_double2(0.0, 0.0);
-                    G[pk * GLD + pk] = b00;
-                    G[qk * GLD + qk] = b11;
-                    G[qk * GLD + pk] = b01;
-                    G[pk * GLD + qk] = b10;
-                } else {
-                    G[pl * GLD + pk] = b00;
-                    G[ql * GLD + pk] = b01;
-                    G[pl * GLD + qk] = b10;
-                    G[ql * GLD + qk] = b11;
-                    G[pk * GLD + pl] = cconj(b00);
-                    G[pk * GLD + ql] = cconj(b01);
-                    G[qk * GLD + pl] = cconj(b10);
-                    G[qk * GLD + ql] = cconj(b11);
-                }
-            }
-            __syncthreads();
         }
-        if (!any_rot) break;
+        __syncthreads();
     }
     c128* dst = Wout + (size_t)pair * (JP * JP);
     for (int e = tid; e < JP * JP; e += EVD_THREADS) {
@@ -599,14 +632,27 @@ __global__ void __launch_bounds__(256, 1)
     const int tid = threadIdx.x;
     if (tid == 0) bad = 0;
     // every gram CTA holds one partial of this single pair in slot 2c
-    for (int e = tid; e < JP * JP; e += 256) {
-        double sx = 0.0, sy = 0.0;
+    {
+        constexpr int PER = JP * JP / 256;  // 16 elements per thread, the loads of one slot issued together
+        double sx[PER], sy[PER];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) sx[j] = sy[j] = 0.0;
         for (int c = 0; c < gram_ctas; ++c) {
-            c128 v = Gpart[(size_t)(2 * c) * (JP * JP) + e];
-            sx += v.x;
-            sy += v.y;
+            const c128* src = Gpart + (size_t)(2 * c) * (JP * JP);
+            c128 v[PER];
+#pragma unroll
+            for (int j = 0; j < PER; ++j) v[j] = src[tid + 256 * j];
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                sx[j] += v[j].x;
+                sy[j] += v[j].y;
+            }
         }
-        G[(e >> 6) * GLD + (e & 63)] = make_double2(sx, sy);
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const int e = tid + 256 * j;
+            G[(e >> 6) * GLD + (e & 63)] = make_double2(sx[j], sy[j]);
+        }
     }
     __syncthreads();
     if (tid < JP) {
@@ -941,14 +987,14 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
         ctx->launches++;
         std::vector<double> h((size_t)(m + n));
         cudaError_t e = cudaMemcpyAsync(h.data(), nr, sizeof(double) * (m + n), cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e == cudaSuccess) e = qb_stream_sync(ctx);
         if (e != cudaSuccess) return cuda_fail(e);
         const double* cn = st->tall ? h.data() + m : h.data();  // column norms of B
         std::vector<int> cp((size_t)k);
         std::iota(cp.begin(), cp.end(), 0);
         std::stable_sort(cp.begin(), cp.end(), [&](int a, int b) { return cn[a] > cn[b]; });
         e = cudaMemcpyAsync(st->colperm_dev, cp.data(), sizeof(int) * k, cudaMemcpyHostToDevice, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e == cudaSuccess) e = qb_stream_sync(ctx);
         if (e != cudaSuccess) return cuda_fail(e);
         svd_gather_cols_kernel<<<grid_cap(ctx, rb * k, 256), 256, 0, ctx->stream>>>(A, lda, st->tall ? 1 : 0, rb, k,
                                                                                    st->colperm_dev, B0);
@@ -1020,7 +1066,7 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
         }
         cudaMemcpyAsync(scale, scale + 1, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
         cudaError_t e = cudaMemcpyAsync(ctx->scratch_host, stat, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e == cudaSuccess) e = qb_stream_sync(ctx);
         if (e == cudaSuccess) e = cudaGetLastError();
         if (e != cudaSuccess) return cuda_fail(e);
         double worst = ctx->scratch_host[0];
@@ -1039,7 +1085,7 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
     std::vector<double> sig(st->np);
     cudaError_t e = cudaMemcpyAsync(sig.data(), st->sigma_dev, sizeof(double) * st->np, cudaMemcpyDeviceToHost,
                                     ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = qb_stream_sync(ctx);
     if (e != cudaSuccess) return cuda_fail(e);
     // descending, ties broken by the lower column index (first occurrence); padded columns come last
     st->perm.resize(st->np);
@@ -1053,7 +1099,7 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
     for (int64_t i = 0; i < k; ++i) sigma[i] = sig[st->perm[i]];
     st->sigma_sorted = sigma;
     e = cudaMemcpyAsync(st->perm_dev, st->perm.data(), sizeof(int) * st->np, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = qb_stream_sync(ctx);
     if (e != cudaSuccess) return cuda_fail(e);
     *out = st;
     return QB200_OK;
