@@ -37,6 +37,39 @@ def random_fsim_circuit(n, depth, seed=3000):
     return gates
 
 
+def circuit_network(n, gates):
+    """`Quantum(circuit)` of the reference's circuit front-ends (ext/QrochetYaoExt.jl:15-48, ext/QrochetQuacExt.jl:17-48):
+    one rank-2k tensor per k-qubit gate, array = reshape(matrix, 2,...,2) with dims labelled [in_1..in_k, out_1..out_k]
+    (as the reference does, :30-36), a SWAP only exchanges the wires.  `gates` = [(qubits, matrix)] with 0-based
+    qubit tuples and matrix = None / "swap" for a SWAP.  Returns (arrays, modes, inputs, outputs): inputs[q] /
+    outputs[q] are the open mode labels of wire q (Site(q; dual=true) / Site(q))."""
+    nxt = [0]
+
+    def fresh():
+        nxt[0] += 1
+        return nxt[0] - 1
+
+    wire = [[fresh()] for _ in range(n)]
+    arrays, modes = [], []
+    for qubits, mat in gates:
+        qubits = tuple(int(q) for q in qubits)
+        if mat is None or (isinstance(mat, str) and mat == "swap"):
+            a, b = qubits
+            wire[a], wire[b] = wire[b], wire[a]
+            continue
+        k = len(qubits)
+        mat = np.asarray(mat, dtype=np.complex128)
+        assert mat.shape == (2 ** k, 2 ** k)
+        froms, tos = [], []
+        for q in qubits:
+            froms.append(wire[q][-1])
+            wire[q].append(fresh())
+            tos.append(wire[q][-1])
+        arrays.append(np.reshape(mat, (2,) * (2 * k), order="F"))
+        modes.append(tuple(froms + tos))
+    return arrays, modes, [w[0] for w in wire], [w[-1] for w in wire]
+
+
 def amplitude_network(n, gates, ket=None, bra=None):
     """Leaves (arrays, modes) of the closed network <bra|U|ket>; `ket` / `bra` are product states given as lists of
     n local vectors (default `zeros(Product, n)`, i.e. <0..0|U|0..0> as in examples/distributed.jl:26-28; the bra

@@ -98,3 +98,48 @@ def test_oracle_sliced_sum_equals_statevector():
     # every slice exactly once when dealt round-robin to 3 ranks
     parts = [ocirc.contract_sliced(arrays, modes, pl, r, 3)[0] for r in range(3)]
     assert abs(sum(parts) - exact) < 1e-12
+
+
+def test_circuit_front_end_structure():
+    """`Quantum(circuit)` structure as test/integration/Quac_test.jl:4-16 checks it for QFT(3): n inputs, n outputs,
+    every open index is a site index; plus the SWAP-as-wire-relabel rule (QrochetYaoExt.jl:23-27)."""
+    import qrochet_b200 as qb
+    h = np.array([[1, 1], [1, -1]]) / np.sqrt(2)
+
+    def cphase(k):
+        return np.diag([1, 1, 1, np.exp(2j * np.pi / 2 ** k)])
+    # QFT(3): H0 CP(0,1) CP(0,2) H1 CP(1,2) H2 SWAP(0,2)
+    gates = [((0,), h), ((0, 1), cphase(2)), ((0, 2), cphase(3)), ((1,), h), ((1, 2), cphase(2)), ((2,), h),
+             ((0, 2), "swap")]
+    arrays, modes, inputs, outputs = qb.circuit_network(3, gates)
+    assert len(arrays) == 6 and len(inputs) == len(outputs) == 3
+    count = {}
+    for m in modes:
+        for x in m:
+            count[x] = count.get(x, 0) + 1
+    opened = {x for x, c in count.items() if c == 1}
+    assert opened == set(inputs) | set(outputs)
+    # dense check: contracting the network gives the circuit unitary (with the reference's in/out labelling the
+    # tensors are the transposed gates: symmetric here), SWAP applied as a relabelling
+    letters = {x: i for i, x in enumerate(sorted(count))}
+    args = []
+    for a, m in zip(arrays, modes):
+        args += [a, [letters[x] for x in m]]
+    out = np.einsum(*args, [letters[x] for x in outputs] + [letters[x] for x in inputs])
+    U = np.reshape(out, (8, 8), order="F")
+    assert np.allclose(U.conj().T @ U, np.eye(8))
+    # known answer: state-vector application of the gate list.  Two quirks of the reference are replicated knowingly
+    # (SURVEY.md Appendix A): array dims 1..k are labelled as the incoming wires (every tensor is the transposed gate:
+    # all gates here are symmetric), and a SWAP exchanges the two WHOLE wires (QrochetYaoExt.jl:23-27,
+    # QrochetQuacExt.jl:26-30) -- inputs included -- so a trailing SWAP yields P U P, not P U.
+    from oracle import statevector as sv
+
+    def swap02(psi):
+        return np.reshape(np.swapaxes(np.reshape(psi, (2, 2, 2), order="F"), 0, 2), -1, order="F")
+    for col in range(8):
+        psi = np.zeros(8, complex)
+        psi[col] = 1.0
+        psi = swap02(psi)
+        for qubits, mat in gates[:-1]:
+            psi = sv.apply_gate(psi, np.asarray(mat).T, [q + 1 for q in qubits], 3)
+        assert np.allclose(U[:, col], swap02(psi))
