@@ -13,8 +13,9 @@
  *     boundary; message via qb200_last_error(ctx).
  *   - tensors are dense, COLUMN-MAJOR (first mode fastest, as Julia arrays), extents are int64,
  *     modes are caller-chosen int32 labels (the Symbol <-> int32 map lives on the Julia side).
- *   - dtype: QB200_C128 (ComplexF64, primary) and QB200_F64 (Schmidt vectors).  QB200_C64/QB200_F32
- *     are reserved and currently rejected with QB200_E_UNSUPPORTED.
+ *   - dtype: QB200_C128 (ComplexF64, primary) and QB200_F64 (Schmidt vectors).  QB200_C64 / QB200_F32
+ *     tensors are accepted at the boundary (upload / download convert) but are held widened to FP64 on the
+ *     device and every kernel computes in FP64; native FP32/TF32 tiles are future work.
  *   - one context = one device + one stream; calls on a context are serialised by the caller.
  *     Kernels are asynchronous on that stream; only *_download, scalar-returning calls and calls
  *     with `kept` outputs synchronise.

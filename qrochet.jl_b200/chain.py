@@ -54,7 +54,7 @@ class Tensor:
         return Tensor(self.data, tuple(mapping.get(i, i) for i in self.inds))
 
     def conj(self):
-        if self.data.dtype != 0:  # real Λ vector
+        if self.data.dtype in (2, 3):  # real Λ vector
             return Tensor(self.data, self.inds)
         return Tensor(dev.conj(self.data), self.inds)
 
@@ -73,7 +73,7 @@ class _Modes:
 
 
 def _is_vector(t: Tensor):
-    return t.data.dtype != 0
+    return t.data.dtype in (2, 3)  # F64 / F32: a real Schmidt vector
 
 
 def contract(a: Tensor, b: Tensor, dims=None) -> Tensor:

@@ -13,7 +13,8 @@
 typedef double2 c128;
 
 struct qb200_tensor {
-    int32_t dtype;
+    int32_t dtype;       // arithmetic / storage type on the device (C128 or F64)
+    int32_t user_dtype;  // what the caller asked for: C64 / F32 tensors are widened at upload, narrowed at download
     int32_t rank;
     int64_t ext[QB200_MAX_RANK];
     void* data;

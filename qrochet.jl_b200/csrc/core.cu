@@ -171,9 +171,14 @@ int32_t qb200_prof_read(qb200_ctx* ctx, int32_t nphases, int64_t* counts, double
 static int32_t make_tensor(qb200_ctx* ctx, int32_t dtype, int32_t rank, const int64_t* ext, void* ptr,
                            qb200_tensor** out) {
     if (!ctx || !out || rank < 0 || rank > QB200_MAX_RANK) QB_FAIL(ctx, QB200_E_INVALID, "bad tensor rank %d", rank);
-    if (dtype != QB200_C128 && dtype != QB200_F64)
-        QB_FAIL(ctx, QB200_E_UNSUPPORTED, "dtype %d not implemented (ComplexF64 / Float64 only)", dtype);
+    if (dtype < QB200_C128 || dtype > QB200_F32) QB_FAIL(ctx, QB200_E_UNSUPPORTED, "unknown dtype %d", dtype);
+    if ((dtype == QB200_C64 || dtype == QB200_F32) && ptr)
+        QB_FAIL(ctx, QB200_E_UNSUPPORTED, "wrapping external single-precision memory is not supported (arithmetic is FP64)");
     qb200_tensor* t = new qb200_tensor();
+    // ComplexF32 / Float32 tensors are held widened to FP64 on the device: every kernel computes in FP64
+    // (results exceed the reference's 1e-5 ComplexF32 tolerance; native FP32/TF32 tiles are future work)
+    t->user_dtype = dtype;
+    dtype = (dtype == QB200_C64) ? QB200_C128 : (dtype == QB200_F32 ? QB200_F64 : dtype);
     t->dtype = dtype;
     t->rank = rank;
     int64_t n = 1;
@@ -218,6 +223,15 @@ int32_t qb200_tensor_free(qb200_ctx* ctx, qb200_tensor* t) {
 }
 int32_t qb200_tensor_upload(qb200_ctx* ctx, qb200_tensor* t, const void* host) {
     if (!t || !host) QB_FAIL(ctx, QB200_E_INVALID, "null argument");
+    if (t->user_dtype != t->dtype) {  // widen float -> double on the host, then one copy
+        size_t cnt = (size_t)t->numel() * (t->dtype == QB200_C128 ? 2 : 1);
+        std::vector<double> wide(cnt);
+        const float* src = (const float*)host;
+        for (size_t i = 0; i < cnt; ++i) wide[i] = (double)src[i];
+        QB_CUDA(ctx, cudaMemcpyAsync(t->data, wide.data(), cnt * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return QB200_OK;
+    }
     size_t n = (size_t)t->numel() * dtype_size(t->dtype);
     QB_CUDA(ctx, cudaMemcpyAsync(t->data, host, n, cudaMemcpyHostToDevice, ctx->stream));
     QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host buffer is only borrowed for the call
@@ -225,13 +239,22 @@ int32_t qb200_tensor_upload(qb200_ctx* ctx, qb200_tensor* t, const void* host) {
 }
 int32_t qb200_tensor_download(qb200_ctx* ctx, const qb200_tensor* t, void* host) {
     if (!t || !host) QB_FAIL(ctx, QB200_E_INVALID, "null argument");
+    if (t->user_dtype != t->dtype) {  // narrow double -> float on the host
+        size_t cnt = (size_t)t->numel() * (t->dtype == QB200_C128 ? 2 : 1);
+        std::vector<double> wide(cnt);
+        QB_CUDA(ctx, cudaMemcpyAsync(wide.data(), t->data, cnt * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        float* dst = (float*)host;
+        for (size_t i = 0; i < cnt; ++i) dst[i] = (float)wide[i];
+        return QB200_OK;
+    }
     size_t n = (size_t)t->numel() * dtype_size(t->dtype);
     QB_CUDA(ctx, cudaMemcpyAsync(host, t->data, n, cudaMemcpyDeviceToHost, ctx->stream));
     QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return QB200_OK;
 }
 int32_t qb200_tensor_rank(const qb200_tensor* t) { return t ? t->rank : -1; }
-int32_t qb200_tensor_dtype(const qb200_tensor* t) { return t ? t->dtype : -1; }
+int32_t qb200_tensor_dtype(const qb200_tensor* t) { return t ? t->user_dtype : -1; }
 int64_t qb200_tensor_extent(const qb200_tensor* t, int32_t i) { return (t && i >= 0 && i < t->rank) ? t->ext[i] : -1; }
 void* qb200_tensor_data(const qb200_tensor* t) { return t ? t->data : nullptr; }
 

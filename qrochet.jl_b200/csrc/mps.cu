@@ -628,6 +628,7 @@ namespace {
 qb200_tensor view3(c128* p, int64_t a, int64_t b, int64_t c) {
     qb200_tensor t;
     t.dtype = QB200_C128;
+    t.user_dtype = QB200_C128;
     t.rank = 3;
     t.ext[0] = a;
     t.ext[1] = b;

@@ -76,7 +76,11 @@ class Context:
     def array(self, host) -> "DeviceArray":
         """`adapt(B200Array, ::Array)`: upload a host array (column-major semantics)."""
         host = np.asarray(host)
-        if np.iscomplexobj(host):
+        if host.dtype == np.complex64:       # ComplexF32: widened to FP64 on the device, narrowed at download
+            buf, dt = np.asfortranarray(host), capi.C64
+        elif host.dtype == np.float32:
+            buf, dt = np.asfortranarray(host), capi.F32
+        elif np.iscomplexobj(host):
             buf = np.asfortranarray(host, dtype=np.complex128)
             dt = capi.C128
         else:
@@ -127,7 +131,8 @@ class DeviceArray:
 
     def to_host(self) -> np.ndarray:
         shape = self.shape
-        out = np.empty(shape, dtype=np.complex128 if self.dtype == capi.C128 else np.float64, order="F")
+        np_dtype = {capi.C128: np.complex128, capi.C64: np.complex64, capi.F64: np.float64, capi.F32: np.float32}
+        out = np.empty(shape, dtype=np_dtype[self.dtype], order="F")
         if out.size:
             check(self.ctx.h, lib.qb200_tensor_download(self.ctx.h, self.h, out.ctypes.data_as(C.c_void_p)))
         return out

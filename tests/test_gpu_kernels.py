@@ -214,3 +214,21 @@ def test_svd_graded_kept_spectrum_keeps_factors_orthonormal(qb, ctx):
         assert np.abs(u.conj().T @ u - np.eye(k)).max() < 1e-10
         assert np.abs(vc.T @ vc.conj() - np.eye(k)).max() < 1e-6    # small-sigma vectors: eps sigma_1 / sigma_j
         assert np.abs((u * s) @ vc.T - a).max() < 1e-12
+
+
+def test_complexf32_tensors_cross_the_boundary(qb, ctx):
+    """ComplexF32 / Float32 arrays are accepted (widened to FP64 on the device, FP64 arithmetic): the reference's
+    ComplexF32 tolerance is 1e-5 relative."""
+    rng = np.random.default_rng(12)
+    a = crand(rng, 40, 30).astype(np.complex64)
+    b = crand(rng, 30, 20).astype(np.complex64)
+    da, db = ctx.array(a), ctx.array(b)
+    assert da.to_host().dtype == np.complex64 and np.array_equal(da.to_host(), a)
+    c = qb.contract(da, (0, 1), db, (1, 2), (0, 2)).to_host()
+    want = a.astype(np.complex128) @ b.astype(np.complex128)
+    assert np.abs(c - want).max() <= 1e-5 * np.abs(want).max()
+    u, s, vc, kept, _ = qb.svd(da, (0, 1), 1)
+    s_ref = np.linalg.svd(a.astype(np.complex128), compute_uv=False)
+    assert np.abs(s.to_host() - s_ref).max() <= 1e-5 * s_ref[0]
+    v32 = ctx.array(rng.random(30).astype(np.float32))
+    assert v32.to_host().dtype == np.float32
