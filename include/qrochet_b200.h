@@ -218,6 +218,8 @@ int32_t qb200_comm_destroy(qb200_ctx* ctx);
 /* ---- diagnostics --------------------------------------------------------------------------- */
 /* FP64 tensor-core (DMMA m8n8k4) peak micro-benchmark: returns achieved TFLOP/s */
 int32_t qb200_bench_dmma_peak(qb200_ctx* ctx, double* tflops);
+/* FP64 pipes micro-benchmark: TFLOP/s of {DMMA only, DFMA only, both issued from alternating warps} */
+int32_t qb200_bench_dual_pipe(qb200_ctx* ctx, double* tflops3);
 
 #ifdef __cplusplus
 }

@@ -239,10 +239,8 @@ __global__ void __launch_bounds__(EVD_THREADS, 1)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     c128* G = reinterpret_cast<c128*>(smem_raw);
     c128* W = G + JP * GLD;
-    double* rcs = reinterpret_cast<double*>(W + JP * GLD);
-    c128* rsn = reinterpret_cast<c128*>(rcs + 32);
-    int* rpq = reinterpret_cast<int*>(rsn + 32);
-    double* red = reinterpret_cast<double*>(rpq + 64);
+    double* rcs = reinterpret_cast<double*>(W + JP * GLD);   // rotation cosines, buffer 0
+    double* red = rcs + 32 + 64 + 32;                          // reduction scratch (64 doubles), later cosines buffer 1
     short* tri = reinterpret_cast<short*>(red + 64);
 
     const int tid = threadIdx.x, pair = blockIdx.x;

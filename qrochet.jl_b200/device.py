@@ -86,6 +86,8 @@ class Context:
         else:
             buf = np.asfortranarray(host, dtype=np.float64)
             dt = capi.F64
+        if host.ndim == 0:  # np.asfortranarray promotes 0-d arrays to 1-d
+            buf = buf.reshape(())
         out = DeviceArray(self, buf.shape, dt)
         if buf.size:
             check(self.h, lib.qb200_tensor_upload(self.h, out.h, buf.ctypes.data_as(C.c_void_p)))

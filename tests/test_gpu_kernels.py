@@ -232,3 +232,64 @@ def test_complexf32_tensors_cross_the_boundary(qb, ctx):
     assert np.abs(s.to_host() - s_ref).max() <= 1e-5 * s_ref[0]
     v32 = ctx.array(rng.random(30).astype(np.float32))
     assert v32.to_host().dtype == np.float32
+
+
+def test_contract_random_label_orders(qb, ctx):
+    """Seeded random einsum cases: random ranks, extents, label permutations, batch / summed / free modes and conj
+    flags (what a Tenet contraction path throws at K1), each checked against numpy.einsum."""
+    rng = np.random.default_rng(2024)
+    for case in range(40):
+        n_m, n_n, n_k, n_b = rng.integers(0, 4), rng.integers(0, 4), rng.integers(0, 4), rng.integers(0, 2)
+        labels = list(range(n_m + n_n + n_k + n_b))
+        ext = {l: int(rng.integers(1, 6)) for l in labels}
+        m_modes, rest = labels[:n_m], labels[n_m:]
+        n_modes, rest = rest[:n_n], rest[n_n:]
+        k_modes, b_modes = rest[:n_k], rest[n_k:]
+        ma = list(rng.permutation(m_modes + k_modes + b_modes))
+        mb = list(rng.permutation(n_modes + k_modes + b_modes))
+        mc = list(rng.permutation(m_modes + n_modes + b_modes))
+        a = crand(rng, *[ext[l] for l in ma]) if ma else np.array(crand(rng, 1)[0])
+        b = crand(rng, *[ext[l] for l in mb]) if mb else np.array(crand(rng, 1)[0])
+        conj = (bool(rng.integers(0, 2)), bool(rng.integers(0, 2)))
+        want = einsum_ref(a, [int(x) for x in ma], b, [int(x) for x in mb], [int(x) for x in mc], *conj)
+        got = qb.contract(ctx.array(a), [int(x) for x in ma], ctx.array(b), [int(x) for x in mb],
+                          [int(x) for x in mc], conj_a=conj[0], conj_b=conj[1]).to_host()
+        assert got.shape == np.shape(want), (case, ma, mb, mc)
+        assert np.abs(got - want).max() <= 1e-12 * max(1.0, np.abs(want).max()), (case, ma, mb, mc)
+
+
+@pytest.mark.parametrize("name", ["zero", "identity", "rank1", "skinny", "scalar", "row", "column", "repeated"])
+def test_svd_degenerate_inputs(qb, ctx, name):
+    rng = np.random.default_rng(13)
+    a = {
+        "zero": np.zeros((40, 24), complex),
+        "identity": np.eye(70, dtype=complex),
+        "rank1": np.outer(crand(rng, 90), crand(rng, 33)),
+        "skinny": crand(rng, 1000, 3),
+        "scalar": np.array([[2.0 - 1.0j]]),
+        "row": crand(rng, 1, 50),
+        "column": crand(rng, 50, 1),
+        "repeated": np.kron(np.eye(4), crand(rng, 16, 16)),       # every singular value four-fold degenerate
+    }[name]
+    u, s, vc, kept, dw = qb.svd(ctx.array(a), (0, 1), 1)
+    u, s, vc = u.to_host(), s.to_host(), vc.to_host()
+    s_ref = np.linalg.svd(a, compute_uv=False)
+    scale = max(s_ref[0], 1e-300)
+    assert np.all(np.isfinite(u)) and np.all(np.isfinite(vc)) and np.all(np.isfinite(s))
+    assert np.abs(s - s_ref).max() <= 1e-12 * scale
+    assert np.abs((u * s) @ vc.T - a).max() <= 1e-12 * max(scale, 1.0)
+    r = int(np.sum(s_ref > 1e-10 * scale))                     # the numerically non-zero part is orthonormal
+    if r:
+        assert np.abs(u[:, :r].conj().T @ u[:, :r] - np.eye(r)).max() < 1e-11
+        assert np.abs(vc[:, :r].T @ vc[:, :r].conj() - np.eye(r)).max() < 1e-11
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (5, 1), (1, 5), (65, 64), (64, 65), (129, 3)])
+def test_qr_edge_shapes(qb, ctx, shape):
+    rng = np.random.default_rng(14)
+    a = crand(rng, *shape)
+    q, r = qb.qr(ctx.array(a), (0, 1), 1)
+    q, r = q.to_host(), r.to_host()
+    k = min(shape)
+    assert np.abs(q.conj().T @ q - np.eye(k)).max() < 1e-13
+    assert np.abs(q @ r - a).max() < 1e-12 * max(1.0, np.abs(a).max())
