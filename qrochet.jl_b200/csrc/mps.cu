@@ -546,7 +546,15 @@ int32_t qb200_mps_evolve2_layer(qb200_ctx* ctx, qb200_mps* m, int32_t nb, const 
             QB_FAIL(ctx, QB200_E_INVALID, "evolve2_layer: bonds %d and %d overlap", sorted[i - 1], sorted[i]);
     }
     if (nb == 0) return QB200_OK;
+    // worker streams: 12 by default, fewer when the host is small for the number of ranks sharing it (the workers
+    // sleep on blocking events, so a 2x oversubscription of the cores is harmless)
     int nworkers = 12;
+    {
+        int hw = (int)std::thread::hardware_concurrency();
+        int lws = 1;
+        if (const char* e = getenv("LOCAL_WORLD_SIZE")) lws = std::max(1, atoi(e));
+        if (hw > 0) nworkers = std::min(12, std::max(4, 2 * hw / lws));
+    }
     if (const char* e = getenv("QB200_WORKERS")) nworkers = std::max(1, atoi(e));
     nworkers = std::min(nworkers, (int)nb);
     std::vector<int64_t> kept_tmp(nb, 0);
