@@ -171,8 +171,9 @@ int32_t qb_gemm(qb200_ctx* ctx, int opA, int opB, int64_t M, int64_t N, int64_t 
 
 // thin QR of a column-major m x n matrix (ld = lda); Q: m x k (ldq), R: k x n (ldr), k = min(m,n).
 // A is not modified.
+// passes = 2: Q orthonormal to machine precision; passes = 1: only R is trustworthy (SVD preconditioner)
 int32_t qb_qr_matrix(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64_t lda, c128* Q, int64_t ldq,
-                     c128* R, int64_t ldr);
+                     c128* R, int64_t ldr, int passes = 2);
 
 struct SvdOut {
     // sigma sorted descending on host (k = min(m,n)), filled by qb_svd_factor

@@ -61,7 +61,7 @@ int32_t qb_scale_rows_cols(qb200_ctx* ctx, const c128* in, c128* out, int64_t ro
     return QB200_OK;
 }
 
-// B = A (conj_transpose = 0) or B = A^H (conj_transpose = 1, B is n x m); tiled through shared memory
+// B = A (ct = 0), B = A^H (ct = 1, B is n x m) or B = conj(A) (ct = 2); tiled through shared memory
 __global__ void copy_matrix_kernel(int64_t m, int64_t n, const c128* __restrict__ A, int64_t lda,
                                    c128* __restrict__ B, int64_t ldb, int ct) {
     __shared__ c128 tile[32][33];
@@ -71,10 +71,10 @@ __global__ void copy_matrix_kernel(int64_t m, int64_t n, const c128* __restrict_
         if (i < m && j < n) tile[jj][threadIdx.x] = A[i + j * lda];
     }
     __syncthreads();
-    if (!ct) {
+    if (ct != 1) {  // ct == 2: conjugate without transposing
         for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
             int64_t i = i0 + threadIdx.x, j = j0 + jj;
-            if (i < m && j < n) B[i + j * ldb] = tile[jj][threadIdx.x];
+            if (i < m && j < n) B[i + j * ldb] = (ct == 2) ? cconj(tile[jj][threadIdx.x]) : tile[jj][threadIdx.x];
         }
     } else {
         for (int ii = threadIdx.y; ii < 32; ii += blockDim.y) {

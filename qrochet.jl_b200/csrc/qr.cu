@@ -302,7 +302,7 @@ int32_t qb_qr_init(qb200_ctx* ctx) {
 }
 
 int32_t qb_qr_matrix(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64_t lda, c128* Q, int64_t ldq,
-                     c128* R, int64_t ldr) {
+                     c128* R, int64_t ldr, int passes) {
     if (m <= 0 || n <= 0) QB_FAIL(ctx, QB200_E_INVALID, "qr: empty matrix");
     if (m > INT32_MAX / 2) QB_FAIL(ctx, QB200_E_UNSUPPORTED, "qr: too many rows");
     const int64_t k = std::min(m, n);
@@ -312,9 +312,15 @@ int32_t qb_qr_matrix(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64_
     c128* R1 = ws.get<c128>((size_t)k * k);
     c128* R2 = ws.get<c128>((size_t)k * k);
     if (!R1 || !R2) QB_FAIL(ctx, QB200_E_CUDA, "qr: workspace allocation failed");
-    QB_TRY(bgs_pass(ctx, m, k, Q, ldq, R1, k));
-    QB_TRY(bgs_pass(ctx, m, k, Q, ldq, R2, k));
-    QB_TRY(qb_gemm(ctx, 0, 0, k, k, k, one, R2, k, R1, k, zero, R, ldr));
+    if (passes <= 1) {
+        // one pass: R is backward stable (as for modified Gram-Schmidt), Q is orthonormal only to kappa(A) eps
+        QB_TRY(bgs_pass(ctx, m, k, Q, ldq, R1, k));
+        QB_TRY(qb_copy_matrix(ctx, k, k, R1, k, R, ldr, 0));
+    } else {
+        QB_TRY(bgs_pass(ctx, m, k, Q, ldq, R1, k));
+        QB_TRY(bgs_pass(ctx, m, k, Q, ldq, R2, k));
+        QB_TRY(qb_gemm(ctx, 0, 0, k, k, k, one, R2, k, R1, k, zero, R, ldr));
+    }
     if (n > k) QB_TRY(qb_gemm(ctx, 2, 0, k, n - k, m, one, Q, ldq, A + k * lda, lda, zero, R + k * ldr, ldr));
     return QB200_OK;
 }
@@ -329,5 +335,5 @@ extern "C" int32_t qb200_qr(qb200_ctx* ctx, const qb200_tensor* A, const int32_t
     int64_t k = std::min(m, n);
     if (Q->dtype != QB200_C128 || R->dtype != QB200_C128 || Q->numel() != m * k || R->numel() != k * n)
         QB_FAIL(ctx, QB200_E_INVALID, "qr: Q must hold rows*k and R k*cols ComplexF64 entries");
-    return qb_qr_matrix(ctx, m, n, mat, m, (c128*)Q->data, m, (c128*)R->data, k);
+    return qb_qr_matrix(ctx, m, n, mat, m, (c128*)Q->data, m, (c128*)R->data, k, 2);
 }

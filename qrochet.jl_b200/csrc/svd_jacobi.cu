@@ -880,8 +880,7 @@ struct SvdState {
     int mp, np;         // padded k (rows of X, columns)
     int64_t ldz;
     c128* Z = nullptr;  // X (mp x np); the rotations are NOT accumulated (see qb_svd_emit)
-    c128* Q = nullptr;  // rb x k, orthonormal columns
-    c128* R = nullptr;  // k x k upper triangular, B P = Q R
+    c128* B0 = nullptr;  // rb x k: B with its columns sorted by norm (B0 = Q R; Q itself is never needed)
     std::vector<double> sigma_sorted;
     double* sigma_dev = nullptr;
     int* perm_dev = nullptr;     // sigma order (descending) -> column of Z
@@ -897,8 +896,7 @@ static unsigned grid_cap(qb200_ctx* ctx, int64_t n, int threads) {
 void qb_svd_release(qb200_ctx* ctx, SvdState* st) {
     if (!st) return;
     if (st->Z) cudaFreeAsync(st->Z, ctx->stream);
-    if (st->Q) cudaFreeAsync(st->Q, ctx->stream);
-    if (st->R) cudaFreeAsync(st->R, ctx->stream);
+    if (st->B0) cudaFreeAsync(st->B0, ctx->stream);
     if (st->sigma_dev) cudaFreeAsync(st->sigma_dev, ctx->stream);
     if (st->perm_dev) cudaFreeAsync(st->perm_dev, ctx->stream);
     if (st->colperm_dev) cudaFreeAsync(st->colperm_dev, ctx->stream);
@@ -960,8 +958,7 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
         return fail(QB200_E_CUDA);
     };
     if (cudaMallocAsync(&st->Z, sizeof(c128) * st->ldz * st->np, ctx->stream) != cudaSuccess ||
-        cudaMallocAsync(&st->Q, sizeof(c128) * rb * k, ctx->stream) != cudaSuccess ||
-        cudaMallocAsync(&st->R, sizeof(c128) * k * k, ctx->stream) != cudaSuccess ||
+        cudaMallocAsync(&st->B0, sizeof(c128) * rb * k, ctx->stream) != cudaSuccess ||
         cudaMallocAsync(&st->sigma_dev, sizeof(double) * st->np, ctx->stream) != cudaSuccess ||
         cudaMallocAsync(&st->perm_dev, sizeof(int) * st->np, ctx->stream) != cudaSuccess ||
         cudaMallocAsync(&st->colperm_dev, sizeof(int) * k, ctx->stream) != cudaSuccess) {
@@ -975,9 +972,11 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
     //      sweeps on graded matrices and gives the small singular vectors relative accuracy. ----
     {
         double* nr = ws.get<double>((size_t)(m + n));
-        c128* B0 = ws.get<c128>((size_t)(rb * k));
-        c128* R = st->R;
-        if (!nr || !B0) {
+        c128* B0 = st->B0;
+        Workspace wsq(ctx);  // Q and R only live until X = R^H is set up
+        c128* Qtmp = wsq.get<c128>((size_t)(rb * k));
+        c128* R = wsq.get<c128>((size_t)(k * k));
+        if (!nr || !Qtmp || !R) {
             ctx->err = "svd: workspace allocation failed";
             return fail(QB200_E_CUDA);
         }
@@ -999,7 +998,10 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
         ctx->launches++;
         {
             PhaseTimer pt(ctx, QB_PH_QR, 8.0 * (2.0 * rb * k * k - 2.0 / 3.0 * k * k * k));
-            int32_t r = qb_qr_matrix(ctx, rb, k, B0, rb, st->Q, rb, R, k);
+            // only R is used afterwards (U S = A V, see qb_svd_emit).  Both Gram-Schmidt passes are still needed:
+            // with one pass the singular values of R deviate from those of A by the loss of orthogonality of Q,
+            // ~ kappa(A) eps (measured 1e-10 sigma_1 on a 1e10-graded matrix), R = R2 R1 restores eps sigma_1.
+            int32_t r = qb_qr_matrix(ctx, rb, k, B0, rb, Qtmp, rb, R, k, 2);
             if (r != QB200_OK) return fail(r);
         }
         // Z = R^H zero-padded
@@ -1103,9 +1105,8 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
     return QB200_OK;
 }
 
-// B P = Q R, R^H = Xn S Vs^H  =>  B = (Q Vs) S (P Xn)^H.  tall: A = B, U = Q Vs, V = P Xn.  wide: A = B^H,
-// U = P Xn, V = Q Vs.  (Xn = normalised columns of X, Vs = accumulated rotations, both in sigma order;
-// (P Xn)(colperm[j], :) = Xn(j, :).)
+// B P = Q R, R^H = Xn S Vs^H  =>  B = (Q Vs) S (P Xn)^H with Q Vs = B P Xn S^-1 =: Y.  tall: A = B, U = Y, V = P Xn.
+// wide: A = B^H, U = P Xn, V = Y.  (Xn = normalised columns of X in sigma order; (P Xn)(colperm[j], :) = Xn(j, :).)
 int32_t qb_svd_emit(qb200_ctx* ctx, SvdState* st, int64_t kept, c128* U, int64_t ldu, double* S, c128* V,
                     int64_t ldv, int vmode, const double* uinv, int64_t uinv_len, const double* vinv,
                     int64_t vinv_div, double sigma_scale) {
@@ -1114,44 +1115,46 @@ int32_t qb_svd_emit(qb200_ctx* ctx, SvdState* st, int64_t kept, c128* U, int64_t
     const c128* X = st->Z;
     const c128 ONE = make_double2(1.0, 0.0), ZERO = make_double2(0.0, 0.0);
     Workspace ws(ctx);
-    // The rotations were not accumulated.  With R^H = Xn S Vs^H and Xn orthonormal, R Xn = Vs S, so
-    // Vs = R Xn S^-1: one triangular-times-dense GEMM instead of dragging a k x k block through every update
-    // (a third of the Jacobi flops).  Column j comes out with a relative error ~ eps sigma_1 / sigma_j, harmless
-    // (norm-wise backward stable) but it costs orthogonality when the kept spectrum is graded; in that case the
-    // columns are re-orthonormalised in order of decreasing sigma (K4), which leaves A = U S V^H intact to
-    // eps sigma_1 and keeps U orthonormal to machine precision.
-    c128* Vs = nullptr;
-    auto need_vs = [&]() -> int32_t {
-        if (Vs) return QB200_OK;
+    // Neither the rotations nor Q were kept.  With B0 = B P = Q R and R^H = Xn S Vs^H (Xn orthonormal):
+    // B0 Xn = Q R Xn = Q Vs S, so the "Q side" factor is Y = B0 Xn S^-1 -- ONE GEMM with the (sorted) input matrix.
+    // Column j of Y carries a relative error ~ eps sigma_1 / sigma_j: harmless (norm-wise backward stable), but it
+    // costs orthogonality when the kept spectrum is graded; then the columns are re-orthonormalised in order of
+    // decreasing sigma (K4, phases fixed), which keeps A = U S V^H to eps sigma_1 and Y orthonormal to eps.
+    auto make_y = [&](c128* Y) -> int32_t {  // Y: rb x kept, ld = rb
         c128* Xsel = ws.get<c128>((size_t)(k * kept));
-        Vs = ws.get<c128>((size_t)(k * kept));
         double* isg = ws.get<double>((size_t)kept);
-        if (!Xsel || !Vs || !isg) QB_FAIL(ctx, QB200_E_CUDA, "svd: workspace allocation failed");
+        if (!Xsel || !isg) QB_FAIL(ctx, QB200_E_CUDA, "svd: workspace allocation failed");
         svd_emit_kernel<<<grid_cap(ctx, k * kept, 256), 256, 0, ctx->stream>>>(
             X, st->ldz, k, kept, st->perm_dev, st->sigma_dev, 1, 0, 0, nullptr, Xsel, k, nullptr, 0, 1);
         QB_LAUNCH_CHECK(ctx);
         svd_emit_sigma_kernel<<<(unsigned)((kept + 255) / 256), 256, 0, ctx->stream>>>(st->sigma_dev, st->perm_dev, kept,
                                                                                       -1.0, isg);
         QB_LAUNCH_CHECK(ctx);
-        QB_TRY(qb_gemm(ctx, 0, 0, k, kept, k, ONE, st->R, k, Xsel, k, ZERO, Vs, k));
-        QB_TRY(qb_scale_rows_cols(ctx, Vs, Vs, k, kept, nullptr, 1, isg, 1));
+        QB_TRY(qb_gemm(ctx, 0, 0, st->rb, kept, k, ONE, st->B0, st->rb, Xsel, k, ZERO, Y, st->rb));
+        QB_TRY(qb_scale_rows_cols(ctx, Y, Y, st->rb, kept, nullptr, 1, isg, 1));
         const std::vector<double>& sg = st->sigma_sorted;
         bool graded = !(sg[kept - 1] > 1e-3 * sg[0]);
         if (graded) {
-            c128* Qv = ws.get<c128>((size_t)(k * kept));
-            c128* Rv = ws.get<c128>((size_t)(kept * kept));
-            if (!Qv || !Rv) QB_FAIL(ctx, QB200_E_CUDA, "svd: workspace allocation failed");
-            QB_TRY(qb_qr_matrix(ctx, k, kept, Vs, k, Qv, k, Rv, kept));
-            fix_phase_kernel<<<grid_cap(ctx, k * kept, 256), 256, 0, ctx->stream>>>(Qv, k, kept, Rv, kept, Vs);
+            c128* Qy = ws.get<c128>((size_t)(st->rb * kept));
+            c128* Ry = ws.get<c128>((size_t)(kept * kept));
+            if (!Qy || !Ry) QB_FAIL(ctx, QB200_E_CUDA, "svd: workspace allocation failed");
+            QB_TRY(qb_qr_matrix(ctx, st->rb, kept, Y, st->rb, Qy, st->rb, Ry, kept, 2));
+            fix_phase_kernel<<<grid_cap(ctx, st->rb * kept, 256), 256, 0, ctx->stream>>>(Qy, st->rb, kept, Ry, kept, Y);
             QB_LAUNCH_CHECK(ctx);
         }
         return QB200_OK;
     };
     PhaseTimer pt(ctx, QB_PH_EMIT, 8.0 * st->rb * k * kept);
     if (U) {
-        if (st->tall) {  // U = Q Vs, rows scaled by uinv[i % uinv_len]
-            QB_TRY(need_vs());
-            QB_TRY(qb_gemm(ctx, 0, 0, st->m, kept, k, ONE, st->Q, st->rb, Vs, k, ZERO, U, ldu));
+        if (st->tall) {  // U = Y, rows scaled by uinv[i % uinv_len]
+            if (ldu == st->rb) {
+                QB_TRY(make_y(U));
+            } else {
+                c128* Y = ws.get<c128>((size_t)(st->rb * kept));
+                if (!Y) QB_FAIL(ctx, QB200_E_CUDA, "svd: workspace allocation failed");
+                QB_TRY(make_y(Y));
+                QB_TRY(qb_copy_matrix(ctx, st->m, kept, Y, st->rb, U, ldu, 0));
+            }
             if (uinv) QB_TRY(qb_scale_rows_cols(ctx, U, U, st->m, kept, uinv, uinv_len, nullptr, 1));
         } else {  // U = P Xn
             if (ldu != st->m && uinv) QB_FAIL(ctx, QB200_E_UNSUPPORTED, "svd: strided U with fused scaling");
@@ -1162,13 +1165,15 @@ int32_t qb_svd_emit(qb200_ctx* ctx, SvdState* st, int64_t kept, c128* U, int64_t
         }
     }
     if (V) {
-        if (!st->tall) {  // V = Q Vs (n x kept): Vc = conj(Q) conj(Vs) or Vh = Vs^H Q^H
-            QB_TRY(need_vs());
+        if (!st->tall) {  // V = Y (n x kept): written as Vc = conj(Y) or Vh = Y^H
+            c128* Y = ws.get<c128>((size_t)(st->rb * kept));
+            if (!Y) QB_FAIL(ctx, QB200_E_CUDA, "svd: workspace allocation failed");
+            QB_TRY(make_y(Y));
             if (vmode == 0) {
-                QB_TRY(qb_gemm(ctx, 3, 3, st->n, kept, k, ONE, st->Q, st->rb, Vs, k, ZERO, V, ldv));
                 if (vinv) QB_FAIL(ctx, QB200_E_UNSUPPORTED, "svd: fused V scaling needs vmode 1");
+                QB_TRY(qb_copy_matrix(ctx, st->n, kept, Y, st->rb, V, ldv, 2));
             } else {
-                QB_TRY(qb_gemm(ctx, 2, 2, kept, st->n, k, ONE, Vs, k, st->Q, st->rb, ZERO, V, ldv));
+                QB_TRY(qb_copy_matrix(ctx, st->n, kept, Y, st->rb, V, ldv, 1));
                 if (vinv) {
                     if (ldv != kept) QB_FAIL(ctx, QB200_E_UNSUPPORTED, "svd: strided Vh with fused scaling");
                     QB_TRY(qb_scale_rows_cols(ctx, V, V, kept, st->n, nullptr, 1, vinv, vinv_div));
