@@ -167,6 +167,14 @@ int32_t qb200_mps_evolve2(qb200_ctx* ctx, qb200_mps* mps, int32_t bond, const vo
 int32_t qb200_mps_evolve2_layer(qb200_ctx* ctx, qb200_mps* mps, int32_t nb, const int32_t* bonds, const void* gates_c128,
                                 int64_t maxdim, double threshold, int32_t renormalize, int64_t* kept,
                                 double* discarded_weight);
+/* A circuit of nearest-neighbour two-site gates in program order -- the user loop
+ * `for (G, bond) in circuit evolve!(psi, G; ...)` (Chain.jl:543-584 called repeatedly; the Quac/Yao front-ends of
+ * SURVEY.md §8 f2 produce such lists).  Bonds may repeat and touch: an update starts as soon as the earlier updates
+ * on its two sites are complete, so consecutive TEBD layers overlap.  Results are identical to nops calls of
+ * qb200_mps_evolve2 in the given order.  kept / discarded_weight: arrays of nops (may be NULL). */
+int32_t qb200_mps_evolve2_circuit(qb200_ctx* ctx, qb200_mps* mps, int32_t nops, const int32_t* bonds,
+                                  const void* gates_c128, int64_t maxdim, double threshold, int32_t renormalize,
+                                  int64_t* kept, double* discarded_weight);
 /* evolve_1site! (Chain.jl:586-603): gate = p*p c128 numbers (o, i) column-major */
 int32_t qb200_mps_evolve1(qb200_ctx* ctx, qb200_mps* mps, int32_t site, const void* gate_c128);
 /* ---- MPO x MPS (no function exists in the reference: composed from MPO(arrays) Chain.jl:133-172,

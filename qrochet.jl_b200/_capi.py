@@ -84,6 +84,7 @@ _protos = {
     "qb200_mps_truncate": (_i32, [_p, _p, _i32, _i64, _dbl, _pi64]),
     "qb200_mps_evolve2": (_i32, [_p, _p, _i32, _p, _i64, _dbl, _i32, _pi64, _pdbl]),
     "qb200_mps_evolve2_layer": (_i32, [_p, _p, _i32, _pi32, _p, _i64, _dbl, _i32, _pi64, _pdbl]),
+    "qb200_mps_evolve2_circuit": (_i32, [_p, _p, _i32, _pi32, _p, _i64, _dbl, _i32, _pi64, _pdbl]),
     "qb200_mps_evolve1": (_i32, [_p, _p, _i32, _p]),
     "qb200_mps_apply_mpo": (_i32, [_p, _p, _pi64, _pi64, _p]),
     "qb200_mps_compress": (_i32, [_p, _p, _i64, _dbl]),

@@ -14,6 +14,9 @@
 #include "common.cuh"
 
 #include <cstdlib>
+#include <array>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 
 struct qb200_mps {
@@ -528,11 +531,113 @@ int32_t qb200_mps_evolve2(qb200_ctx* ctx, qb200_mps* m, int32_t b, const void* g
     return evolve2_core(ctx, m, b, gate, maxdim, threshold, renormalize, kept_out, discarded_weight, true);
 }
 
-// One TEBD layer: `nb` two-site gates on pairwise non-adjacent bonds (e.g. all odd or all even bonds).  The
-// updates commute (disjoint sites; the Schmidt vectors between them are only read), so they are independent
-// units: they run concurrently on worker streams, which hides the latency-bound phases of one update (QR panels,
-// the shared-memory Jacobi solves) behind the DMMA-bound phases of the others.  Results are identical to
-// calling evolve! bond by bond.
+namespace {
+// Dependency-scheduled pool of two-site updates.  ops are given in program order; op i must wait for every earlier
+// op that touches one of its two sites (bonds b-1, b, b+1) -- updates further apart only READ the Schmidt vector
+// that sits between them, so they commute and run concurrently on worker streams, which hides the latency-bound
+// phases of one update (QR panels, the shared-memory Jacobi solves) behind the DMMA-bound phases of the others.
+// Every op sees exactly the inputs it would see in a sequential run => results are bit-identical to it.
+int32_t run_evolve2_ops(qb200_ctx* ctx, qb200_mps* m, int32_t nops, const int32_t* bonds, const c128* g, int64_t maxdim,
+                        double threshold, int32_t renormalize, int64_t* kept_out, double* discarded_weight) {
+    // worker streams: 12 by default, fewer when the host is small for the number of ranks sharing it (the workers
+    // sleep on blocking events, so a 2x oversubscription of the cores is harmless)
+    int nworkers = 12;
+    {
+        int hw = (int)std::thread::hardware_concurrency();
+        int lws = 1;
+        if (const char* e = getenv("LOCAL_WORLD_SIZE")) lws = std::max(1, atoi(e));
+        if (hw > 0) nworkers = std::min(12, std::max(4, 2 * hw / lws));
+    }
+    if (const char* e = getenv("QB200_WORKERS")) nworkers = std::max(1, atoi(e));
+    nworkers = std::min(nworkers, (int)nops);
+    std::vector<int64_t> kept_tmp(nops, 0);
+    std::vector<double> dw_tmp(nops, 0.0);
+    if (nworkers <= 1) {
+        for (int i = 0; i < nops; ++i)
+            QB_TRY(evolve2_core(ctx, m, bonds[i], g + 16 * i, maxdim, threshold, renormalize, &kept_tmp[i], &dw_tmp[i], false));
+    } else {
+        // dependencies: the latest earlier op on each of the bonds b-1, b, b+1
+        std::vector<std::array<int, 3>> dep(nops);
+        {
+            std::vector<int> last(m->n + 1, -1);
+            for (int i = 0; i < nops; ++i) {
+                for (int d = 0; d < 3; ++d) {
+                    int bb = bonds[i] - 1 + d;
+                    dep[i][d] = (bb >= 0 && bb < m->n - 1) ? last[bb] : -1;
+                }
+                last[bonds[i]] = i;
+            }
+        }
+        // workers start after everything already queued on the parent stream
+        QB_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        std::vector<qb200_ctx*> w(nworkers);
+        for (int t = 0; t < nworkers; ++t) {
+            w[t] = qb_worker(ctx, t);
+            w[t]->prof_on = ctx->prof_on;
+            QB_CUDA(ctx, cudaStreamWaitEvent(w[t]->stream, ctx->ev1, 0));
+        }
+        std::mutex mu;
+        std::condition_variable cv;
+        std::vector<char> state(nops, 0);  // 0 pending, 1 running, 2 done
+        int remaining = nops;
+        int32_t first_rc = QB200_OK;
+        int failed_worker = -1;
+        // among the ready ops: the largest theta first (longest job), ties in program order
+        auto cost = [&](int i) { return m->chil[bonds[i]] * m->chir[bonds[i] + 1]; };
+        auto pick = [&]() {
+            int best = -1;
+            int64_t bc = -1;
+            for (int i = 0; i < nops; ++i) {
+                if (state[i] != 0) continue;
+                bool ready = true;
+                for (int d = 0; d < 3; ++d)
+                    if (dep[i][d] >= 0 && state[dep[i][d]] != 2) ready = false;
+                if (!ready) continue;
+                int64_t c = cost(i);
+                if (c > bc) { bc = c; best = i; }
+            }
+            return best;
+        };
+        std::vector<std::thread> threads;
+        for (int t = 0; t < nworkers; ++t)
+            threads.emplace_back([&, t]() {
+                cudaSetDevice(ctx->device);
+                std::unique_lock<std::mutex> lk(mu);
+                for (;;) {
+                    int i = -1;
+                    cv.wait(lk, [&]() { return remaining == 0 || first_rc != QB200_OK || (i = pick()) >= 0; });
+                    if (i < 0) break;
+                    state[i] = 1;
+                    lk.unlock();
+                    // evolve2_core returns with its stream drained: the op is complete on the device
+                    int32_t r = evolve2_core(w[t], m, bonds[i], g + 16 * i, maxdim, threshold, renormalize, &kept_tmp[i],
+                                             &dw_tmp[i], false);
+                    lk.lock();
+                    state[i] = 2;
+                    --remaining;
+                    if (r != QB200_OK && first_rc == QB200_OK) { first_rc = r; failed_worker = t; }
+                    cv.notify_all();
+                }
+                lk.unlock();
+                qb_stream_sync(w[t]);
+            });
+        for (auto& th : threads) th.join();
+        if (first_rc != QB200_OK) {
+            if (failed_worker >= 0 && !w[failed_worker]->err.empty()) ctx->err = w[failed_worker]->err;
+            return first_rc;
+        }
+    }
+    for (int i = 0; i < nops; ++i) {
+        if (kept_out) kept_out[i] = kept_tmp[i];
+        if (discarded_weight) discarded_weight[i] = dw_tmp[i];
+    }
+    return QB200_OK;
+}
+}  // namespace
+
+// One TEBD layer: `nb` two-site gates on pairwise non-adjacent bonds (e.g. all odd or all even bonds): the updates
+// commute (disjoint sites; the Schmidt vectors between them are only read) and run as concurrent independent units.
+// Results are identical to calling evolve! bond by bond.
 int32_t qb200_mps_evolve2_layer(qb200_ctx* ctx, qb200_mps* m, int32_t nb, const int32_t* bonds, const void* gates,
                                 int64_t maxdim, double threshold, int32_t renormalize, int64_t* kept_out,
                                 double* discarded_weight) {
@@ -546,64 +651,24 @@ int32_t qb200_mps_evolve2_layer(qb200_ctx* ctx, qb200_mps* m, int32_t nb, const 
             QB_FAIL(ctx, QB200_E_INVALID, "evolve2_layer: bonds %d and %d overlap", sorted[i - 1], sorted[i]);
     }
     if (nb == 0) return QB200_OK;
-    // worker streams: 12 by default, fewer when the host is small for the number of ranks sharing it (the workers
-    // sleep on blocking events, so a 2x oversubscription of the cores is harmless)
-    int nworkers = 12;
-    {
-        int hw = (int)std::thread::hardware_concurrency();
-        int lws = 1;
-        if (const char* e = getenv("LOCAL_WORLD_SIZE")) lws = std::max(1, atoi(e));
-        if (hw > 0) nworkers = std::min(12, std::max(4, 2 * hw / lws));
-    }
-    if (const char* e = getenv("QB200_WORKERS")) nworkers = std::max(1, atoi(e));
-    nworkers = std::min(nworkers, (int)nb);
-    std::vector<int64_t> kept_tmp(nb, 0);
-    std::vector<double> dw_tmp(nb, 0.0);
-    std::vector<int32_t> rc(nb, QB200_OK);
-    const c128* g = (const c128*)gates;
-    if (nworkers == 1) {
-        for (int i = 0; i < nb; ++i)
-            QB_TRY(evolve2_core(ctx, m, bonds[i], g + 16 * i, maxdim, threshold, renormalize, &kept_tmp[i], &dw_tmp[i], false));
-    } else {
-        // workers start after everything already queued on the parent stream
-        QB_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-        std::vector<qb200_ctx*> w(nworkers);
-        for (int t = 0; t < nworkers; ++t) {
-            w[t] = qb_worker(ctx, t);
-            w[t]->prof_on = ctx->prof_on;
-            QB_CUDA(ctx, cudaStreamWaitEvent(w[t]->stream, ctx->ev1, 0));
-        }
-        // longest jobs first (largest bond dimension), dealt round robin
-        std::vector<int> order(nb);
-        for (int i = 0; i < nb; ++i) order[i] = i;
-        std::stable_sort(order.begin(), order.end(), [&](int a, int c) {
-            return m->chil[bonds[a]] * m->chir[bonds[a] + 1] > m->chil[bonds[c]] * m->chir[bonds[c] + 1];
-        });
-        std::vector<std::thread> threads;
-        for (int t = 0; t < nworkers; ++t)
-            threads.emplace_back([&, t]() {
-                cudaSetDevice(ctx->device);
-                for (int j = t; j < nb; j += nworkers) {
-                    int i = order[j];
-                    rc[i] = evolve2_core(w[t], m, bonds[i], g + 16 * i, maxdim, threshold, renormalize, &kept_tmp[i],
-                                         &dw_tmp[i], false);
-                    if (rc[i] != QB200_OK) break;
-                }
-                qb_stream_sync(w[t]);
-            });
-        for (auto& th : threads) th.join();
-        for (int i = 0; i < nb; ++i)
-            if (rc[i] != QB200_OK) {
-                for (int t = 0; t < nworkers; ++t)
-                    if (!w[t]->err.empty()) ctx->err = w[t]->err;
-                return rc[i];
-            }
-    }
-    for (int i = 0; i < nb; ++i) {
-        if (kept_out) kept_out[i] = kept_tmp[i];
-        if (discarded_weight) discarded_weight[i] = dw_tmp[i];
-    }
-    return QB200_OK;
+    return run_evolve2_ops(ctx, m, nb, bonds, (const c128*)gates, maxdim, threshold, renormalize, kept_out,
+                           discarded_weight);
+}
+
+// A gate list in program order (a circuit of nearest-neighbour two-site gates, e.g. several TEBD layers or whole
+// sweeps): the user loop `for (G, bond) in circuit evolve!(psi, G; ...)`.  Bonds may repeat and touch; an update
+// starts as soon as the earlier updates on its two sites are complete, so consecutive layers overlap and no worker
+// idles at a layer boundary.  Results are identical to nops calls of qb200_mps_evolve2 in the given order.
+int32_t qb200_mps_evolve2_circuit(qb200_ctx* ctx, qb200_mps* m, int32_t nops, const int32_t* bonds, const void* gates,
+                                  int64_t maxdim, double threshold, int32_t renormalize, int64_t* kept_out,
+                                  double* discarded_weight) {
+    QB_TRY(check_complete(ctx, m));
+    if (nops < 0 || (nops > 0 && (!bonds || !gates))) QB_FAIL(ctx, QB200_E_INVALID, "evolve2_circuit: bad argument");
+    for (int i = 0; i < nops; ++i)
+        if (bonds[i] < 0 || bonds[i] >= m->n - 1) QB_FAIL(ctx, QB200_E_INVALID, "evolve2_circuit: bond out of range");
+    if (nops == 0) return QB200_OK;
+    return run_evolve2_ops(ctx, m, nops, bonds, (const c128*)gates, maxdim, threshold, renormalize, kept_out,
+                           discarded_weight);
 }
 
 // canonize! with truncate! applied to each bond right after its SVD: the composition a user of the reference

@@ -186,15 +186,26 @@ class B200MPS:
         """One TEBD layer: `gates[i]` (dims (o1,o2,i1,i2)) on sites (bonds[i], bonds[i]+1), 1-based, pairwise
         non-adjacent -- the user loop `for b in bonds: evolve!(ψ, G_b; ...)` run as concurrent independent units.
         Returns (kept[], discarded_weight[])."""
+        return self._evolve_ops(lib.qb200_mps_evolve2_layer, gates, bonds, threshold, maxdim, renormalize)
+
+    def evolve_circuit(self, gates, bonds, threshold=None, maxdim=None, renormalize=False):
+        """A gate list in program order: `gates[i]` on sites (bonds[i], bonds[i]+1), 1-based; bonds may repeat and
+        touch -- the user loop `for (G, b) in circuit: evolve!(ψ, G; ...)` (Chain.jl:543-584).  Updates start as soon
+        as the earlier updates on their two sites are done (consecutive layers overlap); results are identical to
+        the sequential loop.  Returns (kept[], discarded_weight[])."""
+        return self._evolve_ops(lib.qb200_mps_evolve2_circuit, gates, bonds, threshold, maxdim, renormalize)
+
+    def _evolve_ops(self, fn, gates, bonds, threshold, maxdim, renormalize):
         nb = len(bonds)
+        if len(gates) != nb:
+            raise ValueError("one gate per bond expected")
         flat = np.concatenate([np.asarray(g, dtype=np.complex128).reshape(-1, order="F") for g in gates]) \
             if nb else np.zeros(0, np.complex128)
         kept = (C.c_int64 * max(nb, 1))()
         dw = (C.c_double * max(nb, 1))()
-        check(self.ctx.h, lib.qb200_mps_evolve2_layer(self.ctx.h, self.h, nb, capi.i32arr(b - 1 for b in bonds),
-                                                      flat.ctypes.data_as(C.c_void_p), int(maxdim or 0),
-                                                      -1.0 if threshold is None else float(threshold),
-                                                      int(bool(renormalize)), kept, dw))
+        check(self.ctx.h, fn(self.ctx.h, self.h, nb, capi.i32arr(b - 1 for b in bonds),
+                             flat.ctypes.data_as(C.c_void_p), int(maxdim or 0),
+                             -1.0 if threshold is None else float(threshold), int(bool(renormalize)), kept, dw))
         return [int(kept[i]) for i in range(nb)], [float(dw[i]) for i in range(nb)]
 
     @staticmethod
