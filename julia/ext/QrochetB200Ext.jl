@@ -115,6 +115,20 @@ function Qrochet.evolve!(ψ::B200Chain, gate::Qrochet.Dense; threshold = nothing
     end
     ψ
 end
+# a gate list in program order (the loop `for g in gates evolve!(ψ, g; ...)`): one call, dependency-scheduled on the device
+function Qrochet.evolve!(ψ::B200Chain, gates::AbstractVector{<:Qrochet.Dense}; threshold = nothing, maxdim = nothing, iscanonical = true, renormalize = false)
+    bonds = Int32[]; flat = ComplexF64[]
+    for gate in gates
+        lanes = sort!(id.(outputs(gate)))
+        length(lanes) == 2 && lanes[2] == lanes[1] + 1 || throw(ArgumentError("Gate lanes must be contiguous"))   # Chain.jl:574
+        push!(bonds, lanes[1] - 1); append!(flat, vec(ComplexF64.(Array(parent(only(tensors(gate)))))))
+    end
+    kept = zeros(Int64, length(bonds)); dw = zeros(Float64, length(bonds))
+    check(context().h, ccall((:qb200_mps_evolve2_circuit, lib), Int32,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Cvoid}, Int64, Float64, Int32, Ptr{Int64}, Ptr{Float64}),
+        context().h, ψ.h, length(bonds), bonds, flat, something(maxdim, 0), something(threshold, -1.0), renormalize, kept, dw))
+    ψ
+end
 function Qrochet.overlap(a::B200Chain, b::B200Chain)
     r = zeros(2)
     check(context().h, ccall((:qb200_mps_overlap, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}), context().h, a.h, b.h, r))

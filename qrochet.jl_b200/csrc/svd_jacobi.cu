@@ -556,11 +556,13 @@ __global__ void __launch_bounds__(UPD_THREADS, 1)
             cp_async_wait<0>();  // W (and the current chunk) have landed
             cur_pair = pair;
         }
+        // ONE barrier per chunk: it publishes the landed chunk AND says every warp has left the previous chunk,
+        // whose buffer the prefetch below overwrites
+        cp_async_wait<0>();
+        __syncthreads();
         const int nxt = next_active(item + 1);
         if (nxt < hi) load_chunk(nxt, stage ^ 1);
         cp_async_commit();
-        cp_async_wait<1>();
-        __syncthreads();
         int I, J;
         rr_pair(nb, step, pair, I, J);
         const c128* za = Zs + (size_t)stage * JP * U_ZP + wi * 16 + g;
@@ -606,7 +608,6 @@ __global__ void __launch_bounds__(UPD_THREADS, 1)
                     int n = wj * 16 + b * 8 + 2 * t + h;
                     Z[r0 + a * 8 + panel_col(I, J, n) * ldz] = make_double2(cr[a][b][h], ci[a][b][h]);
                 }
-        __syncthreads();  // stage is free again before the next iteration refills it
         stage ^= 1;
         item = nxt;
     }
