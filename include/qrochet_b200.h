@@ -228,6 +228,9 @@ int32_t qb200_comm_destroy(qb200_ctx* ctx);
 int32_t qb200_bench_dmma_peak(qb200_ctx* ctx, double* tflops);
 /* FP64 pipes micro-benchmark: TFLOP/s of {DMMA only, DFMA only, both issued from alternating warps} */
 int32_t qb200_bench_dual_pipe(qb200_ctx* ctx, double* tflops3);
+/* DMMA issue-pattern micro-benchmark: TFLOP/s for {independent accumulators, complex-multiply pattern with register
+ * operands, the same with A fragments re-loaded from shared memory} x {8, 16, 32 warps per SM}; row-major [3][3] */
+int32_t qb200_bench_dmma_patterns(qb200_ctx* ctx, double* tflops9);
 
 #ifdef __cplusplus
 }

@@ -92,3 +92,94 @@ extern "C" int32_t qb200_bench_dual_pipe(qb200_ctx* ctx, double* tflops3) {
     }
     return QB200_OK;
 }
+
+// Experiment: which issue pattern of DMMA m8n8k4 reaches the pipe peak?  MODE 0: 16 independent accumulators,
+// operands fixed (the peak benchmark); 1: the complex-multiply pattern of the update kernel (8 accumulators, each
+// used twice per k-step, 4 distinct A pairs); 2: pattern 1 with the A operands re-loaded from shared memory every
+// k-step (LDS.128, conflict-free pitch) and 16 different B operands from registers.
+template <int MODE>
+__global__ void __launch_bounds__(256) dmma_pattern_kernel(double* out, int iters) {
+    __shared__ __align__(16) double2 zs[64 * 34];
+    for (int i = threadIdx.x; i < 64 * 34; i += 256) zs[i] = make_double2(1.0 + i * 1e-9, 1.0 - i * 1e-9);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+    double s = 0.0;
+    if (MODE == 0) {
+        double acc[16][2];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i][0] = acc[i][1] = 0.0;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dmma884(acc[i], a, b);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s += acc[i][0] + acc[i][1];
+    } else {
+        double cr[4][2], ci[4][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cr[i][0] = cr[i][1] = ci[i][0] = ci[i][1] = 0.0;
+        double2 breg[16];
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) breg[kk] = make_double2(a + kk, b - kk);
+        const double2* za = zs + g;
+        for (int it = 0; it < iters; it += 16) {
+#pragma unroll
+            for (int kk = 0; kk < 16; ++kk) {
+                double ar[4], ai[4];
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    if (MODE == 2) {
+                        double2 v = za[(kk * 4 + t) * 34 + x * 8];
+                        ar[x] = v.x;
+                        ai[x] = v.y;
+                    } else {
+                        ar[x] = a + x;
+                        ai[x] = b + x;
+                    }
+                }
+                const double br = breg[kk].x, bi = breg[kk].y;
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    dmma884(cr[x], ar[x], br);
+                    dmma884(ci[x], ar[x], bi);
+                }
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    dmma884(cr[x], -ai[x], bi);
+                    dmma884(ci[x], ai[x], br);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s += cr[i][0] + cr[i][1] + ci[i][0] + ci[i][1];
+    }
+    if (s == 123.456) out[0] = s;
+}
+
+// tflops[3 modes][3 occupancies: 8, 16, 32 warps per SM]
+extern "C" int32_t qb200_bench_dmma_patterns(qb200_ctx* ctx, double* tflops9) {
+    if (!ctx || !tflops9) return QB200_E_INVALID;
+    Workspace ws(ctx);
+    double* out = ws.get<double>(1);
+    const int iters = 4096;
+    for (int mode = 0; mode < 3; ++mode)
+        for (int occ = 0; occ < 3; ++occ) {
+            const int blocks = ctx->sm_count * (1 << occ);
+            auto launch = [&](int n) {
+                if (mode == 0) dmma_pattern_kernel<0><<<blocks, 256, 0, ctx->stream>>>(out, n);
+                if (mode == 1) dmma_pattern_kernel<1><<<blocks, 256, 0, ctx->stream>>>(out, n);
+                if (mode == 2) dmma_pattern_kernel<2><<<blocks, 256, 0, ctx->stream>>>(out, n);
+            };
+            launch(64);
+            QB_LAUNCH_CHECK(ctx);
+            QB_TRY(qb200_timer_begin(ctx));
+            launch(iters);
+            QB_LAUNCH_CHECK(ctx);
+            double ms = 0.0;
+            QB_TRY(qb200_timer_end(ctx, &ms));
+            double flops = (double)blocks * 8 * iters * 16.0 * 512.0;
+            tflops9[mode * 3 + occ] = flops / (ms * 1e-3) / 1e12;
+        }
+    return QB200_OK;
+}

@@ -149,18 +149,23 @@ __global__ void __launch_bounds__(256, 2)
     gram_item_range(blockIdx.x, gridDim.x, total, lo, hi);
     const int nitems = hi - lo;
 
+    // prefetch cursor: (pair, chunk, I, J) carried incrementally, no division per item
     const int l_row = tid & 31, l_col0 = tid >> 5;
-    auto load_item = [&](int it, int st) {
+    const int first_pair = (nitems > 0) ? lo / nchunk : 0;
+    int pf_pair = first_pair, pf_chunk = lo - first_pair * nchunk, pf_I = 0, pf_J = 1;
+    if (nitems > 0) rr_pair(nb, step, pf_pair, pf_I, pf_J);
+    auto load_next = [&](int st) {
         c128* ps = Ps + (size_t)st * JP * G_PITCH;
-        int item = lo + it;
-        int pair = item / nchunk, chunk = item - pair * nchunk;
-        int I, J;
-        rr_pair(nb, step, pair, I, J);
-        int row = chunk * G_BKR + l_row;
+        const c128* src = Z + (int64_t)pf_chunk * G_BKR + l_row;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             int col = l_col0 + 8 * i;
-            cp_async16(ps + col * G_PITCH + l_row, Z + row + panel_col(I, J, col) * ldz, true);
+            cp_async16(ps + col * G_PITCH + l_row, src + panel_col(pf_I, pf_J, col) * ldz, true);
+        }
+        if (++pf_chunk == nchunk) {
+            pf_chunk = 0;
+            ++pf_pair;
+            if (pf_pair < npairs) rr_pair(nb, step, pf_pair, pf_I, pf_J);
         }
     };
 
@@ -170,16 +175,16 @@ __global__ void __launch_bounds__(256, 2)
 
 #pragma unroll
     for (int s = 0; s < G_NST - 1; ++s) {
-        if (s < nitems) load_item(s, s);
+        if (s < nitems) load_next(s);
         cp_async_commit();
     }
-    const int first_pair = (nitems > 0) ? lo / nchunk : 0;
+    int pair = first_pair, chunk = lo - first_pair * nchunk;
     for (int it = 0; it < nitems; ++it) {
         cp_async_wait<G_NST - 2>();
         __syncthreads();
         {
             int nx = it + G_NST - 1;
-            if (nx < nitems) load_item(nx, nx % G_NST);
+            if (nx < nitems) load_next(nx % G_NST);
             cp_async_commit();
         }
         const c128* ps = Ps + (size_t)(it % G_NST) * JP * G_PITCH;
@@ -193,8 +198,7 @@ __global__ void __launch_bounds__(256, 2)
             case 6: gram_mma_chunk<6, CROSS>(ps, g, t, cr, ci); break;
             default: gram_mma_chunk<7, CROSS>(ps, g, t, cr, ci); break;
         }
-        int pair = (lo + it) / nchunk;
-        bool last_of_pair = (it + 1 == nitems) || ((lo + it + 1) / nchunk != pair);
+        const bool last_of_pair = (it + 1 == nitems) || (chunk + 1 == nchunk);
         if (last_of_pair) {
             c128* out = Gpart + ((size_t)2 * blockIdx.x + (pair != first_pair ? 1 : 0)) * (JP * JP);
             switch (warp) {
@@ -207,6 +211,10 @@ __global__ void __launch_bounds__(256, 2)
                 case 6: gram_flush<6, CROSS>(out, g, t, cr, ci); break;
                 default: gram_flush<7, CROSS>(out, g, t, cr, ci); break;
             }
+        }
+        if (++chunk == nchunk) {
+            chunk = 0;
+            ++pair;
         }
     }
     cp_async_wait<0>();
@@ -497,119 +505,134 @@ __global__ void __launch_bounds__(EVD_THREADS, 1)
 }
 
 // ---------------------------------------------------------------------------------------------
-// update kernel: X_p <- X_p W_p in place.  Work items are (pair, 64-row chunk), flattened pair-major and cut into
-// equal contiguous ranges over a persistent grid of #SM CTAs (1024 items over 148 CTAs at chi = 1024: no tail
-// wave).  W_p stays in shared memory while the CTA walks the chunks of a pair (reloaded at most once), chunks
-// are double buffered with cp.async, results go straight from the DMMA accumulators to global memory.
-constexpr int U_ZP = 66, U_WP = 68;
-constexpr size_t UPD_SMEM = (size_t)(JP * U_WP + 2 * JP * U_ZP) * sizeof(c128);
+// update kernel: X_p <- X_p W_p in place.  Work items are (pair, 32-row chunk), flattened pair-major and cut into
+// equal contiguous ranges over a persistent grid of 2 x #SM CTAs (2048 items over 296 CTAs at chi = 1024: no tail
+// wave).  Each of the 8 warps owns 8 output columns and keeps ITS 64 x 8 slice of W_p in registers as DMMA B
+// fragments (16 complex per lane) for as long as the CTA stays on the pair, so shared memory holds nothing but
+// the 3-stage cp.async ring of chunks (102 KB): two CTAs fit on an SM and the prologue, barrier and store phases of
+// one overlap the DMMA stream of the other.  Results go straight from the accumulators to global memory.
+constexpr int U_ROWS = 32, U_ZP = 34, U_NST = 3;  // pitch = 2 mod 8 (in c128): conflict-free 16-byte fragment loads
+constexpr size_t UPD_SMEM = (size_t)U_NST * JP * U_ZP * sizeof(c128);
+constexpr int UPD_THREADS = 256;
 
-constexpr int UPD_THREADS = 512;  // 16 warps = 4 per SMSP: enough to hide the fragment loads and the barriers
-
-__global__ void __launch_bounds__(UPD_THREADS, 1)
+__global__ void __launch_bounds__(UPD_THREADS, 2)
     jacobi_update_kernel(c128* __restrict__ Z, int64_t ldz, int nb, int step, const c128* __restrict__ Wg,
                          const int* __restrict__ flags, int npairs, int nchunk) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    c128* Ws = reinterpret_cast<c128*>(smem_raw);  // [n][k] pitch 68
-    c128* Zs = Ws + JP * U_WP;                     // [2][col][row] pitch 66
+    c128* Zs = reinterpret_cast<c128*>(smem_raw);  // [stage][col][row] pitch 34
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int total = npairs * nchunk;
     int lo, hi;
     gram_item_range(blockIdx.x, gridDim.x, total, lo, hi);
 
-    const int l_row = tid & 63, l_col0 = tid >> 6;
-    auto load_chunk = [&](int item, int st) {
+    // The items of a CTA are walked by two cursors (compute, and prefetch U_NST - 1 items ahead) that carry
+    // (pair, chunk, I, J) incrementally: no division and no global load on the critical path.  The "pair is already
+    // orthogonal (W = I)" flags of the <= 32 pairs a range can touch are fetched once into a bit mask.
+    const int p0 = (lo < hi) ? lo / nchunk : 0;
+    unsigned amask;
+    {
+        const int p = p0 + lane;
+        const int f = (lo < hi && p < npairs) ? flags[p] : 0;
+        amask = __ballot_sync(0xffffffffu, f != 0);
+    }
+    struct Cursor {
+        int item, pair, chunk, I, J;
+    };
+    auto pair_active = [&](int pair) {
+        const int d = pair - p0;
+        return d < 32 ? ((amask >> d) & 1u) != 0 : flags[pair] != 0;
+    };
+    auto settle = [&](Cursor& c) {  // skip the pairs with W = I, then resolve the block indices of the pair
+        while (c.item < hi && !pair_active(c.pair)) {
+            c.item += nchunk - c.chunk;
+            c.chunk = 0;
+            ++c.pair;
+        }
+        if (c.item < hi) rr_pair(nb, step, c.pair, c.I, c.J);
+    };
+    auto advance = [&](Cursor& c) {
+        ++c.item;
+        if (++c.chunk == nchunk) {
+            c.chunk = 0;
+            ++c.pair;
+            settle(c);
+        }
+    };
+    const int l_row = tid & 31, l_col0 = tid >> 5;
+    auto load_chunk = [&](const Cursor& c, int st) {
         c128* zs = Zs + (size_t)st * JP * U_ZP;
-        int pair = item / nchunk, chunk = item - pair * nchunk;
-        int I, J;
-        rr_pair(nb, step, pair, I, J);
-        int64_t row = (int64_t)chunk * 64 + l_row;
+        const c128* src = Z + (int64_t)c.chunk * U_ROWS + l_row;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             int col = l_col0 + 8 * i;
-            cp_async16(zs + col * U_ZP + l_row, Z + row + panel_col(I, J, col) * ldz, true);
+            cp_async16(zs + col * U_ZP + l_row, src + panel_col(c.I, c.J, col) * ldz, true);
         }
     };
-    // skip the items of pairs that are already orthogonal (W = I)
-    auto next_active = [&](int item) {
-        while (item < hi && !flags[item / nchunk]) item = (item / nchunk + 1) * nchunk;
-        return min(item, hi);
-    };
 
-    const int wi = warp & 3, wj = warp >> 2;  // 16 rows x 16 columns per warp
-    int cur_pair = -1, stage = 0;
-    int item = next_active(lo);
-    if (item < hi) load_chunk(item, 0);
-    cp_async_commit();
-    while (item < hi) {
-        const int pair = item / nchunk, chunk = item - pair * nchunk;
-        if (pair != cur_pair) {
-            __syncthreads();  // every warp is done with the previous W
-            const c128* wsrc = Wg + (size_t)pair * (JP * JP);
+    Cursor cur{lo, p0, lo - p0 * nchunk, 0, 1};
+    settle(cur);
+    Cursor pf = cur;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                int e = tid + UPD_THREADS * i;
-                cp_async16(Ws + (e >> 6) * U_WP + (e & 63), wsrc + e, true);
-            }
-            cp_async_commit();
-            cp_async_wait<0>();  // W (and the current chunk) have landed
-            cur_pair = pair;
+    for (int s = 0; s < U_NST - 1; ++s) {
+        if (pf.item < hi) {
+            load_chunk(pf, s);
+            advance(pf);
+        }
+        cp_async_commit();
+    }
+    int cur_pair = -1, stage = 0;
+    c128 breg[JP / 4];  // W[kk*4 + t][warp*8 + g], kk = 0..15
+    while (cur.item < hi) {
+        if (cur.pair != cur_pair) {
+            const c128* wsrc = Wg + (size_t)cur.pair * (JP * JP) + (warp * 8 + g) * JP + t;
+#pragma unroll
+            for (int kk = 0; kk < JP / 4; ++kk) breg[kk] = wsrc[kk * 4];
+            cur_pair = cur.pair;
         }
         // ONE barrier per chunk: it publishes the landed chunk AND says every warp has left the previous chunk,
         // whose buffer the prefetch below overwrites
-        cp_async_wait<0>();
+        cp_async_wait<U_NST - 2>();
         __syncthreads();
-        const int nxt = next_active(item + 1);
-        if (nxt < hi) load_chunk(nxt, stage ^ 1);
+        if (pf.item < hi) {
+            load_chunk(pf, (stage + U_NST - 1) % U_NST);
+            advance(pf);
+        }
         cp_async_commit();
-        int I, J;
-        rr_pair(nb, step, pair, I, J);
-        const c128* za = Zs + (size_t)stage * JP * U_ZP + wi * 16 + g;
-        const c128* wb = Ws + (wj * 16 + g) * U_WP + t;
-        double cr[2][2][2], ci[2][2][2];
+        const c128* za = Zs + (size_t)stage * JP * U_ZP + g;
+        double cr[4][2], ci[4][2];
 #pragma unroll
-        for (int a = 0; a < 2; ++a)
+        for (int a = 0; a < 4; ++a) cr[a][0] = cr[a][1] = ci[a][0] = ci[a][1] = 0.0;
 #pragma unroll
-            for (int b = 0; b < 2; ++b) cr[a][b][0] = cr[a][b][1] = ci[a][b][0] = ci[a][b][1] = 0.0;
-#pragma unroll 4
         for (int kk = 0; kk < JP / 4; ++kk) {
-            double ar[2], ai[2], nai[2], br[2], bi[2];
+            const double br = breg[kk].x, bi = breg[kk].y;
+            double ar[4], ai[4];
 #pragma unroll
-            for (int a = 0; a < 2; ++a) {
+            for (int a = 0; a < 4; ++a) {
                 c128 v = za[(kk * 4 + t) * U_ZP + a * 8];
                 ar[a] = v.x;
                 ai[a] = v.y;
-                nai[a] = -v.y;
             }
 #pragma unroll
-            for (int b = 0; b < 2; ++b) {
-                c128 v = wb[b * 8 * U_WP + kk * 4];
-                br[b] = v.x;
-                bi[b] = v.y;
+            for (int a = 0; a < 4; ++a) {
+                dmma884(cr[a], ar[a], br);
+                dmma884(ci[a], ar[a], bi);
             }
 #pragma unroll
-            for (int a = 0; a < 2; ++a)
-#pragma unroll
-                for (int b = 0; b < 2; ++b) {
-                    dmma884(cr[a][b], ar[a], br[b]);
-                    dmma884(ci[a][b], ar[a], bi[b]);
-                    dmma884(cr[a][b], nai[a], bi[b]);
-                    dmma884(ci[a][b], ai[a], br[b]);
-                }
+            for (int a = 0; a < 4; ++a) {
+                dmma884(cr[a], -ai[a], bi);
+                dmma884(ci[a], ai[a], br);
+            }
         }
-        int64_t r0 = (int64_t)chunk * 64 + wi * 16 + g;
+        const int64_t r0 = (int64_t)cur.chunk * U_ROWS + g;
 #pragma unroll
-        for (int a = 0; a < 2; ++a)
+        for (int h = 0; h < 2; ++h) {
+            c128* zc = Z + r0 + panel_col(cur.I, cur.J, warp * 8 + 2 * t + h) * ldz;
 #pragma unroll
-            for (int b = 0; b < 2; ++b)
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    int n = wj * 16 + b * 8 + 2 * t + h;
-                    Z[r0 + a * 8 + panel_col(I, J, n) * ldz] = make_double2(cr[a][b][h], ci[a][b][h]);
-                }
-        stage ^= 1;
-        item = nxt;
+            for (int a = 0; a < 4; ++a) zc[a * 8] = make_double2(cr[a][h], ci[a][h]);
+        }
+        stage = (stage + 1) % U_NST;
+        advance(cur);
     }
     cp_async_wait<0>();
 }
@@ -1011,10 +1034,10 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
         ctx->launches++;
     }
 
-    // persistent grids: gram 2 CTAs per SM, update 1 per SM, never more CTAs than work items
-    const int g_nchunk = st->mp / G_BKR, u_nchunk = (int)(st->ldz / 64);
+    // persistent grids: gram and update 2 CTAs per SM, never more CTAs than work items
+    const int g_nchunk = st->mp / G_BKR, u_nchunk = (int)(st->ldz / U_ROWS);
     const int gram_ctas = std::max(1, std::min(2 * ctx->sm_count, npairs * g_nchunk));
-    const int upd_ctas = std::max(1, std::min(ctx->sm_count, npairs * u_nchunk));
+    const int upd_ctas = std::max(1, std::min(2 * ctx->sm_count, npairs * u_nchunk));
 
     c128* Gpart = ws.get<c128>((size_t)2 * gram_ctas * JP * JP);
     c128* Wg = ws.get<c128>((size_t)npairs * JP * JP);
@@ -1280,8 +1303,8 @@ int32_t qb_cholqr_panel_step(qb200_ctx* ctx, c128* P, int64_t ld, int64_t m, c12
     QB_LAUNCH_CHECK(ctx);
     panel_chol_kernel<<<1, 256, CHOL_SMEM, ctx->stream>>>(Gpart, gram_ctas, nchunk, Wbuf, R, ldr, flags_dev, fail_dev, 1e-11);
     QB_LAUNCH_CHECK(ctx);
-    const int u_nchunk = mp / 64;
-    const int upd_ctas = std::max(1, std::min(ctx->sm_count, u_nchunk));
+    const int u_nchunk = mp / U_ROWS;
+    const int upd_ctas = std::max(1, std::min(2 * ctx->sm_count, u_nchunk));
     jacobi_update_kernel<<<upd_ctas, UPD_THREADS, UPD_SMEM, ctx->stream>>>(P, ld, 2, -1, Wbuf, flags_dev, 1, u_nchunk);
     QB_LAUNCH_CHECK(ctx);
     return QB200_OK;
