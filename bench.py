@@ -315,9 +315,10 @@ def run_b200(args):
             svd_cnt, svd_ms, svd_work = pp["svd"]
             roof = {"bound": "tensor", "kernel": "jacobi_update_kernel (FP64 DMMA)", "achieved": ach, "peak": peak_tf,
                     "unit": "TFLOP/s", "frac": ach / peak_tf,
-                    "traffic": 71.3e6, "traffic_note": "dram read+write bytes per launch from the ncu --set full capture "
-                                                      "profiles/r1_update_full_summary.txt (algorithmic: 2 x 32 MiB of X "
-                                                      "+ 2 MiB of W per launch)",
+                    "traffic": 79.3e6, "traffic_note": "dram read (69.3 MB) + write (10.0 MB) bytes per launch from the "
+                                                      "ncu --set full capture profiles/r1_final2_ncu_update_gram_summary.txt "
+                                                      "(algorithmic: 2 x 32 MiB of X + 2 MiB of W per launch; most "
+                                                      "of the written X stays in the 126 MB L2)",
                     "peak_source": "measured here: DMMA m8n8k4 issue-bound micro-benchmark (qb200_bench_dmma_peak); "
                                    "MEASURED_PEAKS.json has no FP64 figure",
                     "launches": cnt, "avg_launch_ms": pms / cnt, "share_of_step": pms / tot_ms,
