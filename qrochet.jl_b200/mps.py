@@ -59,6 +59,16 @@ class B200MPS:
         check(ctx.h, lib.qb200_mps_set_form(h, form))
         return self
 
+    @classmethod
+    def from_product(cls, ctx: Context, vectors) -> "B200MPS":
+        """`convert(Chain, ::Product)` (Chain.jl:174-183): a product state |v_1> ... |v_n> as a bond-dimension-1 chain.
+        `a.overlap(b)` with it is the reference's `overlap(::Product, ::Chain)` (Chain.jl:751-752)."""
+        vecs = [np.asarray(v, dtype=np.complex128).reshape(-1) for v in vectors]
+        if len(vecs) < 2:
+            raise ValueError("a chain needs at least two sites")
+        sites = [np.asfortranarray(v.reshape(1, -1, 1)) for v in vecs]
+        return cls.from_sites(ctx, sites)
+
     def site_into(self, s: int, out: np.ndarray):
         """Download site s into a caller-provided (pinned) Fortran-ordered buffer."""
         check(self.ctx.h, lib.qb200_mps_get_site(self.ctx.h, self.h, s, out.ctypes.data_as(C.c_void_p)))

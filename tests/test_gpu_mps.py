@@ -229,6 +229,29 @@ def test_evolve_layer_equals_sequential_evolve(qb, ctx):
         g1.evolve_layer([gates[0], gates[1]], [3, 4], maxdim=16)   # adjacent bonds do not commute
 
 
+def test_product_state_as_chain_and_its_overlap(qb, ctx):
+    """convert(Chain, Product) (Chain.jl:174-183) and overlap(Product, Chain) = <chain|product> (Chain.jl:751-752)
+    against dense vectors."""
+    from oracle import circuit as ocirc
+    n = 9
+    rng = np.random.default_rng(41)
+    vecs = [rng.standard_normal(2) + 1j * rng.standard_normal(2) for _ in range(n)]
+    prod = qb.B200MPS.from_product(ctx, vecs)
+    assert prod.bond_dims() == [1] * (n - 1)
+    dense_p = ocirc.product_vector(vecs)
+    assert np.allclose(dense_from_gpu(prod), dense_p, atol=1e-14)
+    o, g = make(qb, ctx, 42, n, 8)
+    dense_c = o.to_dense()
+    want = np.vdot(dense_c, dense_p)                    # overlap(a, b) = <b|a>
+    assert abs(prod.overlap(g) - want) <= OBS_TOL * max(1.0, abs(want))
+    assert abs(g.overlap(prod) - np.conj(want)) <= OBS_TOL * max(1.0, abs(want))
+    assert abs(prod.norm() - np.linalg.norm(dense_p)) <= OBS_TOL * np.linalg.norm(dense_p)
+    # a product state evolves like any chain: one gate, bond 1 -> 2 (rank of the gate across the cut)
+    U = oc.haar_unitary(rng)
+    prod.evolve(np.reshape(U, (2, 2, 2, 2), order="F"), [4, 5])
+    assert prod.bond_dims()[3] == 2
+
+
 def test_evolve_circuit_equals_sequential_evolve(qb, ctx):
     """A gate list in program order with repeated and touching bonds (dependency-scheduled on worker streams) gives
     bit-identical results to the evolve! loop, and matches the oracle."""
