@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
             c128 f = cmul(cconj(tj), s);                          // conj(tau) * s
             for (int r = j + 1 + lane; r < rows; r += 32)
                 T[c * QPITCH + r] = csub(T[c * QPITCH + r], cmul(f, T[j * QPITCH + r]));
+            __syncwarp();  // every lane has read ajc before lane 0 overwrites it
             if (lane == 0) T[c * QPITCH + j] = csub(ajc, f);
         }
         __syncthreads();
@@ -130,6 +131,7 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
             c128 f = cmul(tj, s);
             for (int r = j + 1 + lane; r < rows; r += 32)
                 T[c * QPITCH + r] = csub(T[c * QPITCH + r], cmul(f, T[j * QPITCH + r]));
+            __syncwarp();  // every lane has read ajc before lane 0 overwrites it
             if (lane == 0) T[c * QPITCH + j] = csub(ajc, f);
         }
         __syncthreads();
