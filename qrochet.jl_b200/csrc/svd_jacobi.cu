@@ -1,19 +1,23 @@
-// K5: one-sided block-Jacobi SVD of a ComplexF64 matrix, hand-written for sm_100a.
+// K5: QR-preconditioned one-sided block-Jacobi SVD of a ComplexF64 matrix, hand-written for sm_100a.
 //
-// Work matrix Z = [X ; V] (stacked, column-major, ld = mp + np): X starts as A (zero-padded to
-// mp x np, both multiples of 64), V as the identity.  Columns are grouped in blocks of 32; a step of
-// the round-robin tournament pairs the nb = np/32 blocks into nb/2 disjoint pairs and runs three
-// kernels over all pairs at once:
-//   gram   : G_p = P_p^H P_p (64 x 64) for the panel P_p = [X_I X_J], split along the rows over
-//            several CTAs (DMMA tiles, 3-stage cp.async pipeline), partial sums written per split;
-//   evd    : one CTA per pair sums the partials in a fixed order (deterministic), then runs a
-//            two-sided cyclic Jacobi on the 64 x 64 Hermitian G in shared memory (32 disjoint
-//            rotations per parallel step) and accumulates the rotations into the unitary W_p;
-//   update : [X;V]_p <- [X;V]_p W_p with DMMA tiles, double-buffered over 64-row chunks, in place.
-// nb-1 steps make a sweep; sweeps repeat until the largest |x_i^H x_j| / (|x_i||x_j|) seen in a sweep
-// is below tolerance.  sigma_j = |x_j|, U = X / sigma, V accumulated.  The rotations only ever come
-// from Gram entries of the columns they are applied to, and W_p is a product of exact plane
-// rotations, so singular values keep norm-wise accuracy ~ eps * sigma_1 (same class as LAPACK gesdd).
+// A (m x n), k = min(m, n): B = A (m >= n) or A^H, columns sorted by norm (B0 = B P), B0 = Q R by K4 (qr.cu; only
+// R is kept), and the Jacobi iteration runs on X = R^H (k x k, zero-padded to multiples of 64) -- Drmac-Veselic
+// preconditioning.  Columns are grouped in blocks of 32; a step of the round-robin tournament pairs the
+// nb = np/32 blocks into nb/2 disjoint pairs and runs three kernels over all pairs at once:
+//   gram   : G_p = P_p^H P_p (64 x 64) for the panel P_p = [X_I X_J] -- the full Hermitian-upper Gram at step 0
+//            of a sweep, only the 32 x 32 cross block X_I^H X_J afterwards (the diagonal blocks are carried by
+//            the evd kernel) -- persistent grid over (pair, 32-row chunk) items, DMMA tiles, 3-stage cp.async
+//            pipeline, partial sums written per CTA;
+//   evd    : one CTA per pair sums the partials in a fixed order (deterministic), runs a two-sided cyclic
+//            Jacobi on the 64 x 64 Hermitian G in shared memory (32 disjoint rotations per parallel step)
+//            and leaves the product of the rotations, the unitary W_p; pairs that are already orthogonal
+//            are flagged and skipped by the update;
+//   update : X_p <- X_p W_p in place with DMMA tiles, the W slice of each warp in registers.
+// nb-1 steps make a sweep; sweeps repeat until the largest |x_i^H x_j| / (|x_i||x_j|) seen in a sweep is below
+// tolerance.  sigma_j = |x_j|.  The rotations are NOT accumulated: with R^H = Xn S Vs^H the right factor is
+// V = P Xn and the left factor comes from ONE GEMM, Y = B0 Xn S^-1 (qb_svd_emit).  The rotations only ever come
+// from Gram entries of the columns they are applied to, and W_p is a product of exact plane rotations, so
+// singular values keep norm-wise accuracy ~ eps * sigma_1 (same class as LAPACK gesdd).
 #include <algorithm>
 #include <cmath>
 #include <numeric>
