@@ -226,6 +226,9 @@ int32_t qb200_comm_destroy(qb200_ctx* ctx);
 /* ---- diagnostics --------------------------------------------------------------------------- */
 /* FP64 tensor-core (DMMA m8n8k4) peak micro-benchmark: returns achieved TFLOP/s */
 int32_t qb200_bench_dmma_peak(qb200_ctx* ctx, double* tflops);
+/* legacy warp-level tensor path (mma.sync) peaks, dense, FP32 accumulate: tflops2 = {TF32 m16n8k8, BF16 m16n8k16};
+ * the denominators for the ComplexF32 kernels */
+int32_t qb200_bench_hmma_peak(qb200_ctx* ctx, double* tflops2);
 /* FP64 pipes micro-benchmark: TFLOP/s of {DMMA only, DFMA only, both issued from alternating warps} */
 int32_t qb200_bench_dual_pipe(qb200_ctx* ctx, double* tflops3);
 /* DMMA issue-pattern micro-benchmark: TFLOP/s for {independent accumulators, complex-multiply pattern with register

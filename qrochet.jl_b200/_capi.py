@@ -104,6 +104,7 @@ _protos = {
     "qb200_comm_allreduce_sum": (_i32, [_p, _pdbl, _i32]),
     "qb200_comm_destroy": (_i32, [_p]),
     "qb200_bench_dmma_peak": (_i32, [_p, _pdbl]),
+    "qb200_bench_hmma_peak": (_i32, [_p, _pdbl]),
     "qb200_bench_dual_pipe": (_i32, [_p, _pdbl]),
     "qb200_bench_dmma_patterns": (_i32, [_p, _pdbl]),
 }

@@ -275,13 +275,20 @@ class Chain:
         phys = [nextindex() for _ in range(n)]
         tensors = []
         for k, a in enumerate(arrays):
-            a = np.asarray(a, dtype=np.complex128)
+            a = np.asarray(a)
+            if a.dtype != np.complex64:  # ComplexF32 chains stay ComplexF32 on the device (native float2 tensors)
+                a = a.astype(np.complex128)
             lab = {"o": phys[k], "l": bonds[k - 1] if k > 0 else None, "r": bonds[k] if k < n - 1 else None}
             inds = [lab[c] for c in order if lab[c] is not None]
             assert a.ndim == len(inds)  # Chain.jl:65-67
             tensors.append(Tensor(ctx.array(a), inds))
         self.tn = TensorNetwork(tensors)
         self.sites = {site(k + 1): phys[k] for k in range(n)}
+
+    @property
+    def eltype(self):
+        """Element type of the site tensors (ComplexF64, or ComplexF32 when built from complex64 arrays)."""
+        return np.complex64 if any(t.data.dtype == 1 for t in self.tn.tensors) else np.complex128
 
     # ---- bookkeeping (src/Quantum.jl, src/Ansatz.jl) ----
     def copy(self):
@@ -464,7 +471,7 @@ class Chain:
         lanes = list(lanes)
         k = len(lanes)
         g_inds = [nextindex() for _ in range(2 * k)]
-        g = Tensor(self.ctx.array(np.asarray(gate_array, dtype=np.complex128)), g_inds)
+        g = Tensor(self.ctx.array(np.asarray(gate_array, dtype=self.eltype)), g_inds)
         g_sites = {**{site(l): g_inds[j] for j, l in enumerate(lanes)},
                    **{site(l, True): g_inds[k + j] for j, l in enumerate(lanes)}}
         if not {site(l) for l in lanes} <= set(self.outputs()):

@@ -13,8 +13,8 @@
 typedef double2 c128;
 
 struct qb200_tensor {
-    int32_t dtype;       // arithmetic / storage type on the device (C128 or F64)
-    int32_t user_dtype;  // what the caller asked for: C64 / F32 tensors are widened at upload, narrowed at download
+    int32_t dtype;       // storage type on the device: C128, C64 (native float2) or F64
+    int32_t user_dtype;  // what the caller asked for: F32 vectors are widened to F64 at upload, narrowed at download
     int32_t rank;
     int64_t ext[QB200_MAX_RANK];
     void* data;
@@ -215,3 +215,6 @@ int32_t qb_copy_matrix(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int6
 int32_t qb_apply_gate2(qb200_ctx* ctx, c128* theta, int64_t chil, int64_t chir, const c128* gate_dev);
 int32_t qb_apply_gate1(qb200_ctx* ctx, c128* t, int64_t inner, int64_t p, int64_t outer, const c128* gate_dev);
 int32_t qb_sumsq(qb200_ctx* ctx, const double* x, int64_t n_doubles, double* result_host);
+// ComplexF32 <-> ComplexF64 conversion of `n` dense elements (factorisations of C64 tensors run in FP64)
+int32_t qb_widen_c64(qb200_ctx* ctx, const void* src_float2, c128* dst, int64_t n);
+int32_t qb_narrow_c128(qb200_ctx* ctx, const c128* src, void* dst_float2, int64_t n);

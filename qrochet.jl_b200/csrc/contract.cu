@@ -164,8 +164,9 @@ extern "C" int32_t qb200_contract(qb200_ctx* ctx, const qb200_tensor* A, const i
                                   const int32_t* modesC, const double alpha[2], const double beta[2]) {
     using namespace qb;
     if (!ctx || !A || !B || !C) QB_FAIL(ctx, QB200_E_INVALID, "contract: null argument");
-    if (A->dtype != QB200_C128 || B->dtype != QB200_C128 || C->dtype != QB200_C128)
-        QB_FAIL(ctx, QB200_E_UNSUPPORTED, "contract: ComplexF64 only");
+    const bool c64 = (A->dtype == QB200_C64);
+    if ((A->dtype != QB200_C128 && !c64) || B->dtype != A->dtype || C->dtype != A->dtype)
+        QB_FAIL(ctx, QB200_E_UNSUPPORTED, "contract: operands must all be ComplexF64 or all ComplexF32");
     ContractSpec spec;
     std::string err;
     int32_t r = make_contract_spec(A->rank, A->ext, modesA, B->rank, B->ext, modesB, C->rank, C->ext, modesC, &spec,
@@ -186,5 +187,5 @@ extern "C" int32_t qb200_contract(qb200_ctx* ctx, const qb200_tensor* A, const i
     g.alpha = alpha ? make_double2(alpha[0], alpha[1]) : make_double2(1.0, 0.0);
     g.beta = beta ? make_double2(beta[0], beta[1]) : make_double2(0.0, 0.0);
     g.beta_zero = (g.beta.x == 0.0 && g.beta.y == 0.0);
-    return launch_gemm(ctx, g);
+    return c64 ? launch_gemm_c64(ctx, g) : launch_gemm(ctx, g);
 }

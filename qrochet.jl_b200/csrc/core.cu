@@ -35,6 +35,7 @@ int32_t qb200_create(int32_t device, qb200_ctx** out) {
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
     int32_t r = qb::init_gemm(ctx);
+    if (r == QB200_OK) r = qb::init_gemm_c64(ctx);
     if (r == QB200_OK) r = qb_qr_init(ctx);
     if (r == QB200_OK) r = qb_svd_init(ctx);
     if (r != QB200_OK) {
@@ -172,13 +173,13 @@ static int32_t make_tensor(qb200_ctx* ctx, int32_t dtype, int32_t rank, const in
                            qb200_tensor** out) {
     if (!ctx || !out || rank < 0 || rank > QB200_MAX_RANK) QB_FAIL(ctx, QB200_E_INVALID, "bad tensor rank %d", rank);
     if (dtype < QB200_C128 || dtype > QB200_F32) QB_FAIL(ctx, QB200_E_UNSUPPORTED, "unknown dtype %d", dtype);
-    if ((dtype == QB200_C64 || dtype == QB200_F32) && ptr)
-        QB_FAIL(ctx, QB200_E_UNSUPPORTED, "wrapping external single-precision memory is not supported (arithmetic is FP64)");
+    if (dtype == QB200_F32 && ptr)
+        QB_FAIL(ctx, QB200_E_UNSUPPORTED, "wrapping external Float32 memory is not supported (real vectors are held in FP64)");
     qb200_tensor* t = new qb200_tensor();
-    // ComplexF32 / Float32 tensors are held widened to FP64 on the device: every kernel computes in FP64
-    // (results exceed the reference's 1e-5 ComplexF32 tolerance; native FP32/TF32 tiles are future work)
+    // ComplexF32 tensors are stored natively (float2; contraction on the TF32 tensor path, gemm_c64.cu).  Float32
+    // tensors (Schmidt vectors: a few KB) are held widened to FP64, which is what every scaling kernel consumes.
     t->user_dtype = dtype;
-    dtype = (dtype == QB200_C64) ? QB200_C128 : (dtype == QB200_F32 ? QB200_F64 : dtype);
+    dtype = (dtype == QB200_F32) ? QB200_F64 : dtype;
     t->dtype = dtype;
     t->rank = rank;
     int64_t n = 1;

@@ -183,3 +183,63 @@ extern "C" int32_t qb200_bench_dmma_patterns(qb200_ctx* ctx, double* tflops9) {
         }
     return QB200_OK;
 }
+
+// Legacy warp-level tensor path (mma.sync, SASS HMMA) peak for the ComplexF32 kernels: TF32 m16n8k8 and BF16 m16n8k16
+// with FP32 accumulation, issue-bound, 8 independent accumulator tiles per warp.
+__device__ __forceinline__ void mma_tf32_1688(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) hmma_peak_kernel(float* out, int iters) {
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    uint32_t a[4] = {threadIdx.x, threadIdx.x + 1, threadIdx.x + 2, threadIdx.x + 3}, b[2] = {threadIdx.x * 3, 7};
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (KIND == 0)
+                mma_tf32_1688(acc[i], a, b);
+            else
+                mma_bf16_16816(acc[i], a, b);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += acc[i][0] + acc[i][1] + acc[i][2] + acc[i][3];
+    if (s == 123.456f) out[0] = s;
+}
+
+// tflops2[0] = TF32 m16n8k8, tflops2[1] = BF16 m16n8k16 (dense, FP32 accumulate)
+extern "C" int32_t qb200_bench_hmma_peak(qb200_ctx* ctx, double* tflops2) {
+    if (!ctx || !tflops2) return QB200_E_INVALID;
+    Workspace ws(ctx);
+    float* out = ws.get<float>(1);
+    const int iters = 4096, blocks = ctx->sm_count * 4;
+    for (int kind = 0; kind < 2; ++kind) {
+        double best = 0.0;
+        for (int rep = 0; rep < 4; ++rep) {
+            QB_TRY(qb200_timer_begin(ctx));
+            if (kind == 0)
+                hmma_peak_kernel<0><<<blocks, 256, 0, ctx->stream>>>(out, rep ? iters : 64);
+            else
+                hmma_peak_kernel<1><<<blocks, 256, 0, ctx->stream>>>(out, rep ? iters : 64);
+            QB_LAUNCH_CHECK(ctx);
+            double ms = 0.0;
+            QB_TRY(qb200_timer_end(ctx, &ms));
+            if (!rep) continue;
+            double flops = (double)blocks * 8 * iters * 8.0 * (2.0 * 16 * 8 * (kind ? 16 : 8));
+            best = std::max(best, flops / (ms * 1e-3) / 1e12);
+        }
+        tflops2[kind] = best;
+    }
+    return QB200_OK;
+}

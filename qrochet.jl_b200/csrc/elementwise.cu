@@ -15,15 +15,19 @@ static inline unsigned grid_for(qb200_ctx* ctx, int64_t n, int threads) {
 }
 
 // out[i, j, o] = in[i, j, o] * f(vec[j])
-__global__ void scale_mode_kernel(const c128* __restrict__ in, c128* __restrict__ out, int64_t inner, int64_t d,
+template <typename T>  // T = double2 (ComplexF64) or float2 (ComplexF32); the factor is applied in FP64
+__global__ void scale_mode_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t inner, int64_t d,
                                   int64_t total, const double* __restrict__ vec, int inverse, double atol) {
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (int64_t)gridDim.x * blockDim.x) {
         int64_t j = (idx / inner) % d;
         double v = vec[j];
         if (inverse) v = (fabs(v) > atol) ? 1.0 / v : 0.0;
-        c128 x = in[idx];
-        out[idx] = make_double2(x.x * v, x.y * v);
+        T x = in[idx];
+        T o;
+        o.x = (decltype(o.x))(x.x * v);
+        o.y = (decltype(o.y))(x.y * v);
+        out[idx] = o;
     }
 }
 
@@ -31,7 +35,7 @@ int32_t qb_scale_mode_raw(qb200_ctx* ctx, const c128* in, c128* out, int64_t inn
                           const double* vec, int inverse, double atol) {
     int64_t total = inner * d * outer;
     if (total == 0) return QB200_OK;
-    scale_mode_kernel<<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(in, out, inner, d, total, vec, inverse, atol);
+    scale_mode_kernel<c128><<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(in, out, inner, d, total, vec, inverse, atol);
     QB_LAUNCH_CHECK(ctx);
     return QB200_OK;
 }
@@ -210,13 +214,75 @@ int32_t qb_sumsq(qb200_ctx* ctx, const double* x, int64_t n, double* result_host
     return QB200_OK;
 }
 
+// sum of squares of FP32 data with FP64 accumulation (norm of a ComplexF32 tensor), same two-pass scheme
+__global__ void sumsq_f32_partial_kernel(const float* __restrict__ x, int64_t n, double* __restrict__ partial) {
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double v = (double)x[i];
+        s += v * v;
+    }
+    s = warp_sum(s);
+    __shared__ double sh[32];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) sh[w] = s;
+    __syncthreads();
+    if (w == 0) {
+        s = (lane < (int)(blockDim.x >> 5)) ? sh[lane] : 0.0;
+        s = warp_sum(s);
+        if (lane == 0) partial[blockIdx.x] = s;
+    }
+}
+
+static int32_t qb_sumsq_f32(qb200_ctx* ctx, const float* x, int64_t n, double* result_host) {
+    *result_host = 0.0;
+    if (n == 0) return QB200_OK;
+    Workspace ws(ctx);
+    int blocks = (int)grid_for(ctx, n, 256);
+    double* partial = ws.get<double>((size_t)blocks + 1);
+    if (!partial) QB_FAIL(ctx, QB200_E_CUDA, "norm: workspace allocation failed");
+    sumsq_f32_partial_kernel<<<blocks, 256, 0, ctx->stream>>>(x, n, partial);
+    QB_LAUNCH_CHECK(ctx);
+    sum_final_kernel<<<1, 256, 0, ctx->stream>>>(partial, blocks, partial + blocks);
+    QB_LAUNCH_CHECK(ctx);
+    QB_CUDA(ctx, cudaMemcpyAsync(ctx->scratch_host, partial + blocks, sizeof(double), cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+    QB_CUDA(ctx, qb_stream_sync(ctx));
+    *result_host = ctx->scratch_host[0];
+    return QB200_OK;
+}
+
+__global__ void widen_c64_kernel(const float2* __restrict__ src, c128* __restrict__ dst, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float2 v = src[i];
+        dst[i] = make_double2((double)v.x, (double)v.y);
+    }
+}
+__global__ void narrow_c128_kernel(const c128* __restrict__ src, float2* __restrict__ dst, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        c128 v = src[i];
+        dst[i] = make_float2((float)v.x, (float)v.y);
+    }
+}
+int32_t qb_widen_c64(qb200_ctx* ctx, const void* src, c128* dst, int64_t n) {
+    if (n <= 0) return QB200_OK;
+    widen_c64_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>((const float2*)src, dst, n);
+    QB_LAUNCH_CHECK(ctx);
+    return QB200_OK;
+}
+int32_t qb_narrow_c128(qb200_ctx* ctx, const c128* src, void* dst, int64_t n) {
+    if (n <= 0) return QB200_OK;
+    narrow_c128_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(src, (float2*)dst, n);
+    QB_LAUNCH_CHECK(ctx);
+    return QB200_OK;
+}
+
 // generic gather: out[idx] = in[sum_j coord_j(idx) * stride_j] (optionally conjugated); out is dense
 struct GatherModes {
     int n;
     int64_t ext[QB200_MAX_RANK];
     int64_t stride[QB200_MAX_RANK];
 };
-template <typename T>
+template <typename T, bool CPLX>
 __global__ void gather_kernel(const T* __restrict__ in, T* __restrict__ out, const GatherModes gm, int64_t total,
                               int64_t base, int conj) {
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -228,7 +294,7 @@ __global__ void gather_kernel(const T* __restrict__ in, T* __restrict__ out, con
             off += c * gm.stride[j];
         }
         T v = in[off];
-        if constexpr (sizeof(T) == 16) {
+        if constexpr (CPLX) {
             if (conj) v.y = -v.y;
         }
         out[idx] = v;
@@ -241,10 +307,13 @@ static int32_t gather(qb200_ctx* ctx, const qb200_tensor* A, qb200_tensor* out, 
     for (int j = 0; j < gm.n; ++j) total *= gm.ext[j];
     if (total == 0) return QB200_OK;
     if (A->dtype == QB200_C128)
-        gather_kernel<c128><<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>((const c128*)A->data, (c128*)out->data,
-                                                                                gm, total, base, conj);
+        gather_kernel<c128, true><<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(
+            (const c128*)A->data, (c128*)out->data, gm, total, base, conj);
+    else if (A->dtype == QB200_C64)
+        gather_kernel<float2, true><<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(
+            (const float2*)A->data, (float2*)out->data, gm, total, base, conj);
     else
-        gather_kernel<double><<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(
+        gather_kernel<double, false><<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(
             (const double*)A->data, (double*)out->data, gm, total, base, 0);
     QB_LAUNCH_CHECK(ctx);
     return QB200_OK;
@@ -263,13 +332,22 @@ extern "C" {
 int32_t qb200_scale_mode(qb200_ctx* ctx, const qb200_tensor* A, int32_t mode_pos, const qb200_tensor* vec,
                          int32_t inverse, double atol, qb200_tensor* out) {
     if (!A || !vec || !out || mode_pos < 0 || mode_pos >= A->rank) QB_FAIL(ctx, QB200_E_INVALID, "scale_mode: bad argument");
-    if (A->dtype != QB200_C128 || vec->dtype != QB200_F64 || out->dtype != QB200_C128)
-        QB_FAIL(ctx, QB200_E_UNSUPPORTED, "scale_mode: needs C128 tensor and F64 vector");
+    if ((A->dtype != QB200_C128 && A->dtype != QB200_C64) || vec->dtype != QB200_F64 || out->dtype != A->dtype)
+        QB_FAIL(ctx, QB200_E_UNSUPPORTED, "scale_mode: needs a complex tensor (same type in and out) and a real vector");
     if (vec->numel() != A->ext[mode_pos] || out->numel() != A->numel())
         QB_FAIL(ctx, QB200_E_INVALID, "scale_mode: extent mismatch");
     int64_t inner = 1, outer = 1;
     for (int i = 0; i < mode_pos; ++i) inner *= A->ext[i];
     for (int i = mode_pos + 1; i < A->rank; ++i) outer *= A->ext[i];
+    if (A->dtype == QB200_C64) {
+        int64_t total = inner * A->ext[mode_pos] * outer;
+        if (total == 0) return QB200_OK;
+        scale_mode_kernel<float2><<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(
+            (const float2*)A->data, (float2*)out->data, inner, A->ext[mode_pos], total, (const double*)vec->data, inverse,
+            atol);
+        QB_LAUNCH_CHECK(ctx);
+        return QB200_OK;
+    }
     return qb_scale_mode_raw(ctx, (const c128*)A->data, (c128*)out->data, inner, A->ext[mode_pos], outer,
                              (const double*)vec->data, inverse, atol);
 }
@@ -343,9 +421,13 @@ int32_t qb200_permute(qb200_ctx* ctx, const qb200_tensor* A, const int32_t* perm
 
 int32_t qb200_norm2(qb200_ctx* ctx, const qb200_tensor* A, double* result) {
     if (!A || !result) QB_FAIL(ctx, QB200_E_INVALID, "norm2: bad argument");
-    int64_t nd = A->numel() * (A->dtype == QB200_C128 ? 2 : 1);
     double ss = 0.0;
-    QB_TRY(qb_sumsq(ctx, (const double*)A->data, nd, &ss));
+    if (A->dtype == QB200_C64) {
+        QB_TRY(qb_sumsq_f32(ctx, (const float*)A->data, A->numel() * 2, &ss));
+    } else {
+        int64_t nd = A->numel() * (A->dtype == QB200_C128 ? 2 : 1);
+        QB_TRY(qb_sumsq(ctx, (const double*)A->data, nd, &ss));
+    }
     *result = sqrt(ss);
     return QB200_OK;
 }
@@ -353,6 +435,12 @@ int32_t qb200_norm2(qb200_ctx* ctx, const qb200_tensor* A, double* result) {
 __global__ void scale_all_kernel(c128* x, int64_t n, c128 f) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         x[i] = cmul(x[i], f);
+}
+__global__ void scale_all_c64_kernel(float2* x, int64_t n, c128 f) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        c128 v = cmul(make_double2(x[i].x, x[i].y), f);
+        x[i] = make_float2((float)v.x, (float)v.y);
+    }
 }
 __global__ void scale_all_real_kernel(double* x, int64_t n, double f) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -366,6 +454,9 @@ int32_t qb200_scale(qb200_ctx* ctx, qb200_tensor* A, const double factor[2]) {
     if (A->dtype == QB200_C128)
         scale_all_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>((c128*)A->data, n,
                                                                          make_double2(factor[0], factor[1]));
+    else if (A->dtype == QB200_C64)
+        scale_all_c64_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>((float2*)A->data, n,
+                                                                             make_double2(factor[0], factor[1]));
     else
         scale_all_real_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>((double*)A->data, n, factor[0]);
     QB_LAUNCH_CHECK(ctx);

@@ -3,9 +3,15 @@
 #include "mma.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace qb {
 
+// M3 = 1: 3M complex product (Gauss).  Per complex 8x8x4 tile P += Ar Br, Q += Ai Bi, S += (Ar + Ai)(Br + Bi) and
+// Cr = P - Q, Ci = S - P - Q at the end: 3 DMMA + operand sums (DADD) instead of 4 DMMA.  The component-wise error
+// bound becomes eps (|Ar| + |Ai|)(|Br| + |Bi|) -- norm-wise the same class as the 4M product.  accr/acci/accs hold
+// P/Q/S in that mode.
+template <int M3>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_c128_kernel(const GemmArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     c128* As = reinterpret_cast<c128*>(smem_raw);  // [STAGES][BK][PA]
@@ -95,13 +101,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_c128_kernel(const GemmAr
     };
 
     constexpr int NJ = 2;  // 8-column tiles per warp
-    double accr[4][NJ][2], acci[4][NJ][2];
+    double accr[4][NJ][2], acci[4][NJ][2], accs[M3 ? 4 : 1][NJ][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
             accr[i][j][0] = accr[i][j][1] = 0.0;
             acci[i][j][0] = acci[i][j][1] = 0.0;
+            if constexpr (M3) accs[i][j][0] = accs[i][j][1] = 0.0;
         }
     if (p.acc_init) {
         // C += (+-1) A B: start the accumulators from +-C so that the epilogue is a pure store (the loads overlap
@@ -120,7 +127,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_c128_kernel(const GemmAr
                     if (n >= p.N) continue;
                     c128 v = C[mo + p.cn.at(n)];
                     accr[i][j][h] = sgn * v.x;
-                    acci[i][j][h] = sgn * v.y;
+                    if constexpr (M3) {  // P = c_r, Q = 0, S = c_r + c_i
+                        accs[i][j][h] = sgn * (v.x + v.y);
+                    } else {
+                        acci[i][j][h] = sgn * v.y;
+                    }
                 }
         }
     }
@@ -145,6 +156,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_c128_kernel(const GemmAr
         const c128* bs = Bs + (size_t)(kt % STAGES) * BK * PB + wn * 16 + g;
 #pragma unroll
         for (int kk = 0; kk < BK / 4; ++kk) {
+            if constexpr (M3) {
+                double br[NJ], bi[NJ], bsum[NJ];
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    c128 v = bs[(kk * 4 + t) * PB + j * 8];
+                    br[j] = v.x;
+                    bi[j] = flip_sign(v.y, sgnB);
+                    bsum[j] = br[j] + bi[j];
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    c128 v = as[(kk * 4 + t) * PA + i * 8];
+                    const double ar = v.x, ai = flip_sign(v.y, sgnA), asum = ar + ai;
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) {
+                        dmma884(accr[i][j], ar, br[j]);
+                        dmma884(acci[i][j], ai, bi[j]);
+                        dmma884(accs[i][j], asum, bsum[j]);
+                    }
+                }
+            } else {
             double ar[4], ai[4], nai[4], br[NJ], bi[NJ];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -168,9 +200,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_c128_kernel(const GemmAr
                     dmma884(accr[i][j], nai[i], bi[j]);
                     dmma884(acci[i][j], ai[i], br[j]);
                 }
+            }
         }
     }
     cp_async_wait<0>();
+    if constexpr (M3) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const double P = accr[i][j][h], Q = acci[i][j][h];
+                    accr[i][j][h] = P - Q;
+                    acci[i][j][h] = accs[i][j][h] - P - Q;
+                }
+    }
 
     if (p.ksplit > 1) {
         // split-K: raw partial sums, dense M x N per split; splitk_reduce_kernel finishes the job
@@ -264,7 +309,8 @@ int32_t build_offsets(qb200_ctx* ctx, const ModeList& ml, int64_t total, int64_t
 }
 
 int32_t init_gemm(qb200_ctx* ctx) {
-    QB_CUDA(ctx, cudaFuncSetAttribute(gemm_c128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+    QB_CUDA(ctx, cudaFuncSetAttribute(gemm_c128_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+    QB_CUDA(ctx, cudaFuncSetAttribute(gemm_c128_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
     return QB200_OK;
 }
 
@@ -305,7 +351,11 @@ int32_t launch_gemm(qb200_ctx* ctx, const GemmArgs& args_in) {
         args.acc_init = 1;
     dim3 grid((args.M + BM - 1) / BM, (args.N + BN - 1) / BN, args.ksplit > 1 ? args.ksplit : args.batch);
     if (grid.y > 65535 || grid.z > 65535) QB_FAIL(ctx, QB200_E_UNSUPPORTED, "gemm grid too large");
-    gemm_c128_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, ctx->stream>>>(args);
+    static const bool gemm_3m = [] {  // QB200_GEMM_3M=0 selects the 4-DMMA complex product
+        const char* e = getenv("QB200_GEMM_3M");
+        return !(e && e[0] == '0');
+    }();
+    (gemm_3m ? gemm_c128_kernel<1> : gemm_c128_kernel<0>)<<<grid, GEMM_THREADS, GEMM_SMEM, ctx->stream>>>(args);
     QB_LAUNCH_CHECK(ctx);
     if (args.ksplit > 1) {
         int64_t total = (int64_t)args.M * args.N;

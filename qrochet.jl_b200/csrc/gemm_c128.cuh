@@ -51,6 +51,9 @@ struct ModeList {
 
 int32_t launch_gemm(qb200_ctx* ctx, const GemmArgs& args);
 int32_t init_gemm(qb200_ctx* ctx);  // kernel attributes, once per process (called by qb200_create)
+// ComplexF32 twin (gemm_c64.cu): same GemmArgs, A / B / C / partial point at float2 data
+int32_t launch_gemm_c64(qb200_ctx* ctx, const GemmArgs& args);
+int32_t init_gemm_c64(qb200_ctx* ctx);
 // offsets[idx] = sum_j coord_j(idx) * stride[j], first mode fastest
 int32_t build_offsets(qb200_ctx* ctx, const ModeList& ml, int64_t total, int64_t* out);
 

@@ -335,7 +335,15 @@ extern "C" int32_t qb200_qr(qb200_ctx* ctx, const qb200_tensor* A, const int32_t
     int64_t m, n;
     QB_TRY(qb_matricize(ctx, A, order, nleft, ws, &mat, &m, &n));
     int64_t k = std::min(m, n);
-    if (Q->dtype != QB200_C128 || R->dtype != QB200_C128 || Q->numel() != m * k || R->numel() != k * n)
-        QB_FAIL(ctx, QB200_E_INVALID, "qr: Q must hold rows*k and R k*cols ComplexF64 entries");
+    if (Q->dtype != A->dtype || R->dtype != A->dtype || Q->numel() != m * k || R->numel() != k * n)
+        QB_FAIL(ctx, QB200_E_INVALID, "qr: Q must hold rows*k and R k*cols entries of the type of A");
+    if (A->dtype == QB200_C64) {  // factorised in FP64, factors narrowed to float2
+        c128* Qw = ws.get<c128>((size_t)std::max<int64_t>(m * k, 1));
+        c128* Rw = ws.get<c128>((size_t)std::max<int64_t>(k * n, 1));
+        if (!Qw || !Rw) QB_FAIL(ctx, QB200_E_CUDA, "qr: workspace allocation failed");
+        QB_TRY(qb_qr_matrix(ctx, m, n, mat, m, Qw, m, Rw, k, 2));
+        QB_TRY(qb_narrow_c128(ctx, Qw, Q->data, m * k));
+        return qb_narrow_c128(ctx, Rw, R->data, k * n);
+    }
     return qb_qr_matrix(ctx, m, n, mat, m, (c128*)Q->data, m, (c128*)R->data, k, 2);
 }

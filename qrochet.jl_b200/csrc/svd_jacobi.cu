@@ -519,6 +519,7 @@ constexpr int U_ROWS = 32, U_ZP = 34, U_NST = 3;  // pitch = 2 mod 8 (in c128): 
 constexpr size_t UPD_SMEM = (size_t)U_NST * JP * U_ZP * sizeof(c128);
 constexpr int UPD_THREADS = 256;
 
+template <int M3>
 __global__ void __launch_bounds__(UPD_THREADS, 2)
     jacobi_update_kernel(c128* __restrict__ Z, int64_t ldz, int nb, int step, const c128* __restrict__ Wg,
                          const int* __restrict__ flags, int npairs, int nchunk) {
@@ -604,36 +605,67 @@ __global__ void __launch_bounds__(UPD_THREADS, 2)
         }
         cp_async_commit();
         const c128* za = Zs + (size_t)stage * JP * U_ZP + g;
-        double cr[4][2], ci[4][2];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) cr[a][0] = cr[a][1] = ci[a][0] = ci[a][1] = 0.0;
-#pragma unroll
-        for (int kk = 0; kk < JP / 4; ++kk) {
-            const double br = breg[kk].x, bi = breg[kk].y;
-            double ar[4], ai[4];
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                c128 v = za[(kk * 4 + t) * U_ZP + a * 8];
-                ar[a] = v.x;
-                ai[a] = v.y;
-            }
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                dmma884(cr[a], ar[a], br);
-                dmma884(ci[a], ar[a], bi);
-            }
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                dmma884(cr[a], -ai[a], bi);
-                dmma884(ci[a], ai[a], br);
-            }
-        }
         const int64_t r0 = (int64_t)cur.chunk * U_ROWS + g;
+        if constexpr (M3) {
+            // 3M complex product (Gauss): P = Ar Br, Q = Ai Bi, S = (Ar + Ai)(Br + Bi); Cr = P - Q, Ci = S - P - Q.
+            // 3 DMMA + the operand sums instead of 4 DMMA per complex 8x8x4 tile; the error stays norm-wise
+            // eps (|Ar| + |Ai|)(|Br| + |Bi|), the class the Jacobi update needs.  Two 16-row halves keep the three
+            // accumulator sets inside the 128-register budget of 2 CTAs/SM.
+#pragma unroll 1
+            for (int hh = 0; hh < 2; ++hh) {
+                double pp[2][2], qq[2][2], ss[2][2];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            c128* zc = Z + r0 + panel_col(cur.I, cur.J, warp * 8 + 2 * t + h) * ldz;
+                for (int a = 0; a < 2; ++a) pp[a][0] = pp[a][1] = qq[a][0] = qq[a][1] = ss[a][0] = ss[a][1] = 0.0;
 #pragma unroll
-            for (int a = 0; a < 4; ++a) zc[a * 8] = make_double2(cr[a][h], ci[a][h]);
+                for (int kk = 0; kk < JP / 4; ++kk) {
+                    const double br = breg[kk].x, bi = breg[kk].y, bs = br + bi;
+#pragma unroll
+                    for (int a = 0; a < 2; ++a) {
+                        c128 v = za[(kk * 4 + t) * U_ZP + (hh * 2 + a) * 8];
+                        dmma884(pp[a], v.x, br);
+                        dmma884(qq[a], v.y, bi);
+                        dmma884(ss[a], v.x + v.y, bs);
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    c128* zc = Z + r0 + panel_col(cur.I, cur.J, warp * 8 + 2 * t + h) * ldz;
+#pragma unroll
+                    for (int a = 0; a < 2; ++a)
+                        zc[(hh * 2 + a) * 8] = make_double2(pp[a][h] - qq[a][h], ss[a][h] - pp[a][h] - qq[a][h]);
+                }
+            }
+        } else {
+            double cr[4][2], ci[4][2];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) cr[a][0] = cr[a][1] = ci[a][0] = ci[a][1] = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < JP / 4; ++kk) {
+                const double br = breg[kk].x, bi = breg[kk].y;
+                double ar[4], ai[4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    c128 v = za[(kk * 4 + t) * U_ZP + a * 8];
+                    ar[a] = v.x;
+                    ai[a] = v.y;
+                }
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    dmma884(cr[a], ar[a], br);
+                    dmma884(ci[a], ar[a], bi);
+                }
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    dmma884(cr[a], -ai[a], bi);
+                    dmma884(ci[a], ai[a], br);
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                c128* zc = Z + r0 + panel_col(cur.I, cur.J, warp * 8 + 2 * t + h) * ldz;
+#pragma unroll
+                for (int a = 0; a < 4; ++a) zc[a * 8] = make_double2(cr[a][h], ci[a][h]);
+            }
         }
         stage = (stage + 1) % U_NST;
         advance(cur);
@@ -916,6 +948,15 @@ struct SvdState {
     std::vector<int> perm;
 };
 
+// QB200_UPDATE_3M=0 selects the 4-DMMA complex product in the update kernel (default: 3M, see the kernel)
+static bool update_3m() {
+    static const bool on = [] {
+        const char* e = getenv("QB200_UPDATE_3M");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
 static unsigned grid_cap(qb200_ctx* ctx, int64_t n, int threads) {
     int64_t b = (n + threads - 1) / threads, cap = (int64_t)ctx->sm_count * 16;
     return (unsigned)std::max<int64_t>(1, std::min(b, cap));
@@ -956,7 +997,8 @@ int32_t qb_svd_init(qb200_ctx* ctx) {
     QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_gram_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRAM_SMEM));
     QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_gram_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRAM_SMEM));
     QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_evd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EVD_SMEM));
-    QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM));
+    QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_update_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM));
+    QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_update_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM));
     QB_CUDA(ctx, cudaFuncSetAttribute(panel_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)((size_t)2 * JP * GLD * sizeof(c128))));
     return QB200_OK;
@@ -1087,7 +1129,7 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
             }
             {
                 PhaseTimer pt(ctx, QB_PH_JUPDATE, 8.0 * npairs * (double)st->ldz * JP * JP);  // ldz = rows of X
-                jacobi_update_kernel<<<upd_ctas, UPD_THREADS, UPD_SMEM, ctx->stream>>>(st->Z, st->ldz, nb, step, Wg, flags,
+                (update_3m() ? jacobi_update_kernel<1> : jacobi_update_kernel<0>)<<<upd_ctas, UPD_THREADS, UPD_SMEM, ctx->stream>>>(st->Z, st->ldz, nb, step, Wg, flags,
                                                                               npairs, u_nchunk);
             }
             ctx->launches += 3;
@@ -1228,7 +1270,8 @@ extern "C" int32_t qb200_svd_last_sweeps(qb200_ctx* ctx) { return ctx ? ctx->las
 
 int32_t qb_matricize(qb200_ctx* ctx, const qb200_tensor* A, const int32_t* order, int32_t nleft, Workspace& ws,
                      const c128** mat, int64_t* rows, int64_t* cols) {
-    if (!A || A->dtype != QB200_C128) QB_FAIL(ctx, QB200_E_UNSUPPORTED, "factorisation: ComplexF64 tensor required");
+    if (!A || (A->dtype != QB200_C128 && A->dtype != QB200_C64))
+        QB_FAIL(ctx, QB200_E_UNSUPPORTED, "factorisation: complex tensor required");
     if (nleft < 0 || nleft > A->rank) QB_FAIL(ctx, QB200_E_INVALID, "factorisation: bad nleft");
     bool seen[QB200_MAX_RANK] = {false}, identity = true;
     int64_t r = 1, c = 1;
@@ -1241,18 +1284,32 @@ int32_t qb_matricize(qb200_ctx* ctx, const qb200_tensor* A, const int32_t* order
     }
     *rows = r;
     *cols = c;
-    if (identity) {
+    if (identity && A->dtype == QB200_C128) {
         *mat = (const c128*)A->data;
         return QB200_OK;
     }
     c128* tmp = ws.get<c128>((size_t)A->numel());
     if (!tmp) QB_FAIL(ctx, QB200_E_CUDA, "factorisation: workspace allocation failed");
+    *mat = tmp;
+    if (A->dtype == QB200_C64) {
+        // ComplexF32 tensors are factorised in FP64: permute in FP32 (half the bytes), then widen
+        const void* src = A->data;
+        if (!identity) {
+            float2* p32 = ws.get<float2>((size_t)A->numel());
+            if (!p32) QB_FAIL(ctx, QB200_E_CUDA, "factorisation: workspace allocation failed");
+            qb200_tensor view = *A, outv = *A;
+            outv.data = p32;
+            for (int i = 0; i < A->rank; ++i) outv.ext[i] = A->ext[order[i]];
+            QB_TRY(qb200_permute(ctx, &view, order, &outv));
+            src = p32;
+        }
+        return qb_widen_c64(ctx, src, tmp, A->numel());
+    }
     qb200_tensor view = *A;
     qb200_tensor outv = *A;
     outv.data = tmp;
     for (int i = 0; i < A->rank; ++i) outv.ext[i] = A->ext[order[i]];
     QB_TRY(qb200_permute(ctx, &view, order, &outv));
-    *mat = tmp;
     return QB200_OK;
 }
 
@@ -1265,8 +1322,9 @@ extern "C" int32_t qb200_svd(qb200_ctx* ctx, const qb200_tensor* A, const int32_
     int64_t m, n;
     QB_TRY(qb_matricize(ctx, A, order, nleft, ws, &mat, &m, &n));
     int64_t k = std::min(m, n);
-    if (U->dtype != QB200_C128 || Vc->dtype != QB200_C128 || S->dtype != QB200_F64)
-        QB_FAIL(ctx, QB200_E_INVALID, "svd: U, Vc must be C128 and S F64");
+    const bool c64 = (A->dtype == QB200_C64);
+    if (U->dtype != A->dtype || Vc->dtype != A->dtype || S->dtype != QB200_F64)
+        QB_FAIL(ctx, QB200_E_INVALID, "svd: U, Vc must have the type of A and S must be real");
     if (U->numel() < m * k || Vc->numel() < n * k || S->numel() < k)
         QB_FAIL(ctx, QB200_E_INVALID, "svd: outputs too small (need k = min(rows, cols) columns)");
     SvdState* st = nullptr;
@@ -1280,10 +1338,22 @@ extern "C" int32_t qb200_svd(qb200_ctx* ctx, const qb200_tensor* A, const int32_
         else break;
     double dw = 0.0;
     for (int64_t i = k - 1; i >= kept; --i) dw += sigma[i] * sigma[i];
-    int32_t r = qb_svd_emit(ctx, st, kept, (c128*)U->data, m, (double*)S->data, (c128*)Vc->data, n, 0, nullptr, 0,
-                            nullptr, 1, 1.0);
+    c128 *Uw = (c128*)U->data, *Vw = (c128*)Vc->data;
+    if (c64) {  // factors leave the FP64 factorisation through a workspace and are narrowed to float2
+        Uw = ws.get<c128>((size_t)std::max<int64_t>(m * kept, 1));
+        Vw = ws.get<c128>((size_t)std::max<int64_t>(n * kept, 1));
+        if (!Uw || !Vw) {
+            qb_svd_release(ctx, st);
+            QB_FAIL(ctx, QB200_E_CUDA, "svd: workspace allocation failed");
+        }
+    }
+    int32_t r = qb_svd_emit(ctx, st, kept, Uw, m, (double*)S->data, Vw, n, 0, nullptr, 0, nullptr, 1, 1.0);
     qb_svd_release(ctx, st);
     QB_TRY(r);
+    if (c64) {
+        QB_TRY(qb_narrow_c128(ctx, Uw, U->data, m * kept));
+        QB_TRY(qb_narrow_c128(ctx, Vw, Vc->data, n * kept));
+    }
     // shrink the trailing (bond) extent of the outputs to `kept`
     U->ext[U->rank - 1] = kept;
     Vc->ext[Vc->rank - 1] = kept;
@@ -1309,7 +1379,7 @@ int32_t qb_cholqr_panel_step(qb200_ctx* ctx, c128* P, int64_t ld, int64_t m, c12
     QB_LAUNCH_CHECK(ctx);
     const int u_nchunk = mp / U_ROWS;
     const int upd_ctas = std::max(1, std::min(2 * ctx->sm_count, u_nchunk));
-    jacobi_update_kernel<<<upd_ctas, UPD_THREADS, UPD_SMEM, ctx->stream>>>(P, ld, 2, -1, Wbuf, flags_dev, 1, u_nchunk);
+    (update_3m() ? jacobi_update_kernel<1> : jacobi_update_kernel<0>)<<<upd_ctas, UPD_THREADS, UPD_SMEM, ctx->stream>>>(P, ld, 2, -1, Wbuf, flags_dev, 1, u_nchunk);
     QB_LAUNCH_CHECK(ctx);
     return QB200_OK;
 }

@@ -61,6 +61,12 @@ class Context:
         check(self.h, lib.qb200_bench_dmma_peak(self.h, C.byref(v)))
         return v.value
 
+    def hmma_peak_tflops(self):
+        """(TF32, BF16) dense mma.sync peaks with FP32 accumulation -- denominators of the ComplexF32 kernels."""
+        v = (C.c_double * 2)()
+        check(self.h, lib.qb200_bench_hmma_peak(self.h, v))
+        return float(v[0]), float(v[1])
+
     def svd_last_sweeps(self) -> int:
         return int(lib.qb200_svd_last_sweeps(self.h))
 
@@ -76,7 +82,7 @@ class Context:
     def array(self, host) -> "DeviceArray":
         """`adapt(B200Array, ::Array)`: upload a host array (column-major semantics)."""
         host = np.asarray(host)
-        if host.dtype == np.complex64:       # ComplexF32: widened to FP64 on the device, narrowed at download
+        if host.dtype == np.complex64:       # ComplexF32: native float2 storage, TF32-split tensor-core contraction
             buf, dt = np.asfortranarray(host), capi.C64
         elif host.dtype == np.float32:
             buf, dt = np.asfortranarray(host), capi.F32
@@ -95,7 +101,7 @@ class Context:
 
 
 class DeviceArray:
-    """Dense column-major device array (ComplexF64 or Float64) owned through a qb200_tensor handle."""
+    """Dense column-major device array (ComplexF64, ComplexF32 or real) owned through a qb200_tensor handle."""
 
     def __init__(self, ctx: Context, shape, dtype=capi.C128, _handle=None):
         self.ctx = ctx
@@ -166,7 +172,7 @@ def contract(a: DeviceArray, modes_a, b: DeviceArray, modes_b, modes_c, conj_a=F
     for m, e in zip(modes_b, b.shape):
         ext[m] = e
     if out is None:
-        out = DeviceArray(ctx, tuple(ext[m] for m in modes_c), capi.C128)
+        out = DeviceArray(ctx, tuple(ext[m] for m in modes_c), a.dtype)
     al = (C.c_double * 2)(complex(alpha).real, complex(alpha).imag)
     be = (C.c_double * 2)(complex(beta).real, complex(beta).imag)
     check(ctx.h, lib.qb200_contract(ctx.h, a.h, capi.i32arr(modes_a), int(conj_a), b.h, capi.i32arr(modes_b),
@@ -175,7 +181,7 @@ def contract(a: DeviceArray, modes_a, b: DeviceArray, modes_b, modes_c, conj_a=F
 
 
 def scale_mode(a: DeviceArray, mode_pos: int, vec: DeviceArray, inverse=False, atol=0.0, inplace=False) -> DeviceArray:
-    out = a if inplace else DeviceArray(a.ctx, a.shape, capi.C128)
+    out = a if inplace else DeviceArray(a.ctx, a.shape, a.dtype)
     check(a.ctx.h, lib.qb200_scale_mode(a.ctx.h, a.h, mode_pos, vec.h, int(inverse), float(atol), out.h))
     return out
 
@@ -227,8 +233,8 @@ def qr(a: DeviceArray, order, nleft: int):
     rows = int(np.prod([shape[p] for p in order[:nleft]], dtype=np.int64))
     cols = int(np.prod([shape[p] for p in order[nleft:]], dtype=np.int64))
     k = min(rows, cols)
-    q = DeviceArray(a.ctx, tuple(shape[p] for p in order[:nleft]) + (k,), capi.C128)
-    r = DeviceArray(a.ctx, (k,) + tuple(shape[p] for p in order[nleft:]), capi.C128)
+    q = DeviceArray(a.ctx, tuple(shape[p] for p in order[:nleft]) + (k,), a.dtype)
+    r = DeviceArray(a.ctx, (k,) + tuple(shape[p] for p in order[nleft:]), a.dtype)
     check(a.ctx.h, lib.qb200_qr(a.ctx.h, a.h, capi.i32arr(order), nleft, q.h, r.h))
     return q, r
 
@@ -239,9 +245,9 @@ def svd(a: DeviceArray, order, nleft: int, maxdim: int = 0, threshold: float = -
     rows = int(np.prod([shape[p] for p in order[:nleft]], dtype=np.int64))
     cols = int(np.prod([shape[p] for p in order[nleft:]], dtype=np.int64))
     k = min(rows, cols)
-    u = DeviceArray(a.ctx, tuple(shape[p] for p in order[:nleft]) + (k,), capi.C128)
-    s = DeviceArray(a.ctx, (k,), capi.F64)
-    vc = DeviceArray(a.ctx, tuple(shape[p] for p in order[nleft:]) + (k,), capi.C128)
+    u = DeviceArray(a.ctx, tuple(shape[p] for p in order[:nleft]) + (k,), a.dtype)
+    s = DeviceArray(a.ctx, (k,), capi.F32 if a.dtype == capi.C64 else capi.F64)  # Float32 spectrum for ComplexF32
+    vc = DeviceArray(a.ctx, tuple(shape[p] for p in order[nleft:]) + (k,), a.dtype)
     kept = C.c_int64()
     dw = C.c_double()
     check(a.ctx.h, lib.qb200_svd(a.ctx.h, a.h, capi.i32arr(order), nleft, int(maxdim or 0), float(threshold), u.h, s.h,
