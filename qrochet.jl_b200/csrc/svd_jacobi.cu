@@ -225,6 +225,121 @@ __global__ void __launch_bounds__(256, 2)
 }
 
 // ---------------------------------------------------------------------------------------------
+// low-precision cross Gram (mixed-precision Jacobi): G_IJ = X_I^H X_J from the FP32 shadow copy X32 of X on the
+// TF32 tensor path (mma.sync m16n8k8, FP32 accumulate).  The rotations W_p that the evd kernel derives from a Gram
+// matrix are exact plane rotations whatever the accuracy of that Gram matrix, and X <- X W_p is applied in FP64, so
+// the singular values are untouched by the Gram precision; only the QUALITY of the rotations depends on it.  While
+// the couplings |g_ij| / (|x_i||x_j|) are still >~ 1e-2 (the linear phase: 7-8 of ~11 sweeps) a Gram matrix with
+// ~1e-4 relative noise steers the rotations just as well, at half the bytes and none of the FP64 tensor pipe.
+// The last sweeps (quadratic phase, convergence test) always use the FP64 Gram kernel above.
+// Same work partition, partial-slot convention and cross-block flush as jacobi_gram_kernel<1>.
+constexpr int G32_PITCH = G_BKR + 4;  // in float2: 4 k x 4 m fragment loads of a half warp hit 16 distinct 8-byte banks
+constexpr size_t GRAM32_SMEM = (size_t)G_NST * JP * G32_PITCH * sizeof(float2);
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void hmma1688_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__global__ void __launch_bounds__(256, 2)
+    jacobi_gram32_kernel(const float2* __restrict__ Z32, int64_t ldz, int mp, int nb, int step, int npairs,
+                         c128* __restrict__ Gpart) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* Ps = reinterpret_cast<float2*>(smem_raw);  // [stage][panel column][row], pitch G32_PITCH
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int mi = warp >> 2, nj = warp & 3;  // warp tile: rows (columns of block I) mi*16.., columns (of block J) nj*8..
+    const int nchunk = mp / G_BKR, total = npairs * nchunk;
+    int lo, hi;
+    gram_item_range(blockIdx.x, gridDim.x, total, lo, hi);
+    const int nitems = hi - lo;
+
+    // loader: 16-byte cp.async = two consecutive rows of one column; 64 columns x 16 row pairs = 1024 / 256 threads
+    const int l_rp = tid & 15, l_col0 = tid >> 4;
+    const int first_pair = (nitems > 0) ? lo / nchunk : 0;
+    int pf_pair = first_pair, pf_chunk = lo - first_pair * nchunk, pf_I = 0, pf_J = 1;
+    if (nitems > 0) rr_pair(nb, step, pf_pair, pf_I, pf_J);
+    auto load_next = [&](int st) {
+        float2* ps = Ps + (size_t)st * JP * G32_PITCH;
+        const float2* src = Z32 + (int64_t)pf_chunk * G_BKR + 2 * l_rp;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int col = l_col0 + 16 * i;
+            cp_async16(ps + col * G32_PITCH + 2 * l_rp, src + panel_col(pf_I, pf_J, col) * ldz, true);
+        }
+        if (++pf_chunk == nchunk) {
+            pf_chunk = 0;
+            ++pf_pair;
+            if (pf_pair < npairs) rr_pair(nb, step, pf_pair, pf_I, pf_J);
+        }
+    };
+
+    float cr[4] = {0.f, 0.f, 0.f, 0.f}, ci[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int s = 0; s < G_NST - 1; ++s) {
+        if (s < nitems) load_next(s);
+        cp_async_commit();
+    }
+    int pair = first_pair, chunk = lo - first_pair * nchunk;
+    for (int it = 0; it < nitems; ++it) {
+        cp_async_wait<G_NST - 2>();
+        __syncthreads();
+        {
+            int nx = it + G_NST - 1;
+            if (nx < nitems) load_next(nx % G_NST);
+            cp_async_commit();
+        }
+        const float2* pa = Ps + (size_t)(it % G_NST) * JP * G32_PITCH + (mi * 16 + g) * G32_PITCH + t;
+        const float2* pb = Ps + (size_t)(it % G_NST) * JP * G32_PITCH + (JB + nj * 8 + g) * G32_PITCH + t;
+#pragma unroll
+        for (int kk = 0; kk < G_BKR / 8; ++kk) {
+            uint32_t ar[4], ai[4], nai[4], br[2], bi[2];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {  // a0 = A[g][t], a1 = A[g+8][t], a2 = A[g][t+4], a3 = A[g+8][t+4]; A = X_I^H
+                float2 v = pa[(e & 1) * 8 * G32_PITCH + kk * 8 + 4 * (e >> 1)];
+                ar[e] = to_tf32(v.x);
+                ai[e] = to_tf32(v.y);
+                nai[e] = ai[e] ^ 0x80000000u;
+            }
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {  // b0 = B[t][g], b1 = B[t+4][g]; B = X_J
+                float2 v = pb[kk * 8 + 4 * e];
+                br[e] = to_tf32(v.x);
+                bi[e] = to_tf32(v.y);
+            }
+            // conj(a) b = (ar br + ai bi) + i (ar bi - ai br)
+            hmma1688_tf32(cr, ar, br);
+            hmma1688_tf32(cr, ai, bi);
+            hmma1688_tf32(ci, ar, bi);
+            hmma1688_tf32(ci, nai, br);
+        }
+        const bool last_of_pair = (it + 1 == nitems) || (chunk + 1 == nchunk);
+        if (last_of_pair) {
+            c128* out = Gpart + ((size_t)2 * blockIdx.x + (pair != first_pair ? 1 : 0)) * (JP * JP);
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const int row = mi * 16 + g + 8 * (h >> 1), col = JB + nj * 8 + 2 * t + (h & 1);
+                out[row + JP * col] = make_double2((double)cr[h], (double)ci[h]);
+                out[col + JP * row] = make_double2((double)cr[h], -(double)ci[h]);
+                cr[h] = 0.f;
+                ci[h] = 0.f;
+            }
+        }
+        if (++chunk == nchunk) {
+            chunk = 0;
+            ++pair;
+        }
+    }
+    cp_async_wait<0>();
+}
+
+// ---------------------------------------------------------------------------------------------
 // evd kernel: two-sided Jacobi on the 64 x 64 Hermitian Gram matrix of one block pair.
 //
 // Each parallel step applies 32 disjoint plane rotations J = prod_k J_k:
@@ -522,7 +637,7 @@ constexpr int UPD_THREADS = 256;
 template <int M3>
 __global__ void __launch_bounds__(UPD_THREADS, 2)
     jacobi_update_kernel(c128* __restrict__ Z, int64_t ldz, int nb, int step, const c128* __restrict__ Wg,
-                         const int* __restrict__ flags, int npairs, int nchunk) {
+                         const int* __restrict__ flags, int npairs, int nchunk, float2* __restrict__ Z32) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     c128* Zs = reinterpret_cast<c128*>(smem_raw);  // [stage][col][row] pitch 34
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -629,10 +744,13 @@ __global__ void __launch_bounds__(UPD_THREADS, 2)
                 }
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    c128* zc = Z + r0 + panel_col(cur.I, cur.J, warp * 8 + 2 * t + h) * ldz;
+                    const int64_t zo = r0 + panel_col(cur.I, cur.J, warp * 8 + 2 * t + h) * ldz;
 #pragma unroll
-                    for (int a = 0; a < 2; ++a)
-                        zc[(hh * 2 + a) * 8] = make_double2(pp[a][h] - qq[a][h], ss[a][h] - pp[a][h] - qq[a][h]);
+                    for (int a = 0; a < 2; ++a) {
+                        const double re = pp[a][h] - qq[a][h], im = ss[a][h] - pp[a][h] - qq[a][h];
+                        Z[zo + (hh * 2 + a) * 8] = make_double2(re, im);
+                        if (Z32) Z32[zo + (hh * 2 + a) * 8] = make_float2((float)re, (float)im);  // FP32 shadow (gram32)
+                    }
                 }
             }
         } else {
@@ -662,9 +780,12 @@ __global__ void __launch_bounds__(UPD_THREADS, 2)
             }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                c128* zc = Z + r0 + panel_col(cur.I, cur.J, warp * 8 + 2 * t + h) * ldz;
+                const int64_t zo = r0 + panel_col(cur.I, cur.J, warp * 8 + 2 * t + h) * ldz;
 #pragma unroll
-                for (int a = 0; a < 4; ++a) zc[a * 8] = make_double2(cr[a][h], ci[a][h]);
+                for (int a = 0; a < 4; ++a) {
+                    Z[zo + a * 8] = make_double2(cr[a][h], ci[a][h]);
+                    if (Z32) Z32[zo + a * 8] = make_float2((float)cr[a][h], (float)ci[a][h]);
+                }
             }
         }
         stage = (stage + 1) % U_NST;
@@ -941,6 +1062,7 @@ struct SvdState {
     int64_t ldz;
     c128* Z = nullptr;  // X (mp x np); the rotations are NOT accumulated (see qb_svd_emit)
     c128* B0 = nullptr;  // rb x k: B with its columns sorted by norm (B0 = Q R; Q itself is never needed)
+    float2* Z32 = nullptr;  // FP32 shadow of X for the low-precision Gram of the early sweeps (null: not used)
     std::vector<double> sigma_sorted;
     double* sigma_dev = nullptr;
     int* perm_dev = nullptr;     // sigma order (descending) -> column of Z
@@ -957,6 +1079,18 @@ static bool update_3m() {
     return on;
 }
 
+// QB200_GRAM_LOWP=1 switches the mixed-precision Gram on (TF32 Gram while couplings > LOWP_TOL).  Default OFF:
+// measured on B200 at k = 2048 (profiles/r1b_lowp_gram.txt) the Gram phase drops 19.5 -> 15.0 ms per bond (the
+// per-launch cost is ramp / flush / tail, not DMMA) while the FP32 shadow stores cost the update kernel 3.3 ms:
+// 1.8 % on the sweep, not worth a second code path in the convergence loop.  Kept for the experiment.
+static bool gram_lowp() {
+    static const bool on = [] {
+        const char* e = getenv("QB200_GRAM_LOWP");
+        return e && e[0] == '1';
+    }();
+    return on;
+}
+
 static unsigned grid_cap(qb200_ctx* ctx, int64_t n, int threads) {
     int64_t b = (n + threads - 1) / threads, cap = (int64_t)ctx->sm_count * 16;
     return (unsigned)std::max<int64_t>(1, std::min(b, cap));
@@ -966,6 +1100,7 @@ void qb_svd_release(qb200_ctx* ctx, SvdState* st) {
     if (!st) return;
     if (st->Z) cudaFreeAsync(st->Z, ctx->stream);
     if (st->B0) cudaFreeAsync(st->B0, ctx->stream);
+    if (st->Z32) cudaFreeAsync(st->Z32, ctx->stream);
     if (st->sigma_dev) cudaFreeAsync(st->sigma_dev, ctx->stream);
     if (st->perm_dev) cudaFreeAsync(st->perm_dev, ctx->stream);
     if (st->colperm_dev) cudaFreeAsync(st->colperm_dev, ctx->stream);
@@ -997,6 +1132,7 @@ int32_t qb_svd_init(qb200_ctx* ctx) {
     QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_gram_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRAM_SMEM));
     QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_gram_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRAM_SMEM));
     QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_evd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EVD_SMEM));
+    QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_gram32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRAM32_SMEM));
     QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_update_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM));
     QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_update_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM));
     QB_CUDA(ctx, cudaFuncSetAttribute(panel_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1105,6 +1241,19 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
     col_norm_kernel<<<(st->np + 7) / 8, 256, 0, ctx->stream>>>(st->Z, st->ldz, st->mp, st->np, st->sigma_dev);
     max_reduce_kernel<<<1, 256, 0, ctx->stream>>>(st->sigma_dev, st->np, scale);
     ctx->launches += 2;
+    // mixed-precision Gram (see jacobi_gram32_kernel): sweep 0 runs in FP64 and measures the couplings; while the
+    // largest coupling of the previous sweep is above LOWP_TOL the cross Grams come from the FP32 shadow of X, which
+    // the update kernel keeps in step.  Once below, the iteration is FP64 only for good.
+    const double LOWP_TOL = 1e-2;
+    bool shadow = gram_lowp() && nb >= 8, lowp = false;
+    if (shadow) {
+        if (cudaMallocAsync(&st->Z32, sizeof(float2) * st->ldz * st->np, ctx->stream) != cudaSuccess) {
+            ctx->err = "svd: out of device memory";
+            return fail(QB200_E_CUDA);
+        }
+        int32_t r = qb_narrow_c128(ctx, st->Z, st->Z32, st->ldz * st->np);
+        if (r != QB200_OK) return fail(r);
+    }
     const int max_sweeps = 40;
     int sweep = 0;
     bool converged = false;
@@ -1114,7 +1263,10 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
             const int mode = (nb == 2) ? 0 : (step == 0 ? 1 : 2);
             {
                 PhaseTimer pt(ctx, QB_PH_JGRAM, 8.0 * npairs * (double)st->mp * JP * JP);  // full-product count
-                if (mode == 2)
+                if (mode == 2 && lowp)
+                    jacobi_gram32_kernel<<<gram_ctas, 256, GRAM32_SMEM, ctx->stream>>>(st->Z32, st->ldz, st->mp, nb, step,
+                                                                                      npairs, Gpart);
+                else if (mode == 2)
                     jacobi_gram_kernel<1><<<gram_ctas, 256, GRAM_SMEM, ctx->stream>>>(st->Z, st->ldz, st->mp, nb, step,
                                                                                      npairs, Gpart);
                 else
@@ -1129,8 +1281,8 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
             }
             {
                 PhaseTimer pt(ctx, QB_PH_JUPDATE, 8.0 * npairs * (double)st->ldz * JP * JP);  // ldz = rows of X
-                (update_3m() ? jacobi_update_kernel<1> : jacobi_update_kernel<0>)<<<upd_ctas, UPD_THREADS, UPD_SMEM, ctx->stream>>>(st->Z, st->ldz, nb, step, Wg, flags,
-                                                                              npairs, u_nchunk);
+                (update_3m() ? jacobi_update_kernel<1> : jacobi_update_kernel<0>)<<<upd_ctas, UPD_THREADS, UPD_SMEM, ctx->stream>>>(
+                    st->Z, st->ldz, nb, step, Wg, flags, npairs, u_nchunk, shadow ? st->Z32 : nullptr);
             }
             ctx->launches += 3;
         }
@@ -1141,9 +1293,13 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
         if (e != cudaSuccess) return cuda_fail(e);
         double worst = ctx->scratch_host[0];
         if (getenv("QB200_DEBUG"))
-            fprintf(stderr, "[qb200 svd] %lld x %lld (jacobi on %lld^2, nb %d) sweep %d worst %.3e\n", (long long)m,
-                    (long long)n, (long long)k, nb, sweep, worst);
+            fprintf(stderr, "[qb200 svd] %lld x %lld (jacobi on %lld^2, nb %d) sweep %d%s worst %.3e\n", (long long)m,
+                    (long long)n, (long long)k, nb, sweep, lowp ? " (tf32 gram)" : "", worst);
         if (!(worst > conv_tol)) converged = true;
+        if (shadow) {
+            lowp = worst > LOWP_TOL;
+            if (!lowp) shadow = false;  // quadratic phase ahead: FP64 Gram from here on, the shadow is no longer kept
+        }
     }
     ctx->last_svd_sweeps = sweep;
     if (!converged) {
@@ -1379,7 +1535,7 @@ int32_t qb_cholqr_panel_step(qb200_ctx* ctx, c128* P, int64_t ld, int64_t m, c12
     QB_LAUNCH_CHECK(ctx);
     const int u_nchunk = mp / U_ROWS;
     const int upd_ctas = std::max(1, std::min(2 * ctx->sm_count, u_nchunk));
-    (update_3m() ? jacobi_update_kernel<1> : jacobi_update_kernel<0>)<<<upd_ctas, UPD_THREADS, UPD_SMEM, ctx->stream>>>(P, ld, 2, -1, Wbuf, flags_dev, 1, u_nchunk);
+    (update_3m() ? jacobi_update_kernel<1> : jacobi_update_kernel<0>)<<<upd_ctas, UPD_THREADS, UPD_SMEM, ctx->stream>>>(P, ld, 2, -1, Wbuf, flags_dev, 1, u_nchunk, nullptr);
     QB_LAUNCH_CHECK(ctx);
     return QB200_OK;
 }
