@@ -1,6 +1,8 @@
 // K2/K3/K6/K7/K8: HBM-bound helpers -- mode scale (with pinv), slice, select, conj, permute, norms,
 // gate application on the two-site wave function.  All are single-pass, 16-byte vectorised
 // (one ComplexF64 per access), grid-stride with grids sized as multiples of the SM count.
+#include <algorithm>
+
 #include "common.cuh"
 #include "mma.cuh"
 
@@ -28,6 +30,22 @@ __global__ void scale_mode_kernel(const T* __restrict__ in, T* __restrict__ out,
         o.x = (decltype(o.x))(x.x * v);
         o.y = (decltype(o.y))(x.y * v);
         out[idx] = o;
+    }
+}
+
+// ComplexF32, two elements (16 bytes) per thread
+__global__ void scale_mode_c64x2_kernel(const float4* __restrict__ in, float4* __restrict__ out, int64_t inner, int64_t d,
+                                        int64_t npairs, const double* __restrict__ vec, int inverse, double atol) {
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < npairs;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = 2 * idx;
+        double v0 = vec[(e / inner) % d], v1 = vec[((e + 1) / inner) % d];
+        if (inverse) {
+            v0 = (fabs(v0) > atol) ? 1.0 / v0 : 0.0;
+            v1 = (fabs(v1) > atol) ? 1.0 / v1 : 0.0;
+        }
+        float4 x = in[idx];
+        out[idx] = make_float4((float)(x.x * v0), (float)(x.y * v0), (float)(x.z * v1), (float)(x.w * v1));
     }
 }
 
@@ -171,6 +189,17 @@ int32_t qb_apply_gate1(qb200_ctx* ctx, c128* t, int64_t inner, int64_t p, int64_
 __global__ void sumsq_partial_kernel(const double* __restrict__ x, int64_t n, double* __restrict__ partial) {
     __shared__ double sh[32];
     double acc = 0.0;
+    if (n % 2 == 0 && ((uintptr_t)x & 15) == 0) {  // 16-byte loads, two running sums
+        const double2* x2 = reinterpret_cast<const double2*>(x);
+        double acc2 = 0.0;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n / 2;
+             i += (int64_t)gridDim.x * blockDim.x) {
+            double2 v = x2[i];
+            acc += v.x * v.x;
+            acc2 += v.y * v.y;
+        }
+        acc += acc2;
+    } else
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         double v = x[i];
         acc += v * v;
@@ -217,6 +246,17 @@ int32_t qb_sumsq(qb200_ctx* ctx, const double* x, int64_t n, double* result_host
 // sum of squares of FP32 data with FP64 accumulation (norm of a ComplexF32 tensor), same two-pass scheme
 __global__ void sumsq_f32_partial_kernel(const float* __restrict__ x, int64_t n, double* __restrict__ partial) {
     double s = 0.0;
+    if (n % 4 == 0 && ((uintptr_t)x & 15) == 0) {  // 16-byte loads
+        const float4* x4 = reinterpret_cast<const float4*>(x);
+        double s2 = 0.0;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n / 4;
+             i += (int64_t)gridDim.x * blockDim.x) {
+            float4 v = x4[i];
+            s += (double)v.x * v.x + (double)v.y * v.y;
+            s2 += (double)v.z * v.z + (double)v.w * v.w;
+        }
+        s += s2;
+    } else
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         double v = (double)x[i];
         s += v * v;
@@ -301,11 +341,236 @@ __global__ void gather_kernel(const T* __restrict__ in, T* __restrict__ out, con
     }
 }
 
-static int32_t gather(qb200_ctx* ctx, const qb200_tensor* A, qb200_tensor* out, const GatherModes& gm, int64_t base,
+// Fast path of the gather (every slice / select / conj / permute that fits): modes that are contiguous after one
+// another in the input are merged on the host, ComplexF32 / Float64 data whose fastest output mode is unit-stride in
+// the input moves as 16-byte pairs, indices are 32-bit and decomposed with multiply-high "magic" divisions
+// (q = umulhi(n, mul) >> shr, exact for n < 2^31) instead of 64-bit div/mod chains, and every thread keeps four
+// independent 16-byte loads in flight.  KIND: 0 real, 1 one complex number per element, 2 two complex numbers (float4).
+constexpr int FG_MAX = 16;
+struct FastGather {
+    int n;
+    uint32_t ext[FG_MAX], mul[FG_MAX], shr[FG_MAX];
+    int64_t stride[FG_MAX];
+};
+template <typename T, int KIND>
+__global__ void __launch_bounds__(256) gather_fast_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                          const FastGather fg, uint32_t total, int64_t base, int conj) {
+    constexpr int ILP = 4;
+    for (uint32_t idx0 = blockIdx.x * (256u * ILP) + threadIdx.x; idx0 < total; idx0 += gridDim.x * (256u * ILP)) {
+        T v[ILP];
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) {
+            const uint32_t idx = idx0 + 256u * u;
+            if (idx < total) {
+                uint32_t rem = idx;
+                int64_t off = base;
+                for (int j = 0; j < fg.n - 1; ++j) {
+                    const uint32_t q = fg.ext[j] == 1 ? rem : (__umulhi(rem, fg.mul[j]) >> fg.shr[j]);
+                    off += (int64_t)(rem - q * fg.ext[j]) * fg.stride[j];
+                    rem = q;
+                }
+                off += (int64_t)rem * fg.stride[fg.n - 1];
+                v[u] = in[off];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) {
+            const uint32_t idx = idx0 + 256u * u;
+            if (idx < total) {
+                if constexpr (KIND >= 1) {
+                    if (conj) v[u].y = -v[u].y;
+                }
+                if constexpr (KIND == 2) {
+                    if (conj) v[u].w = -v[u].w;
+                }
+                out[idx] = v[u];
+            }
+        }
+    }
+}
+
+// Transposing gathers (the fastest output mode is strided in the input while another output mode is unit-stride in
+// the input, e.g. permutedims (l,o,r) -> (r,o,l)): 32 x 32 tiles through shared memory so that both the reads (along
+// the input-contiguous mode) and the writes (along the output-contiguous mode) are full 512-byte / 256-byte warp
+// transactions instead of one element per 32-byte sector.  The remaining modes are enumerated per tile.
+struct TileGather {
+    int n;  // modes other than the two tiled ones
+    uint32_t ext[FG_MAX], mul[FG_MAX], shr[FG_MAX];
+    int64_t istride[FG_MAX], ostride[FG_MAX];
+    uint32_t e0, ec, tiles0, tilesc, mul0, shr0, mulc, shrc;
+    int64_t s0;  // input stride of output mode 0 (its output stride is 1)
+    int64_t oc;  // output stride of the input-contiguous mode (its input stride is 1)
+};
+template <typename T, int KIND>
+__global__ void __launch_bounds__(256) gather_tiled_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                           const TileGather tg, uint32_t ntiles, int64_t base, int conj) {
+    __shared__ T tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (uint32_t tid = blockIdx.x; tid < ntiles; tid += gridDim.x) {
+        uint32_t q = tg.tiles0 == 1 ? tid : (__umulhi(tid, tg.mul0) >> tg.shr0);
+        const uint32_t t0 = tid - q * tg.tiles0;
+        uint32_t rest = tg.tilesc == 1 ? q : (__umulhi(q, tg.mulc) >> tg.shrc);
+        const uint32_t tc = q - rest * tg.tilesc;
+        int64_t ioff = base, ooff = 0;
+        for (int j = 0; j < tg.n; ++j) {
+            const uint32_t qq = tg.ext[j] == 1 ? rest : (__umulhi(rest, tg.mul[j]) >> tg.shr[j]);
+            const uint32_t c = rest - qq * tg.ext[j];
+            ioff += (int64_t)c * tg.istride[j];
+            ooff += (int64_t)c * tg.ostride[j];
+            rest = qq;
+        }
+        {
+            const uint32_t ic = tc * 32 + tx;  // along the input-contiguous mode
+#pragma unroll
+            for (int r = 0; r < 32; r += 8) {
+                const uint32_t i0 = t0 * 32 + ty + r;
+                if (i0 < tg.e0 && ic < tg.ec) tile[ty + r][tx] = in[ioff + (int64_t)i0 * tg.s0 + ic];
+            }
+        }
+        __syncthreads();
+        {
+            const uint32_t i0 = t0 * 32 + tx;  // along the output-contiguous mode
+#pragma unroll
+            for (int r = 0; r < 32; r += 8) {
+                const uint32_t ic = tc * 32 + ty + r;
+                if (i0 < tg.e0 && ic < tg.ec) {
+                    T v = tile[tx][ty + r];
+                    if constexpr (KIND >= 1) {
+                        if (conj) v.y = -v.y;
+                    }
+                    out[ooff + i0 + (int64_t)ic * tg.oc] = v;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+static void make_fastdiv(uint32_t d, uint32_t* mul, uint32_t* shr) {
+    if (d <= 1) {
+        *mul = 0;
+        *shr = 0;
+        return;
+    }
+    int l = 0;
+    while ((1ull << l) < d) ++l;  // ceil(log2 d)
+    const int p = 31 + l;
+    *mul = (uint32_t)(((1ull << p) + d - 1) / d);
+    *shr = (uint32_t)(p - 32);
+}
+
+template <typename T, int KIND>
+static void launch_gather_fast(qb200_ctx* ctx, const void* in, void* out, const FastGather& fg, int64_t total, int64_t base,
+                               int conj) {
+    int64_t blocks = (total + 1023) / 1024, cap = (int64_t)ctx->sm_count * 8;
+    gather_fast_kernel<T, KIND><<<(unsigned)std::max<int64_t>(1, std::min(blocks, cap)), 256, 0, ctx->stream>>>(
+        (const T*)in, (T*)out, fg, (uint32_t)total, base, conj);
+}
+
+static int32_t gather(qb200_ctx* ctx, const qb200_tensor* A, qb200_tensor* out, const GatherModes& gm_in, int64_t base,
                       int conj) {
     int64_t total = 1;
-    for (int j = 0; j < gm.n; ++j) total *= gm.ext[j];
+    for (int j = 0; j < gm_in.n; ++j) total *= gm_in.ext[j];
     if (total == 0) return QB200_OK;
+    // merge: drop extent-1 modes, fuse a mode into its predecessor when it continues it contiguously in the input
+    GatherModes gm;
+    gm.n = 0;
+    for (int j = 0; j < gm_in.n; ++j) {
+        if (gm_in.ext[j] == 1) continue;
+        if (gm.n > 0 && gm_in.stride[j] == gm.stride[gm.n - 1] * gm.ext[gm.n - 1]) {
+            gm.ext[gm.n - 1] *= gm_in.ext[j];
+            continue;
+        }
+        gm.ext[gm.n] = gm_in.ext[j];
+        gm.stride[gm.n] = gm_in.stride[j];
+        gm.n++;
+    }
+    if (gm.n == 0) {
+        gm.n = 1;
+        gm.ext[0] = 1;
+        gm.stride[0] = 1;
+    }
+    // transposing gather: tile through shared memory
+    if (gm.n >= 2 && gm.stride[0] != 1 && gm.ext[0] >= 8) {
+        int jc = -1;
+        for (int j = 1; j < gm.n; ++j)
+            if (gm.stride[j] == 1 && gm.ext[j] >= 8) jc = j;
+        const int64_t tiles0 = (gm.ext[0] + 31) / 32, tilesc = jc > 0 ? (gm.ext[jc] + 31) / 32 : 0;
+        int64_t ntiles = tiles0 * tilesc;
+        for (int j = 1; j < gm.n && jc > 0; ++j)
+            if (j != jc) ntiles *= gm.ext[j];
+        if (jc > 0 && gm.n - 2 <= FG_MAX && ntiles < (1ll << 31) && gm.ext[0] < (1ll << 31) && gm.ext[jc] < (1ll << 31)) {
+            TileGather tg;
+            tg.n = 0;
+            int64_t ostr = 1;
+            for (int j = 0; j < gm.n; ++j) {
+                if (j == jc) tg.oc = ostr;
+                if (j != 0 && j != jc) {
+                    tg.ext[tg.n] = (uint32_t)gm.ext[j];
+                    tg.istride[tg.n] = gm.stride[j];
+                    tg.ostride[tg.n] = ostr;
+                    make_fastdiv((uint32_t)gm.ext[j], &tg.mul[tg.n], &tg.shr[tg.n]);
+                    tg.n++;
+                }
+                ostr *= gm.ext[j];
+            }
+            tg.e0 = (uint32_t)gm.ext[0];
+            tg.ec = (uint32_t)gm.ext[jc];
+            tg.s0 = gm.stride[0];
+            tg.tiles0 = (uint32_t)tiles0;
+            tg.tilesc = (uint32_t)tilesc;
+            make_fastdiv(tg.tiles0, &tg.mul0, &tg.shr0);
+            make_fastdiv(tg.tilesc, &tg.mulc, &tg.shrc);
+            const unsigned blocks = (unsigned)std::min<int64_t>(ntiles, (int64_t)ctx->sm_count * 16);
+            if (A->dtype == QB200_C128)
+                gather_tiled_kernel<c128, 1><<<blocks, 256, 0, ctx->stream>>>((const c128*)A->data, (c128*)out->data, tg,
+                                                                              (uint32_t)ntiles, base, conj);
+            else if (A->dtype == QB200_C64)
+                gather_tiled_kernel<float2, 1><<<blocks, 256, 0, ctx->stream>>>(
+                    (const float2*)A->data, (float2*)out->data, tg, (uint32_t)ntiles, base, conj);
+            else
+                gather_tiled_kernel<double, 0><<<blocks, 256, 0, ctx->stream>>>(
+                    (const double*)A->data, (double*)out->data, tg, (uint32_t)ntiles, base, 0);
+            QB_LAUNCH_CHECK(ctx);
+            return QB200_OK;
+        }
+    }
+    // 16-byte pairs for 8-byte element types
+    bool pairs = false;
+    if (A->dtype != QB200_C128 && gm.stride[0] == 1 && gm.ext[0] % 2 == 0 && base % 2 == 0 &&
+        ((uintptr_t)A->data % 16 == 0) && ((uintptr_t)out->data % 16 == 0)) {
+        pairs = true;
+        for (int j = 1; j < gm.n; ++j) pairs = pairs && (gm.stride[j] % 2 == 0);
+    }
+    int64_t vtotal = pairs ? total / 2 : total;
+    if (gm.n <= FG_MAX && vtotal < (1ll << 31)) {
+        FastGather fg;
+        fg.n = gm.n;
+        for (int j = 0; j < gm.n; ++j) {
+            int64_t e = gm.ext[j], st = gm.stride[j];
+            if (pairs) {
+                if (j == 0) e /= 2;
+                else st /= 2;
+            }
+            fg.ext[j] = (uint32_t)e;
+            fg.stride[j] = st;
+            make_fastdiv((uint32_t)e, &fg.mul[j], &fg.shr[j]);
+        }
+        const int64_t vbase = pairs ? base / 2 : base;
+        if (A->dtype == QB200_C128)
+            launch_gather_fast<c128, 1>(ctx, A->data, out->data, fg, vtotal, vbase, conj);
+        else if (A->dtype == QB200_C64 && pairs)
+            launch_gather_fast<float4, 2>(ctx, A->data, out->data, fg, vtotal, vbase, conj);
+        else if (A->dtype == QB200_C64)
+            launch_gather_fast<float2, 1>(ctx, A->data, out->data, fg, vtotal, vbase, conj);
+        else if (pairs)
+            launch_gather_fast<double2, 0>(ctx, A->data, out->data, fg, vtotal, vbase, 0);
+        else
+            launch_gather_fast<double, 0>(ctx, A->data, out->data, fg, vtotal, vbase, 0);
+        QB_LAUNCH_CHECK(ctx);
+        return QB200_OK;
+    }
+    // general fallback (more than 2^31 elements or more than FG_MAX non-mergeable modes): 64-bit index arithmetic
     if (A->dtype == QB200_C128)
         gather_kernel<c128, true><<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(
             (const c128*)A->data, (c128*)out->data, gm, total, base, conj);
@@ -342,6 +607,13 @@ int32_t qb200_scale_mode(qb200_ctx* ctx, const qb200_tensor* A, int32_t mode_pos
     if (A->dtype == QB200_C64) {
         int64_t total = inner * A->ext[mode_pos] * outer;
         if (total == 0) return QB200_OK;
+        if (total % 2 == 0 && (uintptr_t)A->data % 16 == 0 && (uintptr_t)out->data % 16 == 0) {
+            scale_mode_c64x2_kernel<<<grid_for(ctx, total / 2, 256), 256, 0, ctx->stream>>>(
+                (const float4*)A->data, (float4*)out->data, inner, A->ext[mode_pos], total / 2,
+                (const double*)vec->data, inverse, atol);
+            QB_LAUNCH_CHECK(ctx);
+            return QB200_OK;
+        }
         scale_mode_kernel<float2><<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(
             (const float2*)A->data, (float2*)out->data, inner, A->ext[mode_pos], total, (const double*)vec->data, inverse,
             atol);

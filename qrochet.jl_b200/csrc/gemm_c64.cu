@@ -33,11 +33,13 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src, 
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(gmem_src), "r"(sz) : "memory");
 }
 
-// x = hi + lo, both representable in TF32 (10-bit mantissa); the bit patterns are valid mma operands
+// x = hi + lo with hi = x rounded to TF32 (10-bit mantissa, round to nearest done with integer arithmetic: add half a
+// TF32 ulp to the bit pattern, clear the 13 low bits) and lo = x - hi (exact in FP32; the tensor core reads its top
+// 10 mantissa bits).  IADD + LOP3 + FADD run at full rate; cvt.rna.tf32 is a quarter-rate conversion-pipe
+// instruction and two of them per value made the kernel conversion-bound (measured: 45 -> see profiles/).
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-    float r = x - __uint_as_float(hi);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+    hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
 // D(16x8) += A(16x8, row) * B(8x8, col), TF32 inputs, FP32 accumulate.  lane = 4 g + t:

@@ -293,3 +293,37 @@ def test_qr_edge_shapes(qb, ctx, shape):
     k = min(shape)
     assert np.abs(q.conj().T @ q - np.eye(k)).max() < 1e-13
     assert np.abs(q @ r - a).max() < 1e-12 * max(1.0, np.abs(a).max())
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64, np.float64])
+def test_gather_paths_bit_exact(qb, ctx, dtype):
+    """slice / select / conj / permute are pure data movement: bit-exact against NumPy on every code path of the
+    gather -- merged modes, 16-byte pairs, 32-bit magic-number index decomposition, the 32 x 32 tiled transpose
+    (full, ragged and many-mode cases) and extent-1 modes."""
+    rng = np.random.default_rng(77)
+
+    def rnd(*shape):
+        a = rng.standard_normal(shape)
+        if np.issubdtype(dtype, np.complexfloating):
+            a = a + 1j * rng.standard_normal(shape)
+        return a.astype(dtype)
+
+    cases = [((33, 70), (1, 0)), ((64, 64), (1, 0)), ((40, 3, 50), (2, 1, 0)), ((40, 3, 50), (2, 0, 1)),
+             ((9, 8, 7, 10), (3, 1, 0, 2)), ((16, 2, 16), (1, 0, 2)), ((5, 1, 12, 1, 9), (4, 3, 2, 1, 0)),
+             ((2, 2, 2, 2, 2, 2, 2, 2, 2, 2), (9, 0, 8, 1, 7, 2, 6, 3, 5, 4)), ((100,), (0,)), ((8, 129), (1, 0))]
+    for shape, perm in cases:
+        a = rnd(*shape)
+        d = ctx.array(a)
+        assert np.array_equal(qb.permute(d, perm).to_host(), np.transpose(a, perm)), (shape, perm)
+        if np.issubdtype(dtype, np.complexfloating):
+            assert np.array_equal(qb.conj(d).to_host(), a.conj())
+        for pos in range(len(shape)):
+            cnt = max(1, shape[pos] // 2)
+            idx = [slice(None)] * len(shape)
+            idx[pos] = slice(0, cnt)
+            assert np.array_equal(qb.slice_mode(d, pos, cnt).to_host(), a[tuple(idx)]), (shape, pos)
+            idx[pos] = shape[pos] - 1
+            assert np.array_equal(qb.select_mode(d, pos, shape[pos] - 1).to_host(), a[tuple(idx)]), (shape, pos)
+    v = rnd(257)
+    assert abs(qb.norm2(ctx.array(v)) - np.linalg.norm(v.astype(np.complex128 if np.iscomplexobj(v) else np.float64))) \
+        <= 1e-12 * np.linalg.norm(v)
