@@ -103,35 +103,57 @@ __host__ __device__ constexpr GramTiles gram_tile_table() {
     return CROSS ? gram_tiles_cross(W) : gram_tiles(W);
 }
 
+// The cross-block instantiation (CROSS = 1, all but one step of a sweep) uses the 3M complex product:
+// conj(a) b = (P + Q) + i (S - P + Q) with P = ar br, Q = ai bi, S = (ar - ai)(br + bi): 3 DMMA + operand sums per
+// complex 8x8x4 tile instead of 4.  cr / ci / cs then hold P / Q / S until the flush.
 template <int W, int CROSS>
 __device__ __forceinline__ void gram_mma_chunk(const c128* __restrict__ ps, int g, int t, double (&cr)[5][2],
-                                               double (&ci)[5][2]) {
+                                               double (&ci)[5][2], double (&cs)[2][2]) {
     constexpr GramTiles T = gram_tile_table<W, CROSS>();
 #pragma unroll
     for (int kk = 0; kk < G_BKR / 4; ++kk) {
+        if constexpr (CROSS) {
+            // both tiles of a warp share the row tile: one A fragment, two B fragments
+            const c128 a = ps[(T.r[0] * 8 + g) * G_PITCH + t + kk * 4];
+            const double as = a.x - a.y;
 #pragma unroll
-        for (int i = 0; i < T.n; ++i) {
-            c128 a = ps[(T.r[i] * 8 + g) * G_PITCH + t + kk * 4];
-            c128 b = ps[(T.c[i] * 8 + g) * G_PITCH + t + kk * 4];
-            // G = P^H P: A operand is conj(P)
-            dmma884(cr[i], a.x, b.x);
-            dmma884(ci[i], a.x, b.y);
-            dmma884(cr[i], a.y, b.y);
-            dmma884(ci[i], -a.y, b.x);
+            for (int i = 0; i < 2; ++i) {
+                const c128 b = ps[(T.c[i] * 8 + g) * G_PITCH + t + kk * 4];
+                dmma884(cr[i], a.x, b.x);
+                dmma884(ci[i], a.y, b.y);
+                dmma884(cs[i], as, b.x + b.y);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < T.n; ++i) {
+                c128 a = ps[(T.r[i] * 8 + g) * G_PITCH + t + kk * 4];
+                c128 b = ps[(T.c[i] * 8 + g) * G_PITCH + t + kk * 4];
+                // G = P^H P: A operand is conj(P)
+                dmma884(cr[i], a.x, b.x);
+                dmma884(ci[i], a.x, b.y);
+                dmma884(cr[i], a.y, b.y);
+                dmma884(ci[i], -a.y, b.x);
+            }
         }
     }
 }
 
 template <int W, int CROSS>
 __device__ __forceinline__ void gram_flush(c128* __restrict__ out, int g, int t, double (&cr)[5][2],
-                                           double (&ci)[5][2]) {
+                                           double (&ci)[5][2], double (&cs)[2][2]) {
     constexpr GramTiles T = gram_tile_table<W, CROSS>();
 #pragma unroll
     for (int i = 0; i < T.n; ++i) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             int row = T.r[i] * 8 + g, col = T.c[i] * 8 + 2 * t + h;
-            c128 v = make_double2(cr[i][h], ci[i][h]);
+            c128 v;
+            if constexpr (CROSS) {
+                v = make_double2(cr[i][h] + ci[i][h], cs[i][h] - cr[i][h] + ci[i][h]);
+                cs[i][h] = 0.0;
+            } else {
+                v = make_double2(cr[i][h], ci[i][h]);
+            }
             out[row + JP * col] = v;
             if (T.r[i] != T.c[i]) out[col + JP * row] = make_double2(v.x, -v.y);
             cr[i][h] = 0.0;
@@ -173,7 +195,7 @@ __global__ void __launch_bounds__(256, 2)
         }
     };
 
-    double cr[5][2], ci[5][2];
+    double cr[5][2], ci[5][2], cs[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
     for (int i = 0; i < 5; ++i) cr[i][0] = cr[i][1] = ci[i][0] = ci[i][1] = 0.0;
 
@@ -193,27 +215,27 @@ __global__ void __launch_bounds__(256, 2)
         }
         const c128* ps = Ps + (size_t)(it % G_NST) * JP * G_PITCH;
         switch (warp) {
-            case 0: gram_mma_chunk<0, CROSS>(ps, g, t, cr, ci); break;
-            case 1: gram_mma_chunk<1, CROSS>(ps, g, t, cr, ci); break;
-            case 2: gram_mma_chunk<2, CROSS>(ps, g, t, cr, ci); break;
-            case 3: gram_mma_chunk<3, CROSS>(ps, g, t, cr, ci); break;
-            case 4: gram_mma_chunk<4, CROSS>(ps, g, t, cr, ci); break;
-            case 5: gram_mma_chunk<5, CROSS>(ps, g, t, cr, ci); break;
-            case 6: gram_mma_chunk<6, CROSS>(ps, g, t, cr, ci); break;
-            default: gram_mma_chunk<7, CROSS>(ps, g, t, cr, ci); break;
+            case 0: gram_mma_chunk<0, CROSS>(ps, g, t, cr, ci, cs); break;
+            case 1: gram_mma_chunk<1, CROSS>(ps, g, t, cr, ci, cs); break;
+            case 2: gram_mma_chunk<2, CROSS>(ps, g, t, cr, ci, cs); break;
+            case 3: gram_mma_chunk<3, CROSS>(ps, g, t, cr, ci, cs); break;
+            case 4: gram_mma_chunk<4, CROSS>(ps, g, t, cr, ci, cs); break;
+            case 5: gram_mma_chunk<5, CROSS>(ps, g, t, cr, ci, cs); break;
+            case 6: gram_mma_chunk<6, CROSS>(ps, g, t, cr, ci, cs); break;
+            default: gram_mma_chunk<7, CROSS>(ps, g, t, cr, ci, cs); break;
         }
         const bool last_of_pair = (it + 1 == nitems) || (chunk + 1 == nchunk);
         if (last_of_pair) {
             c128* out = Gpart + ((size_t)2 * blockIdx.x + (pair != first_pair ? 1 : 0)) * (JP * JP);
             switch (warp) {
-                case 0: gram_flush<0, CROSS>(out, g, t, cr, ci); break;
-                case 1: gram_flush<1, CROSS>(out, g, t, cr, ci); break;
-                case 2: gram_flush<2, CROSS>(out, g, t, cr, ci); break;
-                case 3: gram_flush<3, CROSS>(out, g, t, cr, ci); break;
-                case 4: gram_flush<4, CROSS>(out, g, t, cr, ci); break;
-                case 5: gram_flush<5, CROSS>(out, g, t, cr, ci); break;
-                case 6: gram_flush<6, CROSS>(out, g, t, cr, ci); break;
-                default: gram_flush<7, CROSS>(out, g, t, cr, ci); break;
+                case 0: gram_flush<0, CROSS>(out, g, t, cr, ci, cs); break;
+                case 1: gram_flush<1, CROSS>(out, g, t, cr, ci, cs); break;
+                case 2: gram_flush<2, CROSS>(out, g, t, cr, ci, cs); break;
+                case 3: gram_flush<3, CROSS>(out, g, t, cr, ci, cs); break;
+                case 4: gram_flush<4, CROSS>(out, g, t, cr, ci, cs); break;
+                case 5: gram_flush<5, CROSS>(out, g, t, cr, ci, cs); break;
+                case 6: gram_flush<6, CROSS>(out, g, t, cr, ci, cs); break;
+                default: gram_flush<7, CROSS>(out, g, t, cr, ci, cs); break;
             }
         }
         if (++chunk == nchunk) {
