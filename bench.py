@@ -235,12 +235,17 @@ def run_b200(args):
     sampler.start()
     ctx.profile(True)
     l0 = ctx.launches
+    svd0 = ctx.svd_totals()
+    step_wall_ms = []
     ctx.timer_begin()
     for _ in range(args.steps):
-        sweep(psi, layer)
+        t_s = time.perf_counter()
+        sweep(psi, layer)  # returns the kept counts: the call ends with the stream drained
+        step_wall_ms.append((time.perf_counter() - t_s) * 1e3)
         layer += 1
     ms = ctx.timer_end()
     launches = ctx.launches - l0
+    svd1 = ctx.svd_totals()
     prof = ctx.profile_read()
     ctx.profile(False)
     barrier()
@@ -337,6 +342,8 @@ def run_b200(args):
                        "l2": f"inputs larger than L2: MPS {mps_bytes / 2**20:.0f} MiB resident in HBM, "
                              f"each bulk bond touches >= 192 MiB",
                        "algorithmic_tflop_per_step": sweep_flops(n, chi) / 1e12, "setup_s": setup_s,
+                       "step_wall_ms": [round(x, 1) for x in step_wall_ms],
+                       "jacobi_sweeps_per_svd": (svd1[1] - svd0[1]) / max(1, svd1[0] - svd0[0]),
                        "norm_after": norm_after},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "sweeps/s", "h2d_bytes_per_step": mps_bytes + lam_bytes + gate_bytes,

@@ -130,6 +130,8 @@ int32_t qb200_svd(qb200_ctx* ctx, const qb200_tensor* A, const int32_t* order, i
                   double* discarded_weight);
 /* statistics of the last qb200_svd on this context: Jacobi sweeps executed */
 int32_t qb200_svd_last_sweeps(qb200_ctx* ctx);
+/* totals over the context and its worker streams since creation: SVDs factorised, Jacobi sweeps executed */
+int32_t qb200_svd_totals(qb200_ctx* ctx, int64_t* calls, int64_t* sweeps);
 
 /* ---- fused MPS path (Chain.jl:460-752 on a device-resident open-boundary MPS) -------------------
  * A qb200_mps owns n site tensors in the private layout (l, o, r) column-major plus the Schmidt

@@ -69,6 +69,7 @@ _protos = {
     "qb200_qr": (_i32, [_p, _p, _pi32, _i32, _p, _p]),
     "qb200_svd": (_i32, [_p, _p, _pi32, _i32, _i64, _dbl, _p, _p, _p, _pi64, _pdbl]),
     "qb200_svd_last_sweeps": (_i32, [_p]),
+    "qb200_svd_totals": (_i32, [_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "qb200_mps_create": (_i32, [_p, _i32, C.POINTER(_p)]),
     "qb200_mps_free": (_i32, [_p, _p]),
     "qb200_mps_copy": (_i32, [_p, _p, C.POINTER(_p)]),

@@ -36,6 +36,7 @@ struct qb200_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int sm_count = 148;
     int last_svd_sweeps = 0;
+    int64_t svd_calls = 0, svd_sweeps = 0;  // totals since creation (this context only; workers are summed by the getter)
     void* nccl_comm = nullptr;
     void* nccl_lib = nullptr;
     double* scratch_host = nullptr;  // pinned, 64 KiB

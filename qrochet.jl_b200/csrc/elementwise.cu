@@ -33,12 +33,13 @@ __global__ void scale_mode_kernel(const T* __restrict__ in, T* __restrict__ out,
     }
 }
 
-// ComplexF32, two elements (16 bytes) per thread
-__global__ void scale_mode_c64x2_kernel(const float4* __restrict__ in, float4* __restrict__ out, int64_t inner, int64_t d,
-                                        int64_t npairs, const double* __restrict__ vec, int inverse, double atol) {
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < npairs;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t e = 2 * idx;
+// ComplexF32, two elements (16 bytes) per thread; IDX = uint32_t when the tensor has < 2^31 elements (32-bit
+// divisions instead of emulated 64-bit ones: the kernel is index-arithmetic bound otherwise)
+template <typename IDX>
+__global__ void scale_mode_c64x2_kernel(const float4* __restrict__ in, float4* __restrict__ out, IDX inner, IDX d,
+                                        IDX npairs, const double* __restrict__ vec, int inverse, double atol) {
+    for (IDX idx = (IDX)blockIdx.x * blockDim.x + threadIdx.x; idx < npairs; idx += (IDX)gridDim.x * blockDim.x) {
+        const IDX e = 2 * idx;
         double v0 = vec[(e / inner) % d], v1 = vec[((e + 1) / inner) % d];
         if (inverse) {
             v0 = (fabs(v0) > atol) ? 1.0 / v0 : 0.0;
@@ -608,9 +609,14 @@ int32_t qb200_scale_mode(qb200_ctx* ctx, const qb200_tensor* A, int32_t mode_pos
         int64_t total = inner * A->ext[mode_pos] * outer;
         if (total == 0) return QB200_OK;
         if (total % 2 == 0 && (uintptr_t)A->data % 16 == 0 && (uintptr_t)out->data % 16 == 0) {
-            scale_mode_c64x2_kernel<<<grid_for(ctx, total / 2, 256), 256, 0, ctx->stream>>>(
-                (const float4*)A->data, (float4*)out->data, inner, A->ext[mode_pos], total / 2,
-                (const double*)vec->data, inverse, atol);
+            if (total < (1ll << 31))
+                scale_mode_c64x2_kernel<uint32_t><<<grid_for(ctx, total / 2, 256), 256, 0, ctx->stream>>>(
+                    (const float4*)A->data, (float4*)out->data, (uint32_t)inner, (uint32_t)A->ext[mode_pos],
+                    (uint32_t)(total / 2), (const double*)vec->data, inverse, atol);
+            else
+                scale_mode_c64x2_kernel<int64_t><<<grid_for(ctx, total / 2, 256), 256, 0, ctx->stream>>>(
+                    (const float4*)A->data, (float4*)out->data, inner, A->ext[mode_pos], total / 2,
+                    (const double*)vec->data, inverse, atol);
             QB_LAUNCH_CHECK(ctx);
             return QB200_OK;
         }

@@ -374,7 +374,11 @@ __global__ void __launch_bounds__(256, 2)
 // (i, 32 + (i + t) mod 32): the blocks of a pair were made orthogonal internally at step 0 of the sweep, so
 // the later steps of a sweep only need the cross rotations -- one outer sweep then rotates every column pair
 // exactly once, like scalar cyclic Jacobi, at a quarter of the shared-memory work of a full inner solve.
-constexpr int EVD_THREADS = 512;
+// 17 warps: warp 0 prepares rotations while 16 warps = 512 threads apply them -- exactly 4 W items per thread -- and
+// the 528 upper 2 x 2 blocks of the G update fit in ONE pass (with 512 threads 16 of them did two: the step took
+// two rounds of a latency-bound block update).
+constexpr int EVD_THREADS = 544;
+constexpr int EVD_LOADERS = 512;  // threads that assemble G (8 elements each)
 constexpr int EVD_NBLK = 32 * 33 / 2;
 constexpr size_t EVD_SMEM = (size_t)2 * JP * GLD * sizeof(c128) + 32 * sizeof(double) + 32 * sizeof(c128) +
                             64 * sizeof(int) + 64 * sizeof(double) + EVD_NBLK * sizeof(short);
@@ -417,14 +421,14 @@ __global__ void __launch_bounds__(EVD_THREADS, 1)
     // carried along exactly by the two-sided update; refreshed from a full Gram at step 0 of every sweep).
     int blkI = 0, blkJ = 0;
     if (Dstore) rr_pair(nb, step, pair, blkI, blkJ);
-    {
+    if (tid < EVD_LOADERS) {
         // 8 elements per thread; the loads of one slot are issued together (memory-level parallelism), slots in order
-        constexpr int PER = JP * JP / EVD_THREADS;
+        constexpr int PER = JP * JP / EVD_LOADERS;
         double sx[PER], sy[PER];
         bool from_d[PER];
 #pragma unroll
         for (int j = 0; j < PER; ++j) {
-            const int e = tid + EVD_THREADS * j, er = e & 63, ec = e >> 6;
+            const int e = tid + EVD_LOADERS * j, er = e & 63, ec = e >> 6;
             from_d[j] = (mode == 2) && ((er < JB) == (ec < JB));
             sx[j] = sy[j] = 0.0;
             if (from_d[j]) {
@@ -438,7 +442,7 @@ __global__ void __launch_bounds__(EVD_THREADS, 1)
             c128 v[PER];
 #pragma unroll
             for (int j = 0; j < PER; ++j)
-                v[j] = from_d[j] ? make_double2(0.0, 0.0) : src[tid + EVD_THREADS * j];
+                v[j] = from_d[j] ? make_double2(0.0, 0.0) : src[tid + EVD_LOADERS * j];
 #pragma unroll
             for (int j = 0; j < PER; ++j) {
                 sx[j] += v[j].x;
@@ -447,7 +451,7 @@ __global__ void __launch_bounds__(EVD_THREADS, 1)
         }
 #pragma unroll
         for (int j = 0; j < PER; ++j) {
-            const int e = tid + EVD_THREADS * j, r = e & 63, c = e >> 6;
+            const int e = tid + EVD_LOADERS * j, r = e & 63, c = e >> 6;
             G[c * GLD + r] = make_double2(sx[j], sy[j]);
             W[c * GLD + r] = make_double2(r == c ? 1.0 : 0.0, 0.0);
         }
@@ -1324,6 +1328,8 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
         }
     }
     ctx->last_svd_sweeps = sweep;
+    ctx->svd_calls++;
+    ctx->svd_sweeps += sweep;
     if (!converged) {
         ctx->err = "svd: Jacobi did not converge within the sweep limit";
         return fail(QB200_E_NOCONVERGE);
@@ -1445,6 +1451,16 @@ int32_t qb_svd_emit(qb200_ctx* ctx, SvdState* st, int64_t kept, c128* U, int64_t
 // ---------------------------------------------------------------------------------------------
 // C-ABI: svd of the (left | right) matricisation of a tensor
 extern "C" int32_t qb200_svd_last_sweeps(qb200_ctx* ctx) { return ctx ? ctx->last_svd_sweeps : -1; }
+extern "C" int32_t qb200_svd_totals(qb200_ctx* ctx, int64_t* calls, int64_t* sweeps) {
+    if (!ctx || !calls || !sweeps) return QB200_E_INVALID;
+    *calls = ctx->svd_calls;
+    *sweeps = ctx->svd_sweeps;
+    for (qb200_ctx* w : ctx->workers) {
+        *calls += w->svd_calls;
+        *sweeps += w->svd_sweeps;
+    }
+    return QB200_OK;
+}
 
 int32_t qb_matricize(qb200_ctx* ctx, const qb200_tensor* A, const int32_t* order, int32_t nleft, Workspace& ws,
                      const c128** mat, int64_t* rows, int64_t* cols) {

@@ -67,6 +67,12 @@ class Context:
         check(self.h, lib.qb200_bench_hmma_peak(self.h, v))
         return float(v[0]), float(v[1])
 
+    def svd_totals(self):
+        """(SVDs factorised, Jacobi sweeps executed) over this context and its worker streams since creation."""
+        a, b = C.c_int64(), C.c_int64()
+        check(self.h, lib.qb200_svd_totals(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def svd_last_sweeps(self) -> int:
         return int(lib.qb200_svd_last_sweeps(self.h))
 
