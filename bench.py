@@ -320,10 +320,14 @@ def run_b200(args):
             svd_cnt, svd_ms, svd_work = pp["svd"]
             roof = {"bound": "tensor", "kernel": "jacobi_update_kernel (FP64 DMMA)", "achieved": ach, "peak": peak_tf,
                     "unit": "TFLOP/s", "frac": ach / peak_tf,
-                    "traffic": 79.3e6, "traffic_note": "dram read (69.3 MB) + write (10.0 MB) bytes per launch from the "
-                                                      "ncu --set full capture profiles/r1_final2_ncu_update_gram_summary.txt "
+                    "traffic": 78.5e6, "traffic_note": "dram read (69.26 MB) + write (9.28 MB) bytes per launch from the "
+                                                      "ncu --set full capture profiles/r1b_ncu_jacobi_summary.txt "
                                                       "(algorithmic: 2 x 32 MiB of X + 2 MiB of W per launch; most "
                                                       "of the written X stays in the 126 MB L2)",
+                    "flop_note": "achieved = ALGORITHMIC flops (8 per complex multiply-add) / time.  The kernel uses the "
+                                 "3M complex product: it executes 6 DMMA flops + 3/32 FP64 adds per complex "
+                                 "multiply-add, so the executed-DMMA fraction of the pipe is 0.75 x frac (ncu: tensor "
+                                 "pipe 65.8 % of elapsed) and frac can exceed 1 only above 4/3",
                     "peak_source": "measured here: DMMA m8n8k4 issue-bound micro-benchmark (qb200_bench_dmma_peak); "
                                    "MEASURED_PEAKS.json has no FP64 figure",
                     "launches": cnt, "avg_launch_ms": pms / cnt, "share_of_step": pms / tot_ms,

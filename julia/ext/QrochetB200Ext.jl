@@ -11,7 +11,11 @@ using Adapt
 using LinearAlgebra
 
 const lib = "libqrochet_b200"          # on LD_LIBRARY_PATH
-const C128 = Int32(0); const F64 = Int32(2)
+const C128 = Int32(0); const C64 = Int32(1); const F64 = Int32(2); const F32 = Int32(3)
+# dtype enum of include/qrochet_b200.h.  ComplexF32 tensors are native float2 on the device (TF32-split tensor-core
+# contraction); Float32 Schmidt vectors are held in FP64.
+dtypecode(::Type{ComplexF64}) = C128; dtypecode(::Type{ComplexF32}) = C64
+dtypecode(::Type{Float64}) = F64;     dtypecode(::Type{Float32}) = F32
 
 mutable struct Context
     h::Ptr{Cvoid}
@@ -39,20 +43,21 @@ mutable struct B200Array{T,N} <: AbstractArray{T,N}
     dims::NTuple{N,Int}
 end
 Base.size(a::B200Array) = a.dims
-function B200Array(x::Array{ComplexF64,N}) where {N}
+const B200Elt = Union{ComplexF64,ComplexF32,Float64,Float32}
+function B200Array(x::Array{T,N}) where {T<:B200Elt,N}
     ctx = context(); r = Ref{Ptr{Cvoid}}(C_NULL)
     check(ctx.h, ccall((:qb200_tensor_alloc, lib), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Int64}, Ref{Ptr{Cvoid}}),
-                       ctx.h, C128, N, collect(Int64, size(x)), r))
+                       ctx.h, dtypecode(T), N, collect(Int64, size(x)), r))
     check(ctx.h, ccall((:qb200_tensor_upload, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), ctx.h, r[], x))
-    a = B200Array{ComplexF64,N}(r[], size(x))
+    a = B200Array{T,N}(r[], size(x))
     finalizer(t -> ccall((:qb200_tensor_free, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), context().h, t.h), a)  # stream-ordered, never blocks
 end
-function Base.Array(a::B200Array{ComplexF64,N}) where {N}
-    out = Array{ComplexF64,N}(undef, a.dims)
+function Base.Array(a::B200Array{T,N}) where {T,N}
+    out = Array{T,N}(undef, a.dims)
     check(context().h, ccall((:qb200_tensor_download, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), context().h, a.h, out))
     out
 end
-Adapt.adapt_storage(::Type{B200Array}, x::Array{ComplexF64}) = B200Array(x)
+Adapt.adapt_storage(::Type{B200Array}, x::Array{<:B200Elt}) = B200Array(x)
 Adapt.adapt_storage(::Type{Array}, x::B200Array) = Array(x)
 # the reference has no adapt method for gates (Dense): add it so evolve! can take device gates
 Adapt.adapt_structure(to, x::Qrochet.Dense) = Qrochet.Dense(adapt(to, Quantum(x)))
@@ -62,7 +67,7 @@ modeids(inds, table) = Int32[get!(table, i, Int32(length(table))) for i in inds]
 function Tenet.contract(a::Tensor{T,N,<:B200Array}, b::Tensor{T,M,<:B200Array}; dims = (∩(inds(a), inds(b)))) where {T,N,M}
     table = Dict{Symbol,Int32}()
     ic = [i for i in vcat(collect(inds(a)), [j for j in inds(b) if j ∉ inds(a)]) if i ∉ dims]
-    c = B200Array(Array{ComplexF64}(undef, (i -> i ∈ inds(a) ? size(a, i) : size(b, i)).(ic)...))
+    c = B200Array(Array{T}(undef, (i -> i ∈ inds(a) ? size(a, i) : size(b, i)).(ic)...))   # T = ComplexF64 or ComplexF32 (same in, same out)
     check(context().h, ccall((:qb200_contract, lib), Int32,
         (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int32}, Int32, Ptr{Cvoid}, Ptr{Int32}, Int32, Ptr{Cvoid}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}),
         context().h, parent(a).h, modeids(inds(a), table), 0, parent(b).h, modeids(inds(b), table), 0, c.h, modeids(ic, table),

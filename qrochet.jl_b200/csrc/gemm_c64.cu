@@ -66,6 +66,12 @@ struct Frag32B {  // one 8 x 8 complex B fragment; nih / nil hold -imag (for the
     uint32_t rh[2], rl[2], ih[2], il[2], nih[2], nil[2];
 };
 
+// AFFINE = true: none of the M / N / K parts needs an offset table (plain strided matrices, or mode groups that
+// merged into one stride).  The loader then walks K with one pointer increment per element and stage instead of
+// re-deriving every address (64-bit multiply-adds, table-or-stride branches: ~100 instructions per element, which
+// made the kernel issue-bound at 48 % of the HMMA pipe -- the TF32 pipe is 4x faster per flop than DMMA, so the
+// loader overhead the ComplexF64 kernel hides shows here).
+template <bool AFFINE>
 __global__ void __launch_bounds__(F_THREADS, 1) gemm_c64_kernel(const GemmArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* As = reinterpret_cast<float2*>(smem_raw);  // [FSTAGES][FBK][FPA]
@@ -131,22 +137,54 @@ __global__ void __launch_bounds__(F_THREADS, 1) gemm_c64_kernel(const GemmArgs p
     const int kt0 = split * kt_per;
     const int KT = max(0, min(KT_all, kt0 + kt_per) - kt0);
 
+    // affine walk: per-element source pointers advanced by one K tile per call (tiles are loaded in order)
+    const float2* a_ptr[A_PER];
+    const float2* b_ptr[B_PER];
+    int a_so[A_PER], b_so[B_PER];  // shared-memory offsets inside a stage
+#pragma unroll
+    for (int i = 0; i < A_PER; ++i) {
+        a_so[i] = a_kl[i] * FPA + a_ml[i];
+        a_ptr[i] = AFFINE ? A + a_moff[i] + (int64_t)(kt0 * FBK + a_kl[i]) * p.ak.stride : A;
+    }
+#pragma unroll
+    for (int i = 0; i < B_PER; ++i) {
+        b_so[i] = b_kl[i] * FPB + b_nl[i];
+        b_ptr[i] = AFFINE ? B + b_noff[i] + (int64_t)(kt0 * FBK + b_kl[i]) * p.bk.stride : B;
+    }
+    const int64_t a_step = (int64_t)FBK * p.ak.stride, b_step = (int64_t)FBK * p.bk.stride;
+
     auto load_tile = [&](int kt, int s) {
         float2* as = As + (size_t)s * FBK * FPA;
         float2* bs = Bs + (size_t)s * FBK * FPB;
+        if constexpr (AFFINE) {
+            const int kbase = (kt0 + kt) * FBK;
 #pragma unroll
-        for (int i = 0; i < A_PER; ++i) {
-            int kg = (kt0 + kt) * FBK + a_kl[i];
-            bool ok = a_ok[i] && kg < p.K;
-            const float2* src = ok ? (A + a_moff[i] + p.ak.at(kg)) : reinterpret_cast<const float2*>(p.A);
-            cp_async8(as + a_kl[i] * FPA + a_ml[i], src, ok);
-        }
+            for (int i = 0; i < A_PER; ++i) {
+                const bool ok = a_ok[i] && (kbase + a_kl[i]) < p.K;
+                cp_async8(as + a_so[i], ok ? a_ptr[i] : reinterpret_cast<const float2*>(p.A), ok);
+                a_ptr[i] += a_step;
+            }
 #pragma unroll
-        for (int i = 0; i < B_PER; ++i) {
-            int kg = (kt0 + kt) * FBK + b_kl[i];
-            bool ok = b_ok[i] && kg < p.K;
-            const float2* src = ok ? (B + b_noff[i] + p.bk.at(kg)) : reinterpret_cast<const float2*>(p.B);
-            cp_async8(bs + b_kl[i] * FPB + b_nl[i], src, ok);
+            for (int i = 0; i < B_PER; ++i) {
+                const bool ok = b_ok[i] && (kbase + b_kl[i]) < p.K;
+                cp_async8(bs + b_so[i], ok ? b_ptr[i] : reinterpret_cast<const float2*>(p.B), ok);
+                b_ptr[i] += b_step;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < A_PER; ++i) {
+                int kg = (kt0 + kt) * FBK + a_kl[i];
+                bool ok = a_ok[i] && kg < p.K;
+                const float2* src = ok ? (A + a_moff[i] + p.ak.at(kg)) : reinterpret_cast<const float2*>(p.A);
+                cp_async8(as + a_so[i], src, ok);
+            }
+#pragma unroll
+            for (int i = 0; i < B_PER; ++i) {
+                int kg = (kt0 + kt) * FBK + b_kl[i];
+                bool ok = b_ok[i] && kg < p.K;
+                const float2* src = ok ? (B + b_noff[i] + p.bk.at(kg)) : reinterpret_cast<const float2*>(p.B);
+                cp_async8(bs + b_so[i], src, ok);
+            }
         }
     };
 
@@ -280,7 +318,8 @@ __global__ void splitk_reduce_c64_kernel(const GemmArgs p) {
 }  // namespace
 
 int32_t init_gemm_c64(qb200_ctx* ctx) {
-    QB_CUDA(ctx, cudaFuncSetAttribute(gemm_c64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM32_SMEM));
+    QB_CUDA(ctx, cudaFuncSetAttribute(gemm_c64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM32_SMEM));
+    QB_CUDA(ctx, cudaFuncSetAttribute(gemm_c64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM32_SMEM));
     return QB200_OK;
 }
 
@@ -316,7 +355,11 @@ int32_t launch_gemm_c64(qb200_ctx* ctx, const GemmArgs& args_in) {
     }
     dim3 grid((args.M + FBM - 1) / FBM, (args.N + FBN - 1) / FBN, args.ksplit > 1 ? args.ksplit : args.batch);
     if (grid.y > 65535 || grid.z > 65535) QB_FAIL(ctx, QB200_E_UNSUPPORTED, "gemm_c64 grid too large");
-    gemm_c64_kernel<<<grid, F_THREADS, GEMM32_SMEM, ctx->stream>>>(args);
+    const bool affine = !args.am.tab && !args.ak.tab && !args.bk.tab && !args.bn.tab;
+    if (affine)
+        gemm_c64_kernel<true><<<grid, F_THREADS, GEMM32_SMEM, ctx->stream>>>(args);
+    else
+        gemm_c64_kernel<false><<<grid, F_THREADS, GEMM32_SMEM, ctx->stream>>>(args);
     QB_LAUNCH_CHECK(ctx);
     if (args.ksplit > 1) {
         int64_t total = (int64_t)args.M * args.N;
