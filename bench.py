@@ -356,6 +356,14 @@ def run_b200(args):
 
     if not args.no_sliced:
         line["sliced_contraction"] = run_sliced(ctx, qb, rank, world, peak_tf, barrier)
+        if world == 1:
+            # the same network with the slice target an on-GPU budget allows (2^28 elements = 4 GiB per intermediate
+            # instead of the 2^24 of examples/distributed.jl:46): fewer cuts, larger GEMMs.  Reported separately.
+            try:
+                line["sliced_contraction_large_target"] = run_sliced(ctx, qb, rank, world, peak_tf, barrier,
+                                                                     target=2 ** 28, reps=2)
+            except Exception as e:  # never lose the headline line to the extra measurement
+                line["sliced_contraction_large_target"] = {"error": str(e)[:200]}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sec, desc = cpu_tebd_sample(n, chi, 3 if chi >= 512 else 1)
