@@ -99,36 +99,75 @@ def gate(matrix, sites):
     return Dense(arr, [site(s) for s in sites] + [site(s, True) for s in sites])
 
 
-class Chain(Quantum):
-    """Open-boundary MPS (`Chain(State(), Open(), arrays)`, Chain.jl:64-100)."""
+def _chain_labels(shapes, order, boundary, socket):
+    """Index labels of the site tensors of a Chain, one list per site, plus the site map -- the four constructors
+    `Chain(::State|::Operator, ::Open|::Periodic, arrays; order)` (Chain.jl:36-62, 64-100, 102-131, 133-172):
+    site i holds o_i (and i_i for an operator), its right bond r_i = b_i and its left bond l_i = b_{i-1}, the bond
+    ring closed (b_n between site n and site 1) for Periodic and cut there for Open (first array without `l`, last
+    without `r`)."""
+    default = ("o", "l", "r") if socket == "state" else ("o", "i", "l", "r")
+    order = tuple(default if order is None else order)
+    if sorted(order) != sorted(default):
+        raise ValueError(f"order must be a permutation of {default}")                 # Chain.jl:39-40,68-69,105-106,137-138
+    if boundary not in ("open", "periodic") or socket not in ("state", "operator"):
+        raise ValueError("boundary must be 'open' or 'periodic', socket 'state' or 'operator'")
+    n = len(shapes)
+    full = len(default)
+    out_ = [nextindex() for _ in range(n)]
+    in_ = [nextindex() for _ in range(n)] if socket == "operator" else None
+    bonds = [nextindex() for _ in range(n if boundary == "periodic" else n - 1)]
+    labels = []
+    for k in range(n):
+        lab = {"o": out_[k], "i": in_[k] if in_ else None, "r": bonds[k % n] if (boundary == "periodic" or k < n - 1) else None,
+               "l": bonds[(k - 1) % n] if (boundary == "periodic" or k > 0) else None}
+        inds = [lab[c] for c in order if lab[c] is not None]
+        want = full if boundary == "periodic" else full - (k == 0) - (k == n - 1)
+        assert len(shapes[k]) == want == len(inds), f"array {k + 1} must have {want} dimensions"  # Chain.jl:37,65-67,103,134-136
+        labels.append(inds)
+    sites = {site(k + 1): out_[k] for k in range(n)}
+    if in_:
+        sites.update({site(k + 1, True): in_[k] for k in range(n)})
+    return labels, sites
 
-    def __init__(self, arrays=None, order=("o", "l", "r"), _q: Quantum | None = None):
+
+class Chain(Quantum):
+    """`Chain(socket, boundary, arrays; order)`: MPS / MPO with open or periodic boundary (Chain.jl:6-31, 36-172).
+    The default (`Chain(arrays)`) is the open-boundary MPS the algorithms of Chain.jl work on."""
+
+    def __init__(self, arrays=None, order=None, _q: Quantum | None = None, boundary="open", socket="state"):
+        self.boundary, self.socket = boundary, socket
         if _q is not None:
             super().__init__(_q.tn, _q.sites)
             return
-        n = len(arrays)
-        bonds = [nextindex() for _ in range(n - 1)]
-        phys = [nextindex() for _ in range(n)]
-        tensors = []
-        for k, a in enumerate(arrays):
-            a = np.asarray(a)
-            lab = {"o": phys[k], "l": bonds[k - 1] if k > 0 else None, "r": bonds[k] if k < n - 1 else None}
-            inds = [lab[c] for c in order if lab[c] is not None]
-            assert a.ndim == len(inds), (k, a.shape, inds)
-            tensors.append(Tensor(a, inds))
-        super().__init__(TensorNetwork(tensors), {site(k + 1): phys[k] for k in range(n)})
+        arrays = [np.asarray(a) for a in arrays]
+        labels, sites = _chain_labels([a.shape for a in arrays], order, boundary, socket)
+        super().__init__(TensorNetwork([Tensor(a, inds) for a, inds in zip(arrays, labels)]), sites)
 
     # -- bookkeeping ---------------------------------------------------------------------
     def copy(self):
-        return Chain(_q=Quantum(self.tn.copy(), self.sites))
+        return Chain(_q=Quantum(self.tn.copy(), self.sites), boundary=self.boundary, socket=self.socket)
 
     def deepcopy(self):
-        return Chain(_q=Quantum(self.tn.deepcopy(), self.sites))
+        return Chain(_q=Quantum(self.tn.deepcopy(), self.sites), boundary=self.boundary, socket=self.socket)
 
     def adjoint(self):
-        return Chain(_q=super().adjoint())
+        """`Chain(adjoint(Quantum(chain)), boundary(chain))` (Chain.jl:204)."""
+        return Chain(_q=super().adjoint(), boundary=self.boundary, socket=self.socket)
+
+    def leftsite(self, s):
+        """Chain.jl:185-188."""
+        if self.boundary == "periodic":
+            return ((s[0] - 2) % self.nlanes() + 1, s[1])
+        return (s[0] - 1, s[1]) if 2 <= s[0] <= self.nlanes() else None
+
+    def rightsite(self, s):
+        """Chain.jl:190-193."""
+        if self.boundary == "periodic":
+            return (s[0] % self.nlanes() + 1, s[1])
+        return (s[0] + 1, s[1]) if 1 <= s[0] <= self.nlanes() - 1 else None
 
     def nsites(self):
+        """`nsites` = number of sites in the site map (2n for an operator; Quantum.jl)."""
         return len(self.sites)
 
     def bond_ind(self, s1, s2):
@@ -141,12 +180,14 @@ class Chain(Quantum):
         return only
 
     def leftindex(self, s):
-        """Chain.jl:193-196."""
-        return None if s[0] == 1 else self.bond_ind(s, (s[0] - 1, s[1]))
+        """Chain.jl:195-197."""
+        ls = self.leftsite(s)
+        return None if ls is None else self.bond_ind(s, ls)
 
     def rightindex(self, s):
-        """Chain.jl:198-202."""
-        return None if s[0] == self.nlanes() else self.bond_ind(s, (s[0] + 1, s[1]))
+        """Chain.jl:199-202."""
+        rs = self.rightsite(s)
+        return None if rs is None else self.bond_ind(s, rs)
 
     def lambda_between(self, s1, s2):
         """`tensors(tn; between=(s1,s2))` (Ansatz.jl:78-89): `tn[bond]`, i.e. the tensor whose

@@ -261,29 +261,56 @@ class TensorNetwork:
         return len(self.tensors)
 
 
-class Chain:
-    """Open-boundary MPS, `Chain(State(), Open(), arrays)` (Chain.jl:64-100), arrays uploaded at construction
-    (= `adapt(B200Array, ψ)`, ext/QrochetAdaptExt.jl:9)."""
+def _site_labels(shapes, order, boundary, socket):
+    """Index labels per site tensor + site map for the four reference constructors
+    `Chain(::State|::Operator, ::Open|::Periodic, arrays; order)` (Chain.jl:36-62, 64-100, 102-131, 133-172)."""
+    default = ("o", "l", "r") if socket == "state" else ("o", "i", "l", "r")
+    order = tuple(default if order is None else order)
+    if sorted(order) != sorted(default):
+        raise ValueError(f"order must be a permutation of {default}")      # ArgumentError, Chain.jl:39-40,68-69,105-106
+    if boundary not in ("open", "periodic") or socket not in ("state", "operator"):
+        raise ValueError("boundary must be 'open' or 'periodic', socket 'state' or 'operator'")
+    n = len(shapes)
+    ring = boundary == "periodic"
+    phys = [nextindex() for _ in range(n)]
+    dual = [nextindex() for _ in range(n)] if socket == "operator" else None
+    bonds = [nextindex() for _ in range(n if ring else n - 1)]
+    labels = []
+    for k in range(n):
+        lab = {"o": phys[k], "i": dual[k] if dual else None,
+               "l": bonds[(k - 1) % n] if (ring or k > 0) else None,
+               "r": bonds[k % n] if (ring or k < n - 1) else None}
+        inds = [lab[c] for c in order if lab[c] is not None]
+        if len(shapes[k]) != len(inds):                                     # the @asserts of Chain.jl:37,65-67,103,134-136
+            raise AssertionError(f"array {k + 1} must have {len(inds)} dimensions")
+        labels.append(inds)
+    sites = {site(k + 1): phys[k] for k in range(n)}
+    if dual:
+        sites.update({site(k + 1, True): dual[k] for k in range(n)})
+    return labels, sites
 
-    def __init__(self, ctx: dev.Context | None = None, arrays=None, order=("o", "l", "r"), _state=None):
+
+class Chain:
+    """`Chain(socket, boundary, arrays; order)` (Chain.jl:6-31, 36-172) with the arrays uploaded at construction
+    (= `adapt(B200Array, ψ)`, ext/QrochetAdaptExt.jl:9).  The default is the open-boundary MPS the algorithms of
+    Chain.jl work on; periodic chains and operators (MPO) carry the same bookkeeping and go through the generic
+    network contraction (`norm`, `overlap`, `adjoint`)."""
+
+    def __init__(self, ctx: dev.Context | None = None, arrays=None, order=None, _state=None, boundary="open",
+                 socket="state"):
+        self.boundary, self.socket = boundary, socket
         if _state is not None:
             self.ctx, self.tn, self.sites = _state
             return
         self.ctx = ctx
-        n = len(arrays)
-        bonds = [nextindex() for _ in range(n - 1)]
-        phys = [nextindex() for _ in range(n)]
-        tensors = []
-        for k, a in enumerate(arrays):
+        host = []
+        for a in arrays:
             a = np.asarray(a)
             if a.dtype != np.complex64:  # ComplexF32 chains stay ComplexF32 on the device (native float2 tensors)
                 a = a.astype(np.complex128)
-            lab = {"o": phys[k], "l": bonds[k - 1] if k > 0 else None, "r": bonds[k] if k < n - 1 else None}
-            inds = [lab[c] for c in order if lab[c] is not None]
-            assert a.ndim == len(inds)  # Chain.jl:65-67
-            tensors.append(Tensor(ctx.array(a), inds))
-        self.tn = TensorNetwork(tensors)
-        self.sites = {site(k + 1): phys[k] for k in range(n)}
+            host.append(a)
+        labels, self.sites = _site_labels([a.shape for a in host], order, boundary, socket)
+        self.tn = TensorNetwork([Tensor(ctx.array(a), inds) for a, inds in zip(host, labels)])
 
     @property
     def eltype(self):
@@ -292,15 +319,31 @@ class Chain:
 
     # ---- bookkeeping (src/Quantum.jl, src/Ansatz.jl) ----
     def copy(self):
-        return Chain(_state=(self.ctx, self.tn.copy(), dict(self.sites)))
+        return Chain(_state=(self.ctx, self.tn.copy(), dict(self.sites)), boundary=self.boundary, socket=self.socket)
 
     def nsites(self):
         return len(self.sites)
 
-    nlanes = nsites
+    def nlanes(self):
+        return len({s[0] for s in self.sites})
 
     def outputs(self):
         return sorted(s for s in self.sites if not s[1])
+
+    def inputs(self):
+        return sorted(s for s in self.sites if s[1])
+
+    def leftsite(self, s):
+        """Chain.jl:185-188."""
+        if self.boundary == "periodic":
+            return ((s[0] - 2) % self.nlanes() + 1, s[1])
+        return (s[0] - 1, s[1]) if 2 <= s[0] <= self.nlanes() else None
+
+    def rightsite(self, s):
+        """Chain.jl:190-193."""
+        if self.boundary == "periodic":
+            return (s[0] % self.nlanes() + 1, s[1])
+        return (s[0] + 1, s[1]) if 1 <= s[0] <= self.nlanes() - 1 else None
 
     def tensor_at(self, s):
         (t,) = self.tn.intersecting(self.sites[s])
@@ -315,10 +358,14 @@ class Chain:
         return only
 
     def leftindex(self, s):
-        return None if s[0] == 1 else self.bond_ind(s, (s[0] - 1, s[1]))
+        """Chain.jl:195-197."""
+        ls = self.leftsite(s)
+        return None if ls is None else self.bond_ind(s, ls)
 
     def rightindex(self, s):
-        return None if s[0] == self.nlanes() else self.bond_ind(s, (s[0] + 1, s[1]))
+        """Chain.jl:199-202."""
+        rs = self.rightsite(s)
+        return None if rs is None else self.bond_ind(s, rs)
 
     def lambda_between(self, s1, s2):
         b = self.bond_ind(s1, s2)
@@ -335,7 +382,7 @@ class Chain:
         tn = self.tn.conj()
         phys = set(sites.values())
         tn.replace_inds({i: i + "'" for i in tn.inds() if i not in phys})
-        return Chain(_state=(self.ctx, tn, sites))
+        return Chain(_state=(self.ctx, tn, sites), boundary=self.boundary, socket=self.socket)  # Chain.jl:204
 
     def _pinv(self, lam: Tensor, atol):
         """`Tensor(diag(pinv(Diagonal(parent(Λ)), atol)), inds(Λ))` (Chain.jl:491,710,713): tiny host round trip of

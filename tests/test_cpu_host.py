@@ -143,3 +143,26 @@ def test_circuit_front_end_structure():
         for qubits, mat in gates[:-1]:
             psi = sv.apply_gate(psi, np.asarray(mat).T, [q + 1 for q in qubits], 3)
         assert np.allclose(U[:, col], swap02(psi))
+
+
+# ---- the device Chain's bookkeeping (site map, bonds, boundary, socket) is host logic: run the reference's
+# ---- constructor tests (Chain_test.jl:2-188) against it with a stand-in for the device array type
+class _HostArray:
+    """Carries only what the bookkeeping reads from a DeviceArray: shape / ndim / dtype."""
+
+    def __init__(self, a):
+        self.shape, self.ndim, self.dtype = tuple(a.shape), a.ndim, 1 if a.dtype == np.complex64 else 0
+
+
+class _HostCtx:
+    def array(self, a):
+        return _HostArray(np.asarray(a))
+
+
+import _chain_ctor_cases as ctor  # noqa: E402
+
+
+@pytest.mark.parametrize("case", ctor.ALL, ids=lambda f: f.__name__)
+def test_device_chain_constructors_host_logic(case):
+    import qrochet_b200 as qb
+    case(lambda arrays, **kw: qb.chain.Chain(_HostCtx(), arrays, **kw), qb.chain.site)

@@ -137,3 +137,17 @@ def test_evolve_generic_path_matches_statevector_and_fused_path(qb, ctx, iscanon
         if x is not None:
             k = min(len(x), len(y))
             assert np.abs(x[:k] - y[:k]).max() <= 1e-12 * max(y[0], 1e-300)
+
+
+# ---- Chain_test.jl:2-188 on device arrays: State / Operator x Open / Periodic constructors, site map, left/right sites
+import _chain_ctor_cases as ctor  # noqa: E402
+
+
+@pytest.mark.parametrize("case", ctor.ALL, ids=lambda f: f.__name__)
+def test_chain_constructors_on_device(qb, ctx, case):
+    case(lambda arrays, **kw: qb.chain.Chain(ctx, arrays, **kw), qb.chain.site)
+
+
+def test_periodic_ring_contractions_on_device(qb, ctx):
+    ctor.check_periodic_ring_contractions(lambda arrays, **kw: qb.chain.Chain(ctx, arrays, **kw), qb.chain.site,
+                                          lambda q: q.to_dense())

@@ -221,3 +221,16 @@ def test_mpo_composition_against_dense():
     assert np.allclose(oc.compress(hp.copy()).to_dense(), Hd @ v)
     c = oc.compress(hp.copy(), maxdim=6)
     assert max(len(l) for l in c.lambdas()) == 6
+
+
+# Chain_test.jl:2-188 (constructors: State / Operator x Open / Periodic, orders, site map, left/right sites)
+import _chain_ctor_cases as ctor  # noqa: E402  (tests/ is on sys.path: rootdir-relative import mode)
+
+
+@pytest.mark.parametrize("case", ctor.ALL, ids=lambda f: f.__name__)
+def test_chain_constructors(case):
+    case(lambda arrays, **kw: Chain(arrays, **kw), site)
+
+
+def test_periodic_ring_contractions():
+    ctor.check_periodic_ring_contractions(lambda arrays, **kw: Chain(arrays, **kw), site, lambda q: q.to_dense())
