@@ -525,6 +525,36 @@ def rand_mps(rng, n, chi, p=2, dtype=np.complex128, fast=False) -> Chain:
     return Chain(rand_mps_arrays(rng, n, chi, p, dtype, fast))
 
 
+def rand_mpo_arrays(rng, n, chi, p=2, dtype=np.float64):
+    """Arrays of `rand(Chain, Open, Operator; n, χ, p, eltype)` (Chain.jl:260-297), default order (o,i,l,r):
+    per site a random χl x (χr p²) matrix (first site χr x p², last χl x p²) with its ROWS orthonormalised
+    (`Muscle.gramschmidt!`), reshaped and permuted to (p, p, χl, χr) / (p, p, χ); bond b has
+    min(χ, p^(2b), p^(2(n-b))); site 1 divided by sqrt(min(χ, p²)) => Frobenius norm 1.  eltype defaults to Float64
+    as in the reference (:264)."""
+    arrays = []
+    for i in range(1, n + 1):
+        after_mid = i > n // 2
+        j = (n + 1 - abs(2 * i - n - 1)) // 2
+        chil, chir = min(chi, p ** (2 * (j - 1))), min(chi, p ** (2 * j))
+        if n % 2 == 1 and i == n // 2 + 1:
+            chil, chir = chil, chil
+        elif after_mid:
+            chil, chir = chir, chil
+        shape = (chir, p, p) if i == 1 else ((chil, p, p) if i == n else (chil, chir, p, p))
+        cols = int(np.prod(shape[1:]))
+        a = rng.random((shape[0], cols))
+        if np.issubdtype(dtype, np.complexfloating):
+            a = a + 1j * rng.random((shape[0], cols))
+        a = np.reshape(gramschmidt_rows(a.astype(dtype)), shape, order="F")
+        arrays.append(np.transpose(a, (1, 2, 0)) if i in (1, n) else np.transpose(a, (2, 3, 0, 1)))
+    arrays[0] = arrays[0] / np.sqrt(min(chi, p * p))
+    return arrays
+
+
+def rand_mpo(rng, n, chi, p=2, dtype=np.float64) -> Chain:
+    return Chain(rand_mpo_arrays(rng, n, chi, p, dtype), socket="operator")
+
+
 def haar_unitary(rng, d=4):
     """Haar-random d x d unitary: QR of complex Ginibre, phases fixed."""
     z = (rng.standard_normal((d, d)) + 1j * rng.standard_normal((d, d))) / np.sqrt(2)

@@ -10,7 +10,7 @@ from .tn import SlicedContraction, amplitude_network, circuit_network, fsim, ran
 from .parallel import (comm_allreduce_sum, comm_allreduce_sum_vec, comm_init, comm_unique_id,
                        contract_sliced_distributed, expect_batch_distributed, my_slices, torch_allreduce_sum,
                        torch_allreduce_sum_vec)
-from .rand import bond_dims, haar_gate, heisenberg_mpo_arrays, rand_mps_arrays
+from .rand import bond_dims, haar_gate, heisenberg_mpo_arrays, rand_mpo_arrays, rand_mps_arrays
 
 __all__ = ["Context", "DeviceArray", "B200MPS", "contract", "scale_mode", "slice_mode", "select_mode", "conj",
            "permute", "norm2", "scale", "qr", "svd", "QB200Error", "MissingSchmidtCoefficientsException"]

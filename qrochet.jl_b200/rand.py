@@ -36,6 +36,31 @@ def rand_mps_arrays(rng: np.random.Generator, n: int, chi: int, p: int = 2):
     return arrays
 
 
+def rand_mpo_arrays(rng: np.random.Generator, n: int, chi: int, p: int = 2, complex_entries: bool = False):
+    """`rand(Chain, Open, Operator; n, χ, p, eltype)` (Chain.jl:260-297): site arrays in the default MPO order
+    (o, i, l, r), first (o, i, r), last (o, i, l).  Each site is a random row-orthonormal χl x (χr p²) matrix (QR of
+    the adjoint, as in rand_mps_arrays), bond b = min(χ, p^(2b), p^(2(n-b))), site 1 / sqrt(min(χ, p²)) so that the
+    operator has Frobenius norm 1.  Real entries by default like the reference (eltype = Float64, :264)."""
+    arrays = []
+    for i in range(1, n + 1):
+        j = (n + 1 - abs(2 * i - n - 1)) // 2
+        chil, chir = min(chi, p ** (2 * (j - 1))), min(chi, p ** (2 * j))
+        if n % 2 == 1 and i == n // 2 + 1:
+            chir = chil
+        elif i > n // 2:
+            chil, chir = chir, chil
+        shape = (chir, p, p) if i == 1 else ((chil, p, p) if i == n else (chil, chir, p, p))
+        cols = int(np.prod(shape[1:]))
+        a = rng.random((shape[0], cols))
+        if complex_entries:
+            a = a + 1j * rng.random((shape[0], cols))
+        q, _ = np.linalg.qr(a.conj().T)
+        a = np.reshape(q.conj().T, shape, order="F")
+        arrays.append(np.transpose(a, (1, 2, 0)) if i in (1, n) else np.transpose(a, (2, 3, 0, 1)))
+    arrays[0] = arrays[0] / np.sqrt(min(chi, p * p))
+    return arrays
+
+
 def haar_gate(rng: np.random.Generator, d: int = 4):
     """Haar-random d x d unitary (QR of complex Ginibre, phases fixed) as the reference's gate array with
     dims (o1, o2, i1, i2), column-major reshape, first lane = fastest bit."""

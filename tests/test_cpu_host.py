@@ -166,3 +166,16 @@ import _chain_ctor_cases as ctor  # noqa: E402
 def test_device_chain_constructors_host_logic(case):
     import qrochet_b200 as qb
     case(lambda arrays, **kw: qb.chain.Chain(_HostCtx(), arrays, **kw), qb.chain.site)
+
+
+def test_rand_mpo_generator_matches_reference_properties():
+    """`rand(Chain, Open, Operator)` (Chain.jl:260-297, Chain_test.jl:223-235): Frobenius norm 1, bonds <= chi,
+    shapes identical to the oracle's restatement (which orthonormalises with Gram-Schmidt like the reference)."""
+    import qrochet_b200 as qb
+    for n, chi in [(8, 10), (5, 3), (7, 100)]:
+        arrays = qb.rand_mpo_arrays(np.random.default_rng(0), n, chi)
+        ref = oc.rand_mpo_arrays(np.random.default_rng(0), n, chi)
+        assert [a.shape for a in arrays] == [a.shape for a in ref]
+        q = oc.Chain(arrays, socket="operator")
+        assert np.isclose(q.norm(), 1.0)
+        assert max(d for a in arrays for d in a.shape[2:]) <= chi

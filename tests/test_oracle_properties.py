@@ -234,3 +234,17 @@ def test_chain_constructors(case):
 
 def test_periodic_ring_contractions():
     ctor.check_periodic_ring_contractions(lambda arrays, **kw: Chain(arrays, **kw), site, lambda q: q.to_dense())
+
+
+# Chain_test.jl:223-235: rand(Chain, Open, Operator; n, p, χ)
+@pytest.mark.parametrize("n,chi", [(8, 10), (5, 3), (7, 100), (2, 4)])
+def test_rand_operator(n, chi):
+    q = oc.rand_mpo(np.random.default_rng(3), n, chi)
+    assert q.socket == "operator" and len(q.inputs()) == n and len(q.outputs()) == n
+    assert set(q.sites) == {site(i, d) for i in range(1, n + 1) for d in (False, True)} and q.boundary == "open"
+    assert np.isclose(q.norm(), 1.0)
+    phys = set(q.sites.values())
+    assert max(q.tn.size(i) for t in q.tn.tensors for i in t.inds if i not in phys) <= chi
+    # default eltype is Float64 (Chain.jl:264) and a complex eltype works too
+    assert all(np.isrealobj(t.data) for t in q.tn.tensors)
+    assert np.isclose(oc.rand_mpo(np.random.default_rng(4), n, chi, dtype=np.complex128).norm(), 1.0)
