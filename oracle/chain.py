@@ -36,8 +36,26 @@ class Quantum:
     """`Quantum` = TensorNetwork + Dict{Site,Symbol} (src/Quantum.jl:54-76)."""
 
     def __init__(self, tn: TensorNetwork, sites: dict):
+        open_inds = set(tn.inds("open"))
+        all_inds = set(tn.inds())
+        for index in dict(sites).values():                      # src/Quantum.jl:61-67
+            if index not in all_inds:
+                raise RuntimeError(f"Index {index} not found in TensorNetwork")
+            if index not in open_inds:
+                raise RuntimeError(f"Index {index} must be open")
         self.tn = tn
         self.sites = dict(sites)
+
+    def socket_type(self):
+        """`socket(q)` (src/Quantum.jl): Scalar, State (dual when it only has inputs) or Operator."""
+        ni, no = len(self.inputs()), len(self.outputs())
+        if ni == 0 and no == 0:
+            return "scalar"
+        if ni == 0:
+            return "state"
+        if no == 0:
+            return "state'"
+        return "operator"
 
     def copy(self):
         return Quantum(self.tn.copy(), self.sites)
@@ -72,6 +90,81 @@ class Quantum:
         phys = set(sites.values())
         tn.replace_inds({i: i + "'" for i in tn.inds() if i not in phys})
         return Quantum(tn, sites)
+
+
+class Product(Quantum):
+    """`Product` ansatz (src/Ansatz/Product.jl): one tensor per lane, no inner indices.  Vectors give a State
+    (:24-33), matrices an Operator with array dims (output, input) = inds [symbols[i+n], symbols[i]] (:35-46)."""
+
+    def __init__(self, arrays=None, _q: Quantum | None = None):
+        if _q is not None:
+            assert not _q.tn.inds("inner"), "Product ansatz must not have inner indices"   # Product.jl:15
+            super().__init__(_q.tn, _q.sites)
+            return
+        arrays = [np.asarray(a) for a in arrays]
+        n = len(arrays)
+        if all(a.ndim == 1 for a in arrays):
+            sym = [nextindex() for _ in range(n)]
+            tensors = [Tensor(a, [sym[k]]) for k, a in enumerate(arrays)]
+            sites = {site(k + 1): sym[k] for k in range(n)}
+        elif all(a.ndim == 2 for a in arrays):
+            sym = [nextindex() for _ in range(2 * n)]
+            tensors = [Tensor(a, [sym[k + n], sym[k]]) for k, a in enumerate(arrays)]
+            sites = {site(k + 1, True): sym[k] for k in range(n)}
+            sites.update({site(k + 1): sym[k + n] for k in range(n)})
+        else:
+            raise TypeError("Product takes a list of vectors (State) or of matrices (Operator)")
+        super().__init__(TensorNetwork(tensors), sites)
+
+    @staticmethod
+    def zeros(n, p=2, dtype=bool):
+        """`zeros(Product, n; p, eltype)` (Product.jl:48-50): |0...0>."""
+        v = np.zeros(p, dtype=dtype)
+        v[0] = 1
+        return Product([v.copy() for _ in range(n)])
+
+    @staticmethod
+    def ones(n, p=2, dtype=bool):
+        """`ones(Product, n; p, eltype)` (Product.jl:52-58): |1...1>."""
+        v = np.zeros(p, dtype=dtype)
+        v[1] = 1
+        return Product([v.copy() for _ in range(n)])
+
+    def copy(self):
+        return Product(_q=Quantum(self.tn.deepcopy(), self.sites))
+
+    def norm(self, p=2):
+        """Product.jl:60-65 as written: (prod_i ||t_i||_p)^(1/p) -- for p = 2 the SQUARE ROOT of the product of the
+        site norms (a defect of the reference: the norm of a product state is the plain product; replicated
+        knowingly, it is exact for normalised sites, which is all the reference tests)."""
+        prod = 1.0
+        for t in self.tn.tensors:
+            prod *= np.linalg.norm(np.ravel(t.data), p)
+        return prod ** (1.0 / p)
+
+    def opnorm(self, p=2):
+        """Product.jl:67-72 (operators only), same outer exponent."""
+        assert self.socket_type() == "operator"
+        prod = 1.0
+        for t in self.tn.tensors:
+            prod *= np.linalg.norm(t.data, p)      # matrix p-norm: spectral norm for p = 2
+        return prod ** (1.0 / p)
+
+    def normalize_(self, p=2):
+        """`normalize!` (Product.jl:74-80): every site tensor to unit p-norm."""
+        for t in self.tn.tensors:
+            t.data = t.data / np.linalg.norm(np.ravel(t.data), p)
+        return self
+
+    def overlap(self, other: "Product"):
+        """`overlap(a::Product, b::Product)` (Product.jl:82-90): prod_i dot(a_i, conj(b_i)) -- Julia's `dot`
+        conjugates its first argument, so this is prod_i sum_s conj(a_i[s]) conj(b_i[s])."""
+        assert self.socket_type() == "state" and other.socket_type() == "state"
+        assert set(self.sites) == set(other.sites), "Ansatzes must have the same sites"
+        out = 1.0 + 0.0j
+        for s in sorted(self.sites):
+            out *= np.vdot(self.tensor_at(s).data, np.conj(other.tensor_at(s).data))
+        return out
 
 
 class Dense(Quantum):

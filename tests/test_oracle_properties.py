@@ -248,3 +248,59 @@ def test_rand_operator(n, chi):
     # default eltype is Float64 (Chain.jl:264) and a complex eltype works too
     assert all(np.isrealobj(t.data) for t in q.tn.tensors)
     assert np.isclose(oc.rand_mpo(np.random.default_rng(4), n, chi, dtype=np.complex128).norm(), 1.0)
+
+
+# test/Quantum_test.jl:1-45 (sockets, site bookkeeping, error detection) and test/Site_test.jl (sites are (id, dual))
+def test_quantum_sockets_and_errors():
+    from oracle.chain import Quantum
+    from oracle.tenet import TensorNetwork
+    q = Quantum(TensorNetwork([Tensor(np.zeros(2), ["i"])]), {site(1): "i"})
+    assert (len(q.inputs()), len(q.outputs()), set(q.sites), q.socket_type()) == (0, 1, {site(1)}, "state")
+    q = Quantum(TensorNetwork([Tensor(np.zeros(2), ["i"])]), {site(1, True): "i"})
+    assert (len(q.inputs()), len(q.outputs()), set(q.sites), q.socket_type()) == (1, 0, {site(1, True)}, "state'")
+    q = Quantum(TensorNetwork([Tensor(np.zeros((2, 2)), ["i", "j"])]), {site(1): "i", site(1, True): "j"})
+    assert (len(q.inputs()), len(q.outputs()), q.socket_type()) == (1, 1, "operator")
+    q = Quantum(TensorNetwork([Tensor(np.zeros(()), [])]), {})
+    assert (len(q.inputs()), len(q.outputs()), q.socket_type()) == (0, 0, "scalar") and not q.sites
+    tn = TensorNetwork([Tensor(np.zeros(2), ["i"]), Tensor(np.zeros(2), ["i"])])
+    with pytest.raises(RuntimeError):
+        Quantum(tn, {site(1): "j"})      # index not in the network
+    with pytest.raises(RuntimeError):
+        Quantum(tn, {site(1): "i"})      # index not open
+    s = site(1)
+    assert s[0] == 1 and s[1] is False and site(1, True)[1] is True   # Site(id; dual)
+    adj = (s[0], not s[1])
+    assert adj == site(1, True) and (adj[0], not adj[1]) == s          # adjoint flips dual
+
+
+# test/Ansatz/Product_test.jl:1-29 + zeros / ones / overlap (Product.jl:48-90)
+def test_product_ansatz():
+    from oracle.chain import Product
+    r = np.random.default_rng(21)
+    q = Product([r.random(2) for _ in range(3)])
+    assert q.socket_type() == "state" and not q.inputs() and len(q.outputs()) == 3
+    assert np.isscalar(q.norm()) or np.ndim(q.norm()) == 0
+    assert np.isclose(q.normalize_().norm(), 1.0)
+    q = Product([r.random((2, 2)) for _ in range(3)])
+    assert q.socket_type() == "operator" and len(q.inputs()) == 3 and len(q.outputs()) == 3
+    assert np.ndim(q.norm()) == 0 and np.ndim(q.opnorm()) == 0
+    assert np.isclose(q.normalize_().norm(), 1.0)
+    z, o = Product.zeros(4), Product.ones(4)
+    assert [t.data.tolist() for t in z.tn.tensors] == [[True, False]] * 4
+    assert [t.data.tolist() for t in o.tn.tensors] == [[False, True]] * 4
+    assert z.overlap(z) == 1 and z.overlap(o) == 0
+    a, b = Product([r.random(2) + 1j * r.random(2) for _ in range(3)]), Product([r.random(2) + 1j * r.random(2) for _ in range(3)])
+    want = np.prod([np.vdot(x.data, np.conj(y.data)) for x, y in zip(a.tn.tensors, b.tn.tensors)])
+    assert np.isclose(a.overlap(b), want)
+    with pytest.raises(AssertionError):     # Product.jl:15: no inner indices
+        from oracle.chain import Quantum
+        from oracle.tenet import TensorNetwork
+        Product(_q=Quantum(TensorNetwork([Tensor(np.zeros((2, 2)), ["a", "k"]), Tensor(np.zeros((2, 2)), ["k", "b"])]),
+                           {site(1): "a", site(2): "b"}))
+    # the product state as a chain (convert(Chain, Product), Chain.jl:174-183) has the same amplitudes
+    vs = [r.random(2) + 1j * r.random(2) for _ in range(4)]
+    chain = Chain([vs[0].reshape(2, 1)] + [v.reshape(2, 1, 1) for v in vs[1:-1]] + [vs[-1].reshape(2, 1)])
+    dense_want = vs[0]
+    for v in vs[1:]:
+        dense_want = np.kron(v, dense_want)          # site 1 fastest
+    assert np.allclose(chain.to_dense(), dense_want)
