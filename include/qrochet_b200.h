@@ -233,6 +233,10 @@ int32_t qb200_bench_dmma_peak(qb200_ctx* ctx, double* tflops);
 /* legacy warp-level tensor path (mma.sync) peaks, dense, FP32 accumulate: tflops2 = {TF32 m16n8k8, BF16 m16n8k16};
  * the denominators for the ComplexF32 kernels */
 int32_t qb200_bench_hmma_peak(qb200_ctx* ctx, double* tflops2);
+/* tcgen05 / TMEM building block of the ComplexF32 path (hand-written PTX: tcgen05.alloc / mma.kind::tf32 / commit /
+ * ld): out3 = {max |D - expected| of a self-checked M = 128, N = 128 / 256 product (must be 0), issue-bound TF32
+ * TFLOP/s at N = 128, at N = 256} */
+int32_t qb200_bench_tcgen05_tf32(qb200_ctx* ctx, double* out3);
 /* FP64 pipes micro-benchmark: TFLOP/s of {DMMA only, DFMA only, both issued from alternating warps} */
 int32_t qb200_bench_dual_pipe(qb200_ctx* ctx, double* tflops3);
 /* DMMA issue-pattern micro-benchmark: TFLOP/s for {independent accumulators, complex-multiply pattern with register

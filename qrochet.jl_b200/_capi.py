@@ -106,6 +106,7 @@ _protos = {
     "qb200_comm_destroy": (_i32, [_p]),
     "qb200_bench_dmma_peak": (_i32, [_p, _pdbl]),
     "qb200_bench_hmma_peak": (_i32, [_p, _pdbl]),
+    "qb200_bench_tcgen05_tf32": (_i32, [_p, _pdbl]),
     "qb200_bench_dual_pipe": (_i32, [_p, _pdbl]),
     "qb200_bench_dmma_patterns": (_i32, [_p, _pdbl]),
 }
