@@ -54,6 +54,10 @@ int32_t init_gemm(qb200_ctx* ctx);  // kernel attributes, once per process (call
 // ComplexF32 twin (gemm_c64.cu): same GemmArgs, A / B / C / partial point at float2 data
 int32_t launch_gemm_c64(qb200_ctx* ctx, const GemmArgs& args);
 int32_t init_gemm_c64(qb200_ctx* ctx);
+// ComplexF32 on tcgen05 / TMEM (gemm_c64_tc5.cu); opt-in with QB200_C64_TCGEN05=1
+int32_t launch_gemm_c64_tc5(qb200_ctx* ctx, const GemmArgs& args);
+int32_t init_gemm_c64_tc5(qb200_ctx* ctx);
+bool gemm_c64_tc5_enabled();
 // offsets[idx] = sum_j coord_j(idx) * stride[j], first mode fastest
 int32_t build_offsets(qb200_ctx* ctx, const ModeList& ml, int64_t total, int64_t* out);
 

@@ -340,6 +340,7 @@ int32_t launch_gemm_c64(qb200_ctx* ctx, const GemmArgs& args_in) {
     args.ksplit = 1;
     args.partial = nullptr;
     args.acc_init = 0;
+    if (gemm_c64_tc5_enabled()) return launch_gemm_c64_tc5(ctx, args);
     Workspace ws(ctx);
     {
         int64_t tiles = (int64_t)((args.M + FBM - 1) / FBM) * ((args.N + FBN - 1) / FBN);

@@ -1,0 +1,312 @@
+// K1 for ComplexF32 on the 5th-generation tensor cores: permutation-fused complex GEMM with the 3xTF32 split on
+// `tcgen05.mma.cta_group::1.kind::tf32`, accumulators in tensor memory.  Hand-written PTX (primitives validated by
+// tc5_probe.cu).  Same GemmArgs contract as gemm_c64.cu / gemm_c128.cu.
+//
+// Real embedding of the complex product, per K block of 16 complex numbers (x = xh + xl, TF32 split):
+//
+//   [D_re | D_im] (128 x 128 FP32, TMEM)  +=  sum over terms (lh, hl, hh)   [A_r  A_i] (128 x 32)  .  | B_r   B_i |  (32 x 128)
+//                                                                                                    | -B_i  B_r |
+//
+// Shared memory holds, per stage, A as four 16-wide K blocks {Ah_r, Ah_i, Al_r, Al_i} (128 rows) and B as four blocks
+// {Bh, Bl} x {pairs with A_r, pairs with A_i} (128 rows = 64 real-part + 64 imaginary-part output columns), all in the
+// canonical K-major no-swizzle UMMA layout (8-row x 16-byte core matrices, LBO = 2048 B between 4-wide K chunks, SBO =
+// 128 B between 8-row groups).  The SAME Ah chunks feed the hh and hl terms through two descriptors, so nothing is
+// stored twice.  12 MMAs (M = 128, N = 128, K = 8) per stage.
+//
+// The operands have to pass through registers (hi/lo split, [re | im] embedding, the gather of the fused permutation),
+// so the loader is ordinary code: every thread loads 4 consecutive k of one row, splits, and writes 16-byte vectors
+// (conflict-free: consecutive lanes = consecutive rows = consecutive 16-byte slots of a core-matrix column), then
+// fence.proxy.async + barrier, and ONE thread issues the MMAs of the stage and commits them to the stage's mbarrier,
+// which is what the loaders wait on before they overwrite that stage (2 stages: the fill of one overlaps the MMAs
+// of the other).  Epilogue: 8 warps read their TMEM lane quarter with tcgen05.ld.32x32b (re and im columns of 32
+// output columns each), apply alpha / beta and write C through the offset tables (rows of C across lanes).
+#include "gemm_c128.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+
+namespace qb {
+
+namespace {
+
+constexpr int TM = 128, TN = 64, TBK = 16, T_THREADS = 256;
+constexpr uint32_t T_SBO = 128, T_LBO = 128 * 16;             // both operand tiles have 128 rows
+constexpr uint32_t T_OPER_BYTES = 16 * T_LBO;                 // 16 K chunks of 4 = 64 real K: 32 KB per operand
+constexpr uint32_t T_STAGE_BYTES = 2 * T_OPER_BYTES;          // A + B
+constexpr size_t GEMM_TC5_SMEM = 2 * T_STAGE_BYTES + 1024;    // 2 stages + alignment slack
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((T_LBO >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((T_SBO >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version: Blackwell
+    return d;
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+    for (int spin = 0; spin < (1 << 22); ++spin) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
+
+__device__ __forceinline__ void split4(const float (&x)[4], float4& hi, float4& lo) {
+    float h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        h[j] = __uint_as_float((__float_as_uint(x[j]) + 0x1000u) & 0xffffe000u);  // round to nearest TF32
+        l[j] = x[j] - h[j];                                                      // exact; the MMA reads its top bits
+    }
+    hi = make_float4(h[0], h[1], h[2], h[3]);
+    lo = make_float4(l[0], l[1], l[2], l[3]);
+}
+
+__device__ __forceinline__ float4 neg4(float4 v) { return make_float4(-v.x, -v.y, -v.z, -v.w); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(T_THREADS, 1) gemm_c64_tc5_kernel(const GemmArgs p, int* __restrict__ status) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
+    __shared__ __align__(8) uint64_t mbar_free[2];
+    __shared__ uint32_t tmem_base_smem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    int tile_m, tile_n;
+    {  // grouped rasterisation, as in the other GEMM kernels
+        const int gm = gridDim.x, gn = gridDim.y, GROUP = 8;
+        const int id = blockIdx.x + gm * blockIdx.y;
+        const int per_group = GROUP * gn;
+        const int first_m = (id / per_group) * GROUP;
+        const int gsz = min(gm - first_m, GROUP);
+        tile_m = first_m + (id % per_group) % gsz;
+        tile_n = (id % per_group) / gsz;
+    }
+    const int m0 = tile_m * TM, n0 = tile_n * TN;
+    const int z = blockIdx.z;
+    const float2* __restrict__ A = reinterpret_cast<const float2*>(p.A) + p.ab.at(z);
+    const float2* __restrict__ B = reinterpret_cast<const float2*>(p.B) + p.bb.at(z);
+    float2* __restrict__ C = reinterpret_cast<float2*>(p.C) + p.cb.at(z);
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar_free[0])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar_free[1])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(&tmem_base_smem))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_smem;
+
+    // loader items: A (row, k group) x 2 per thread, B (column, k group) x 1 per thread
+    const int a_row[2] = {tid & 127, tid & 127}, a_g[2] = {tid >> 7, 2 + (tid >> 7)};
+    const int b_col = tid & 63, b_g = tid >> 6;
+    const bool a_ok = (m0 + a_row[0]) < p.M, b_ok = (n0 + b_col) < p.N;
+    const int64_t a_moff = a_ok ? p.am.at(m0 + a_row[0]) : 0;
+    const int64_t b_noff = b_ok ? p.bn.at(n0 + b_col) : 0;
+    const float sa = p.conjA ? -1.f : 1.f, sb = p.conjB ? -1.f : 1.f;
+    const uint32_t a_slot = (uint32_t)((a_row[0] >> 3) * T_SBO + (a_row[0] & 7) * 16);   // inside a K chunk
+    const uint32_t br_slot = (uint32_t)((b_col >> 3) * T_SBO + (b_col & 7) * 16);        // real-part output column
+    const uint32_t bi_slot = (uint32_t)(((64 + b_col) >> 3) * T_SBO + ((64 + b_col) & 7) * 16);  // imaginary-part column
+
+    const int KT = (p.K + TBK - 1) / TBK;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    bool alive = true;
+
+    for (int kt = 0; kt < KT; ++kt) {
+        const int s = kt & 1;
+        unsigned char* sA = smem + (size_t)s * T_STAGE_BYTES;
+        unsigned char* sB = sA + T_OPER_BYTES;
+        if (kt >= 2) alive = mbar_wait(smem_u32(&mbar_free[s]), (uint32_t)(((kt >> 1) + 1) & 1)) && alive;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ---- fill stage s ----
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            float xr[4], xi[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = kt * TBK + a_g[i] * 4 + j;
+                float2 v = make_float2(0.f, 0.f);
+                if (a_ok && k < p.K) v = A[a_moff + p.ak.at(k)];
+                xr[j] = v.x;
+                xi[j] = v.y * sa;
+            }
+            float4 rh, rl, ih, il;
+            split4(xr, rh, rl);
+            split4(xi, ih, il);
+            // K blocks of A: 0 = Ah_r, 1 = Ah_i, 2 = Al_r, 3 = Al_i; chunk = 4 * block + k group
+            *reinterpret_cast<float4*>(sA + (0 * 4 + a_g[i]) * T_LBO + a_slot) = rh;
+            *reinterpret_cast<float4*>(sA + (1 * 4 + a_g[i]) * T_LBO + a_slot) = ih;
+            *reinterpret_cast<float4*>(sA + (2 * 4 + a_g[i]) * T_LBO + a_slot) = rl;
+            *reinterpret_cast<float4*>(sA + (3 * 4 + a_g[i]) * T_LBO + a_slot) = il;
+        }
+        {
+            float xr[4], xi[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = kt * TBK + b_g * 4 + j;
+                float2 v = make_float2(0.f, 0.f);
+                if (b_ok && k < p.K) v = B[b_noff + p.bk.at(k)];
+                xr[j] = v.x;
+                xi[j] = v.y * sb;
+            }
+            float4 rh, rl, ih, il;
+            split4(xr, rh, rl);
+            split4(xi, ih, il);
+            // K blocks of B: 0 = (Bh, pairs with A_r), 1 = (Bh, pairs with A_i), 2 = (Bl, A_r), 3 = (Bl, A_i)
+            // real-part column n:      block(A_r) = B_r, block(A_i) = -B_i;  imaginary-part column 64 + n: B_i, B_r
+            *reinterpret_cast<float4*>(sB + (0 * 4 + b_g) * T_LBO + br_slot) = rh;
+            *reinterpret_cast<float4*>(sB + (1 * 4 + b_g) * T_LBO + br_slot) = neg4(ih);
+            *reinterpret_cast<float4*>(sB + (0 * 4 + b_g) * T_LBO + bi_slot) = ih;
+            *reinterpret_cast<float4*>(sB + (1 * 4 + b_g) * T_LBO + bi_slot) = rh;
+            *reinterpret_cast<float4*>(sB + (2 * 4 + b_g) * T_LBO + br_slot) = rl;
+            *reinterpret_cast<float4*>(sB + (3 * 4 + b_g) * T_LBO + br_slot) = neg4(il);
+            *reinterpret_cast<float4*>(sB + (2 * 4 + b_g) * T_LBO + bi_slot) = il;
+            *reinterpret_cast<float4*>(sB + (3 * 4 + b_g) * T_LBO + bi_slot) = rl;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy (tensor core)
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+            // small terms first: lh (Al x Bh), hl (Ah x Bl), hh (Ah x Bh); blk = 0 (A_r part) / 1 (A_i part); two K = 8 halves
+#pragma unroll
+            for (int term = 0; term < 3; ++term) {
+                const int ablk0 = (term == 0) ? 2 : 0;   // Al blocks 2,3 ; Ah blocks 0,1
+                const int bblk0 = (term == 1) ? 2 : 0;   // Bl blocks 2,3 ; Bh blocks 0,1
+#pragma unroll
+                for (int blk = 0; blk < 2; ++blk)
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        const uint64_t da = umma_desc(a0 + ((ablk0 + blk) * 4 + 2 * half) * T_LBO);
+                        const uint64_t db = umma_desc(b0 + ((bblk0 + blk) * 4 + 2 * half) * T_LBO);
+                        umma_tf32(tmem_d, da, db, idesc, (kt | term | blk | half) ? 1u : 0u);
+                    }
+            }
+            // arrives when the MMAs above (and all earlier ones) have completed: frees stage s for the loaders
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                             smem_u32(&mbar_free[s]))
+                         : "memory");
+        }
+    }
+    // every MMA completes in issue order: the last stage's commit covers the whole product
+    if (KT > 0) alive = mbar_wait(smem_u32(&mbar_free[(KT - 1) & 1]), (uint32_t)(((KT - 1) >> 1) & 1)) && alive;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (!alive && tid == 0) atomicExch(status, 1);
+
+    if (alive) {
+        // warp w: TMEM lanes 32 (w % 4) .. +31 = rows; output columns 32 (w / 4) .. +31: re at TMEM column n, im at 64 + n
+        const int q = warp & 3, hsel = warp >> 2;
+        const int m = m0 + q * 32 + lane;
+        uint32_t vr[32], vi[32];
+        if (KT > 0) {
+            tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(hsel * 32), vr);
+            tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(64 + hsel * 32), vi);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) vr[j] = vi[j] = 0u;
+        }
+        if (m < p.M) {
+            const int64_t mo = p.cm.at(m);
+            const float alr = (float)p.alpha.x, ali = (float)p.alpha.y, ber = (float)p.beta.x, bei = (float)p.beta.y;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int n = n0 + hsel * 32 + j;
+                if (n >= p.N) continue;
+                float2* dst = C + mo + p.cn.at(n);
+                const float re = __uint_as_float(vr[j]), im = __uint_as_float(vi[j]);
+                float2 o = make_float2(alr * re - ali * im, alr * im + ali * re);
+                if (!p.beta_zero) {
+                    float2 old = *dst;
+                    o.x += ber * old.x - bei * old.y;
+                    o.y += ber * old.y + bei * old.x;
+                }
+                *dst = o;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem_d) : "memory");
+}
+
+}  // namespace
+
+int32_t init_gemm_c64_tc5(qb200_ctx* ctx) {
+    QB_CUDA(ctx, cudaFuncSetAttribute(gemm_c64_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_TC5_SMEM));
+    return QB200_OK;
+}
+
+// QB200_C64_TCGEN05=1 routes ComplexF32 contractions through the tcgen05 kernel (opt-in until it has been through the
+// full ComplexF32 parity suite on a B200; the mma.sync kernel of gemm_c64.cu is the default)
+bool gemm_c64_tc5_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("QB200_C64_TCGEN05");
+        return e && e[0] == '1';
+    }();
+    return on;
+}
+
+// `args` already oriented (M >= N side on the 128-wide tile) by launch_gemm_c64; no split-K in this kernel
+int32_t launch_gemm_c64_tc5(qb200_ctx* ctx, const GemmArgs& args) {
+    dim3 grid((args.M + TM - 1) / TM, (args.N + TN - 1) / TN, args.batch);
+    if (grid.y > 65535 || grid.z > 65535) QB_FAIL(ctx, QB200_E_UNSUPPORTED, "gemm_c64_tc5 grid too large");
+    Workspace ws(ctx);
+    int* status = ws.get<int>(1);
+    if (!status) QB_FAIL(ctx, QB200_E_CUDA, "gemm_c64_tc5: workspace allocation failed");
+    QB_CUDA(ctx, cudaMemsetAsync(status, 0, sizeof(int), ctx->stream));
+    gemm_c64_tc5_kernel<<<grid, T_THREADS, GEMM_TC5_SMEM, ctx->stream>>>(args, status);
+    QB_LAUNCH_CHECK(ctx);
+    if (getenv("QB200_C64_TCGEN05_CHECK")) {  // debugging aid: surface an mbarrier timeout instead of wrong numbers
+        int h = 0;
+        QB_CUDA(ctx, cudaMemcpyAsync(&h, status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (h) QB_FAIL(ctx, QB200_E_CUDA, "gemm_c64_tc5: timeout waiting for an MMA commit");
+    }
+    return QB200_OK;
+}
+
+}  // namespace qb
