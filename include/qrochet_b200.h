@@ -14,7 +14,7 @@
  *   - tensors are dense, COLUMN-MAJOR (first mode fastest, as Julia arrays), extents are int64,
  *     modes are caller-chosen int32 labels (the Symbol <-> int32 map lives on the Julia side).
  *   - dtype: QB200_C128 (ComplexF64, primary; FP64 tensor-core DMMA arithmetic) and QB200_C64 (ComplexF32: native
- *     float2 storage; qb200_contract runs on the TF32 tensor path with the 3xTF32 split (FP32-level accuracy), the
+ *     float2 storage; qb200_contract runs on tcgen05 (TF32, 3xTF32 split, TMEM accumulators: FP32-level accuracy), the
  *     HBM-bound helpers run natively, qb200_qr / qb200_svd factorise in FP64 and narrow the factors).  The operands
  *     of one call must share the complex type.  QB200_F64 holds Schmidt vectors; QB200_F32 vectors are accepted and
  *     held widened to FP64 (upload / download convert).  The fused qb200_mps_* / qb200_tn_* paths are ComplexF64.

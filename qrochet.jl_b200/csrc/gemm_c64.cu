@@ -340,13 +340,17 @@ int32_t launch_gemm_c64(qb200_ctx* ctx, const GemmArgs& args_in) {
     args.ksplit = 1;
     args.partial = nullptr;
     args.acc_init = 0;
-    if (gemm_c64_tc5_enabled()) return launch_gemm_c64_tc5(ctx, args);
     Workspace ws(ctx);
     {
         int64_t tiles = (int64_t)((args.M + FBM - 1) / FBM) * ((args.N + FBN - 1) / FBN);
         int KT = (args.K + FBK - 1) / FBK;
+        int want = 1;
+        if (args.batch == 1 && tiles * 2 <= ctx->sm_count && KT >= 32)
+            want = (int)std::min<int64_t>(ctx->sm_count / tiles, KT / 8);
+        // the tcgen05 kernel (gemm_c64_tc5.cu) takes every product except the few-tiles / long-K ones that need
+        // split-K to fill the machine, which stay on the mma.sync kernel below
+        if (want <= 1 && gemm_c64_tc5_enabled()) return launch_gemm_c64_tc5(ctx, args);
         if (args.batch == 1 && tiles * 2 <= ctx->sm_count && KT >= 32) {
-            int want = (int)std::min<int64_t>(ctx->sm_count / tiles, KT / 8);
             if (want > 1) {
                 args.partial = reinterpret_cast<c128*>(ws.get<float2>((size_t)want * args.M * args.N));
                 if (!args.partial) QB_FAIL(ctx, QB200_E_CUDA, "gemm_c64: split-K workspace allocation failed");
