@@ -237,6 +237,9 @@ int32_t qb200_bench_hmma_peak(qb200_ctx* ctx, double* tflops2);
  * ld): out3 = {max |D - expected| of a self-checked M = 128, N = 128 / 256 product (must be 0), issue-bound TF32
  * TFLOP/s at N = 128, at N = 256} */
 int32_t qb200_bench_tcgen05_tf32(qb200_ctx* ctx, double* out3);
+/* the same probe on the INT8 tensor pipe (S8 x S8 -> S32 in TMEM; building block of the planned FP64 emulation):
+ * out3 = {max |D - expected| (must be 0), issue-bound TOP/s at N = 128, at N = 256} */
+int32_t qb200_bench_tcgen05_i8(qb200_ctx* ctx, double* out3);
 /* FP64 pipes micro-benchmark: TFLOP/s of {DMMA only, DFMA only, both issued from alternating warps} */
 int32_t qb200_bench_dual_pipe(qb200_ctx* ctx, double* tflops3);
 /* DMMA issue-pattern micro-benchmark: TFLOP/s for {independent accumulators, complex-multiply pattern with register

@@ -159,6 +159,124 @@ __global__ void __launch_bounds__(128, 1) tc5_probe_kernel(int iters, int check,
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(N) : "memory");
 }
 
+// ---- the same probe on the INT8 tensor pipe (kind::i8, S8 x S8 -> S32 in TMEM): the building block of the FP64
+// ---- emulation by Ozaki splitting planned for the Jacobi update / Gram kernels.  One MMA consumes
+// ---- K = 32 int8 = two 16-byte K chunks; the canonical layout is the same with 16 elements per 16-byte unit.
+constexpr int TI_KBLK = 128;  // int8 K elements resident per tile: 4 MMAs of K = 32
+
+__device__ __forceinline__ uint32_t make_idesc_i8(int M, int N) {
+    // c_format [4,6) = 2 (S32), a_format [7,10) = b_format [10,13) = 1 (signed 8 bit), K-major, n_dim, m_dim
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                        uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+template <int N>
+__global__ void __launch_bounds__(128, 1) tc5_probe_i8_kernel(int iters, int check, unsigned* __restrict__ maxerr,
+                                                              int* __restrict__ status) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    signed char* As = reinterpret_cast<signed char*>(smem_raw);  // 128 x 128 int8 = 16 KB
+    signed char* Bs = As + TC_M * TI_KBLK;                        // N x 128
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t tmem_base_smem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr uint32_t SBO = 128, LBO_A = TC_M * 16, LBO_B = N * 16;
+
+    for (int e = tid; e < TC_M * TI_KBLK; e += 128) {
+        int r = e % TC_M, k = e / TC_M;
+        As[(k >> 4) * LBO_A + (r >> 3) * SBO + (r & 7) * 16 + (k & 15)] = (signed char)a_val(r, k);
+    }
+    for (int e = tid; e < N * TI_KBLK; e += 128) {
+        int n = e % N, k = e / N;
+        Bs[(k >> 4) * LBO_B + (n >> 3) * SBO + (n & 7) * 16 + (k & 15)] = (signed char)b_val(n, k);
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                     "n"(N)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_smem;
+
+    if (tid == 0) {
+        const uint32_t idesc = make_idesc_i8(TC_M, N);
+        const uint32_t a0 = smem_u32(As), b0 = smem_u32(Bs);
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int kk = 0; kk < TI_KBLK / 32; ++kk) {
+                const uint64_t da = make_smem_desc(a0 + kk * 2 * LBO_A, LBO_A, SBO);
+                const uint64_t db = make_smem_desc(b0 + kk * 2 * LBO_B, LBO_B, SBO);
+                umma_i8(tmem_d, da, db, idesc, (it | kk) ? 1u : 0u);
+            }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar))
+                     : "memory");
+    }
+    const bool done = mbar_wait(smem_u32(&mbar), 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (!done && tid == 0) atomicExch(status, 1);
+
+    if (check && done) {
+        const int row = warp * 32 + lane;
+        unsigned worst = 0;
+        for (int c0 = 0; c0 < N; c0 += 32) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                int expect = 0;
+                for (int k = 0; k < TI_KBLK; ++k) expect += a_val(row, k) * b_val(c0 + j, k);
+                int diff = (int)v[j] - expect * iters;
+                worst = max(worst, (unsigned)(diff < 0 ? -diff : diff));
+            }
+        }
+        atomicMax(maxerr, worst);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(N) : "memory");
+}
+
+template <int N>
+int32_t run_probe_i8(qb200_ctx* ctx, int blocks, int iters, int check, unsigned* maxerr, int* status, double* ms) {
+    const size_t smem = (size_t)(TC_M + N) * TI_KBLK + 1024;
+    QB_CUDA(ctx, cudaFuncSetAttribute(tc5_probe_i8_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QB_TRY(qb200_timer_begin(ctx));
+    tc5_probe_i8_kernel<N><<<blocks, 128, smem, ctx->stream>>>(iters, check, maxerr, status);
+    QB_LAUNCH_CHECK(ctx);
+    QB_TRY(qb200_timer_end(ctx, ms));
+    return QB200_OK;
+}
+
 template <int N>
 int32_t run_probe(qb200_ctx* ctx, int blocks, int iters, int check, unsigned* maxerr, int* status, double* ms) {
     const size_t smem = (size_t)(TC_M + N) * TC_KBLK * sizeof(float) + 1024;
@@ -209,5 +327,40 @@ extern "C" int32_t qb200_bench_tcgen05_tf32(qb200_ctx* ctx, double* out3) {
     QB_CUDA(ctx, cudaMemcpyAsync(host, maxerr, sizeof(host), cudaMemcpyDeviceToHost, ctx->stream));
     QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (host[1] != 0) QB_FAIL(ctx, QB200_E_CUDA, "tcgen05 probe: timeout waiting for the MMA commit (timing pass)");
+    return QB200_OK;
+}
+
+// INT8 twin (S8 x S8 -> S32, exact): out3 = {max |D - expected| (must be 0), issue-bound TOP/s at N = 128, at N = 256}.
+// NOT yet run on hardware (written after the round's GPU budget was spent): first thing to run next round
+// (tools/tc5_probe.py --i8).
+extern "C" int32_t qb200_bench_tcgen05_i8(qb200_ctx* ctx, double* out3) {
+    if (!ctx || !out3) return QB200_E_INVALID;
+    Workspace ws(ctx);
+    unsigned* maxerr = ws.get<unsigned>(2);
+    if (!maxerr) QB_FAIL(ctx, QB200_E_CUDA, "tcgen05 i8 probe: workspace allocation failed");
+    int* status = reinterpret_cast<int*>(maxerr + 1);
+    QB_CUDA(ctx, cudaMemsetAsync(maxerr, 0, 2 * sizeof(unsigned), ctx->stream));
+    double ms = 0.0;
+    QB_TRY(run_probe_i8<128>(ctx, 4, 3, 1, maxerr, status, &ms));
+    QB_TRY(run_probe_i8<256>(ctx, 4, 3, 1, maxerr, status, &ms));
+    unsigned host[2] = {0, 0};
+    QB_CUDA(ctx, cudaMemcpyAsync(host, maxerr, sizeof(host), cudaMemcpyDeviceToHost, ctx->stream));
+    QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (host[1] != 0) QB_FAIL(ctx, QB200_E_CUDA, "tcgen05 i8 probe: timeout waiting for the MMA commit");
+    out3[0] = (double)host[0];
+    const int blocks = ctx->sm_count, iters = 20000;
+    for (int which = 0; which < 2; ++which) {
+        double best = 0.0;
+        for (int rep = 0; rep < 3; ++rep) {
+            if (which == 0)
+                QB_TRY(run_probe_i8<128>(ctx, blocks, iters, 0, maxerr, status, &ms));
+            else
+                QB_TRY(run_probe_i8<256>(ctx, blocks, iters, 0, maxerr, status, &ms));
+            const int N = which ? 256 : 128;
+            double ops = (double)blocks * iters * (TI_KBLK / 32) * 2.0 * TC_M * N * 32;
+            best = std::max(best, ops / (ms * 1e-3) / 1e12);
+        }
+        out3[1 + which] = best;
+    }
     return QB200_OK;
 }

@@ -73,6 +73,12 @@ class Context:
         check(self.h, lib.qb200_bench_tcgen05_tf32(self.h, v))
         return float(v[0]), float(v[1]), float(v[2])
 
+    def tcgen05_i8_probe(self):
+        """(max abs error of the self-checked tcgen05 INT8 product, TOP/s at N = 128, TOP/s at N = 256)."""
+        v = (C.c_double * 3)()
+        check(self.h, lib.qb200_bench_tcgen05_i8(self.h, v))
+        return float(v[0]), float(v[1]), float(v[2])
+
     def svd_totals(self):
         """(SVDs factorised, Jacobi sweeps executed) over this context and its worker streams since creation."""
         a, b = C.c_int64(), C.c_int64()
