@@ -8,11 +8,12 @@
 //            of a sweep, only the 32 x 32 cross block X_I^H X_J afterwards (the diagonal blocks are carried by
 //            the evd kernel) -- persistent grid over (pair, 32-row chunk) items, DMMA tiles, 3-stage cp.async
 //            pipeline, partial sums written per CTA;
-//   evd    : one CTA per pair sums the partials in a fixed order (deterministic), runs a two-sided cyclic
+//   evd    : one CTA (17 warps) per pair sums the partials in a fixed order (deterministic), runs a two-sided cyclic
 //            Jacobi on the 64 x 64 Hermitian G in shared memory (32 disjoint rotations per parallel step)
 //            and leaves the product of the rotations, the unitary W_p; pairs that are already orthogonal
 //            are flagged and skipped by the update;
-//   update : X_p <- X_p W_p in place with DMMA tiles, the W slice of each warp in registers.
+//   update : X_p <- X_p W_p in place with DMMA tiles, the W slice of each warp in registers, complex products by the
+//            3M (Gauss) scheme: 3 real DMMA + operand sums per complex tile instead of 4 (also in the cross Gram).
 // nb-1 steps make a sweep; sweeps repeat until the largest |x_i^H x_j| / (|x_i||x_j|) seen in a sweep is below
 // tolerance.  sigma_j = |x_j|.  The rotations are NOT accumulated: with R^H = Xn S Vs^H the right factor is
 // V = P Xn and the left factor comes from ONE GEMM, Y = B0 Xn S^-1 (qb_svd_emit).  The rotations only ever come
