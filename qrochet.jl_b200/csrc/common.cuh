@@ -65,6 +65,22 @@ static inline cudaError_t qb_stream_sync(qb200_ctx* ctx) {
     return cudaEventSynchronize(ctx->ev_block);
 }
 
+// Asynchronous failure word: kernels that can time out on a hardware barrier (the tcgen05 GEMM waiting for an MMA
+// commit) raise it from the device -- it lives in the context's pinned scratch page, which the device addresses
+// directly -- and the next synchronising call (download, synchronize, norm) turns it into an error instead of letting
+// wrong numbers through.  The last double of the 64 KiB page is never used for staging.
+static inline int* qb_async_status(qb200_ctx* ctx) { return reinterpret_cast<int*>(ctx->scratch_host + 8191); }
+static inline int32_t qb_check_async_status(qb200_ctx* ctx) {
+    if (!ctx->scratch_host) return 0;
+    volatile int* st = qb_async_status(ctx);
+    if (*st) {
+        *st = 0;
+        ctx->err = "a tcgen05 kernel timed out waiting for an MMA commit: results of this stream are invalid";
+        return -2;  // QB200_E_CUDA
+    }
+    return 0;
+}
+
 int32_t qb_svd_init(qb200_ctx* ctx);
 int32_t qb_qr_init(qb200_ctx* ctx);
 qb200_ctx* qb_worker(qb200_ctx* parent, int index);  // creates workers lazily

@@ -28,6 +28,7 @@ int32_t qb200_create(int32_t device, qb200_ctx** out) {
     cudaEventCreate(&ctx->ev1);
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaMallocHost(&ctx->scratch_host, 1 << 16);
+    if (ctx->scratch_host) memset(ctx->scratch_host, 0, 1 << 16);  // incl. the asynchronous status word (qb_async_status)
     // keep freed workspace cached in the pool instead of returning it to the driver
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -91,7 +92,7 @@ int32_t qb200_set_stream(qb200_ctx* ctx, void* s) {
 int32_t qb200_synchronize(qb200_ctx* ctx) {
     if (!ctx) return QB200_E_INVALID;
     QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return QB200_OK;
+    return qb_check_async_status(ctx);
 }
 
 int64_t qb200_launch_count(qb200_ctx* ctx) {
@@ -127,6 +128,7 @@ qb200_ctx* qb_worker(qb200_ctx* parent, int index) {
         cudaEventCreate(&w->ev0);
         cudaEventCreate(&w->ev1);
         cudaMallocHost(&w->scratch_host, 1 << 16);
+        if (w->scratch_host) memset(w->scratch_host, 0, 1 << 16);
         cudaEventCreateWithFlags(&w->ev_block, cudaEventBlockingSync | cudaEventDisableTiming);
         parent->workers.push_back(w);
     }
@@ -253,7 +255,7 @@ int32_t qb200_tensor_download(qb200_ctx* ctx, const qb200_tensor* t, void* host)
     size_t n = (size_t)t->numel() * dtype_size(t->dtype);
     QB_CUDA(ctx, cudaMemcpyAsync(host, t->data, n, cudaMemcpyDeviceToHost, ctx->stream));
     QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return QB200_OK;
+    return qb_check_async_status(ctx);
 }
 int32_t qb200_tensor_rank(const qb200_tensor* t) { return t ? t->rank : -1; }
 int32_t qb200_tensor_dtype(const qb200_tensor* t) { return t ? t->user_dtype : -1; }

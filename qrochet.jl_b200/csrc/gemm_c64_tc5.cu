@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) gemm_c64_tc5_kernel(const GemmAr
     // every MMA completes in issue order: the last stage's commit covers the whole product
     if (KT > 0) alive = mbar_wait(smem_u32(&mbar_free[(KT - 1) & 1]), (uint32_t)(((KT - 1) >> 1) & 1)) && alive;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (!alive && tid == 0) atomicExch(status, 1);
+    if (!alive && tid == 0) *reinterpret_cast<volatile int*>(status) = 1;  // pinned host word, read at the next sync
 
     if (alive) {
         // warp w: TMEM lanes 32 (w % 4) .. +31 = rows; output columns 32 (w / 4) .. +31: re at TMEM column n, im at 64 + n
@@ -328,17 +328,13 @@ bool gemm_c64_tc5_enabled() {
 int32_t launch_gemm_c64_tc5(qb200_ctx* ctx, const GemmArgs& args) {
     dim3 grid((args.M + TM - 1) / TM, (args.N + TN - 1) / TN, args.batch);
     if (grid.y > 65535 || grid.z > 65535) QB_FAIL(ctx, QB200_E_UNSUPPORTED, "gemm_c64_tc5 grid too large");
-    Workspace ws(ctx);
-    int* status = ws.get<int>(1);
-    if (!status) QB_FAIL(ctx, QB200_E_CUDA, "gemm_c64_tc5: workspace allocation failed");
-    QB_CUDA(ctx, cudaMemsetAsync(status, 0, sizeof(int), ctx->stream));
+    int* status = qb_async_status(ctx);  // raised by the kernel on an mbarrier timeout, checked at the next sync
     gemm_c64_tc5_kernel<<<grid, T_THREADS, GEMM_TC5_SMEM, ctx->stream>>>(args, status);
     QB_LAUNCH_CHECK(ctx);
-    if (getenv("QB200_C64_TCGEN05_CHECK")) {  // debugging aid: surface an mbarrier timeout instead of wrong numbers
-        int h = 0;
-        QB_CUDA(ctx, cudaMemcpyAsync(&h, status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    static const bool check_now = getenv("QB200_C64_TCGEN05_CHECK") != nullptr;  // debugging aid: check after every launch
+    if (check_now) {
         QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (h) QB_FAIL(ctx, QB200_E_CUDA, "gemm_c64_tc5: timeout waiting for an MMA commit");
+        QB_TRY(qb_check_async_status(ctx));
     }
     return QB200_OK;
 }
