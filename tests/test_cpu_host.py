@@ -179,3 +179,24 @@ def test_rand_mpo_generator_matches_reference_properties():
         q = oc.Chain(arrays, socket="operator")
         assert np.isclose(q.norm(), 1.0)
         assert max(d for a in arrays for d in a.shape[2:]) <= chi
+
+
+def test_bench_reference_arm_line_has_the_contract_keys():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the B200 arm) prints ONE JSON line with the
+    contract's keys; run here on a tiny chain so the whole CPU suite stays fast."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--sites", "8", "--bond-dim", "8"], capture_output=True, text=True,
+                         timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["unit"] == "sweeps/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
