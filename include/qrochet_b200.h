@@ -240,6 +240,10 @@ int32_t qb200_bench_tcgen05_tf32(qb200_ctx* ctx, double* out3);
 /* the same probe on the INT8 tensor pipe (S8 x S8 -> S32 in TMEM; building block of the planned FP64 emulation):
  * out3 = {max |D - expected| (must be 0), issue-bound TOP/s at N = 128, at N = 256} */
 int32_t qb200_bench_tcgen05_i8(qb200_ctx* ctx, double* out3);
+/* EXPERIMENTAL (not yet validated on hardware; not used by any other entry point): FP64 complex panel product on the
+ * INT8 tensor pipe by Ozaki splitting, C (M x 64) = A (M x 64) . B (64 x 64), ComplexF64 rank-2 tensors, C != A.
+ * Bit-exact specification: tools/exp_ozaki.py::ozaki_complex.  Synchronises. */
+int32_t qb200_i8_panel_gemm(qb200_ctx* ctx, const qb200_tensor* A, const qb200_tensor* B, qb200_tensor* C);
 /* FP64 pipes micro-benchmark: TFLOP/s of {DMMA only, DFMA only, both issued from alternating warps} */
 int32_t qb200_bench_dual_pipe(qb200_ctx* ctx, double* tflops3);
 /* DMMA issue-pattern micro-benchmark: TFLOP/s for {independent accumulators, complex-multiply pattern with register

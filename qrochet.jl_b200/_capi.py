@@ -108,6 +108,7 @@ _protos = {
     "qb200_bench_hmma_peak": (_i32, [_p, _pdbl]),
     "qb200_bench_tcgen05_tf32": (_i32, [_p, _pdbl]),
     "qb200_bench_tcgen05_i8": (_i32, [_p, _pdbl]),
+    "qb200_i8_panel_gemm": (_i32, [_p, _p, _p, _p]),
     "qb200_bench_dual_pipe": (_i32, [_p, _pdbl]),
     "qb200_bench_dmma_patterns": (_i32, [_p, _pdbl]),
 }

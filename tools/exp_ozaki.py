@@ -11,36 +11,56 @@ BITS = 7
 
 
 def split_rows(a, ns):
-    """a (m x k) real -> integer slices s[0..ns) (int64 holding 7-bit signed values) and row scales: a ~ 2^e_r * sum_t
-    s_t 2^(-BITS (t+1))"""
+    """a (m x k) real -> ns integer slices (7-bit signed, |s| <= 64) and one exponent per row:
+    a = 2^e_r * sum_t s_t 2^(-BITS (t + 1)) + remainder.  Every operation is exact in FP64, so the device kernel
+    (i8_panel_gemm.cu) reproduces the slices bit for bit: e_r = frexp-exponent of the row maximum + 1 (0 for a zero
+    row), r = a 2^-e_r (|r| < 1/2), then ns times: r <- 128 r, s = rint(r) (ties to even), r <- r - s."""
     amax = np.abs(a).max(axis=1)
-    e = np.where(amax > 0, np.ceil(np.log2(np.maximum(amax, 1e-300))) + 1, 0.0)   # |a| / 2^e < 1/2
-    r = a / np.exp2(e)[:, None]
+    e = np.where(amax > 0, np.frexp(amax)[1] + 1, 0).astype(np.int64)
+    r = np.ldexp(a, -e[:, None])
     slices = []
     for _ in range(ns):
-        r = r * (1 << BITS)
-        s = np.rint(r)          # |s| <= 64: fits a signed 8-bit slice; the remainder is in [-1/2, 1/2]
+        r = r * float(1 << BITS)
+        s = np.rint(r)
         slices.append(s.astype(np.int64))
         r = r - s
     return slices, e
 
 
-def ozaki_real(a, b, ns):
-    """a (m x k) @ b (k x n) with ns slices each, products with i + j < ns (what ns (ns + 1) / 2 INT8 GEMMs give)"""
+def ozaki_orders(a, b, ns):
+    """integer accumulators of a (m x k) @ b (k x n), one per order d = i + j < ns (what TMEM holds), + exponents"""
     sa, ea = split_rows(a, ns)
     sb, eb = split_rows(b.T.copy(), ns)
+    acc = [sum(sa[i] @ sb[d - i].T for i in range(d + 1)) for d in range(ns)]   # exact (int64 here, int32 on device)
+    return acc, ea, eb
+
+
+def ozaki_real(a, b, ns):
+    acc, ea, eb = ozaki_orders(a, b, ns)
     out = np.zeros((a.shape[0], b.shape[1]))
-    for i in range(ns):
-        for j in range(ns - i):
-            p = sa[i] @ sb[j].T      # exact: |entries| <= 64 * 64 * k fits int32 for k = 64
-            out += p.astype(np.float64) * np.exp2(-BITS * (i + j + 2))
-    return out * np.exp2(ea)[:, None] * np.exp2(eb)[None, :]
+    for d in range(ns):
+        out += np.ldexp(acc[d].astype(np.float64), -BITS * (d + 2) + ea[:, None] + eb[None, :])
+    return out
 
 
 def ozaki_complex(x, w, ns):
-    re = ozaki_real(x.real, w.real, ns) - ozaki_real(x.imag, w.imag, ns)
-    im = ozaki_real(x.real, w.imag, ns) + ozaki_real(x.imag, w.real, ns)
-    return re + 1j * im
+    """3M product in the kernel's order of operations: products P = Xr Wr, Q = Xi Wi, S = (Xr + Xi)(Wr + Wi), one after
+    the other, every order d added straight into Cr / Ci:  P: Cr += t, Ci -= t;  Q: Cr -= t, Ci -= t;  S: Ci += t."""
+    cr = np.zeros((x.shape[0], w.shape[1]))
+    ci = np.zeros_like(cr)
+    for which, (a, b) in enumerate(((x.real, w.real), (x.imag, w.imag), (x.real + x.imag, w.real + w.imag))):
+        acc, ea, eb = ozaki_orders(np.ascontiguousarray(a), np.ascontiguousarray(b), ns)
+        for d in range(ns):
+            t = np.ldexp(acc[d].astype(np.float64), -BITS * (d + 2) + ea[:, None] + eb[None, :])
+            if which == 0:
+                cr += t
+                ci -= t
+            elif which == 1:
+                cr -= t
+                ci -= t
+            else:
+                ci += t
+    return cr + 1j * ci
 
 
 def colwise_err(got, want):
