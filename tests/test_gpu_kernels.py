@@ -327,3 +327,13 @@ def test_gather_paths_bit_exact(qb, ctx, dtype):
     v = rnd(257)
     assert abs(qb.norm2(ctx.array(v)) - np.linalg.norm(v.astype(np.complex128 if np.iscomplexobj(v) else np.float64))) \
         <= 1e-12 * np.linalg.norm(v)
+
+
+def test_tcgen05_tf32_building_block_is_exact(qb, ctx):
+    """The hand-written tcgen05 / TMEM primitives under the ComplexF32 GEMM (tc5_probe.cu: UMMA shared-memory layout by
+    st.shared, tcgen05.alloc, mma.kind::tf32 from one thread, commit -> mbarrier, tcgen05.ld): an integer-valued
+    128 x N x 96 product must come back exactly, and the issue-bound rate must be in tcgen05 territory (the mma.sync
+    TF32 path peaks at 277 TFLOP/s on this part)."""
+    err, tf128, tf256 = ctx.tcgen05_tf32_probe()
+    assert err == 0.0
+    assert tf128 > 500.0 and tf256 > 500.0, (tf128, tf256)
