@@ -212,6 +212,10 @@ int32_t qb_svd_emit(qb200_ctx* ctx, SvdState* st, int64_t kept, c128* U, int64_t
                     int64_t vinv_div, double sigma_scale);
 void qb_svd_release(qb200_ctx* ctx, SvdState* st);
 
+// experimental INT8 (Ozaki) Jacobi update step (i8_panel_gemm.cu), selected by QB200_UPDATE_I8=1
+int32_t qb_i8_jacobi_update(qb200_ctx* ctx, c128* Z, int64_t ldz, int rows, int nb, int step, const c128* Wg,
+                            const int* flags, int npairs);
+
 // Cholesky-QR step on a 64-column panel with the Jacobi gram / update kernels (svd_jacobi.cu), used by K4
 int32_t qb_cholqr_panel_step(qb200_ctx* ctx, c128* P, int64_t ld, int64_t m, c128* R, int64_t ldr, c128* Gpart,
                              c128* Wbuf, int* flags_dev, int* fail_dev);

@@ -2,7 +2,8 @@
 // ComplexF64 column-major -- the shape of the Jacobi update X_p <- X_p W_p.
 //
 // STATUS: written after this round's GPU budget was spent -- compiles for sm_100a, NOT yet run on hardware.  It is
-// reachable only through qb200_i8_panel_gemm (tools/i8_panel_check.py), never from the SVD.  The arithmetic it has to
+// reachable only through qb200_i8_panel_gemm (tools/i8_panel_check.py) and, with QB200_UPDATE_I8=1, as the update step of
+// the Jacobi SVD (qb_i8_jacobi_update; off by default).  The arithmetic it has to
 // reproduce BIT FOR BIT is tools/exp_ozaki.py::ozaki_complex (every floating-point operation below is exact or is
 // performed in the same order there), which is how it is to be validated next round.
 //
@@ -119,9 +120,44 @@ __device__ __forceinline__ void slice_and_store(double (&r)[NV], unsigned char* 
     }
 }
 
+// circle-method round robin of svd_jacobi.cu (block pair of `pair` at `step`; nb even)
+__device__ __forceinline__ void i8_rr_pair(int n, int step, int k, int& p, int& q) {
+    if (n == 2) {
+        p = 0;
+        q = 1;
+        return;
+    }
+    int a, b;
+    if (k == 0) {
+        a = n - 1;
+        b = step;
+    } else {
+        a = (step + k) % (n - 1);
+        b = (step - k + (n - 1)) % (n - 1);
+    }
+    p = min(a, b);
+    q = max(a, b);
+}
+
+// JACOBI = false: C (M x 64) = A (M x 64) B, plain column-major panels (blockIdx.y unused).
+// JACOBI = true : the update step of the one-sided block Jacobi, in place: A = C = X (ld lda), blockIdx.y = pair, the
+//                 64 panel columns are the two 32-column blocks (I, J) of the pair, B = Wg + pair * 64 * 64, pairs with
+//                 flags[pair] == 0 (W = identity) are skipped.  In place is safe: a CTA reads its 128 rows of the panel
+//                 for all three products before it writes them, and no other CTA touches them.
+template <bool JACOBI>
 __global__ void __launch_bounds__(I8_THREADS, 1)
-    i8_panel_gemm_kernel(const c128* __restrict__ A, int64_t lda, int M, const c128* __restrict__ B, c128* __restrict__ C,
-                         int64_t ldc, int* __restrict__ status) {
+    i8_panel_gemm_kernel(const c128* A, int64_t lda, int M, const c128* __restrict__ B, c128* C, int64_t ldc,
+                         int* __restrict__ status, int nb, int step, const int* __restrict__ flags) {  // A may alias C
+    int blkI = 0, blkJ = 1;
+    if (JACOBI) {
+        if (!flags[blockIdx.y]) return;  // uniform for the CTA, before anything is allocated
+        i8_rr_pair(nb, step, (int)blockIdx.y, blkI, blkJ);
+        B += (size_t)blockIdx.y * (I8_K * I8_N);
+    }
+    auto col_of = [&](int c) -> int64_t {  // panel column c -> column of the matrix
+        if (!JACOBI) return c;
+        return (c < 32) ? (int64_t)blkI * 32 + c : (int64_t)blkJ * 32 + (c - 32);
+    };
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* sA = smem;                                  // 8 planes of the current product
@@ -194,7 +230,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1)
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
                 c128 v = make_double2(0.0, 0.0);
-                if (row_ok) v = A[(m0 + arow) + (int64_t)(ahalf * 32 + c) * lda];
+                if (row_ok) v = A[(m0 + arow) + col_of(ahalf * 32 + c) * lda];
                 r[c] = prod == 0 ? v.x : (prod == 1 ? v.y : v.x + v.y);
                 mx = fmax(mx, fabs(r[c]));
             }
@@ -269,7 +305,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1)
     if (alive && (m0 + erow) < M) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-            C[(m0 + erow) + (int64_t)(hsel * 32 + j) * ldc] = make_double2(acc_re[j], acc_im[j]);
+            C[(m0 + erow) + col_of(hsel * 32 + j) * ldc] = make_double2(acc_re[j], acc_im[j]);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -291,12 +327,30 @@ extern "C" int32_t qb200_i8_panel_gemm(qb200_ctx* ctx, const qb200_tensor* A, co
     if (M > (1 << 30)) QB_FAIL(ctx, QB200_E_UNSUPPORTED, "i8_panel_gemm: too many rows");
     static bool attr_set = false;
     if (!attr_set) {
-        QB_CUDA(ctx, cudaFuncSetAttribute(i8_panel_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8_SMEM));
+        QB_CUDA(ctx, cudaFuncSetAttribute(i8_panel_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8_SMEM));
         attr_set = true;
     }
-    i8_panel_gemm_kernel<<<(unsigned)((M + I8_M - 1) / I8_M), I8_THREADS, I8_SMEM, ctx->stream>>>(
-        (const c128*)A->data, M, (int)M, (const c128*)B->data, (c128*)C->data, M, qb_async_status(ctx));
+    i8_panel_gemm_kernel<false><<<(unsigned)((M + I8_M - 1) / I8_M), I8_THREADS, I8_SMEM, ctx->stream>>>(
+        (const c128*)A->data, M, (int)M, (const c128*)B->data, (c128*)C->data, M, qb_async_status(ctx), 2, 0, nullptr);
     QB_LAUNCH_CHECK(ctx);
     QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return qb_check_async_status(ctx);
+}
+
+// One update step of the block Jacobi on the INT8 pipe (experimental, QB200_UPDATE_I8=1 in svd_jacobi.cu): X_p <- X_p W_p
+// for every active pair, in place.  Same arguments as jacobi_update_kernel.  Asynchronous; a timeout surfaces at the
+// next synchronising call.  NOTE: no column scaling yet: fine for panels whose column norms are
+// within ~1e6 of each other, not for strongly graded ones.
+int32_t qb_i8_jacobi_update(qb200_ctx* ctx, c128* Z, int64_t ldz, int rows, int nb, int step, const c128* Wg,
+                            const int* flags, int npairs) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        QB_CUDA(ctx, cudaFuncSetAttribute(i8_panel_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8_SMEM));
+        attr_set = true;
+    }
+    dim3 grid((unsigned)((rows + I8_M - 1) / I8_M), (unsigned)npairs);
+    i8_panel_gemm_kernel<true><<<grid, I8_THREADS, I8_SMEM, ctx->stream>>>(Z, ldz, rows, Wg, Z, ldz, qb_async_status(ctx), nb,
+                                                                         step, flags);
+    QB_LAUNCH_CHECK(ctx);
+    return QB200_OK;
 }
