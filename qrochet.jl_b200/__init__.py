@@ -6,6 +6,7 @@ from .device import (Context, DeviceArray, conj, contract, norm2, permute, qr, s
                      slice_mode, svd)
 from . import chain
 from .mps import B200MPS
+from .product import Product
 from .tn import SlicedContraction, amplitude_network, circuit_network, fsim, random_fsim_circuit
 from .parallel import (comm_allreduce_sum, comm_allreduce_sum_vec, comm_init, comm_unique_id,
                        contract_sliced_distributed, expect_batch_distributed, my_slices, torch_allreduce_sum,

@@ -200,3 +200,25 @@ def test_bench_reference_arm_line_has_the_contract_keys():
     assert d["impl"] == "reference" and d["unit"] == "sweeps/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_product_ansatz_host_mirror_matches_oracle():
+    """qrochet_b200.Product (Product.jl restated on the host) against the oracle's restatement and the reference's
+    own test (test/Ansatz/Product_test.jl)."""
+    import qrochet_b200 as qb
+    from oracle.chain import Product as OProduct
+    r = np.random.default_rng(31)
+    vecs = [r.random(2) + 1j * r.random(2) for _ in range(3)]
+    mats = [r.random((2, 2)) for _ in range(3)]
+    p, o = qb.Product(vecs), OProduct(vecs)
+    assert p.socket == "state" and np.isclose(p.norm(), o.norm())
+    assert np.isclose(p.copy().normalize_().norm(), 1.0)
+    pm, om = qb.Product(mats), OProduct(mats)
+    assert pm.socket == "operator" and np.isclose(pm.norm(), om.norm()) and np.isclose(pm.opnorm(), om.opnorm())
+    assert np.isclose(pm.copy().normalize_().norm(), 1.0)
+    q = qb.Product([r.random(2) + 1j * r.random(2) for _ in range(3)])
+    assert np.isclose(p.overlap(q), o.overlap(OProduct(q.arrays)))
+    z, one = qb.Product.zeros(4), qb.Product.ones(4)
+    assert z.overlap(z) == 1 and z.overlap(one) == 0 and [a.tolist() for a in one.arrays] == [[False, True]] * 4
+    with pytest.raises(TypeError):
+        qb.Product([np.zeros((2, 2, 2))])
