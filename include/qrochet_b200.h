@@ -50,6 +50,8 @@ enum {
 };
 
 #define QB200_MAX_RANK 64
+/* largest physical dimension of a site accepted by the fused chain entry points (gates are staged through one pinned page) */
+#define QB200_MAX_PHYS 8
 
 /* ---- context ------------------------------------------------------------------------------ */
 int32_t qb200_create(int32_t device, qb200_ctx** ctx);
@@ -159,18 +161,26 @@ int32_t qb200_mps_mixed_canonize(qb200_ctx* ctx, qb200_mps* mps, int32_t center)
 /* truncate! (Chain.jl:390-422) on a bond holding Λ */
 int32_t qb200_mps_truncate(qb200_ctx* ctx, qb200_mps* mps, int32_t bond, int64_t maxdim, double threshold,
                            int64_t* kept);
-/* evolve!(ψ, gate; threshold, maxdim, iscanonical=true, renormalize) for a 2-site gate on
- * (bond, bond+1) (Chain.jl:606-722): gate = 16 c128 numbers, array dims (o1,o2,i1,i2) column-major.
- * One fused chain: Λ-scale -> θ GEMM -> gate -> Jacobi SVD -> truncate -> Λ^-1 scale (atol 1e-32). */
+/* evolve!(ψ, gate; threshold, maxdim, iscanonical, renormalize) for a 2-site gate on sites (bond, bond+1)
+ * (evolve_2site!, Chain.jl:606-661): gate = (p1 p2)^2 c128 numbers (16 for qubits), array dims (o1,o2,i1,i2)
+ * column-major (Dense.jl:21-34).  maxdim <= 0 / threshold < 0 = the reference's `nothing`.
+ *   iscanonical != 0: contract_2sitewf! / unpack_2sitewf! (Chain.jl:669-722) as ONE fused chain: Λ-scale -> θ GEMM ->
+ *     gate -> Jacobi SVD -> truncate! -> Λ^-1 scale (pinv atol 1e-32); the neighbouring Schmidt vectors are used where
+ *     they exist; renormalize normalises the new Schmidt vector (Chain.jl:653-654).
+ *   iscanonical == 0 (the reference's default): contract!(tn, bond) of the two sites and the Schmidt vector on the bond
+ *     if there is one, svd! leaves U, s, V^H (Chain.jl:615,645); renormalize = normalize!(ψ, sitel) =
+ *     mixed_canonize! + normalisation (Chain.jl:655-656,532-536; QB200_E_INVALID on the first bond, as
+ *     "Cannot right-canonize left-most tensor", Chain.jl:344). */
 int32_t qb200_mps_evolve2(qb200_ctx* ctx, qb200_mps* mps, int32_t bond, const void* gate_c128, int64_t maxdim,
-                          double threshold, int32_t renormalize, int64_t* kept, double* discarded_weight);
-/* One TEBD layer: nb two-site gates (16 c128 each, concatenated) on pairwise non-adjacent bonds -- the user-level
+                          double threshold, int32_t renormalize, int32_t iscanonical, int64_t* kept,
+                          double* discarded_weight);
+/* One TEBD layer: nb two-site gates (concatenated) on pairwise non-adjacent bonds -- the user-level
  * loop `for bond in odd_bonds evolve!(psi, G[bond]; ...)`.  The bond updates are independent
  * units and run concurrently on worker streams; results are identical to nb calls of qb200_mps_evolve2.
  * kept / discarded_weight: arrays of nb (may be NULL). */
 int32_t qb200_mps_evolve2_layer(qb200_ctx* ctx, qb200_mps* mps, int32_t nb, const int32_t* bonds, const void* gates_c128,
-                                int64_t maxdim, double threshold, int32_t renormalize, int64_t* kept,
-                                double* discarded_weight);
+                                int64_t maxdim, double threshold, int32_t renormalize, int32_t iscanonical,
+                                int64_t* kept, double* discarded_weight);
 /* A circuit of nearest-neighbour two-site gates in program order -- the user loop
  * `for (G, bond) in circuit evolve!(psi, G; ...)` (Chain.jl:543-584 called repeatedly; the Quac/Yao front-ends of
  * SURVEY.md §8 f2 produce such lists).  Bonds may repeat and touch: an update starts as soon as the earlier updates
@@ -178,7 +188,7 @@ int32_t qb200_mps_evolve2_layer(qb200_ctx* ctx, qb200_mps* mps, int32_t nb, cons
  * qb200_mps_evolve2 in the given order.  kept / discarded_weight: arrays of nops (may be NULL). */
 int32_t qb200_mps_evolve2_circuit(qb200_ctx* ctx, qb200_mps* mps, int32_t nops, const int32_t* bonds,
                                   const void* gates_c128, int64_t maxdim, double threshold, int32_t renormalize,
-                                  int64_t* kept, double* discarded_weight);
+                                  int32_t iscanonical, int64_t* kept, double* discarded_weight);
 /* evolve_1site! (Chain.jl:586-603): gate = p*p c128 numbers (o, i) column-major */
 int32_t qb200_mps_evolve1(qb200_ctx* ctx, qb200_mps* mps, int32_t site, const void* gate_c128);
 /* ---- MPO x MPS (no function exists in the reference: composed from MPO(arrays) Chain.jl:133-172,
@@ -200,6 +210,12 @@ int32_t qb200_mps_overlap(qb200_ctx* ctx, const qb200_mps* a, const qb200_mps* b
  * built once and reused by every observable. */
 int32_t qb200_mps_expect1_batch(qb200_ctx* ctx, const qb200_mps* mps, int32_t nobs, const int32_t* sites,
                                 const void* ops_c128, double* results);
+/* expect(ψ, observables) with the reference's exact composition (Chain.jl:724-735): ϕ = copy(ψ); evolve!(ϕ, O) for
+ * every observable in order (default keywords: no truncation, iscanonical = false); result = contract(merge(ϕ, ψ')) =
+ * <ψ|O_k ... O_1|ψ>, un-normalised.  nlanes[i] is 1 or 2; sites[i] = 0-based (left) site of observable i; ops = the
+ * operator arrays concatenated, dims (o, i) resp. (o1,o2,i1,i2) column-major. */
+int32_t qb200_mps_expect(qb200_ctx* ctx, const qb200_mps* mps, int32_t nobs, const int32_t* nlanes,
+                         const int32_t* sites, const void* ops_c128, double result[2]);
 
 /* ---- sliced contraction of a general tensor network (examples/distributed.jl:46-101) -------------
  * The network is given as `ntensors` leaves (rank, modes, extents concatenated); the planner runs a
@@ -225,30 +241,14 @@ int32_t qb200_tn_contract_sliced(qb200_ctx* ctx, qb200_tnplan* plan, qb200_tenso
 int32_t qb200_comm_unique_id(char id_out[128]);
 int32_t qb200_comm_init(qb200_ctx* ctx, int32_t nranks, int32_t rank, const char id[128]);
 int32_t qb200_comm_allreduce_sum(qb200_ctx* ctx, double* host_values, int32_t count);
+/* one-to-all replication over NVLink (ncclBroadcast, in place): a tensor (the `@everywhere` broadcast of the leaf
+ * tensors, examples/distributed.jl:58-64) ... */
+int32_t qb200_comm_broadcast(qb200_ctx* ctx, qb200_tensor* t, int32_t root);
+/* ... and a whole device-resident MPS (batched independent expectation values: the state is replicated once, the
+ * observables are dealt i mod W, one sum gathers the values).  Root passes its chain in *inout, every other rank
+ * passes NULL and receives a new handle. */
+int32_t qb200_mps_broadcast(qb200_ctx* ctx, qb200_mps** inout, int32_t root);
 int32_t qb200_comm_destroy(qb200_ctx* ctx);
-
-/* ---- diagnostics --------------------------------------------------------------------------- */
-/* FP64 tensor-core (DMMA m8n8k4) peak micro-benchmark: returns achieved TFLOP/s */
-int32_t qb200_bench_dmma_peak(qb200_ctx* ctx, double* tflops);
-/* legacy warp-level tensor path (mma.sync) peaks, dense, FP32 accumulate: tflops2 = {TF32 m16n8k8, BF16 m16n8k16};
- * the denominators for the ComplexF32 kernels */
-int32_t qb200_bench_hmma_peak(qb200_ctx* ctx, double* tflops2);
-/* tcgen05 / TMEM building block of the ComplexF32 path (hand-written PTX: tcgen05.alloc / mma.kind::tf32 / commit /
- * ld): out3 = {max |D - expected| of a self-checked M = 128, N = 128 / 256 product (must be 0), issue-bound TF32
- * TFLOP/s at N = 128, at N = 256} */
-int32_t qb200_bench_tcgen05_tf32(qb200_ctx* ctx, double* out3);
-/* the same probe on the INT8 tensor pipe (S8 x S8 -> S32 in TMEM; building block of the planned FP64 emulation):
- * out3 = {max |D - expected| (must be 0), issue-bound TOP/s at N = 128, at N = 256} */
-int32_t qb200_bench_tcgen05_i8(qb200_ctx* ctx, double* out3);
-/* EXPERIMENTAL (not yet validated on hardware; not used by any other entry point): FP64 complex panel product on the
- * INT8 tensor pipe by Ozaki splitting, C (M x 64) = A (M x 64) . B (64 x 64), ComplexF64 rank-2 tensors, C != A.
- * Bit-exact specification: tools/exp_ozaki.py::ozaki_complex.  Synchronises. */
-int32_t qb200_i8_panel_gemm(qb200_ctx* ctx, const qb200_tensor* A, const qb200_tensor* B, qb200_tensor* C);
-/* FP64 pipes micro-benchmark: TFLOP/s of {DMMA only, DFMA only, both issued from alternating warps} */
-int32_t qb200_bench_dual_pipe(qb200_ctx* ctx, double* tflops3);
-/* DMMA issue-pattern micro-benchmark: TFLOP/s for {independent accumulators, complex-multiply pattern with register
- * operands, the same with A fragments re-loaded from shared memory} x {8, 16, 32 warps per SM}; row-major [3][3] */
-int32_t qb200_bench_dmma_patterns(qb200_ctx* ctx, double* tflops9);
 
 #ifdef __cplusplus
 }

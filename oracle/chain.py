@@ -780,3 +780,24 @@ def expect_mpo(chain: "Chain", mpo_arrays):
         dense_arrays.append(t.permute(order).data)
     hpsi = Chain(apply_mpo_arrays(dense_arrays, mpo_arrays))
     return hpsi.overlap(Chain(dense_arrays))
+
+
+def chain_from_vidal(sites_lor, lambdas) -> "Chain":
+    """Test helper: an open-boundary MPS from site arrays in the device's private (l, o, r) layout (edge bonds of
+    size 1 kept) plus the Schmidt vectors sitting on its bonds (`None` where absent) -- the labelled network
+    `canonize!` / Vidal `evolve!` leave behind (Λ on a hyperindex, Chain.jl:488-494).  Lets a parity test start the
+    oracle from exactly the state the device holds."""
+    n = len(sites_lor)
+    arrays = []
+    for k, a in enumerate(sites_lor):
+        a = np.transpose(np.asarray(a), (1, 0, 2))  # -> (o, l, r), the reference's default order (Chain.jl:33)
+        if k == 0:
+            a = a[:, 0, :]
+        if k == n - 1:
+            a = a[..., 0]
+        arrays.append(np.array(a))
+    q = Chain(arrays)
+    for b, lam in enumerate(lambdas):
+        if lam is not None:
+            q.tn.push(Tensor(np.array(lam, dtype=np.float64), [q.bond_ind(site(b + 1), site(b + 2))]))
+    return q

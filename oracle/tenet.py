@@ -92,7 +92,8 @@ def contract(a: Tensor, b: Tensor, dims=None) -> Tensor:
     dims = shared if dims is None else [i for i in dims if i in shared]
     out = [i for i in a.inds if i not in dims] + [i for i in b.inds if i not in a.inds]
     t = _letters(a.inds + b.inds)
-    res = np.einsum(a.data, [t[i] for i in a.inds], b.data, [t[i] for i in b.inds], [t[i] for i in out])
+    # optimize=True: a pairwise contraction goes through tensordot (BLAS zgemm, what OMEinsum's TTGT path calls)
+    res = np.einsum(a.data, [t[i] for i in a.inds], b.data, [t[i] for i in b.inds], [t[i] for i in out], optimize=True)
     return Tensor(res, out)
 
 
@@ -105,7 +106,7 @@ def contract_many(tensors: Sequence[Tensor], summed: Iterable[str]) -> Tensor:
     args = []
     for x in tensors:
         args += [x.data, [t[i] for i in x.inds]]
-    res = np.einsum(*args, [t[i] for i in out], optimize="greedy" if len(tensors) > 2 else False)
+    res = np.einsum(*args, [t[i] for i in out], optimize="greedy" if len(tensors) > 1 else False)  # pairwise steps -> BLAS
     return Tensor(res, out)
 
 
@@ -291,21 +292,24 @@ class TensorNetwork:
         work = list(self.tensors)
         if not work:
             raise ValueError("empty network")
+        # how many live tensors hold each index (an index survives a pairwise step while someone else still holds it)
+        holders = {}
+        for t in work:
+            for i in set(t.inds):
+                holders[i] = holders.get(i, 0) + 1
         while len(work) > 1:
             # cheapest-result-first greedy choice among connected pairs
             best = None
+            sets = [set(t.inds) for t in work]
             for a, b in itertools.combinations(range(len(work)), 2):
-                ia, ib = work[a].inds, work[b].inds
-                if not set(ia) & set(ib):
+                if not sets[a] & sets[b]:
                     continue
-                others = set()
-                for k, t in enumerate(work):
-                    if k != a and k != b:
-                        others.update(t.inds)
-                keep = [i for i in dict.fromkeys(ia + ib) if i in opened or i in others]
+                ia, ib = work[a].inds, work[b].inds
+                keep = [i for i in dict.fromkeys(ia + ib)
+                        if i in opened or holders[i] - (i in sets[a]) - (i in sets[b]) > 0]
                 size = 1
                 for i in keep:
-                    size *= work[a].size(i) if i in ia else work[b].size(i)
+                    size *= work[a].size(i) if i in sets[a] else work[b].size(i)
                 cost = (size, a, b)
                 if best is None or cost < best[0]:
                     best = (cost, a, b, keep)
@@ -316,8 +320,13 @@ class TensorNetwork:
                 _, a, b, keep = best
             t = _letters(work[a].inds + work[b].inds)
             res = np.einsum(work[a].data, [t[i] for i in work[a].inds], work[b].data, [t[i] for i in work[b].inds],
-                            [t[i] for i in keep])
+                            [t[i] for i in keep], optimize=True)
             new = Tensor(res, keep)
+            for x in (work[a], work[b]):
+                for i in set(x.inds):
+                    holders[i] -= 1
+            for i in set(keep):
+                holders[i] = holders.get(i, 0) + 1
             work = [x for k, x in enumerate(work) if k not in (a, b)] + [new]
         last = work[0]
         summed = [i for i in last.inds if i not in opened]

@@ -8,7 +8,7 @@ from . import chain
 from .mps import B200MPS
 from .product import Product
 from .tn import SlicedContraction, amplitude_network, circuit_network, fsim, random_fsim_circuit
-from .parallel import (comm_allreduce_sum, comm_allreduce_sum_vec, comm_init, comm_unique_id,
+from .parallel import (broadcast_mps, comm_allreduce_sum, comm_allreduce_sum_vec, comm_init, comm_unique_id,
                        contract_sliced_distributed, expect_batch_distributed, my_slices, torch_allreduce_sum,
                        torch_allreduce_sum_vec)
 from .rand import bond_dims, haar_gate, heisenberg_mpo_arrays, rand_mpo_arrays, rand_mps_arrays

@@ -83,15 +83,16 @@ _protos = {
     "qb200_mps_canonize": (_i32, [_p, _p]),
     "qb200_mps_mixed_canonize": (_i32, [_p, _p, _i32]),
     "qb200_mps_truncate": (_i32, [_p, _p, _i32, _i64, _dbl, _pi64]),
-    "qb200_mps_evolve2": (_i32, [_p, _p, _i32, _p, _i64, _dbl, _i32, _pi64, _pdbl]),
-    "qb200_mps_evolve2_layer": (_i32, [_p, _p, _i32, _pi32, _p, _i64, _dbl, _i32, _pi64, _pdbl]),
-    "qb200_mps_evolve2_circuit": (_i32, [_p, _p, _i32, _pi32, _p, _i64, _dbl, _i32, _pi64, _pdbl]),
+    "qb200_mps_evolve2": (_i32, [_p, _p, _i32, _p, _i64, _dbl, _i32, _i32, _pi64, _pdbl]),
+    "qb200_mps_evolve2_layer": (_i32, [_p, _p, _i32, _pi32, _p, _i64, _dbl, _i32, _i32, _pi64, _pdbl]),
+    "qb200_mps_evolve2_circuit": (_i32, [_p, _p, _i32, _pi32, _p, _i64, _dbl, _i32, _i32, _pi64, _pdbl]),
     "qb200_mps_evolve1": (_i32, [_p, _p, _i32, _p]),
     "qb200_mps_apply_mpo": (_i32, [_p, _p, _pi64, _pi64, _p]),
     "qb200_mps_compress": (_i32, [_p, _p, _i64, _dbl]),
     "qb200_mps_expect_mpo": (_i32, [_p, _p, _pi64, _pi64, _p, _pdbl]),
     "qb200_mps_overlap": (_i32, [_p, _p, _p, _pdbl]),
     "qb200_mps_expect1_batch": (_i32, [_p, _p, _i32, _pi32, _p, _pdbl]),
+    "qb200_mps_expect": (_i32, [_p, _p, _i32, _pi32, _pi32, _p, _pdbl]),
     "qb200_tn_plan": (_i32, [_p, _i32, _pi32, _pi32, _pi64, _i64, C.POINTER(_p)]),
     "qb200_tn_plan_free": (_i32, [_p, _p]),
     "qb200_tn_plan_nslices": (_i64, [_p]),
@@ -103,15 +104,39 @@ _protos = {
     "qb200_comm_unique_id": (_i32, [C.c_char_p]),
     "qb200_comm_init": (_i32, [_p, _i32, _i32, C.c_char_p]),
     "qb200_comm_allreduce_sum": (_i32, [_p, _pdbl, _i32]),
+    "qb200_comm_broadcast": (_i32, [_p, _p, _i32]),
+    "qb200_mps_broadcast": (_i32, [_p, C.POINTER(_p), _i32]),
     "qb200_comm_destroy": (_i32, [_p]),
+}
+
+# micro-benchmarks / probes live in their own library (include/qrochet_b200_diag.h), loaded on first use
+DIAG_LIB_PATH = os.path.join(_HERE, "lib", "libqrochet_b200_diag.so")
+_diag_protos = {
     "qb200_bench_dmma_peak": (_i32, [_p, _pdbl]),
     "qb200_bench_hmma_peak": (_i32, [_p, _pdbl]),
     "qb200_bench_tcgen05_tf32": (_i32, [_p, _pdbl]),
     "qb200_bench_tcgen05_i8": (_i32, [_p, _pdbl]),
-    "qb200_i8_panel_gemm": (_i32, [_p, _p, _p, _p]),
     "qb200_bench_dual_pipe": (_i32, [_p, _pdbl]),
     "qb200_bench_dmma_patterns": (_i32, [_p, _pdbl]),
 }
+DIAG_EXPORTS = sorted(_diag_protos)
+_diag = None
+
+
+def diag():
+    """libqrochet_b200_diag.so (needs a CUDA device to do anything useful)."""
+    global _diag
+    if _diag is None:
+        if not os.path.exists(DIAG_LIB_PATH):
+            raise ImportError(f"{DIAG_LIB_PATH} not found: build it with ./build.sh")
+        d = C.CDLL(DIAG_LIB_PATH)
+        for name, (res, args) in _diag_protos.items():
+            fn = getattr(d, name)
+            fn.restype = res
+            fn.argtypes = args
+        _diag = d
+    return _diag
+
 
 EXPORTS = sorted(_protos)
 for _name, (_res, _args) in _protos.items():

@@ -1,4 +1,6 @@
-// NCCL sum of per-rank partial results (the `sum(fetch.(partial_results))` of examples/distributed.jl:101).
+// NCCL sum of per-rank partial results (the `sum(fetch.(partial_results))` of examples/distributed.jl:101) and the
+// one-to-all replication of the inputs (the `@everywhere` broadcast of the leaf tensors, examples/distributed.jl:58-64;
+// for batched expectation values: the MPS itself).
 // libnccl is resolved at run time (dlopen) so that the library itself has no link-time NCCL dependency;
 // when torch has already loaded its bundled NCCL the same copy is reused.
 #include <dlfcn.h>
@@ -11,13 +13,14 @@ typedef struct {
     char internal[128];
 } ncclUniqueId;
 typedef int ncclResult_t;
-enum { ncclFloat64 = 8, ncclSum = 0 };
+enum { ncclUint8 = 1, ncclFloat64 = 8, ncclSum = 0 };
 
 struct NcclApi {
     void* lib = nullptr;
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
@@ -36,6 +39,7 @@ NcclApi* nccl() {
             api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.lib, "ncclGetUniqueId");
             api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.lib, "ncclCommInitRank");
             api.AllReduce = (decltype(api.AllReduce))dlsym(api.lib, "ncclAllReduce");
+            api.Broadcast = (decltype(api.Broadcast))dlsym(api.lib, "ncclBroadcast");
             api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
             api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.lib, "ncclGetErrorString");
         }
@@ -44,6 +48,17 @@ NcclApi* nccl() {
     return &api;
 }
 }  // namespace
+
+// ncclBroadcast of `bytes` device bytes in place (root's content lands on every rank), on the context's stream
+int32_t qb_comm_broadcast_bytes(qb200_ctx* ctx, void* dev, size_t bytes, int root) {
+    NcclApi* a = nccl();
+    if (!a || !a->Broadcast || !ctx || !ctx->nccl_comm) QB_FAIL(ctx, QB200_E_COMM, "communicator not initialised");
+    if (bytes == 0) return QB200_OK;
+    if (!dev) QB_FAIL(ctx, QB200_E_INVALID, "broadcast: null buffer");
+    ncclResult_t r = a->Broadcast(dev, dev, bytes, ncclUint8, root, (ncclComm_t)ctx->nccl_comm, ctx->stream);
+    if (r != 0) QB_FAIL(ctx, QB200_E_COMM, "ncclBroadcast: %s", a->GetErrorString ? a->GetErrorString(r) : "error");
+    return QB200_OK;
+}
 
 extern "C" {
 
@@ -67,6 +82,8 @@ int32_t qb200_comm_init(qb200_ctx* ctx, int32_t nranks, int32_t rank, const char
     ncclResult_t r = a->CommInitRank(&comm, nranks, uid, rank);
     if (r != 0) QB_FAIL(ctx, QB200_E_COMM, "ncclCommInitRank: %s", a->GetErrorString ? a->GetErrorString(r) : "error");
     ctx->nccl_comm = comm;
+    ctx->comm_rank = rank;
+    ctx->comm_nranks = nranks;
     return QB200_OK;
 }
 
@@ -85,6 +102,11 @@ int32_t qb200_comm_allreduce_sum(qb200_ctx* ctx, double* host_values, int32_t co
     QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     memcpy(host_values, ctx->scratch_host, sizeof(double) * count);
     return QB200_OK;
+}
+
+int32_t qb200_comm_broadcast(qb200_ctx* ctx, qb200_tensor* t, int32_t root) {
+    if (!t) QB_FAIL(ctx, QB200_E_INVALID, "broadcast: null tensor");
+    return qb_comm_broadcast_bytes(ctx, t->data, (size_t)t->numel() * dtype_size(t->dtype), root);
 }
 
 int32_t qb200_comm_destroy(qb200_ctx* ctx) {

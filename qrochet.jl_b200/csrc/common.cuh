@@ -38,6 +38,7 @@ struct qb200_ctx {
     int last_svd_sweeps = 0;
     int64_t svd_calls = 0, svd_sweeps = 0;  // totals since creation (this context only; workers are summed by the getter)
     void* nccl_comm = nullptr;
+    int comm_rank = 0, comm_nranks = 1;  // set by qb200_comm_init
     void* nccl_lib = nullptr;
     double* scratch_host = nullptr;  // pinned, 64 KiB
     // optional phase profiler (CUDA events on the context stream; resolved lazily)
@@ -212,10 +213,6 @@ int32_t qb_svd_emit(qb200_ctx* ctx, SvdState* st, int64_t kept, c128* U, int64_t
                     int64_t vinv_div, double sigma_scale);
 void qb_svd_release(qb200_ctx* ctx, SvdState* st);
 
-// experimental INT8 (Ozaki) Jacobi update step (i8_panel_gemm.cu), selected by QB200_UPDATE_I8=1
-int32_t qb_i8_jacobi_update(qb200_ctx* ctx, c128* Z, int64_t ldz, int rows, int nb, int step, const c128* Wg,
-                            const int* flags, int npairs);
-
 // Cholesky-QR step on a 64-column panel with the Jacobi gram / update kernels (svd_jacobi.cu), used by K4
 int32_t qb_cholqr_panel_step(qb200_ctx* ctx, c128* P, int64_t ld, int64_t m, c128* R, int64_t ldr, c128* Gpart,
                              c128* Wbuf, int* flags_dev, int* fail_dev);
@@ -225,6 +222,9 @@ size_t qb_cholqr_gpart_elems(qb200_ctx* ctx);
 // `ws` unless `order` is the identity)
 int32_t qb_matricize(qb200_ctx* ctx, const qb200_tensor* A, const int32_t* order, int32_t nleft, Workspace& ws,
                      const c128** mat, int64_t* rows, int64_t* cols);
+
+// NCCL broadcast of raw device bytes from `root` (comm.cu); the communicator must have been set up by qb200_comm_init
+int32_t qb_comm_broadcast_bytes(qb200_ctx* ctx, void* dev, size_t bytes, int root);
 
 // elementwise helpers (elementwise.cu)
 int32_t qb_scale_mode_raw(qb200_ctx* ctx, const c128* in, c128* out, int64_t inner, int64_t d, int64_t outer,

@@ -1,7 +1,7 @@
 // FP64 tensor-core (DMMA m8n8k4) peak micro-benchmark: the roofline denominator for K1/K4/K5
 // (MEASURED_PEAKS.json carries no FP64 figure).
-#include "common.cuh"
-#include "mma.cuh"
+#include "../common.cuh"
+#include "../mma.cuh"
 
 using namespace qb;
 

@@ -13,7 +13,7 @@
 //     (k / 4) * LBO + (r / 8) * SBO + (r % 8) * 16 + (k % 4) * 4,   SBO = 128 B, LBO = R * 16 B
 // i.e. 8-row x 16-byte core matrices, core matrices of one 4-wide K chunk contiguous along the rows.  One MMA consumes
 // K = 8 TF32 = two K chunks; the descriptor of the next MMA starts 2 * LBO further.
-#include "common.cuh"
+#include "../common.cuh"
 
 namespace {
 

@@ -212,6 +212,39 @@ int32_t transfer_right(qb200_ctx* ctx, const c128* R, int64_t ra, int64_t rb, co
     return QB200_OK;
 }
 
+// wrap raw device memory as a tensor view for qb200_contract
+qb200_tensor view3(c128* p, int64_t a, int64_t b, int64_t c) {
+    qb200_tensor t;
+    t.dtype = QB200_C128;
+    t.user_dtype = QB200_C128;
+    t.rank = 3;
+    t.ext[0] = a;
+    t.ext[1] = b;
+    t.ext[2] = c;
+    t.data = p;
+    t.bytes = 0;
+    t.owned = false;
+    return t;
+}
+qb200_tensor view4(c128* p, int64_t a, int64_t b, int64_t c, int64_t d) {
+    qb200_tensor t = view3(p, a, b, c);
+    t.rank = 4;
+    t.ext[3] = d;
+    return t;
+}
+qb200_tensor view5(c128* p, int64_t a, int64_t b, int64_t c, int64_t d, int64_t e) {
+    qb200_tensor t = view4(p, a, b, c, d);
+    t.rank = 5;
+    t.ext[4] = e;
+    return t;
+}
+
+// Λ_b -> site b+1 for every bond that holds a Schmidt vector: the chain becomes plain (same state)
+int32_t absorb_lambdas(qb200_ctx* ctx, qb200_mps* m) {
+    QB_TRY(absorb_lambdas(ctx, m));
+    return QB200_OK;
+}
+
 int32_t check_site(qb200_ctx* ctx, const qb200_mps* m, int s) {
     if (!m || s < 0 || s >= m->n) QB_FAIL(ctx, QB200_E_INVALID, "mps: site %d out of range", s);
     if (!m->site[s]) QB_FAIL(ctx, QB200_E_INVALID, "mps: site %d not set", s);
@@ -339,8 +372,8 @@ int32_t qb200_mps_set_form(qb200_mps* m, int32_t form) {
 // canonize! (Chain.jl:469-497)
 int32_t qb200_mps_canonize(qb200_ctx* ctx, qb200_mps* m) {
     QB_TRY(check_complete(ctx, m));
-    for (int b = 0; b < m->n - 1; ++b)
-        if (m->lam[b]) QB_FAIL(ctx, QB200_E_INVALID, "canonize: the chain already holds Schmidt vectors");
+    // Schmidt vectors already sitting on bonds are absorbed by the QR sweep's contract!(tn, virtualind) (Chain.jl:372)
+    QB_TRY(absorb_lambdas(ctx, m));
     for (int s = m->n - 1; s >= 1; --s) QB_TRY(right_canonize_qr(ctx, m, s));
     for (int s = 0; s < m->n - 1; ++s) {
         QB_TRY(left_canonize_svd(ctx, m, s));
@@ -363,12 +396,7 @@ int32_t qb200_mps_mixed_canonize(qb200_ctx* ctx, qb200_mps* m, int32_t center) {
     if (center < 1 || center >= m->n)
         QB_FAIL(ctx, QB200_E_INVALID, "Cannot right-canonize left-most tensor (center must be in 2..n)");
     // absorb any Schmidt vector into the site on its right: the chain becomes plain
-    for (int b = 0; b < m->n - 1; ++b)
-        if (m->lam[b]) {
-            int64_t l = m->chil[b + 1], rest = m->p[b + 1] * m->chir[b + 1];
-            QB_TRY(qb_scale_mode_raw(ctx, m->site[b + 1], m->site[b + 1], 1, l, rest, m->lam[b], 0, 0.0));
-            drop_lambda(ctx, m, b);
-        }
+    QB_TRY(absorb_lambdas(ctx, m));
     for (int s = 0; s < center; ++s) QB_TRY(left_canonize_qr(ctx, m, s));
     for (int s = m->n - 1; s > center; --s) QB_TRY(right_canonize_qr(ctx, m, s));
     QB_TRY(right_canonize_svd(ctx, m, center));
@@ -408,6 +436,7 @@ int32_t qb200_mps_evolve1(qb200_ctx* ctx, qb200_mps* m, int32_t s, const void* g
     QB_TRY(check_site(ctx, m, s));
     if (!gate) QB_FAIL(ctx, QB200_E_INVALID, "evolve1: null gate");
     int64_t p = m->p[s];
+    if (p > QB200_MAX_PHYS) QB_FAIL(ctx, QB200_E_UNSUPPORTED, "evolve1: physical dimension %lld > %d", (long long)p, QB200_MAX_PHYS);
     Workspace ws(ctx);
     c128* g = ws.get<c128>((size_t)(p * p));
     if (!g) QB_FAIL(ctx, QB200_E_CUDA, "evolve1: workspace allocation failed");
@@ -418,32 +447,62 @@ int32_t qb200_mps_evolve1(qb200_ctx* ctx, qb200_mps* m, int32_t s, const void* g
     return QB200_OK;
 }
 
+}  // extern "C"
+
+namespace {
+// device buffers of one bond update that must not outlive a failed call
+struct Evolve2Out {
+    qb200_ctx* ctx;
+    c128 *U = nullptr, *Vh = nullptr;
+    void* S = nullptr;
+    SvdState* st = nullptr;
+    explicit Evolve2Out(qb200_ctx* c) : ctx(c) {}
+    ~Evolve2Out() {
+        if (st) qb_svd_release(ctx, st);
+        if (U) cudaFreeAsync(U, ctx->stream);
+        if (Vh) cudaFreeAsync(Vh, ctx->stream);
+        if (S) cudaFreeAsync(S, ctx->stream);
+    }
+};
+}  // namespace
+
 // evolve!(ψ, gate; threshold, maxdim, iscanonical, renormalize) for a gate on sites (b, b+1)
-// (evolve_2site!, contract_2sitewf!, unpack_2sitewf!: Chain.jl:606-722)
+// (evolve_2site!, contract_2sitewf!, unpack_2sitewf!: Chain.jl:606-722).
+//   iscanonical != 0 (Chain.jl:615, :643): θ = Λl Γl Λ Γr Λr with the neighbouring Schmidt vectors where they exist
+//       (contract_2sitewf!, :669-685), SVD, Γl = U Λl^-1, Γr = Λr^-1 V^H with pinv atol 1e-32 (unpack_2sitewf!, :693-722);
+//       renormalize: Λ <- Λ / |Λ| (:653-654).
+//   iscanonical == 0 (the reference's default): contract!(tn, bond) -- Γl, Γr and the Schmidt vector ON the bond if one
+//       is there, nothing else (:615) --, svd! leaves U, s, V^H (:645); renormalize: normalize!(ψ, bond[1]) =
+//       mixed_canonize!(ψ, sitel) + normalisation of the Schmidt vector left of sitel (:655-656, :532-536).
 static int32_t evolve2_core(qb200_ctx* ctx, qb200_mps* m, int32_t b, const void* gate, int64_t maxdim,
-                            double threshold, int32_t renormalize, int64_t* kept_out, double* discarded_weight,
-                            bool validate) {
+                            double threshold, int32_t renormalize, int32_t iscanonical, int64_t* kept_out,
+                            double* discarded_weight, bool validate) {
     if (validate) QB_TRY(check_complete(ctx, m));
     if (b < 0 || b >= m->n - 1) QB_FAIL(ctx, QB200_E_INVALID, "evolve2: bond %d out of range", b);
     if (!gate) QB_FAIL(ctx, QB200_E_INVALID, "evolve2: null gate");
-    if (m->p[b] != 2 || m->p[b + 1] != 2) QB_FAIL(ctx, QB200_E_UNSUPPORTED, "evolve2: physical dimension must be 2");
-    const bool vidal = (m->form == 1);
+    const int64_t p1 = m->p[b], p2 = m->p[b + 1], pp = p1 * p2;
+    if (p1 > QB200_MAX_PHYS || p2 > QB200_MAX_PHYS || pp * pp * (int64_t)sizeof(c128) > 32768)
+        QB_FAIL(ctx, QB200_E_UNSUPPORTED, "evolve2: physical dimensions %lld x %lld too large", (long long)p1, (long long)p2);
+    const bool truncating = (maxdim > 0 || threshold >= 0.0);
+    if (renormalize && truncating && !iscanonical && b == 0)  // mixed_canonize!(ψ, Site(1)) (Chain.jl:344)
+        QB_FAIL(ctx, QB200_E_INVALID, "Cannot right-canonize left-most tensor");
+    const bool vidal = iscanonical != 0;
     const int64_t chil = m->chil[b], chib = m->chir[b], chir = m->chir[b + 1];
-    const int64_t rows = chil * 2, cols = 2 * chir;
+    const int64_t rows = chil * p1, cols = p2 * chir;
     const double* laml = (vidal && b > 0) ? m->lam[b - 1] : nullptr;
     const double* lamr = (vidal && b + 1 < m->n - 1) ? m->lam[b + 1] : nullptr;
-    const double* lamb = m->lam[b];  // Vidal: always; plain: only if a previous evolve left it there
+    const double* lamb = m->lam[b];  // the Schmidt vector on the bond itself is part of contract!(tn, bond) either way
 
     Workspace ws(ctx);
     c128* Al = ws.get<c128>((size_t)(rows * chib));
     c128* Br = ws.get<c128>((size_t)(chib * cols));
     c128* theta = ws.get<c128>((size_t)(rows * cols));
-    c128* g = ws.get<c128>(16);
+    c128* g = ws.get<c128>((size_t)(pp * pp));
     double* linv = ws.get<double>((size_t)chil);
     double* rinv = ws.get<double>((size_t)chir);
     if (!Al || !Br || !theta || !g || !linv || !rinv) QB_FAIL(ctx, QB200_E_CUDA, "evolve2: workspace allocation failed");
-    memcpy(ctx->scratch_host, gate, sizeof(c128) * 16);
-    QB_CUDA(ctx, cudaMemcpyAsync(g, ctx->scratch_host, sizeof(c128) * 16, cudaMemcpyHostToDevice, ctx->stream));
+    memcpy(ctx->scratch_host, gate, sizeof(c128) * pp * pp);
+    QB_CUDA(ctx, cudaMemcpyAsync(g, ctx->scratch_host, sizeof(c128) * pp * pp, cudaMemcpyHostToDevice, ctx->stream));
 
     // contract_2sitewf!: θ = (Λl Γl Λ)(Γr Λr)   (outer Λ's stay in the network, Chain.jl:679-682)
     const c128* Aop = m->site[b];
@@ -455,7 +514,7 @@ static int32_t evolve2_core(qb200_ctx* ctx, qb200_mps* m, int32_t b, const void*
     }
     if (lamr) {
         PhaseTimer pt(ctx, QB_PH_SCALE, 32.0 * chib * cols);
-        QB_TRY(qb_scale_rows_cols(ctx, m->site[b + 1], Br, chib, cols, nullptr, 1, lamr, 2));
+        QB_TRY(qb_scale_rows_cols(ctx, m->site[b + 1], Br, chib, cols, nullptr, 1, lamr, p2));
         Bop = Br;
     }
     {
@@ -465,33 +524,35 @@ static int32_t evolve2_core(qb200_ctx* ctx, qb200_mps* m, int32_t b, const void*
     // gate on the two physical indices (Chain.jl:635-636)
     {
         PhaseTimer pt(ctx, QB_PH_GATE, 32.0 * rows * cols);
-        QB_TRY(qb_apply_gate2(ctx, theta, chil, chir, g));
+        if (p1 == 2 && p2 == 2) {
+            QB_TRY(qb_apply_gate2(ctx, theta, chil, chir, g));
+        } else {  // general physical dimensions: θ'[l,o1,o2,r] = Σ G[o1,o2,i1,i2] θ[l,i1,i2,r] as one K1 contraction
+            c128* t2 = ws.get<c128>((size_t)(rows * cols));
+            if (!t2) QB_FAIL(ctx, QB200_E_CUDA, "evolve2: workspace allocation failed");
+            qb200_tensor T0 = view4(theta, chil, p1, p2, chir), G = view4(g, p1, p2, p1, p2), T1 = view4(t2, chil, p1, p2, chir);
+            const int32_t mT0[4] = {0, 1, 2, 3}, mG[4] = {4, 5, 1, 2}, mT1[4] = {0, 4, 5, 3};
+            QB_TRY(qb200_contract(ctx, &T0, mT0, 0, &G, mG, 0, &T1, mT1, nullptr, nullptr));
+            theta = t2;
+        }
     }
     // SVD (Chain.jl:705 / :645)
-    SvdState* st = nullptr;
+    Evolve2Out o(ctx);
     std::vector<double> sigma;
     {
         // algorithmic count of a thin complex SVD with U and V: 4 (14 m n^2 + 8 n^3), m >= n
         double mm = (double)std::max(rows, cols), nn = (double)std::min(rows, cols);
         PhaseTimer pt(ctx, QB_PH_SVD, 4.0 * (14.0 * mm * nn * nn + 8.0 * nn * nn * nn));
-        QB_TRY(qb_svd_factor(ctx, rows, cols, theta, rows, &st, sigma));
+        QB_TRY(qb_svd_factor(ctx, rows, cols, theta, rows, &o.st, sigma));
     }
     int64_t k = (int64_t)sigma.size();
     int64_t kept = k;
-    if (maxdim > 0 || threshold >= 0.0) kept = kept_count(sigma, maxdim, threshold >= 0.0 ? threshold : 1e-16);
-    if (kept == 0) {
-        qb_svd_release(ctx, st);
-        QB_FAIL(ctx, QB200_E_INVALID, "evolve2: every Schmidt coefficient is below the threshold");
-    }
+    if (truncating) kept = kept_count(sigma, maxdim, threshold >= 0.0 ? threshold : 1e-16);
+    if (kept == 0) QB_FAIL(ctx, QB200_E_INVALID, "evolve2: every Schmidt coefficient is below the threshold");
     double dw = 0.0, kw = 0.0;
     for (int64_t i = k - 1; i >= kept; --i) dw += sigma[i] * sigma[i];
     for (int64_t i = kept - 1; i >= 0; --i) kw += sigma[i] * sigma[i];
     double sscale = 1.0;
-    if (renormalize && (maxdim > 0 || threshold >= 0.0) && vidal && kw > 0.0) sscale = 1.0 / std::sqrt(kw);
-    if (renormalize && !vidal) {
-        qb_svd_release(ctx, st);
-        QB_FAIL(ctx, QB200_E_UNSUPPORTED, "evolve2: renormalize with iscanonical=false needs mixed_canonize (call it)");
-    }
+    if (renormalize && truncating && vidal && kw > 0.0) sscale = 1.0 / std::sqrt(kw);
     // unpack_2sitewf!: Γl = U Λl^-1, Γr = Λr^-1 V^H, pinv atol 1e-32 (Chain.jl:708-713)
     if (laml) {
         pinv_kernel<<<(unsigned)((chil + 255) / 256), 256, 0, ctx->stream>>>(laml, linv, chil, 1e-32);
@@ -501,34 +562,46 @@ static int32_t evolve2_core(qb200_ctx* ctx, qb200_mps* m, int32_t b, const void*
         pinv_kernel<<<(unsigned)((chir + 255) / 256), 256, 0, ctx->stream>>>(lamr, rinv, chir, 1e-32);
         ctx->launches++;
     }
-    c128* U = dev_alloc(ctx, rows * kept);
-    c128* Vh = dev_alloc(ctx, kept * cols);
-    void* S = nullptr;
-    cudaMallocAsync(&S, sizeof(double) * kept, ctx->stream);
-    if (!U || !Vh || !S) {
-        qb_svd_release(ctx, st);
-        QB_FAIL(ctx, QB200_E_CUDA, "evolve2: out of device memory");
-    }
-    int32_t r = qb_svd_emit(ctx, st, kept, U, rows, (double*)S, Vh, kept, 1, laml ? linv : nullptr, chil,
-                            lamr ? rinv : nullptr, 2, sscale);
-    qb_svd_release(ctx, st);
-    QB_TRY(r);
+    o.U = dev_alloc(ctx, rows * kept);
+    o.Vh = dev_alloc(ctx, kept * cols);
+    cudaMallocAsync(&o.S, sizeof(double) * kept, ctx->stream);
+    if (!o.U || !o.Vh || !o.S) QB_FAIL(ctx, QB200_E_CUDA, "evolve2: out of device memory");
+    QB_TRY(qb_svd_emit(ctx, o.st, kept, o.U, rows, (double*)o.S, o.Vh, kept, 1, laml ? linv : nullptr, chil,
+                       lamr ? rinv : nullptr, p2, sscale));
     QB_CUDA(ctx, qb_stream_sync(ctx));  // scratch_host (gate) is free again
-    set_site_dev(ctx, m, b, U, chil, 2, kept);
-    set_site_dev(ctx, m, b + 1, Vh, kept, 2, chir);
+    set_site_dev(ctx, m, b, o.U, chil, p1, kept);
+    set_site_dev(ctx, m, b + 1, o.Vh, kept, p2, chir);
     drop_lambda(ctx, m, b);
-    m->lam[b] = (double*)S;
+    m->lam[b] = (double*)o.S;
+    o.U = o.Vh = nullptr;  // ownership moved into the chain
+    o.S = nullptr;
     sigma.resize(kept);
     for (auto& v : sigma) v *= sscale;
     m->lam_host[b] = sigma;
+    if (!vidal) m->form = 0;  // U s V^H on the bond: no longer a Vidal chain
+    if (renormalize && truncating && !vidal) {
+        // normalize!(ψ, bond[1]) (Chain.jl:532-536): mixed-canonical form centred on sitel, its Schmidt vector normalised
+        QB_TRY(qb200_mps_mixed_canonize(ctx, m, b));
+        std::vector<double> lam = m->lam_host[b - 1];
+        double n2 = 0.0;
+        for (double v : lam) n2 += v * v;
+        if (n2 > 0.0) {
+            const double f = 1.0 / std::sqrt(n2);
+            for (double& v : lam) v *= f;
+            QB_TRY(set_lambda_host(ctx, m, b - 1, lam.data(), (int64_t)lam.size()));
+        }
+    }
     if (kept_out) *kept_out = kept;
     if (discarded_weight) *discarded_weight = dw;
     return QB200_OK;
 }
 
+extern "C" {
+
 int32_t qb200_mps_evolve2(qb200_ctx* ctx, qb200_mps* m, int32_t b, const void* gate, int64_t maxdim, double threshold,
-                          int32_t renormalize, int64_t* kept_out, double* discarded_weight) {
-    return evolve2_core(ctx, m, b, gate, maxdim, threshold, renormalize, kept_out, discarded_weight, true);
+                          int32_t renormalize, int32_t iscanonical, int64_t* kept_out, double* discarded_weight) {
+    if (!ctx || !m) QB_FAIL(ctx, QB200_E_INVALID, "evolve2: null argument");
+    return evolve2_core(ctx, m, b, gate, maxdim, threshold, renormalize, iscanonical, kept_out, discarded_weight, true);
 }
 
 namespace {
@@ -538,7 +611,14 @@ namespace {
 // phases of one update (QR panels, the shared-memory Jacobi solves) behind the DMMA-bound phases of the others.
 // Every op sees exactly the inputs it would see in a sequential run => results are bit-identical to it.
 int32_t run_evolve2_ops(qb200_ctx* ctx, qb200_mps* m, int32_t nops, const int32_t* bonds, const c128* g, int64_t maxdim,
-                        double threshold, int32_t renormalize, int64_t* kept_out, double* discarded_weight) {
+                        double threshold, int32_t renormalize, int32_t iscanonical, int64_t* kept_out,
+                        double* discarded_weight) {
+    // gate i holds (p_b p_{b+1})^2 numbers (16 for qubits); physical dimensions never change, so the offsets are static
+    std::vector<size_t> goff(nops + 1, 0);
+    for (int i = 0; i < nops; ++i) {
+        const size_t pp = (size_t)(m->p[bonds[i]] * m->p[bonds[i] + 1]);
+        goff[i + 1] = goff[i] + pp * pp;
+    }
     // worker streams: 12 by default, fewer when the host is small for the number of ranks sharing it (the workers
     // sleep on blocking events, so a 2x oversubscription of the cores is harmless)
     int nworkers = 12;
@@ -550,11 +630,14 @@ int32_t run_evolve2_ops(qb200_ctx* ctx, qb200_mps* m, int32_t nops, const int32_
     }
     if (const char* e = getenv("QB200_WORKERS")) nworkers = std::max(1, atoi(e));
     nworkers = std::min(nworkers, (int)nops);
+    // normalize!(ψ, bond[1]) of the non-canonical branch re-canonizes the whole chain: such updates do not commute
+    if (!iscanonical && renormalize && (maxdim > 0 || threshold >= 0.0)) nworkers = 1;
     std::vector<int64_t> kept_tmp(nops, 0);
     std::vector<double> dw_tmp(nops, 0.0);
     if (nworkers <= 1) {
         for (int i = 0; i < nops; ++i)
-            QB_TRY(evolve2_core(ctx, m, bonds[i], g + 16 * i, maxdim, threshold, renormalize, &kept_tmp[i], &dw_tmp[i], false));
+            QB_TRY(evolve2_core(ctx, m, bonds[i], g + goff[i], maxdim, threshold, renormalize, iscanonical, &kept_tmp[i],
+                                &dw_tmp[i], false));
     } else {
         // dependencies: the latest earlier op on each of the bonds b-1, b, b+1
         std::vector<std::array<int, 3>> dep(nops);
@@ -582,8 +665,11 @@ int32_t run_evolve2_ops(qb200_ctx* ctx, qb200_mps* m, int32_t nops, const int32_
         int remaining = nops;
         int32_t first_rc = QB200_OK;
         int failed_worker = -1;
-        // among the ready ops: the largest theta first (longest job), ties in program order
-        auto cost = [&](int i) { return m->chil[bonds[i]] * m->chir[bonds[i] + 1]; };
+        // among the ready ops: the largest theta first (longest job), ties in program order.  The sizes are a
+        // snapshot taken before the workers start (they rewrite chil / chir of their own sites as they finish).
+        std::vector<int64_t> cost_of(nops);
+        for (int i = 0; i < nops; ++i) cost_of[i] = m->chil[bonds[i]] * m->chir[bonds[i] + 1];
+        auto cost = [&](int i) { return cost_of[i]; };
         auto pick = [&]() {
             int best = -1;
             int64_t bc = -1;
@@ -610,8 +696,8 @@ int32_t run_evolve2_ops(qb200_ctx* ctx, qb200_mps* m, int32_t nops, const int32_
                     state[i] = 1;
                     lk.unlock();
                     // evolve2_core returns with its stream drained: the op is complete on the device
-                    int32_t r = evolve2_core(w[t], m, bonds[i], g + 16 * i, maxdim, threshold, renormalize, &kept_tmp[i],
-                                             &dw_tmp[i], false);
+                    int32_t r = evolve2_core(w[t], m, bonds[i], g + goff[i], maxdim, threshold, renormalize, iscanonical,
+                                             &kept_tmp[i], &dw_tmp[i], false);
                     lk.lock();
                     state[i] = 2;
                     --remaining;
@@ -639,8 +725,8 @@ int32_t run_evolve2_ops(qb200_ctx* ctx, qb200_mps* m, int32_t nops, const int32_
 // commute (disjoint sites; the Schmidt vectors between them are only read) and run as concurrent independent units.
 // Results are identical to calling evolve! bond by bond.
 int32_t qb200_mps_evolve2_layer(qb200_ctx* ctx, qb200_mps* m, int32_t nb, const int32_t* bonds, const void* gates,
-                                int64_t maxdim, double threshold, int32_t renormalize, int64_t* kept_out,
-                                double* discarded_weight) {
+                                int64_t maxdim, double threshold, int32_t renormalize, int32_t iscanonical,
+                                int64_t* kept_out, double* discarded_weight) {
     QB_TRY(check_complete(ctx, m));
     if (nb < 0 || (nb > 0 && (!bonds || !gates))) QB_FAIL(ctx, QB200_E_INVALID, "evolve2_layer: bad argument");
     std::vector<int> sorted(bonds, bonds + nb);
@@ -651,7 +737,7 @@ int32_t qb200_mps_evolve2_layer(qb200_ctx* ctx, qb200_mps* m, int32_t nb, const 
             QB_FAIL(ctx, QB200_E_INVALID, "evolve2_layer: bonds %d and %d overlap", sorted[i - 1], sorted[i]);
     }
     if (nb == 0) return QB200_OK;
-    return run_evolve2_ops(ctx, m, nb, bonds, (const c128*)gates, maxdim, threshold, renormalize, kept_out,
+    return run_evolve2_ops(ctx, m, nb, bonds, (const c128*)gates, maxdim, threshold, renormalize, iscanonical, kept_out,
                            discarded_weight);
 }
 
@@ -660,15 +746,15 @@ int32_t qb200_mps_evolve2_layer(qb200_ctx* ctx, qb200_mps* m, int32_t nb, const 
 // starts as soon as the earlier updates on its two sites are complete, so consecutive layers overlap and no worker
 // idles at a layer boundary.  Results are identical to nops calls of qb200_mps_evolve2 in the given order.
 int32_t qb200_mps_evolve2_circuit(qb200_ctx* ctx, qb200_mps* m, int32_t nops, const int32_t* bonds, const void* gates,
-                                  int64_t maxdim, double threshold, int32_t renormalize, int64_t* kept_out,
-                                  double* discarded_weight) {
+                                  int64_t maxdim, double threshold, int32_t renormalize, int32_t iscanonical,
+                                  int64_t* kept_out, double* discarded_weight) {
     QB_TRY(check_complete(ctx, m));
     if (nops < 0 || (nops > 0 && (!bonds || !gates))) QB_FAIL(ctx, QB200_E_INVALID, "evolve2_circuit: bad argument");
     for (int i = 0; i < nops; ++i)
         if (bonds[i] < 0 || bonds[i] >= m->n - 1) QB_FAIL(ctx, QB200_E_INVALID, "evolve2_circuit: bond out of range");
     if (nops == 0) return QB200_OK;
-    return run_evolve2_ops(ctx, m, nops, bonds, (const c128*)gates, maxdim, threshold, renormalize, kept_out,
-                           discarded_weight);
+    return run_evolve2_ops(ctx, m, nops, bonds, (const c128*)gates, maxdim, threshold, renormalize, iscanonical,
+                           kept_out, discarded_weight);
 }
 
 // canonize! with truncate! applied to each bond right after its SVD: the composition a user of the reference
@@ -676,12 +762,7 @@ int32_t qb200_mps_evolve2_circuit(qb200_ctx* ctx, qb200_mps* m, int32_t nops, co
 // plain canonize!.
 int32_t qb200_mps_compress(qb200_ctx* ctx, qb200_mps* m, int64_t maxdim, double threshold) {
     QB_TRY(check_complete(ctx, m));
-    for (int b = 0; b < m->n - 1; ++b)
-        if (m->lam[b]) {  // absorb Schmidt vectors: the sweeps below start from a plain chain
-            int64_t l = m->chil[b + 1], rest = m->p[b + 1] * m->chir[b + 1];
-            QB_TRY(qb_scale_mode_raw(ctx, m->site[b + 1], m->site[b + 1], 1, l, rest, m->lam[b], 0, 0.0));
-            drop_lambda(ctx, m, b);
-        }
+    QB_TRY(absorb_lambdas(ctx, m));  // the sweeps below start from a plain chain
     for (int s = m->n - 1; s >= 1; --s) QB_TRY(right_canonize_qr(ctx, m, s));
     for (int s = 0; s < m->n - 1; ++s) {
         QB_TRY(left_canonize_svd(ctx, m, s, maxdim, threshold));
@@ -697,33 +778,6 @@ int32_t qb200_mps_compress(qb200_ctx* ctx, qb200_mps* m, int64_t maxdim, double 
 }
 
 namespace {
-// wrap raw device memory as a tensor view for qb200_contract
-qb200_tensor view3(c128* p, int64_t a, int64_t b, int64_t c) {
-    qb200_tensor t;
-    t.dtype = QB200_C128;
-    t.user_dtype = QB200_C128;
-    t.rank = 3;
-    t.ext[0] = a;
-    t.ext[1] = b;
-    t.ext[2] = c;
-    t.data = p;
-    t.bytes = 0;
-    t.owned = false;
-    return t;
-}
-qb200_tensor view4(c128* p, int64_t a, int64_t b, int64_t c, int64_t d) {
-    qb200_tensor t = view3(p, a, b, c);
-    t.rank = 4;
-    t.ext[3] = d;
-    return t;
-}
-qb200_tensor view5(c128* p, int64_t a, int64_t b, int64_t c, int64_t d, int64_t e) {
-    qb200_tensor t = view4(p, a, b, c, d);
-    t.rank = 5;
-    t.ext[4] = e;
-    return t;
-}
-
 // upload the MPO sites (host, (o, i, l, r) column-major each, concatenated) to one device buffer
 int32_t upload_mpo(qb200_ctx* ctx, const qb200_mps* m, const int64_t* dl, const int64_t* dr, const void* sites,
                    Workspace& ws, std::vector<c128*>* dev) {
@@ -757,12 +811,7 @@ int32_t qb200_mps_apply_mpo(qb200_ctx* ctx, qb200_mps* m, const int64_t* dl, con
     Workspace ws(ctx);
     std::vector<c128*> W;
     QB_TRY(upload_mpo(ctx, m, dl, dr, sites, ws, &W));
-    for (int b = 0; b < m->n - 1; ++b)
-        if (m->lam[b]) {
-            int64_t l = m->chil[b + 1], rest = m->p[b + 1] * m->chir[b + 1];
-            QB_TRY(qb_scale_mode_raw(ctx, m->site[b + 1], m->site[b + 1], 1, l, rest, m->lam[b], 0, 0.0));
-            drop_lambda(ctx, m, b);
-        }
+    QB_TRY(absorb_lambdas(ctx, m));
     const int32_t mA[3] = {0, 1, 2};        // la, i, ra
     const int32_t mW[4] = {3, 1, 4, 5};     // o, i, lw, rw
     const int32_t mC[5] = {0, 4, 3, 2, 5};  // la, lw, o, ra, rw
@@ -929,6 +978,8 @@ int32_t qb200_mps_expect1_batch(qb200_ctx* ctx, const qb200_mps* m, int32_t nobs
         int64_t off = 0;
         for (int i = 0; i < nobs; ++i) {
             int64_t p = m->p[sites[i]];
+            if (p > QB200_MAX_PHYS)
+                QB_FAIL(ctx, QB200_E_UNSUPPORTED, "expect: physical dimension %lld > %d", (long long)p, QB200_MAX_PHYS);
             memcpy(ctx->scratch_host, src + off, sizeof(c128) * p * p);
             QB_CUDA(ctx, cudaMemcpyAsync(gates + (size_t)i * pmax * pmax, ctx->scratch_host, sizeof(c128) * p * p,
                                          cudaMemcpyHostToDevice, ctx->stream));
@@ -957,6 +1008,113 @@ int32_t qb200_mps_expect1_batch(qb200_ctx* ctx, const qb200_mps* m, int32_t nobs
         results[2 * i + 1] = host[i].y;
     }
     return QB200_OK;
+}
+
+// Replicate a device-resident MPS on every rank of the communicator (batched independent expectation values,
+// "MPS replicated (one ncclBroadcast, <= 1.45 GiB); observables dealt round-robin").  On `root`
+// *inout is the chain to send; on the other ranks *inout must be NULL and receives a new handle.  Shapes travel
+// first (one small broadcast), then every site tensor and Schmidt vector in place over NVLink.
+int32_t qb200_mps_broadcast(qb200_ctx* ctx, qb200_mps** inout, int32_t root) {
+    if (!ctx || !inout) QB_FAIL(ctx, QB200_E_INVALID, "mps_broadcast: null argument");
+    if (!ctx->nccl_comm) QB_FAIL(ctx, QB200_E_COMM, "communicator not initialised");
+    const bool sender = (ctx->comm_rank == root);
+    if (sender && !*inout) QB_FAIL(ctx, QB200_E_INVALID, "mps_broadcast: the root rank must pass its chain");
+    if (!sender && *inout) QB_FAIL(ctx, QB200_E_INVALID, "mps_broadcast: receiving ranks must pass NULL");
+    if (sender) QB_TRY(check_complete(ctx, *inout));
+    Workspace ws(ctx);
+    constexpr int MAXN = 2000;  // header: n, form, then (chil, p, chir, lambda length) per site; fits the pinned page
+    int64_t* hdr_dev = ws.get<int64_t>(2 + 4 * MAXN);
+    if (!hdr_dev) QB_FAIL(ctx, QB200_E_CUDA, "mps_broadcast: workspace allocation failed");
+    int64_t* hdr = reinterpret_cast<int64_t*>(ctx->scratch_host);
+    const size_t hbytes = sizeof(int64_t) * (2 + 4 * MAXN);
+    if (sender) {
+        qb200_mps* m = *inout;
+        if (m->n > MAXN) QB_FAIL(ctx, QB200_E_UNSUPPORTED, "mps_broadcast: more than %d sites", MAXN);
+        memset(hdr, 0, hbytes);
+        hdr[0] = m->n;
+        hdr[1] = m->form;
+        for (int s = 0; s < m->n; ++s) {
+            hdr[2 + 4 * s] = m->chil[s];
+            hdr[3 + 4 * s] = m->p[s];
+            hdr[4 + 4 * s] = m->chir[s];
+            hdr[5 + 4 * s] = (s < m->n - 1 && m->lam[s]) ? (int64_t)m->lam_host[s].size() : -1;
+        }
+        QB_CUDA(ctx, cudaMemcpyAsync(hdr_dev, hdr, hbytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    QB_TRY(qb_comm_broadcast_bytes(ctx, hdr_dev, hbytes, root));
+    QB_CUDA(ctx, cudaMemcpyAsync(hdr, hdr_dev, hbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    QB_CUDA(ctx, qb_stream_sync(ctx));
+    qb200_mps* m = *inout;
+    if (!sender) {
+        QB_TRY(qb200_mps_create(ctx, (int32_t)hdr[0], &m));
+        m->form = (int)hdr[1];
+        for (int s = 0; s < m->n; ++s) {
+            const int64_t cl = hdr[2 + 4 * s], p = hdr[3 + 4 * s], cr = hdr[4 + 4 * s], ll = hdr[5 + 4 * s];
+            c128* d = dev_alloc(ctx, cl * p * cr);
+            if (!d) {
+                qb200_mps_free(ctx, m);
+                QB_FAIL(ctx, QB200_E_CUDA, "mps_broadcast: out of device memory");
+            }
+            set_site_dev(ctx, m, s, d, cl, p, cr);
+            if (s < m->n - 1 && ll >= 0) {
+                void* l = nullptr;
+                if (cudaMallocAsync(&l, sizeof(double) * (size_t)std::max<int64_t>(ll, 1), ctx->stream) != cudaSuccess) {
+                    qb200_mps_free(ctx, m);
+                    QB_FAIL(ctx, QB200_E_CUDA, "mps_broadcast: out of device memory");
+                }
+                m->lam[s] = (double*)l;
+                m->lam_host[s].assign((size_t)ll, 0.0);
+            }
+        }
+    }
+    int32_t r = QB200_OK;
+    for (int s = 0; s < m->n && r == QB200_OK; ++s) {
+        r = qb_comm_broadcast_bytes(ctx, m->site[s], sizeof(c128) * (size_t)(m->chil[s] * m->p[s] * m->chir[s]), root);
+        if (r == QB200_OK && s < m->n - 1 && m->lam[s])
+            r = qb_comm_broadcast_bytes(ctx, m->lam[s], sizeof(double) * m->lam_host[s].size(), root);
+    }
+    if (r == QB200_OK && !sender)  // host mirrors of the Schmidt vectors (truncate! reads them element-wise on the host)
+        for (int s = 0; s < m->n - 1 && r == QB200_OK; ++s)
+            if (m->lam[s] && cudaMemcpyAsync(m->lam_host[s].data(), m->lam[s], sizeof(double) * m->lam_host[s].size(),
+                                             cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+                r = QB200_E_CUDA;
+    if (r == QB200_OK && qb_stream_sync(ctx) != cudaSuccess) r = QB200_E_CUDA;
+    if (r != QB200_OK) {
+        if (!sender) qb200_mps_free(ctx, m);
+        return r;
+    }
+    *inout = m;
+    return QB200_OK;
+}
+
+// expect(ψ, observables) (Chain.jl:724-735): the reference's own composition on the device
+int32_t qb200_mps_expect(qb200_ctx* ctx, const qb200_mps* m, int32_t nobs, const int32_t* nlanes, const int32_t* sites,
+                         const void* ops, double result[2]) {
+    QB_TRY(check_complete(ctx, m));
+    if (nobs < 0 || !result || (nobs > 0 && (!nlanes || !sites || !ops))) QB_FAIL(ctx, QB200_E_INVALID, "expect: bad argument");
+    qb200_mps* phi = nullptr;
+    QB_TRY(qb200_mps_copy(ctx, m, &phi));
+    const c128* src = (const c128*)ops;
+    int32_t r = QB200_OK;
+    for (int i = 0; i < nobs && r == QB200_OK; ++i) {
+        const int s = sites[i];
+        if (nlanes[i] == 1) {
+            if (s < 0 || s >= m->n) { ctx->err = "expect: site out of range"; r = QB200_E_INVALID; break; }
+            r = qb200_mps_evolve1(ctx, phi, s, src);
+            src += m->p[s] * m->p[s];
+        } else if (nlanes[i] == 2) {
+            if (s < 0 || s >= m->n - 1) { ctx->err = "expect: bond out of range"; r = QB200_E_INVALID; break; }
+            r = evolve2_core(ctx, phi, s, src, 0, -1.0, 0, 0, nullptr, nullptr, false);
+            const int64_t pp = m->p[s] * m->p[s + 1];
+            src += pp * pp;
+        } else {
+            ctx->err = "Invalid number of lanes, maximum is 2";  // Chain.jl:580
+            r = QB200_E_INVALID;
+        }
+    }
+    if (r == QB200_OK) r = qb200_mps_overlap(ctx, phi, m, result);
+    qb200_mps_free(ctx, phi);
+    return r;
 }
 
 }  // extern "C"

@@ -1106,16 +1106,6 @@ static bool update_3m() {
     return on;
 }
 
-// QB200_UPDATE_I8=1: EXPERIMENTAL, not validated on hardware -- the update step on the INT8 tensor pipe (Ozaki
-// splitting, i8_panel_gemm.cu) instead of the DMMA kernel.  Off by default.
-static bool update_i8() {
-    static const bool on = [] {
-        const char* e = getenv("QB200_UPDATE_I8");
-        return e && e[0] == '1';
-    }();
-    return on;
-}
-
 // QB200_GRAM_LOWP=1 switches the mixed-precision Gram on (TF32 Gram while couplings > LOWP_TOL).  Default OFF:
 // measured on B200 at k = 2048 (profiles/r1b_lowp_gram.txt) the Gram phase drops 19.5 -> 15.0 ms per bond (the
 // per-launch cost is ramp / flush / tail, not DMMA) while the FP32 shadow stores cost the update kernel 3.3 ms:
@@ -1318,11 +1308,6 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
             }
             {
                 PhaseTimer pt(ctx, QB_PH_JUPDATE, 8.0 * npairs * (double)st->ldz * JP * JP);  // ldz = rows of X
-                if (update_i8() && nb > 2) {
-                    int32_t r8 = qb_i8_jacobi_update(ctx, st->Z, st->ldz, st->mp, nb, step, Wg, flags, npairs);
-                    if (r8 != QB200_OK) return fail(r8);
-                    ctx->launches--;  // counted below with the other two kernels of the step
-                } else
                 (update_3m() ? jacobi_update_kernel<1> : jacobi_update_kernel<0>)<<<upd_ctas, UPD_THREADS, UPD_SMEM, ctx->stream>>>(
                     st->Z, st->ldz, nb, step, Wg, flags, npairs, u_nchunk, shadow ? st->Z32 : nullptr);
             }

@@ -58,25 +58,25 @@ class Context:
 
     def dmma_peak_tflops(self) -> float:
         v = C.c_double()
-        check(self.h, lib.qb200_bench_dmma_peak(self.h, C.byref(v)))
+        check(self.h, capi.diag().qb200_bench_dmma_peak(self.h, C.byref(v)))
         return v.value
 
     def hmma_peak_tflops(self):
         """(TF32, BF16) dense mma.sync peaks with FP32 accumulation -- denominators of the ComplexF32 kernels."""
         v = (C.c_double * 2)()
-        check(self.h, lib.qb200_bench_hmma_peak(self.h, v))
+        check(self.h, capi.diag().qb200_bench_hmma_peak(self.h, v))
         return float(v[0]), float(v[1])
 
     def tcgen05_tf32_probe(self):
         """(max abs error of the self-checked tcgen05 TF32 product, TFLOP/s at N = 128, TFLOP/s at N = 256)."""
         v = (C.c_double * 3)()
-        check(self.h, lib.qb200_bench_tcgen05_tf32(self.h, v))
+        check(self.h, capi.diag().qb200_bench_tcgen05_tf32(self.h, v))
         return float(v[0]), float(v[1]), float(v[2])
 
     def tcgen05_i8_probe(self):
         """(max abs error of the self-checked tcgen05 INT8 product, TOP/s at N = 128, TOP/s at N = 256)."""
         v = (C.c_double * 3)()
-        check(self.h, lib.qb200_bench_tcgen05_i8(self.h, v))
+        check(self.h, capi.diag().qb200_bench_tcgen05_i8(self.h, v))
         return float(v[0]), float(v[1]), float(v[2])
 
     def svd_totals(self):

@@ -169,43 +169,56 @@ class B200MPS:
                                                  -1.0 if threshold is None else float(threshold), C.byref(kept)))
         return kept.value
 
-    def evolve(self, gate, sites, threshold=None, maxdim=None, renormalize=False):
-        """`evolve!(ψ, Dense(Operator(), gate; sites=[s.., s'..]); ...)` (Chain.jl:543-584).  `gate` has array
-        dims (o_1.., i_1..) as in the reference; `sites` are the 1-based lanes.  Returns (kept, discarded)."""
-        gate = np.asfortranarray(np.asarray(gate, dtype=np.complex128))
+    def _lane_gate(self, gate, sites):
+        """Gate array (dims (o_1.., i_1..), Dense.jl:21-34) for 1-based lanes `sites` -> (left site 0-based, nlanes,
+        gate with its lanes in ascending order, flattened column-major)."""
         sites = list(sites)
         if len(sites) == 1:
-            check(self.ctx.h, lib.qb200_mps_evolve1(self.ctx.h, self.h, sites[0] - 1, gate.ctypes.data_as(C.c_void_p)))
-            return None
+            p = self.site_dims(sites[0] - 1)[1]
+            g = np.asarray(gate, dtype=np.complex128).reshape((p, p), order="F")
+            return sites[0] - 1, 1, np.reshape(g, -1, order="F")
         if len(sites) != 2:
             raise ValueError(f"Invalid number of lanes {len(sites)}, maximum is 2")
         a, b = sites
         if abs(a - b) != 1:
             raise ValueError("Gate lanes must be contiguous")
+        pa, pb = self.site_dims(a - 1)[1], self.site_dims(b - 1)[1]
+        g = np.asarray(gate, dtype=np.complex128).reshape((pa, pb, pa, pb), order="F")
         if a > b:  # gate given with lanes in descending order: swap its qubit roles
-            gate = np.asfortranarray(np.transpose(gate.reshape((2, 2, 2, 2), order="F"), (1, 0, 3, 2)))
+            g = np.transpose(g, (1, 0, 3, 2))
             a, b = b, a
+        return a - 1, 2, np.reshape(g, -1, order="F")
+
+    def evolve(self, gate, sites, threshold=None, maxdim=None, iscanonical=False, renormalize=False):
+        """`evolve!(ψ, Dense(Operator(), gate; sites=[s.., s'..]); threshold, maxdim, iscanonical, renormalize)`
+        (Chain.jl:543-584, same keyword defaults).  `gate` has array dims (o_1.., i_1..) as in the reference; `sites`
+        are the 1-based lanes.  Returns (kept, discarded weight) for a 2-lane gate."""
+        left, nl, flat = self._lane_gate(gate, sites)
+        if nl == 1:
+            check(self.ctx.h, lib.qb200_mps_evolve1(self.ctx.h, self.h, left, flat.ctypes.data_as(C.c_void_p)))
+            return None
         kept = C.c_int64()
         dw = C.c_double()
-        check(self.ctx.h, lib.qb200_mps_evolve2(self.ctx.h, self.h, a - 1, gate.ctypes.data_as(C.c_void_p),
+        check(self.ctx.h, lib.qb200_mps_evolve2(self.ctx.h, self.h, left, flat.ctypes.data_as(C.c_void_p),
                                                 int(maxdim or 0), -1.0 if threshold is None else float(threshold),
-                                                int(bool(renormalize)), C.byref(kept), C.byref(dw)))
+                                                int(bool(renormalize)), int(bool(iscanonical)), C.byref(kept),
+                                                C.byref(dw)))
         return kept.value, dw.value
 
-    def evolve_layer(self, gates, bonds, threshold=None, maxdim=None, renormalize=False):
+    def evolve_layer(self, gates, bonds, threshold=None, maxdim=None, iscanonical=False, renormalize=False):
         """One TEBD layer: `gates[i]` (dims (o1,o2,i1,i2)) on sites (bonds[i], bonds[i]+1), 1-based, pairwise
         non-adjacent -- the user loop `for b in bonds: evolve!(ψ, G_b; ...)` run as concurrent independent units.
         Returns (kept[], discarded_weight[])."""
-        return self._evolve_ops(lib.qb200_mps_evolve2_layer, gates, bonds, threshold, maxdim, renormalize)
+        return self._evolve_ops(lib.qb200_mps_evolve2_layer, gates, bonds, threshold, maxdim, iscanonical, renormalize)
 
-    def evolve_circuit(self, gates, bonds, threshold=None, maxdim=None, renormalize=False):
+    def evolve_circuit(self, gates, bonds, threshold=None, maxdim=None, iscanonical=False, renormalize=False):
         """A gate list in program order: `gates[i]` on sites (bonds[i], bonds[i]+1), 1-based; bonds may repeat and
         touch -- the user loop `for (G, b) in circuit: evolve!(ψ, G; ...)` (Chain.jl:543-584).  Updates start as soon
         as the earlier updates on their two sites are done (consecutive layers overlap); results are identical to
         the sequential loop.  Returns (kept[], discarded_weight[])."""
-        return self._evolve_ops(lib.qb200_mps_evolve2_circuit, gates, bonds, threshold, maxdim, renormalize)
+        return self._evolve_ops(lib.qb200_mps_evolve2_circuit, gates, bonds, threshold, maxdim, iscanonical, renormalize)
 
-    def _evolve_ops(self, fn, gates, bonds, threshold, maxdim, renormalize):
+    def _evolve_ops(self, fn, gates, bonds, threshold, maxdim, iscanonical, renormalize):
         nb = len(bonds)
         if len(gates) != nb:
             raise ValueError("one gate per bond expected")
@@ -215,7 +228,8 @@ class B200MPS:
         dw = (C.c_double * max(nb, 1))()
         check(self.ctx.h, fn(self.ctx.h, self.h, nb, capi.i32arr(b - 1 for b in bonds),
                              flat.ctypes.data_as(C.c_void_p), int(maxdim or 0),
-                             -1.0 if threshold is None else float(threshold), int(bool(renormalize)), kept, dw))
+                             -1.0 if threshold is None else float(threshold), int(bool(renormalize)),
+                             int(bool(iscanonical)), kept, dw))
         return [int(kept[i]) for i in range(nb)], [float(dw[i]) for i in range(nb)]
 
     @staticmethod
@@ -267,7 +281,8 @@ class B200MPS:
         return abs(np.sqrt(self.overlap(self)))
 
     def expect(self, ops, sites) -> np.ndarray:
-        """Batch of single-site `expect(ψ, [O])` values, un-normalised (Chain.jl:724-735); sites 1-based."""
+        """Batch of single-site `expect(ψ, [O])` values, un-normalised (Chain.jl:724-735); sites 1-based.  All left
+        and right environments are built once and shared by the batch."""
         ops = [np.asfortranarray(np.asarray(o, dtype=np.complex128)) for o in ops]
         flat = np.concatenate([o.reshape(-1, order="F") for o in ops]) if ops else np.zeros(0, np.complex128)
         res = np.zeros(2 * len(ops))
@@ -275,3 +290,19 @@ class B200MPS:
                                                       flat.ctypes.data_as(C.c_void_p),
                                                       res.ctypes.data_as(C.POINTER(C.c_double))))
         return res[0::2] + 1j * res[1::2]
+
+    def expect_observables(self, observables) -> complex:
+        """`expect(ψ, observables)` for ANY list of 1- and 2-lane observables, with the reference's own composition
+        (Chain.jl:724-735): ϕ = copy(ψ); evolve!(ϕ, O) for each O; contract(merge(ϕ, ψ')).  `observables` is a
+        list of (array, lanes) with 1-based lanes, arrays as for `evolve`."""
+        nl, left, parts = [], [], []
+        for arr, lanes in observables:
+            l, k, flat = self._lane_gate(arr, lanes)
+            nl.append(k)
+            left.append(l)
+            parts.append(flat)
+        flat = np.concatenate(parts) if parts else np.zeros(0, np.complex128)
+        r = (C.c_double * 2)()
+        check(self.ctx.h, lib.qb200_mps_expect(self.ctx.h, self.h, len(nl), capi.i32arr(nl), capi.i32arr(left),
+                                               flat.ctypes.data_as(C.c_void_p), r))
+        return complex(r[0], r[1])

@@ -55,9 +55,19 @@ def contract_sliced_distributed(sc, rank: int, world: int, reducer) -> complex:
     return reducer(partial)
 
 
+def broadcast_mps(ctx, mps, root: int = 0):
+    """Replicate a device-resident MPS on every rank with ncclBroadcast over NVLink (`qb200_mps_broadcast`): `mps` is
+    the chain on `root` and None elsewhere; every rank gets a B200MPS back (the root its own)."""
+    from .mps import B200MPS
+
+    h = C.c_void_p(mps.h.value if mps is not None else None)
+    check(ctx.h, lib.qb200_mps_broadcast(ctx.h, C.byref(h), root))
+    return mps if mps is not None else B200MPS(ctx, _handle=h)
+
+
 def expect_batch_distributed(mps, ops, sites, rank: int, world: int, reducer_vec):
     """Batched independent expectation values, the second path of the north star that shards: the MPS is replicated
-    on every rank (each builds / loads the same state), observable i goes to rank i mod W, every rank reuses its own
+    on every rank (`broadcast_mps`: one ncclBroadcast of the state), observable i goes to rank i mod W, every rank reuses its own
     left/right environments for its share (`qb200_mps_expect1_batch`), and ONE sum-reduction of a zero-initialised
     vector (2 doubles per observable) gathers the results -- `reducer_vec(list_of_floats) -> list_of_floats`
     (comm_allreduce_sum_vec on GPUs, torch_allreduce_sum_vec for any torch.distributed group)."""

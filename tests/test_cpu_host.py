@@ -181,16 +181,24 @@ def test_rand_mpo_generator_matches_reference_properties():
         assert max(d for a in arrays for d in a.shape[2:]) <= chi
 
 
-def test_bench_reference_arm_line_has_the_contract_keys():
+@pytest.mark.parametrize("steps,warmup", [(1, 0), (3, 1)])
+def test_bench_reference_arm_line_has_the_contract_keys(steps, warmup):
     """`bench.py --impl reference` (the CPU arm the driver runs beside the B200 arm) prints ONE JSON line with the
-    contract's keys; run here on a tiny chain so the whole CPU suite stays fast."""
+    contract's keys -- as one real full sweep (--steps 1 --warmup 0) and as the bounded sample (one bulk-bond evolve!
+    per step) -- never maps the product library, and reports a step time that is the step's own wall time.  Run here
+    on a tiny chain so the whole CPU suite stays fast."""
     import json
     import subprocess
     import sys
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "0", "--sites", "8", "--bond-dim", "8"], capture_output=True, text=True,
-                         timeout=300, cwd=ROOT)
+    code = ("import sys, runpy; sys.argv = ['bench.py'] + %r; runpy.run_path(%r, run_name='__main__'); "
+            "print('MAPPED', any('qrochet_b200' in l for l in open('/proc/self/maps')))")
+    argv = ["--impl", "reference", "--steps", str(steps), "--warmup", str(warmup), "--sites", "8", "--bond-dim", "8"]
+    t0 = __import__("time").perf_counter()
+    out = subprocess.run([sys.executable, "-c", code % (argv, os.path.join(ROOT, "bench.py"))], capture_output=True,
+                         text=True, timeout=300, cwd=ROOT)
+    wall = __import__("time").perf_counter() - t0
     assert out.returncode == 0, out.stderr[-2000:]
+    assert "MAPPED False" in out.stdout                     # the reference arm must not load libqrochet_b200.so
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
@@ -200,6 +208,9 @@ def test_bench_reference_arm_line_has_the_contract_keys():
     assert d["impl"] == "reference" and d["unit"] == "sweeps/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["ms_per_step"] * d["steps"] * 1e-3 <= wall      # the timed region fits in the run (no extrapolated time)
+    import bench
+    assert d["config"] == json.loads(json.dumps(bench.config_dict(8, 8)))   # same `config` object as the B200 arm
 
 
 def test_product_ansatz_host_mirror_matches_oracle():

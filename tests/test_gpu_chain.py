@@ -127,7 +127,7 @@ def test_evolve_generic_path_matches_statevector_and_fused_path(qb, ctx, iscanon
         U = oc.haar_unitary(g)
         G = np.reshape(U, (2, 2, 2, 2), order="F")
         q.evolve(G, [bond, bond + 1], iscanonical=iscanonical, maxdim=8)
-        fused.evolve(G, [bond, bond + 1], maxdim=8)
+        fused.evolve(G, [bond, bond + 1], iscanonical=iscanonical, maxdim=8)
         psi = sv.apply_gate(psi, U, [bond, bond + 1], n)
         if iscanonical:
             assert len(q.tn) == ntens

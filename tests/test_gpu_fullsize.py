@@ -77,7 +77,7 @@ def test_bulk_bond_update_at_chi_1024_matches_lapack(qb, ctx, state):
     want_kept = int(np.sum((np.arange(len(sig)) < chi) & (sig > 1e-16)))
     want_dw = float(np.sum(sig[want_kept:] ** 2))
 
-    kept, dw = psi.evolve(gate, [b, b + 1], maxdim=chi)
+    kept, dw = psi.evolve(gate, [b, b + 1], maxdim=chi, iscanonical=True)
     assert kept == want_kept == chi                   # bit-exact kept count
     got = psi.lambdas()[b - 1]
     assert got.shape == (chi,)

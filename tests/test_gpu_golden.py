@@ -59,7 +59,7 @@ def test_tebd_fixtures(qb, ctx):
         psi = qb.B200MPS(ctx, oc.rand_mps_arrays(np.random.default_rng(c["seed"]), n, chi)).canonize()
         rng = np.random.default_rng(c["seed"] + 1)
         gates = [np.reshape(oc.haar_unitary(rng), (2, 2, 2, 2), order="F") for _ in c["bonds"]]
-        kept, _ = psi.evolve_circuit(gates, c["bonds"], maxdim=c["maxdim"], renormalize=True)
+        kept, _ = psi.evolve_circuit(gates, c["bonds"], maxdim=c["maxdim"], iscanonical=True, renormalize=True)
         assert kept == c["kept"]
         check_lams(psi.lambdas(), c["lambdas"])
         assert abs(psi.norm() - c["norm"]) <= OBS_TOL
@@ -107,7 +107,7 @@ def test_analytic_known_answers(qb, ctx):
     for n, key in ((2, "bell"), (5, "ghz5")):
         psi = qb.B200MPS.from_product(ctx, [e0] * n).canonize()
         psi.evolve(H1, [1])
-        psi.evolve_circuit([cnot] * (n - 1), list(range(1, n)))
+        psi.evolve_circuit([cnot] * (n - 1), list(range(1, n)), iscanonical=True)
         for lam in psi.lambdas():
             assert len(lam) == 2 and np.abs(lam - np.array(a[key]["lambda"])).max() <= SIG_TOL
         zz = psi.expect([Z], [1])[0]

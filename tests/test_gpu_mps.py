@@ -140,7 +140,7 @@ def test_evolve_matches_oracle_and_statevector(qb, ctx, vidal):
         U = oc.haar_unitary(rng)
         gate = np.reshape(U, (2, 2, 2, 2), order="F")
         o.evolve(oc.gate(U, [bond, bond + 1]), iscanonical=vidal)
-        g.evolve(gate, [bond, bond + 1])
+        g.evolve(gate, [bond, bond + 1], iscanonical=vidal)
         psi = sv.apply_gate(psi, U, [bond, bond + 1], n)
     H = np.array([[1, 1], [1, -1]]) / np.sqrt(2)
     o.evolve(oc.gate(H, [4]))
@@ -161,7 +161,8 @@ def test_evolve_truncation_counts_and_weights(qb, ctx):
         U = oc.haar_unitary(rng)
         full = o.copy().evolve(oc.gate(U, [bond, bond + 1]), iscanonical=True).lambdas()[bond - 1]
         o.evolve(oc.gate(U, [bond, bond + 1]), iscanonical=True, maxdim=8, renormalize=True)
-        kept, dw = g.evolve(np.reshape(U, (2, 2, 2, 2), order="F"), [bond, bond + 1], maxdim=8, renormalize=True)
+        kept, dw = g.evolve(np.reshape(U, (2, 2, 2, 2), order="F"), [bond, bond + 1], maxdim=8, iscanonical=True,
+                            renormalize=True)
         assert kept == len(o.lambdas()[bond - 1]) == 8            # bit-exact truncation
         assert np.isclose(dw, np.sum(full[8:] ** 2), rtol=1e-9, atol=1e-20)
         assert_lams(g.lambdas(), o.lambdas())
@@ -175,7 +176,7 @@ def test_evolve_truncation_counts_and_weights(qb, ctx):
     full = o.copy().evolve(oc.gate(U, [3, 4]), iscanonical=True).lambdas()[2]
     thr = float(full[3] * 0.99)
     o.evolve(oc.gate(U, [3, 4]), iscanonical=True, threshold=thr)
-    kept, _ = g.evolve(np.reshape(U, (2, 2, 2, 2), order="F"), [3, 4], threshold=thr)
+    kept, _ = g.evolve(np.reshape(U, (2, 2, 2, 2), order="F"), [3, 4], threshold=thr, iscanonical=True)
     assert kept == len(o.lambdas()[2]) == int(np.sum(full > thr))
 
 
@@ -218,8 +219,8 @@ def test_evolve_layer_equals_sequential_evolve(qb, ctx):
             U = oc.haar_unitary(rng)
             gates.append(np.reshape(U, (2, 2, 2, 2), order="F"))
             o.evolve(oc.gate(U, [b, b + 1]), iscanonical=True, maxdim=16, renormalize=True)
-        kept_l, dw_l = g1.evolve_layer(gates, group, maxdim=16, renormalize=True)
-        seq = [g2.evolve(gt, [b, b + 1], maxdim=16, renormalize=True) for gt, b in zip(gates, group)]
+        kept_l, dw_l = g1.evolve_layer(gates, group, maxdim=16, iscanonical=True, renormalize=True)
+        seq = [g2.evolve(gt, [b, b + 1], maxdim=16, iscanonical=True, renormalize=True) for gt, b in zip(gates, group)]
         assert kept_l == [k for k, _ in seq]
         assert np.allclose(dw_l, [d for _, d in seq], rtol=1e-9, atol=1e-20)
     for x, y in zip(g1.lambdas(), g2.lambdas()):
@@ -267,8 +268,8 @@ def test_evolve_circuit_equals_sequential_evolve(qb, ctx):
         U = oc.haar_unitary(rng)
         gates.append(np.reshape(U, (2, 2, 2, 2), order="F"))
         o.evolve(oc.gate(U, [b, b + 1]), iscanonical=True, maxdim=16, renormalize=True)
-    kept_c, dw_c = g1.evolve_circuit(gates, bonds, maxdim=16, renormalize=True)
-    seq = [g2.evolve(gt, [b, b + 1], maxdim=16, renormalize=True) for gt, b in zip(gates, bonds)]
+    kept_c, dw_c = g1.evolve_circuit(gates, bonds, maxdim=16, iscanonical=True, renormalize=True)
+    seq = [g2.evolve(gt, [b, b + 1], maxdim=16, iscanonical=True, renormalize=True) for gt, b in zip(gates, bonds)]
     assert kept_c == [k for k, _ in seq]
     assert np.array_equal(dw_c, [d for _, d in seq])
     for x, y in zip(g1.lambdas(), g2.lambdas()):
@@ -334,7 +335,7 @@ def test_product_state_and_rank_deficient_theta(qb, ctx):
     for bond in [1, 3, 5, 2, 4, 3]:
         U = oc.haar_unitary(rng)
         o.evolve(oc.gate(U, [bond, bond + 1]), iscanonical=True, threshold=1e-12)
-        kept, _ = g.evolve(np.reshape(U, (2, 2, 2, 2), order="F"), [bond, bond + 1], threshold=1e-12)
+        kept, _ = g.evolve(np.reshape(U, (2, 2, 2, 2), order="F"), [bond, bond + 1], threshold=1e-12, iscanonical=True)
         assert kept == len(o.lambdas()[bond - 1])
         psi = sv.apply_gate(psi, U, [bond, bond + 1], n)
     assert np.allclose(dense_from_gpu(g), psi, atol=1e-12)
@@ -355,7 +356,7 @@ def test_config2_shape_properties(qb, ctx):
     odd = list(range(1, n, 2))
     gates = [qb.haar_gate(np.random.default_rng(2000 + b)) for b in odd]
     ref = g.copy()
-    kept, dw = g.evolve_layer(gates, odd, maxdim=chi, renormalize=True)
+    kept, dw = g.evolve_layer(gates, odd, maxdim=chi, iscanonical=True, renormalize=True)
     d = [1] + dims + [1]
     assert kept == [min(chi, 2 * d[b - 1], 2 * d[b + 1]) for b in odd]      # bit-exact truncation
     lams = g.lambdas()
@@ -374,5 +375,5 @@ def test_config2_shape_properties(qb, ctx):
         assert np.abs(m @ m.conj().T - np.eye(m.shape[0])).max() < 1e-10
     # same as three bond-by-bond calls
     for b, gt, k in list(zip(odd, gates, kept))[14:17]:
-        kk, _ = ref.evolve(gt, [b, b + 1], maxdim=chi, renormalize=True)
+        kk, _ = ref.evolve(gt, [b, b + 1], maxdim=chi, iscanonical=True, renormalize=True)
         assert kk == k and np.array_equal(ref.lambdas()[b - 1], lams[b - 1])

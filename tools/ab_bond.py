@@ -21,7 +21,7 @@ for rep in range(3):
     psi = qb.B200MPS.from_sites(ctx, sites, lams, form=1)
     ctx.profile(True)
     ctx.profile_read()
-    kept, dw = psi.evolve(qb.haar_gate(np.random.default_rng(7)), [2, 3], maxdim=chi, renormalize=True)
+    kept, dw = psi.evolve(qb.haar_gate(np.random.default_rng(7)), [2, 3], maxdim=chi, iscanonical=True, renormalize=True)
     pp = ctx.profile_read()
     ctx.profile(False)
     lam = psi.lambdas()[1]

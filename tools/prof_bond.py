@@ -14,6 +14,6 @@ for _ in range(3):
     l = np.sort(rng.random(chi))[::-1] + 0.1
     lams.append(l / np.linalg.norm(l))
 psi = qb.B200MPS.from_sites(ctx, sites, lams, form=1)
-kept, dw = psi.evolve(qb.haar_gate(rng), [2, 3], maxdim=chi, renormalize=True)
+kept, dw = psi.evolve(qb.haar_gate(rng), [2, 3], maxdim=chi, iscanonical=True, renormalize=True)
 ctx.synchronize()
 print("kept", kept, "sweeps", ctx.svd_last_sweeps())

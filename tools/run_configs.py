@@ -55,7 +55,7 @@ gates = [qb.haar_gate(np.random.default_rng(2000 + 64 * (i // 32) + b)) for i, b
 
 def c2():
     psi = psi2.copy()
-    kept, dw = psi.evolve_circuit(gates, order, maxdim=chi, renormalize=True)
+    kept, dw = psi.evolve_circuit(gates, order, maxdim=chi, iscanonical=True, renormalize=True)
     return sum(kept), float(np.sum(dw)), psi.norm()
 
 
