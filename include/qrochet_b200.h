@@ -218,17 +218,25 @@ int32_t qb200_mps_expect(qb200_ctx* ctx, const qb200_mps* mps, int32_t nobs, con
                          const int32_t* sites, const void* ops_c128, double result[2]);
 
 /* ---- sliced contraction of a general tensor network (examples/distributed.jl:46-101) -------------
- * The network is given as `ntensors` leaves (rank, modes, extents concatenated); the planner runs a
- * deterministic greedy path search + findslices(SizeScorer) until the largest intermediate has at
- * most `max_elements` entries. */
+ * The network is given as `ntensors` leaves (rank, modes, extents concatenated).  The planner is deterministic and
+ * replaces the reference's `transform!(tn, ContractSimplification())` + `einexpr(tn; optimizer = HyPar(...))` +
+ * `findslices(SizeScorer(), path; size)` (examples/distributed.jl:29-46): simplification, multi-start greedy,
+ * sub-tree reconfiguration (local search) and slicing until the largest intermediate has at most `max_elements`
+ * entries (rules in csrc/tn_plan.cu; mirrored bit-exactly by oracle/circuit.py::plan). */
 int32_t qb200_tn_plan(qb200_ctx* ctx, int32_t ntensors, const int32_t* ranks, const int32_t* modes,
                       const int64_t* extents, int64_t max_elements, qb200_tnplan** out);
+/* the same with the optimiser chosen: 0 = one greedy tree, no simplification, no local search (the round-1 planner, kept
+ * as the "before" column of the benchmark), 1 = the full planner (what qb200_tn_plan uses) */
+int32_t qb200_tn_plan_opt(qb200_ctx* ctx, int32_t ntensors, const int32_t* ranks, const int32_t* modes,
+                          const int64_t* extents, int64_t max_elements, int32_t optimizer, qb200_tnplan** out);
 int32_t qb200_tn_plan_free(qb200_ctx* ctx, qb200_tnplan* plan);
-/* queries: number of slices, sliced modes (array may be NULL to get the count), flops per slice
- * (8 * complex MACs, the EinExprs `flops` figure x 8), largest intermediate (elements) */
+/* queries: number of slices, sliced modes (array may be NULL to get the count), flops per slice (8 * complex MACs, the
+ * EinExprs `flops` figure x 8, of the tree nodes that depend on a cut index), flops of the slice-invariant nodes
+ * (executed once per contract call), largest intermediate (elements) */
 int64_t qb200_tn_plan_nslices(const qb200_tnplan* plan);
 int32_t qb200_tn_plan_sliced_modes(const qb200_tnplan* plan, int32_t* modes_out);
 double qb200_tn_plan_flops_per_slice(const qb200_tnplan* plan);
+double qb200_tn_plan_flops_invariant(const qb200_tnplan* plan);
 int64_t qb200_tn_plan_max_intermediate(const qb200_tnplan* plan);
 /* contraction order as pairs (i, j) -> new id ntensors + step; returns number of steps */
 int32_t qb200_tn_plan_path(const qb200_tnplan* plan, int32_t* pairs_out);

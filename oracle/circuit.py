@@ -88,108 +88,308 @@ def random_product_state(n, seed):
     return list(v / np.linalg.norm(v, axis=1, keepdims=True))
 
 
-# ---- deterministic planner (same rule as qrochet.jl_b200/csrc/tn.cu) -----------------------------------
-def plan(modes, extents, max_elements):
-    """modes: list of tuples; extents: dict mode -> size.  Returns dict(path, sliced, nodes)."""
-    nodes = [dict(modes=tuple(m), left=-1, right=-1) for m in modes]
-    count = {}
-    for m in modes:
-        for x in m:
-            count[x] = count.get(x, 0) + 1
+# ---- deterministic planner (same rules as qrochet.jl_b200/csrc/tn.cu, compared bit-exactly by the tests) ----------
+# The reference plans with `transform!(tn, ContractSimplification())` + `einexpr(tn; optimizer = HyPar(...))` +
+# `findslices(SizeScorer(), path; size)` (examples/distributed.jl:29-46).  KaHyPar / EinExprs are un-vendored and
+# randomised, so the rules are OURS and are stated here:
+#   simplify    : while some pair of connected tensors contracts to a result no larger than its larger operand, contract
+#                 the first such pair in (position, position) order of the live list and restart the scan
+#                 (ContractSimplification: rank-1 boundary vectors and non-growing pairs are absorbed before planning);
+#   greedy(α/2) : repeatedly contract the connected pair minimising 2 size(out) - α (size(a) + size(b)); ties -> smaller
+#                 output -> earlier pair; disconnected remainder: outer product of the two smallest;
+#   reconfigure : sub-tree reconfiguration (the local search): walk the tree from the root; at each internal node take
+#                 the frontier of up to 8 sub-trees below it (repeatedly open the largest openable one), find by
+#                 exhaustive dynamic programming over the 2^8 subsets the contraction order of those sub-trees with the
+#                 fewest flops (ties: smaller largest intermediate), and adopt it when it is strictly better; rounds
+#                 repeat until nothing improves (at most 32);
+#   candidates  : {simplify on, off} x α in {2, 4}; each is sliced by findslices and the one with the fewest total
+#                 flops (slices x per-slice + slice-invariant work) wins, the first on ties;
+#   findslices  : while the largest intermediate exceeds max_elements, cut the index with the largest
+#                 score = sum of the sizes of the nodes holding it; ties -> the index met first in post-order.
+# All sizes and flop counts are exact integers (Python int here, unsigned __int128 in C++, both saturating at 2^100), so
+# both implementations take identical decisions.
+PLAN_K = 8
+PLAN_ROUNDS = 32
+PLAN_ALPHAS = (2, 4)
+PLAN_CAP = 1 << 100        # sizes saturate here (unsigned __int128 head-room on the C++ side)
+PLAN_CAP_TOTAL = 1 << 126
 
-    def size(ms):
+
+class _Net:
+    def __init__(self, modes, extents):
+        self.leaf_modes = [tuple(m) for m in modes]
+        self.ext = extents
+        self.total = {}
+        for m in self.leaf_modes:
+            for x in m:
+                self.total[x] = self.total.get(x, 0) + 1
+
+    def size(self, ms, cut=()):
         s = 1
         for x in ms:
-            s *= extents[x]
+            if x not in cut:
+                s = min(s * self.ext[x], PLAN_CAP)
         return s
 
-    def out_modes(a, b):
-        out = []
-        for x in a:
-            if count[x] - 1 - (1 if x in b else 0) > 0:
-                out.append(x)
-        for x in b:
-            if x not in a and count[x] - 1 > 0:
-                out.append(x)
-        return tuple(out)
+    def out_modes(self, A, B):
+        """Modes of the node contracting A and B (without building it)."""
+        ca, cb, tot = A["cnt"], B["cnt"], self.total
+        out = [x for x in A["modes"] if ca.get(x, 0) + cb.get(x, 0) < tot[x]]
+        out += [x for x in B["modes"] if x not in ca and cb[x] < tot[x]]
+        return out
 
-    live = list(range(len(nodes)))
-    path = []
+    def leaf(self, i):
+        cnt = {}
+        for x in self.leaf_modes[i]:
+            cnt[x] = cnt.get(x, 0) + 1
+        return dict(left=-1, right=-1, modes=self.leaf_modes[i], cnt=cnt)
+
+    def join(self, nodes, a, b):
+        """The node contracting nodes a and b: an index is summed once every leaf holding it is below the node."""
+        A, B = nodes[a], nodes[b]
+        cnt = dict(A["cnt"])
+        for x, v in B["cnt"].items():
+            cnt[x] = cnt.get(x, 0) + v
+        out = [x for x in A["modes"] if cnt[x] < self.total[x]]
+        out += [x for x in B["modes"] if x not in A["modes"] and cnt[x] < self.total[x]]
+        return dict(left=a, right=b, modes=tuple(out), cnt=cnt)
+
+    def flops(self, nodes, i, cut=()):
+        """complex multiply-adds of node i = product of the extents of every index involved (EinExprs `flops`)."""
+        n = nodes[i]
+        inv = dict.fromkeys(nodes[n["left"]]["modes"] + nodes[n["right"]]["modes"])
+        return self.size(inv, cut)
+
+
+def _connected(a, b):
+    return any(x in b["modes"] for x in a["modes"])
+
+
+def _simplify(net, nodes, live):
+    found = True
+    while found:
+        found = False
+        for xi in range(len(live)):
+            for yi in range(xi + 1, len(live)):
+                a, b = live[xi], live[yi]
+                if not _connected(nodes[a], nodes[b]):
+                    continue
+                o = net.out_modes(nodes[a], nodes[b])
+                if net.size(o) <= max(net.size(nodes[a]["modes"]), net.size(nodes[b]["modes"])):
+                    nodes.append(net.join(nodes, a, b))
+                    del live[yi]
+                    del live[xi]
+                    live.append(len(nodes) - 1)
+                    found = True
+                    break
+            if found:
+                break
+
+
+def _greedy(net, nodes, live, alpha2):
     while len(live) > 1:
         best = None
         for xi in range(len(live)):
-            a = nodes[live[xi]]["modes"]
-            sa = set(a)
+            a = nodes[live[xi]]
+            sa = net.size(a["modes"])
             for yi in range(xi + 1, len(live)):
-                b = nodes[live[yi]]["modes"]
-                if not sa.intersection(b):
+                b = nodes[live[yi]]
+                if not _connected(a, b):
                     continue
-                o = out_modes(a, b)
-                so = size(o)
-                cost = so - size(a) - size(b)
+                so = net.size(net.out_modes(a, b))
+                cost = 2 * so - alpha2 * (sa + net.size(b["modes"]))
                 if best is None or cost < best[0] or (cost == best[0] and so < best[1]):
-                    best = (cost, so, xi, yi, o)
-        if best is None:
-            idx = sorted(range(len(live)), key=lambda i: size(nodes[live[i]]["modes"]))
+                    best = (cost, so, xi, yi)
+        if best is None:  # disconnected components: outer product of the two smallest
+            idx = sorted(range(len(live)), key=lambda i: net.size(nodes[live[i]]["modes"]))
             xi, yi = min(idx[0], idx[1]), max(idx[0], idx[1])
-            o = out_modes(nodes[live[xi]]["modes"], nodes[live[yi]]["modes"])
         else:
-            _, _, xi, yi, o = best
-        ia, ib = live[xi], live[yi]
-        for x in nodes[ia]["modes"]:
-            count[x] -= 1
-        for x in nodes[ib]["modes"]:
-            count[x] -= 1
-        for x in o:
-            count[x] += 1
-        nodes.append(dict(modes=o, left=ia, right=ib))
-        path.append((ia, ib))
+            _, _, xi, yi = best
+        nodes.append(net.join(nodes, live[xi], live[yi]))
         del live[yi]
         del live[xi]
         live.append(len(nodes) - 1)
 
-    order = []
 
-    def post(i):
-        if nodes[i]["left"] >= 0:
-            post(nodes[i]["left"])
-            post(nodes[i]["right"])
-        order.append(i)
+def _reconfigure_at(net, nodes, i):
+    """One sub-tree reconfiguration at internal node i; True when the sub-tree was replaced by a cheaper one."""
+    fr = [nodes[i]["left"], nodes[i]["right"]]
+    while len(fr) < PLAN_K:
+        pick = -1
+        for pos, j in enumerate(fr):
+            if nodes[j]["left"] >= 0 and (pick < 0 or net.size(nodes[j]["modes"]) > net.size(nodes[fr[pick]]["modes"])):
+                pick = pos
+        if pick < 0:
+            break
+        j = fr.pop(pick)
+        fr += [nodes[j]["left"], nodes[j]["right"]]
+    K = len(fr)
+    if K < 3:
+        return False
+    frontier = set(fr)
+    old_fl, old_mx = 0, 0
+    stack = [i]
+    while stack:
+        j = stack.pop()
+        if j in frontier:
+            continue
+        old_fl += net.flops(nodes, j)
+        old_mx = max(old_mx, net.size(nodes[j]["modes"]))
+        stack += [nodes[j]["left"], nodes[j]["right"]]
+    full = (1 << K) - 1
+    # relevant modes: the outer indices of the frontier sub-trees (everything else is summed inside one of them)
+    rel = list(dict.fromkeys(x for j in fr for x in nodes[j]["modes"]))
+    cnt, modes, size = {}, {}, {}
+    for m in range(1, full + 1):
+        low = (m & -m).bit_length() - 1
+        rest = m & (m - 1)
+        c = nodes[fr[low]]["cnt"]
+        cnt[m] = [c.get(x, 0) + (cnt[rest][r] if rest else 0) for r, x in enumerate(rel)]
+        modes[m] = frozenset(x for r, x in enumerate(rel) if 0 < cnt[m][r] < net.total[x])
+        size[m] = net.size(modes[m])
+    best = {1 << j: (0, 0, None) for j in range(K)}
+    for m in range(1, full + 1):
+        if m & (m - 1) == 0:
+            continue
+        low = m & -m
+        choice = None
+        sub = (m - 1) & m
+        while sub:
+            if sub & low:
+                o = m ^ sub
+                fl = best[sub][0] + best[o][0] + net.size(modes[sub] | modes[o])
+                mx = max(best[sub][1], best[o][1], size[m])
+                if choice is None or (fl, mx) < (choice[0], choice[1]):
+                    choice = (fl, mx, (sub, o))
+            sub = (sub - 1) & m
+        best[m] = choice
+    if (best[full][0], best[full][1]) >= (old_fl, old_mx):
+        return False
 
-    post(len(nodes) - 1)
+    def build(m):
+        if m & (m - 1) == 0:
+            return fr[m.bit_length() - 1]
+        sub, o = best[m][2]
+        ia = build(sub)
+        ib = build(o)
+        nd = net.join(nodes, ia, ib)
+        if m == full:
+            nodes[i] = nd
+            return i
+        nodes.append(nd)
+        return len(nodes) - 1
+
+    build(full)
+    return True
+
+
+def _reconfigure(net, nodes, root):
+    for _ in range(PLAN_ROUNDS):
+        improved = False
+        stack = [root]
+        while stack:
+            i = stack.pop()
+            if nodes[i]["left"] < 0:
+                continue
+            if _reconfigure_at(net, nodes, i):
+                improved = True
+            stack += [nodes[i]["right"], nodes[i]["left"]]  # left sub-tree first
+        if not improved:
+            break
+
+
+def _compact(net, nodes, root):
+    """Post-order renumbering of the reachable tree: leaves keep their ids, step s creates node nleaves + s."""
+    nleaves = len(net.leaf_modes)
+    path, newid = [], {}
+    stack = [(root, False)]
+    while stack:
+        i, done = stack.pop()
+        if nodes[i]["left"] < 0:
+            newid[i] = i
+        elif done:
+            path.append((newid[nodes[i]["left"]], newid[nodes[i]["right"]]))
+            newid[i] = nleaves + len(path) - 1
+        else:
+            stack += [(i, True), (nodes[i]["right"], False), (nodes[i]["left"], False)]
+    out = [net.leaf(i) for i in range(nleaves)]
+    for a, b in path:
+        out.append(net.join(out, a, b))
+    return out, path
+
+
+def _findslices(net, nodes, max_elements):
+    nleaves = len(net.leaf_modes)
     cut = []
+    if max_elements <= 0:
+        return cut
+    while True:
+        mx = max((net.size(nodes[i]["modes"], cut) for i in range(nleaves, len(nodes))), default=0)
+        if mx <= max_elements:
+            break
+        score, seen = {}, []
+        for i in range(len(nodes)):  # compacted trees are stored in post-order
+            s = net.size(nodes[i]["modes"], cut)
+            for x in nodes[i]["modes"]:
+                if x in cut or net.ext[x] <= 1:
+                    continue
+                if x not in score:
+                    seen.append(x)
+                    score[x] = 0
+                score[x] += s
+        if not seen:
+            break
+        pick = seen[0]
+        for x in seen:
+            if score[x] > score[pick]:
+                pick = x
+        cut.append(pick)
+    return cut
 
-    def nsize(ms):
-        s = 1
-        for x in ms:
-            if x not in cut:
-                s *= extents[x]
-        return s
 
-    nleaves = len(modes)
-    if max_elements > 0:
-        while True:
-            mx = max((nsize(nodes[i]["modes"]) for i in range(nleaves, len(nodes))), default=0)
-            if mx <= max_elements:
-                break
-            score, seen = {}, []
-            for i in order:
-                s = float(nsize(nodes[i]["modes"]))
-                for x in nodes[i]["modes"]:
-                    if x in cut or extents[x] <= 1:
-                        continue
-                    if x not in score:
-                        seen.append(x)
-                        score[x] = 0.0
-                    score[x] += s
-            if not seen:
-                break
-            pick = seen[0]
-            for x in seen:
-                if score[x] > score[pick]:
-                    pick = x
-            cut.append(pick)
-    return dict(path=path, sliced=cut, nodes=nodes)
+def _sliced_cost(net, nodes, cut):
+    """(complex MACs per slice of the nodes that depend on a cut index, MACs of the slice-invariant nodes, #slices)."""
+    nleaves = len(net.leaf_modes)
+    inv = [not any(x in cut for x in net.leaf_modes[i]) for i in range(nleaves)]
+    per_slice = once = 0
+    for i in range(nleaves, len(nodes)):
+        inv.append(inv[nodes[i]["left"]] and inv[nodes[i]["right"]])
+        f = net.flops(nodes, i, cut)
+        if inv[i]:
+            once += f
+        else:
+            per_slice += f
+    nsl = 1
+    for x in cut:
+        nsl = min(nsl * net.ext[x], 1 << 62)
+    return per_slice, once, nsl
+
+
+def plan(modes, extents, max_elements, optimizer=1):
+    """modes: list of tuples; extents: dict mode -> size.  optimizer 0: the round-1 rule (one greedy tree, α = 1, no
+    simplification, no local search); 1: the full planner above.  Returns dict(path, sliced, nodes, macs_per_slice,
+    macs_invariant, nslices)."""
+    net = _Net(modes, extents)
+    nleaves = len(net.leaf_modes)
+    best = None
+    for simp in ((1, 0) if optimizer else (0,)):
+        for alpha2 in (PLAN_ALPHAS if optimizer else (2,)):
+            nodes = [net.leaf(i) for i in range(nleaves)]
+            live = list(range(nleaves))
+            if simp:
+                _simplify(net, nodes, live)
+            _greedy(net, nodes, live, alpha2)
+            root = live[0]
+            if optimizer:
+                _reconfigure(net, nodes, root)
+            tree, path = _compact(net, nodes, root)
+            cut = _findslices(net, tree, max_elements)
+            per_slice, once, nsl = _sliced_cost(net, tree, cut)
+            total = min(per_slice * nsl + once, PLAN_CAP_TOTAL)
+            if best is None or total < best[0]:
+                best = (total, tree, path, cut, per_slice, once, nsl)
+    _, tree, path, cut, per_slice, once, nsl = best
+    return dict(path=path, sliced=cut, nodes=tree, macs_per_slice=per_slice, macs_invariant=once, nslices=nsl)
 
 
 def contract_sliced(arrays, modes, pl, first_slice=0, stride=1):

@@ -94,10 +94,12 @@ _protos = {
     "qb200_mps_expect1_batch": (_i32, [_p, _p, _i32, _pi32, _p, _pdbl]),
     "qb200_mps_expect": (_i32, [_p, _p, _i32, _pi32, _pi32, _p, _pdbl]),
     "qb200_tn_plan": (_i32, [_p, _i32, _pi32, _pi32, _pi64, _i64, C.POINTER(_p)]),
+    "qb200_tn_plan_opt": (_i32, [_p, _i32, _pi32, _pi32, _pi64, _i64, _i32, C.POINTER(_p)]),
     "qb200_tn_plan_free": (_i32, [_p, _p]),
     "qb200_tn_plan_nslices": (_i64, [_p]),
     "qb200_tn_plan_sliced_modes": (_i32, [_p, _pi32]),
     "qb200_tn_plan_flops_per_slice": (_dbl, [_p]),
+    "qb200_tn_plan_flops_invariant": (_dbl, [_p]),
     "qb200_tn_plan_max_intermediate": (_i64, [_p]),
     "qb200_tn_plan_path": (_i32, [_p, _pi32]),
     "qb200_tn_contract_sliced": (_i32, [_p, _p, C.POINTER(_p), _i64, _i64, _pdbl]),

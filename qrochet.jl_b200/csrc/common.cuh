@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -157,10 +158,22 @@ static inline size_t dtype_size(int32_t dt) {
         if (_r != QB200_OK) return _r; \
     } while (0)
 
-#define QB_LAUNCH_CHECK(ctx)                 \
-    do {                                     \
-        (ctx)->launches++;                   \
-        QB_CUDA(ctx, cudaGetLastError());    \
+// QB200_SYNC_DEBUG=1: every checked launch is announced on stderr and waited for (locates a hanging kernel)
+static inline bool qb_sync_debug() {
+    static const bool on = getenv("QB200_SYNC_DEBUG") != nullptr;
+    return on;
+}
+
+#define QB_LAUNCH_CHECK(ctx)                                                  \
+    do {                                                                      \
+        (ctx)->launches++;                                                    \
+        QB_CUDA(ctx, cudaGetLastError());                                     \
+        if (qb_sync_debug()) {                                                \
+            fprintf(stderr, "[qb200 launch] %s:%d ...", __FILE__, __LINE__);  \
+            fflush(stderr);                                                   \
+            QB_CUDA(ctx, cudaStreamSynchronize((ctx)->stream));               \
+            fprintf(stderr, " done\n");                                       \
+        }                                                                     \
     } while (0)
 
 // stream-ordered workspace from the CUDA memory pool (cached by the driver pool; no sync on free)

@@ -241,7 +241,12 @@ qb200_tensor view5(c128* p, int64_t a, int64_t b, int64_t c, int64_t d, int64_t 
 
 // Λ_b -> site b+1 for every bond that holds a Schmidt vector: the chain becomes plain (same state)
 int32_t absorb_lambdas(qb200_ctx* ctx, qb200_mps* m) {
-    QB_TRY(absorb_lambdas(ctx, m));
+    for (int b = 0; b < m->n - 1; ++b)
+        if (m->lam[b]) {
+            int64_t l = m->chil[b + 1], rest = m->p[b + 1] * m->chir[b + 1];
+            QB_TRY(qb_scale_mode_raw(ctx, m->site[b + 1], m->site[b + 1], 1, l, rest, m->lam[b], 0, 0.0));
+            drop_lambda(ctx, m, b);
+        }
     return QB200_OK;
 }
 

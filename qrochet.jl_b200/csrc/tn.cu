@@ -1,23 +1,18 @@
-// K12 + planner: sliced contraction of a closed tensor network (examples/distributed.jl:29-101).
+// K12: sliced contraction of a closed tensor network (examples/distributed.jl:29-101).
 //
-// Planner (host C++, deterministic; replaces EinExprs' Greedy/HyPar + findslices(SizeScorer), whose own
-// tie-breaks are randomised):
-//   path    : greedy -- among all pairs of tensors sharing an index pick the one minimising
-//             size(out) - size(a) - size(b); ties -> smaller output -> lower ids.  An index is summed
-//             as soon as no other live tensor holds it (hyper-index aware).
-//   slicing : while the largest intermediate exceeds max_elements, slice the index with the largest
-//             score = sum of the sizes of all path nodes holding it; ties -> the index met first in a
-//             post-order walk of the path.
+// Planner: tn_plan.cu (host C++, deterministic; ContractSimplification + multi-start greedy + sub-tree reconfiguration +
+// findslices(SizeScorer) -- replaces EinExprs' Greedy/HyPar + findslices, whose own tie-breaks are randomised).
 // Executor: for slice s (first cut index fastest) every leaf holding a cut index is restricted with
 // select kernels, the fixed tree is replayed with the permutation-fused GEMM (offset tables are built
-// once per plan and kept on the device), sub-trees that hold no cut index are contracted once and
-// reused by every slice, and the final rank-0 node is accumulated on the device (beta = 1).
+// once per plan and kept on the device), sub-trees that hold no cut index are contracted once per call and
+// reused by every slice of that call, and the final rank-0 node is accumulated on the device (beta = 1).
 #include <algorithm>
 #include <cstdlib>
 #include <map>
 #include <set>
 
 #include "contract.cuh"
+#include "tn_plan.cuh"
 
 using namespace qb;
 
@@ -46,11 +41,11 @@ struct qb200_tnplan {
     std::vector<int32_t> sliced;
     std::vector<int64_t> sliced_ext;
     int64_t nslices = 1;
-    double flops_per_slice = 0.0;
+    double flops_per_slice = 0.0;    // 8 x complex MACs of the nodes that depend on a cut index (executed per slice)
+    double flops_invariant = 0.0;    // 8 x complex MACs of the slice-invariant nodes (executed once per call)
     int64_t max_inter = 0;
     std::vector<TNStep> steps;
-    std::vector<c128*> cached;  // results of invariant nodes (device), filled on first use
-    bool cache_valid = false;
+    std::vector<c128*> cached;  // results of the slice-invariant nodes (device): valid inside ONE contract call only
 };
 
 namespace {
@@ -61,38 +56,7 @@ int64_t ext_of(const TNNode& n, int32_t mode) {
     return -1;
 }
 
-bool holds(const TNNode& n, int32_t mode) { return std::find(n.modes.begin(), n.modes.end(), mode) != n.modes.end(); }
 
-// output modes of contracting a and b when `count` tells how many live tensors hold each index
-void out_modes(const TNNode& a, const TNNode& b, const std::map<int32_t, int>& count, TNNode* out) {
-    out->modes.clear();
-    out->ext.clear();
-    for (size_t i = 0; i < a.modes.size(); ++i) {
-        int32_t m = a.modes[i];
-        int users = count.at(m) - 1 - (holds(b, m) ? 1 : 0);
-        if (users > 0) {
-            out->modes.push_back(m);
-            out->ext.push_back(a.ext[i]);
-        }
-    }
-    for (size_t i = 0; i < b.modes.size(); ++i) {
-        int32_t m = b.modes[i];
-        if (holds(a, m)) continue;
-        int users = count.at(m) - 1;
-        if (users > 0) {
-            out->modes.push_back(m);
-            out->ext.push_back(b.ext[i]);
-        }
-    }
-}
-
-void post_order(const std::vector<TNNode>& nodes, int id, std::vector<int>* order) {
-    if (nodes[id].left >= 0) {
-        post_order(nodes, nodes[id].left, order);
-        post_order(nodes, nodes[id].right, order);
-    }
-    order->push_back(id);
-}
 
 }  // namespace
 
@@ -100,6 +64,11 @@ extern "C" {
 
 int32_t qb200_tn_plan(qb200_ctx* ctx, int32_t ntensors, const int32_t* ranks, const int32_t* modes,
                       const int64_t* extents, int64_t max_elements, qb200_tnplan** out) {
+    return qb200_tn_plan_opt(ctx, ntensors, ranks, modes, extents, max_elements, 1, out);
+}
+
+int32_t qb200_tn_plan_opt(qb200_ctx* ctx, int32_t ntensors, const int32_t* ranks, const int32_t* modes,
+                          const int64_t* extents, int64_t max_elements, int32_t optimizer, qb200_tnplan** out) {
     // planning is pure host work: ctx may be NULL (then there is no error string, only the code)
     if (ntensors < 1 || !ranks || !modes || !extents || !out) QB_FAIL(ctx, QB200_E_INVALID, "tn_plan: bad argument");
     qb200_tnplan* P = new qb200_tnplan();
@@ -140,101 +109,54 @@ int32_t qb200_tn_plan(qb200_ctx* ctx, int32_t ntensors, const int32_t* ranks, co
         }
     }
 
-    // ---- greedy path ----
-    std::vector<int> live;
-    for (int t = 0; t < ntensors; ++t) live.push_back(t);
-    while (live.size() > 1) {
-        bool found = false;
-        int64_t best_cost = 0, best_size = 0;
-        int bi = -1, bj = -1;
-        TNNode best_out;
-        for (size_t x = 0; x < live.size(); ++x)
-            for (size_t y = x + 1; y < live.size(); ++y) {
-                const TNNode& a = P->nodes[live[x]];
-                const TNNode& b = P->nodes[live[y]];
-                bool connected = false;
-                for (auto m : a.modes)
-                    if (holds(b, m)) {
-                        connected = true;
-                        break;
-                    }
-                if (!connected) continue;
-                TNNode o;
-                out_modes(a, b, count, &o);
-                int64_t so = o.size();
-                int64_t cost = so - a.size() - b.size();
-                if (!found || cost < best_cost || (cost == best_cost && so < best_size)) {
-                    found = true;
-                    best_cost = cost;
-                    best_size = so;
-                    bi = (int)x;
-                    bj = (int)y;
-                    best_out = o;
-                }
+    // ---- path + slicing: tn_plan.cu on dense mode ids (numbered in order of first appearance) ----
+    std::map<int32_t, int> dense;
+    std::vector<int32_t> label;
+    std::vector<int64_t> dext;
+    std::vector<std::vector<int>> leaf_modes(ntensors);
+    for (int t = 0; t < ntensors; ++t)
+        for (size_t i = 0; i < P->nodes[t].modes.size(); ++i) {
+            int32_t m = P->nodes[t].modes[i];
+            auto it = dense.find(m);
+            if (it == dense.end()) {
+                it = dense.emplace(m, (int)label.size()).first;
+                label.push_back(m);
+                dext.push_back(P->nodes[t].ext[i]);
             }
-        if (!found) {  // disconnected components: outer product of the two smallest
-            std::vector<size_t> idx(live.size());
-            for (size_t i = 0; i < idx.size(); ++i) idx[i] = i;
-            std::stable_sort(idx.begin(), idx.end(),
-                             [&](size_t p, size_t q) { return P->nodes[live[p]].size() < P->nodes[live[q]].size(); });
-            bi = (int)std::min(idx[0], idx[1]);
-            bj = (int)std::max(idx[0], idx[1]);
-            out_modes(P->nodes[live[bi]], P->nodes[live[bj]], count, &best_out);
+            leaf_modes[t].push_back(it->second);
         }
-        int ia = live[bi], ib = live[bj];
-        for (auto m : P->nodes[ia].modes) count[m]--;
-        for (auto m : P->nodes[ib].modes) count[m]--;
-        for (auto m : best_out.modes) count[m]++;
-        best_out.left = ia;
-        best_out.right = ib;
-        P->nodes.push_back(best_out);
-        live.erase(live.begin() + bj);
-        live.erase(live.begin() + bi);
-        live.push_back((int)P->nodes.size() - 1);
+    for (auto& lm : leaf_modes) {  // a label twice on one tensor (a trace) is not a pairwise-contraction network
+        std::vector<int> srt = lm;
+        std::sort(srt.begin(), srt.end());
+        if (std::adjacent_find(srt.begin(), srt.end()) != srt.end()) {
+            delete P;
+            QB_FAIL(ctx, QB200_E_UNSUPPORTED, "tn_plan: repeated index on one tensor");
+        }
     }
-
-    // ---- findslices ----
-    std::vector<int> order;
-    post_order(P->nodes, (int)P->nodes.size() - 1, &order);
+    PlanResult pr = plan_network(leaf_modes, dext, max_elements, optimizer);
+    for (size_t id = ntensors; id < pr.nodes.size(); ++id) {
+        TNNode n;
+        n.left = pr.nodes[id].left;
+        n.right = pr.nodes[id].right;
+        for (int x : pr.nodes[id].modes) {
+            n.modes.push_back(label[x]);
+            n.ext.push_back(dext[x]);
+        }
+        P->nodes.push_back(n);
+    }
     std::set<int32_t> cut;
+    for (int x : pr.cut) {
+        cut.insert(label[x]);
+        P->sliced.push_back(label[x]);
+        P->sliced_ext.push_back(dext[x]);
+    }
+    P->nslices = pr.nslices;
     auto node_size = [&](const TNNode& n) {
         int64_t s = 1;
         for (size_t i = 0; i < n.modes.size(); ++i)
             if (!cut.count(n.modes[i])) s *= n.ext[i];
         return s;
     };
-    if (max_elements > 0) {
-        for (;;) {
-            int64_t mx = 0;
-            for (size_t id = ntensors; id < P->nodes.size(); ++id) mx = std::max(mx, node_size(P->nodes[id]));
-            if (mx <= max_elements) break;
-            std::map<int32_t, double> score;
-            std::vector<int32_t> first_seen;
-            for (int id : order) {
-                const TNNode& n = P->nodes[id];
-                double s = (double)node_size(n);
-                for (size_t i = 0; i < n.modes.size(); ++i) {
-                    int32_t m = n.modes[i];
-                    if (cut.count(m) || n.ext[i] <= 1) continue;
-                    if (!score.count(m)) first_seen.push_back(m);
-                    score[m] += s;
-                }
-            }
-            if (first_seen.empty()) break;
-            int32_t pick = first_seen[0];
-            for (int32_t m : first_seen)
-                if (score[m] > score[pick]) pick = m;
-            cut.insert(pick);
-            P->sliced.push_back(pick);
-            int64_t e = 1;
-            for (auto& n : P->nodes) {
-                int64_t x = ext_of(n, pick);
-                if (x > 0) e = x;
-            }
-            P->sliced_ext.push_back(e);
-            P->nslices *= e;
-        }
-    }
     // ---- statistics and per-step contraction specs on the sliced shapes ----
     P->max_inter = 0;
     P->flops_per_slice = 0.0;
@@ -281,7 +203,7 @@ int32_t qb200_tn_plan(qb200_ctx* ctx, int32_t ntensors, const int32_t* ranks, co
             if (e < 0) e = ext_of(P->nodes[n.right], m);
             macs *= (double)e;
         }
-        P->flops_per_slice += 8.0 * macs;
+        (n.invariant ? P->flops_invariant : P->flops_per_slice) += 8.0 * macs;
         P->max_inter = std::max(P->max_inter, node_size(n));
     }
     P->cached.assign(P->nodes.size(), nullptr);
@@ -307,6 +229,7 @@ int32_t qb200_tn_plan_sliced_modes(const qb200_tnplan* P, int32_t* modes_out) {
     return (int32_t)P->sliced.size();
 }
 double qb200_tn_plan_flops_per_slice(const qb200_tnplan* P) { return P ? P->flops_per_slice : -1.0; }
+double qb200_tn_plan_flops_invariant(const qb200_tnplan* P) { return P ? P->flops_invariant : -1.0; }
 int64_t qb200_tn_plan_max_intermediate(const qb200_tnplan* P) { return P ? P->max_inter : -1; }
 int32_t qb200_tn_plan_path(const qb200_tnplan* P, int32_t* pairs_out) {
     if (!P) return -1;
@@ -338,6 +261,16 @@ int32_t qb200_tn_contract_sliced(qb200_ctx* ctx, qb200_tnplan* P, qb200_tensor* 
         QB_FAIL(ctx, QB200_E_UNSUPPORTED, "tn_contract_sliced: network with a single tensor");
     }
     std::set<int32_t> cut(P->sliced.begin(), P->sliced.end());
+    // slice-invariant sub-trees are contracted once PER CALL: `leaves` belong to the caller and may hold other data
+    // the next time (a cache that outlived the call returned stale sub-trees)
+    auto drop_cache = [&]() {
+        for (auto& p : P->cached)
+            if (p) {
+                cudaFreeAsync(p, ctx->stream);
+                p = nullptr;
+            }
+    };
+    drop_cache();
     std::vector<c128*> buf(nn, nullptr);
     std::vector<bool> owned(nn, false);
     const c128 ONE = {1.0, 0.0}, ZERO = {0.0, 0.0};
@@ -462,7 +395,7 @@ int32_t qb200_tn_contract_sliced(qb200_ctx* ctx, qb200_tnplan* P, qb200_tensor* 
             if (last) {
                 buf[id] = nullptr;
             } else if (n.invariant) {
-                P->cached[id] = outp;  // reused by every later slice (and later calls with the same leaves)
+                P->cached[id] = outp;  // reused by every later slice of this call
                 buf[id] = outp;
                 owned[id] = false;
             } else {
@@ -471,6 +404,7 @@ int32_t qb200_tn_contract_sliced(qb200_ctx* ctx, qb200_tnplan* P, qb200_tensor* 
             }
         }
     }
+    drop_cache();
     QB_CUDA(ctx, cudaMemcpyAsync(ctx->scratch_host, accd, sizeof(c128), cudaMemcpyDeviceToHost, ctx->stream));
     QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     acc[0] += ctx->scratch_host[0];

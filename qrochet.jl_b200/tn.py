@@ -99,9 +99,10 @@ def amplitude_network(n, gates, ket=None, bra=None):
 
 
 class SlicedContraction:
-    """Plan once, replay the tree per slice (qb200_tn_plan / qb200_tn_contract_sliced)."""
+    """Plan once, replay the tree per slice (qb200_tn_plan_opt / qb200_tn_contract_sliced).  optimizer: 1 = full planner
+    (simplification + multi-start greedy + sub-tree reconfiguration), 0 = the round-1 single greedy tree."""
 
-    def __init__(self, ctx: Context | None, arrays, modes, max_elements: int):
+    def __init__(self, ctx: Context | None, arrays, modes, max_elements: int, optimizer: int = 1):
         self.ctx = ctx
         self.modes = [tuple(int(x) for x in m) for m in modes]
         shapes = [tuple(np.shape(a)) for a in arrays]
@@ -110,7 +111,8 @@ class SlicedContraction:
         flat_ext = capi.i64arr(e for s in shapes for e in s)
         h = C.c_void_p()
         ch = ctx.h if ctx is not None else None
-        check(ch, lib.qb200_tn_plan(ch, len(arrays), ranks, flat_modes, flat_ext, int(max_elements), C.byref(h)))
+        check(ch, lib.qb200_tn_plan_opt(ch, len(arrays), ranks, flat_modes, flat_ext, int(max_elements), int(optimizer),
+                                        C.byref(h)))
         self.h = h
         self.leaves = None
         if ctx is not None:
@@ -146,6 +148,11 @@ class SlicedContraction:
     @property
     def flops_per_slice(self) -> float:
         return float(lib.qb200_tn_plan_flops_per_slice(self.h))
+
+    @property
+    def flops_invariant(self) -> float:
+        """8 x complex MACs of the slice-invariant tree nodes (executed once per contract call)."""
+        return float(lib.qb200_tn_plan_flops_invariant(self.h))
 
     @property
     def max_intermediate(self) -> int:

@@ -12,6 +12,10 @@
 
 #define CHECK(call)                                                                               \
     do {                                                                                          \
+        if (verbose) {                                                                            \
+            fprintf(stderr, "[abi_smoke] %s\n", #call);                                           \
+            fflush(stderr);                                                                       \
+        }                                                                                         \
         int32_t rc_ = (call);                                                                     \
         if (rc_ != QB200_OK) {                                                                    \
             fprintf(stderr, "%s:%d: %s -> %d (%s)\n", __FILE__, __LINE__, #call, (int)rc_,        \
@@ -19,6 +23,8 @@
             return 1;                                                                             \
         }                                                                                         \
     } while (0)
+
+static int verbose = 0;
 
 static double frand(unsigned* s) {
     *s = *s * 1664525u + 1013904223u;
@@ -34,6 +40,7 @@ int main(int argc, char** argv) {
         printf("ABI_SYMBOLS_OK %d\n", (int)(sizeof(fns) / sizeof(fns[0])));
         return 0;
     }
+    verbose = getenv("ABI_SMOKE_VERBOSE") != NULL;
     if (qb200_create(0, &ctx) != QB200_OK) {
         fprintf(stderr, "qb200_create failed: %s\n", qb200_last_error(NULL));
         return 2;

@@ -67,19 +67,39 @@ def test_circuit_network_matches_oracle_builder():
     assert len(arrays) == 12 + 16
 
 
-@pytest.mark.parametrize("n,depth,maxel", [(8, 3, 0), (10, 4, 2 ** 6), (12, 4, 2 ** 5), (16, 6, 2 ** 8)])
-def test_planner_matches_oracle_bit_exactly(n, depth, maxel):
+@pytest.mark.parametrize("n,depth,maxel,optimizer", [(8, 3, 0, 1), (10, 4, 2 ** 6, 1), (12, 4, 2 ** 5, 1), (14, 6, 2 ** 7, 1),
+                                                     (12, 4, 2 ** 5, 0), (16, 6, 2 ** 8, 0)])
+def test_planner_matches_oracle_bit_exactly(n, depth, maxel, optimizer):
+    """The C++ planner (csrc/tn_plan.cu: ContractSimplification + multi-start greedy + sub-tree reconfiguration +
+    findslices) against the same rules restated in Python (oracle/circuit.py::plan): same contraction path step by
+    step, same cut indices in the same order, same flop counts.  optimizer = 0 is the round-1 single greedy tree."""
     import qrochet_b200 as qb
     gates = qb.random_fsim_circuit(n, depth)
-    arrays, modes = qb.amplitude_network(n, gates)
-    plan = qb.SlicedContraction(None, arrays, modes, maxel)
+    ket, bra = ocirc.random_product_state(n, 5), ocirc.random_product_state(n, 6)
+    arrays, modes = qb.amplitude_network(n, gates, ket, bra)
+    plan = qb.SlicedContraction(None, arrays, modes, maxel, optimizer=optimizer)
     extents = {x: 2 for m in modes for x in m}
-    want = ocirc.plan(modes, extents, maxel)
+    want = ocirc.plan(modes, extents, maxel, optimizer=optimizer)
     assert plan.path == want["path"]
     assert plan.sliced_modes == want["sliced"]          # first-occurrence slice choice, bit-exact
-    assert plan.nslices == 2 ** len(want["sliced"])
+    assert plan.nslices == want["nslices"] == 2 ** len(want["sliced"])
+    assert plan.flops_per_slice == 8.0 * want["macs_per_slice"]
+    assert plan.flops_invariant == 8.0 * want["macs_invariant"]
     if maxel:
         assert plan.max_intermediate <= maxel
+
+
+def test_planner_local_search_beats_the_single_greedy_tree():
+    """What the local search buys on a circuit of the benchmark's family (pure host work): far fewer flops, never more."""
+    import qrochet_b200 as qb
+    n, depth = 24, 6
+    gates = qb.random_fsim_circuit(n, depth)
+    arrays, modes = qb.amplitude_network(n, gates)
+    old = qb.SlicedContraction(None, arrays, modes, 2 ** 14, optimizer=0)
+    new = qb.SlicedContraction(None, arrays, modes, 2 ** 14, optimizer=1)
+    total = lambda p: p.flops_per_slice * p.nslices + p.flops_invariant  # noqa: E731
+    assert total(new) * 4 <= total(old)
+    assert new.max_intermediate <= 2 ** 14 and old.max_intermediate <= 2 ** 14
 
 
 def test_oracle_sliced_sum_equals_statevector():
