@@ -115,7 +115,7 @@ if __name__ == "__main__":
         "tebd": [case_tebd(201, 8, 8, 6, [1, 3, 5, 7, 2, 4, 6, 4, 4, 1]), case_tebd(204, 10, 16, 16, [5, 4, 6, 3, 7, 5, 9, 1])],
         "mixed_canonize": [case_mixed(301, 9, 8, 5), case_mixed(302, 8, 6, 2)],
         "mpo": [case_mpo(401, 8, 6, 10)],
-        "circuit": [case_circuit(10, 4, 2 ** 5), case_circuit(12, 5, 2 ** 6)],
+        "circuit": [case_circuit(10, 4, 2 ** 5), case_circuit(12, 5, 2 ** 4), case_circuit(14, 6, 2 ** 6)],
         "analytic": analytic(),
     }
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_v1.json")
