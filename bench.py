@@ -486,15 +486,20 @@ def run_b200(args):
     del psi
 
     if not args.no_sliced:
-        line["sliced_contraction"] = run_sliced(ctx, qb, rank, world, peak_tf, barrier, max_over_ranks)
-        if world == 1:
-            # the same network with the slice target an on-GPU budget allows (2^28 elements = 4 GiB per intermediate
-            # instead of the 2^24 of examples/distributed.jl:46): fewer cuts, larger GEMMs.  Reported separately.
-            try:
-                line["sliced_contraction_large_target"] = run_sliced(ctx, qb, rank, world, peak_tf, barrier,
-                                                                     max_over_ranks, target=2 ** 28, reps=2)
-            except Exception as e:  # never lose the headline line to the extra measurement
-                line["sliced_contraction_large_target"] = {"error": str(e)[:200]}
+        try:
+            # reference value: the same amplitude with the on-GPU slice target (2^28 elements = 4 GiB per intermediate
+            # instead of the 2^24 of examples/distributed.jl:46): the round-2 tree needs no cut at all there
+            big, amp_ref = run_sliced(ctx, qb, 0, world=1, peak_tf=peak_tf, barrier=lambda: ctx.synchronize(),
+                                      max_over_ranks=lambda x: x, target=2 ** 28, reps=2)
+            line["sliced_contraction"], _ = run_sliced(ctx, qb, rank, world, peak_tf, barrier, max_over_ranks,
+                                                       check_against=amp_ref)
+            if world == 1:
+                line["sliced_contraction_large_target"] = big
+                line["sliced_contraction_round1_planner"], _ = run_sliced(ctx, qb, rank, world, peak_tf, barrier,
+                                                                          max_over_ranks, reps=1, optimizer=0,
+                                                                          check_against=amp_ref)
+        except Exception as e:  # never lose the headline line to the extra measurement
+            line["sliced_contraction"] = {"error": str(e)[:300]}
     if not args.no_expect:
         try:
             line["expect_batch"] = run_expect_batch(ctx, qb, rank, world, n, chi, barrier, max_over_ranks)
@@ -518,16 +523,28 @@ def ensure_comm(ctx, qb, rank, world):
         ctx._comm_ready = True
 
 
-def run_sliced(ctx, qb, rank, world, peak_tf, barrier, max_over_ranks, qubits=40, depth=6, target=2 ** 24, reps=3):
+def random_product_bra(n, seed=4000):
+    """n normalised random local vectors (the bra of the benchmark amplitude)."""
+    rng = np.random.default_rng(seed)
+    v = rng.standard_normal((n, 2)) + 1j * rng.standard_normal((n, 2))
+    return list(v / np.linalg.norm(v, axis=1, keepdims=True))
+
+
+def run_sliced(ctx, qb, rank, world, peak_tf, barrier, max_over_ranks, qubits=40, depth=6, target=2 ** 24, reps=3,
+               optimizer=1, check_against=None):
     """Second half of BASELINE.json's metric: sliced contraction of the <b|U|0..0> network of a 40-qubit, depth-6
-    random FSim circuit (examples/distributed.jl:11-53 pattern; slice target 2^24 elements, :46).  Slices are dealt
-    s mod W to the ranks (no data-path communication), each rank accumulates on its device, ONE NCCL sum (:101)."""
+    random FSim circuit (examples/distributed.jl:11-53 pattern; slice target 2^24 elements, :46) with a seeded random
+    product bra b (FSim gates leave |0..0> alone, so <0|U|0> = 1 would exercise no phases).  Slices are dealt s mod W
+    to the ranks (no data-path communication), each rank accumulates on its device, ONE NCCL sum (:101).
+    optimizer: 1 = the round-2 planner, 0 = the round-1 single greedy tree (the "before" column)."""
     gates = qb.random_fsim_circuit(qubits, depth)
-    arrays, modes = qb.amplitude_network(qubits, gates)
-    sc = qb.SlicedContraction(ctx, arrays, modes, target)
+    arrays, modes = qb.amplitude_network(qubits, gates, bra=random_product_bra(qubits))
+    t0 = time.perf_counter()
+    sc = qb.SlicedContraction(ctx, arrays, modes, target, optimizer=optimizer)
+    plan_s = time.perf_counter() - t0
     ensure_comm(ctx, qb, rank, world)
     reducer = (lambda v: qb.comm_allreduce_sum(ctx, v)) if world > 1 else (lambda v: v)
-    # warm-up: one slice per rank (builds the offset tables, contracts the slice-invariant sub-trees once)
+    # warm-up: one slice per rank (builds the offset tables, the arena and the slice graph)
     sc.contract(first_slice=rank % sc.nslices, stride=sc.nslices)
     reducer(0j)
     best, amp = None, None
@@ -537,17 +554,28 @@ def run_sliced(ctx, qb, rank, world, peak_tf, barrier, max_over_ranks, qubits=40
         amp = qb.contract_sliced_distributed(sc, rank, world, reducer)
         ms = max_over_ranks(ctx.timer_end())
         best = ms if best is None else min(best, ms)
-    flops = sc.nslices * sc.flops_per_slice
+    flops = sc.nslices * sc.flops_per_slice + sc.flops_invariant * min(world, sc.nslices)
     tf = flops / (best * 1e-3) / 1e12
-    return {"metric": "sliced TN contraction TFLOP/s", "value": tf, "unit": "TFLOP/s", "n_gpus": world,
-            "ms": best, "scaling": "strong",
-            "config": {"workload": f"{qubits}-qubit depth-{depth} random FSim circuit amplitude <0|U|0>, greedy path, "
-                                   f"slice target 2^{int(np.log2(target))} elements (BASELINE configs[4])",
-                       "nslices": sc.nslices, "cut_indices": len(sc.sliced_modes),
-                       "flops_per_slice": sc.flops_per_slice, "max_intermediate_elements": sc.max_intermediate,
-                       "flop_count": "8 x complex MACs over the tree nodes a slice executes x slices (EinExprs flops x 8)"},
-            "amplitude": [amp.real, amp.imag], "frac_of_dmma_peak": tf / (peak_tf * world),
-            "collective": "one ncclAllReduce(sum) of 2 doubles" if world > 1 else "none"}
+    out = {"metric": "sliced TN contraction TFLOP/s", "value": tf, "unit": "TFLOP/s", "n_gpus": world,
+           "ms": best, "time_to_amplitude_ms": best, "scaling": "strong",
+           "config": {"workload": f"{qubits}-qubit depth-{depth} random FSim circuit amplitude <b|U|0..0>, random product "
+                                  f"bra (seed 4000), slice target 2^{int(np.log2(target))} elements (BASELINE configs[4])",
+                      "planner": "round 2: ContractSimplification + multi-start greedy + sub-tree reconfiguration"
+                                 if optimizer else "round 1: one greedy tree",
+                      "plan_s": plan_s, "nslices": sc.nslices, "cut_indices": len(sc.sliced_modes),
+                      "flops_per_slice": sc.flops_per_slice, "flops_slice_invariant": sc.flops_invariant,
+                      "total_flops": sc.nslices * sc.flops_per_slice + sc.flops_invariant,
+                      "max_intermediate_elements": sc.max_intermediate,
+                      "flop_count": "8 x complex MACs (EinExprs flops x 8): per-slice nodes x slices + slice-invariant "
+                                    "nodes once per rank that holds a slice",
+                      "executor": "one CUDA graph launch per slice (leaf gather + tree replay + cursor advance)"},
+           "amplitude": [amp.real, amp.imag], "frac_of_dmma_peak": tf / (peak_tf * world),
+           "collective": "one ncclAllReduce(sum) of 2 doubles" if world > 1 else "none"}
+    if check_against is not None:
+        err = abs(amp - check_against) / abs(check_against)
+        out["amplitude_check"] = {"against": "the same amplitude contracted UNSLICED on one GPU (slice target 2^28)",
+                                  "rel_err": err, "tol": 1e-10, "ok": bool(err <= 1e-10)}
+    return out, amp
 
 
 def run_expect_batch(ctx, qb, rank, world, n, chi, barrier, max_over_ranks, nobs=None):

@@ -5,6 +5,8 @@ from ._capi import MissingSchmidtCoefficientsException, QB200Error
 from .device import (Context, DeviceArray, conj, contract, norm2, permute, qr, scale, scale_mode, select_mode,
                      slice_mode, svd)
 from . import chain
+from . import gates
+from .gates import Gate
 from .mps import B200MPS
 from .product import Product
 from .tn import SlicedContraction, amplitude_network, circuit_network, fsim, random_fsim_circuit

@@ -1284,13 +1284,17 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
     const int max_sweeps = 40;
     int sweep = 0;
     bool converged = false;
-    for (; sweep < max_sweeps && !converged; ++sweep) {
+    // One Jacobi sweep = 3 kernels x (nb - 1) steps whose arguments are the same in every sweep: the sweep is captured
+    // ONCE per SVD as a CUDA graph and replayed (189 launches -> 1 graph launch per sweep at k = 2048; the host thread of
+    // a worker stream issues ~10x fewer driver calls per SVD).  Plain launches with the phase profiler, the
+    // mixed-precision Gram experiment, QB200_SYNC_DEBUG, QB200_SVD_GRAPH=0 and for single-pair problems.
+    auto emit_sweep = [&](bool lowp_now) {
         cudaMemsetAsync(stat, 0, sizeof(unsigned long long), ctx->stream);
         for (int step = 0; step < nsteps; ++step) {
             const int mode = (nb == 2) ? 0 : (step == 0 ? 1 : 2);
             {
                 PhaseTimer pt(ctx, QB_PH_JGRAM, 8.0 * npairs * (double)st->mp * JP * JP);  // full-product count
-                if (mode == 2 && lowp)
+                if (mode == 2 && lowp_now)
                     jacobi_gram32_kernel<<<gram_ctas, 256, GRAM32_SMEM, ctx->stream>>>(st->Z32, st->ldz, st->mp, nb, step,
                                                                                       npairs, Gpart);
                 else if (mode == 2)
@@ -1311,13 +1315,37 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
                 (update_3m() ? jacobi_update_kernel<1> : jacobi_update_kernel<0>)<<<upd_ctas, UPD_THREADS, UPD_SMEM, ctx->stream>>>(
                     st->Z, st->ldz, nb, step, Wg, flags, npairs, u_nchunk, shadow ? st->Z32 : nullptr);
             }
-            ctx->launches += 3;
         }
         cudaMemcpyAsync(scale, scale + 1, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
+    };
+    static const bool graph_enabled = [] {
+        const char* e = getenv("QB200_SVD_GRAPH");
+        return !(e && e[0] == '0');
+    }();
+    cudaGraphExec_t sweep_graph = nullptr;
+    if (graph_enabled && nb > 2 && !ctx->prof_on && !shadow && !qb_sync_debug()) {
+        cudaGraph_t g = nullptr;
+        if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            emit_sweep(false);
+            cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
+            if (ce == cudaSuccess && g && cudaGraphInstantiate(&sweep_graph, g, 0) != cudaSuccess) sweep_graph = nullptr;
+            if (g) cudaGraphDestroy(g);
+            if (!sweep_graph) cudaGetLastError();  // fall back to plain launches
+        }
+    }
+    for (; sweep < max_sweeps && !converged; ++sweep) {
+        if (sweep_graph)
+            cudaGraphLaunch(sweep_graph, ctx->stream);
+        else
+            emit_sweep(lowp);
+        ctx->launches += 3 * (int64_t)nsteps;
         cudaError_t e = cudaMemcpyAsync(ctx->scratch_host, stat, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = qb_stream_sync(ctx);
         if (e == cudaSuccess) e = cudaGetLastError();
-        if (e != cudaSuccess) return cuda_fail(e);
+        if (e != cudaSuccess) {
+            if (sweep_graph) cudaGraphExecDestroy(sweep_graph);
+            return cuda_fail(e);
+        }
         double worst = ctx->scratch_host[0];
         if (getenv("QB200_DEBUG"))
             fprintf(stderr, "[qb200 svd] %lld x %lld (jacobi on %lld^2, nb %d) sweep %d%s worst %.3e\n", (long long)m,
@@ -1328,6 +1356,7 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
             if (!lowp) shadow = false;  // quadratic phase ahead: FP64 Gram from here on, the shadow is no longer kept
         }
     }
+    if (sweep_graph) cudaGraphExecDestroy(sweep_graph);
     ctx->last_svd_sweeps = sweep;
     ctx->svd_calls++;
     ctx->svd_sweeps += sweep;

@@ -45,7 +45,32 @@ struct qb200_tnplan {
     double flops_invariant = 0.0;    // 8 x complex MACs of the slice-invariant nodes (executed once per call)
     int64_t max_inter = 0;
     std::vector<TNStep> steps;
-    std::vector<c128*> cached;  // results of the slice-invariant nodes (device): valid inside ONE contract call only
+    // ---- executor state: built at the first contract call, rebuilt when the caller passes other leaf buffers ----
+    struct LeafSlice {  // one leaf that holds cut indices: how its slice is gathered (device copy in leaf_desc)
+        const c128* src;
+        int64_t dst_off, nout;
+        int32_t rank_out, ncut;
+        int64_t ext_out[QB200_MAX_RANK], stride_out[QB200_MAX_RANK];
+        int32_t cut_id[QB200_MAX_RANK];  // position in `sliced` of each cut index the leaf holds
+        int64_t cut_stride[QB200_MAX_RANK];
+    };
+    bool exec_ready = false;
+    bool exec_graph_mode = false;           // whether the executor was built with the slice graph enabled
+    std::vector<const void*> bound_leaves;  // leaf data pointers the tables / graph were built for
+    std::vector<c128*> node_ptr;            // every node: where its (sliced) data lives during the replay
+    c128* arena = nullptr;                  // intermediates of the per-slice replay (offline first-fit over lifetimes)
+    c128* inv_arena = nullptr;              // results of the slice-invariant nodes (recomputed once per call)
+    c128* leaf_arena = nullptr;             // slices of the leaves that hold a cut index
+    LeafSlice* leaf_desc = nullptr;         // device
+    int nleaf_desc = 0;
+    int64_t max_leaf_out = 0;
+    int64_t* cut_meta = nullptr;            // device: [2 * ncut] = divisor, extent of each cut index
+    int64_t* cursor = nullptr;              // device: [0] = slice to contract next, [1] = stride
+    c128* acc = nullptr;                    // device accumulator of the rank-0 results
+    cudaGraph_t graph = nullptr;            // one slice: gather the leaf slices, replay the tree, advance the cursor
+    cudaGraphExec_t graph_exec = nullptr;
+    int64_t launches_per_slice = 0;
+    size_t arena_bytes = 0, inv_bytes = 0;
 };
 
 namespace {
@@ -206,17 +231,34 @@ int32_t qb200_tn_plan_opt(qb200_ctx* ctx, int32_t ntensors, const int32_t* ranks
         (n.invariant ? P->flops_invariant : P->flops_per_slice) += 8.0 * macs;
         P->max_inter = std::max(P->max_inter, node_size(n));
     }
-    P->cached.assign(P->nodes.size(), nullptr);
     *out = P;
     return QB200_OK;
 }
 
+static void release_executor(qb200_ctx* ctx, qb200_tnplan* P) {
+    if (P->graph_exec) cudaGraphExecDestroy(P->graph_exec);
+    if (P->graph) cudaGraphDestroy(P->graph);
+    P->graph_exec = nullptr;
+    P->graph = nullptr;
+    if (ctx) {
+        for (void* p : {(void*)P->arena, (void*)P->inv_arena, (void*)P->leaf_arena, (void*)P->leaf_desc, (void*)P->cut_meta,
+                        (void*)P->cursor, (void*)P->acc})
+            if (p) cudaFreeAsync(p, ctx->stream);
+        for (auto& st : P->steps) {
+            if (st.tables) cudaFreeAsync(st.tables, ctx->stream);
+            st.tables = nullptr;
+            st.ready = false;
+        }
+    }
+    P->arena = P->inv_arena = P->leaf_arena = P->acc = nullptr;
+    P->leaf_desc = nullptr;
+    P->cut_meta = P->cursor = nullptr;
+    P->exec_ready = false;
+}
+
 int32_t qb200_tn_plan_free(qb200_ctx* ctx, qb200_tnplan* P) {
     if (!P) return QB200_OK;
-    for (auto& s : P->steps)
-        if (s.tables && ctx) cudaFreeAsync(s.tables, ctx->stream);
-    for (auto p : P->cached)
-        if (p && ctx) cudaFreeAsync(p, ctx->stream);
+    release_executor(ctx, P);
     delete P;
     return QB200_OK;
 }
@@ -242,6 +284,270 @@ int32_t qb200_tn_plan_path(const qb200_tnplan* P, int32_t* pairs_out) {
     return nsteps;
 }
 
+// ---- executor ----------------------------------------------------------------------------------------------
+}  // extern "C"
+
+namespace {
+
+// every leaf that holds a cut index, restricted to slice cursor[0] (first cut index fastest): ONE launch per slice
+__global__ void tn_slice_leaves_kernel(const qb200_tnplan::LeafSlice* __restrict__ desc, const int64_t* __restrict__ cursor,
+                                       const int64_t* __restrict__ cut_meta, c128* __restrict__ arena) {
+    const qb200_tnplan::LeafSlice& L = desc[blockIdx.x];
+    const int64_t s = cursor[0];
+    int64_t base = 0;
+    for (int j = 0; j < L.ncut; ++j) {
+        const int64_t div = cut_meta[2 * L.cut_id[j]], ext = cut_meta[2 * L.cut_id[j] + 1];
+        base += ((s / div) % ext) * L.cut_stride[j];
+    }
+    for (int64_t idx = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; idx < L.nout; idx += (int64_t)gridDim.y * blockDim.x) {
+        int64_t rem = idx, off = base;
+        for (int j = 0; j < L.rank_out; ++j) {
+            off += (rem % L.ext_out[j]) * L.stride_out[j];
+            rem /= L.ext_out[j];
+        }
+        arena[L.dst_off + idx] = L.src[off];
+    }
+}
+
+__global__ void tn_advance_cursor_kernel(int64_t* cursor) { cursor[0] += cursor[1]; }
+
+inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// offline first-fit allocator over the lifetimes of the replayed intermediates (one arena, offsets in bytes)
+struct ArenaPlan {
+    struct Block {
+        size_t off, size;
+    };
+    std::vector<Block> free_list;
+    size_t top = 0, peak = 0;  // the arena is sized by the PEAK: `top` shrinks again when trailing blocks are released
+    size_t alloc(size_t bytes) {
+        bytes = align_up(std::max<size_t>(bytes, 16));
+        for (size_t i = 0; i < free_list.size(); ++i)
+            if (free_list[i].size >= bytes) {
+                size_t off = free_list[i].off;
+                free_list[i].off += bytes;
+                free_list[i].size -= bytes;
+                if (free_list[i].size == 0) free_list.erase(free_list.begin() + i);
+                return off;
+            }
+        size_t off = top;
+        top += bytes;
+        peak = std::max(peak, top);
+        return off;
+    }
+    void release(size_t off, size_t bytes) {
+        bytes = align_up(std::max<size_t>(bytes, 16));
+        size_t i = 0;
+        while (i < free_list.size() && free_list[i].off < off) ++i;
+        free_list.insert(free_list.begin() + i, {off, bytes});
+        if (i + 1 < free_list.size() && free_list[i].off + free_list[i].size == free_list[i + 1].off) {
+            free_list[i].size += free_list[i + 1].size;
+            free_list.erase(free_list.begin() + i + 1);
+        }
+        if (i > 0 && free_list[i - 1].off + free_list[i - 1].size == free_list[i].off) {
+            free_list[i - 1].size += free_list[i].size;
+            free_list.erase(free_list.begin() + i);
+        }
+        if (!free_list.empty() && free_list.back().off + free_list.back().size == top) {
+            top = free_list.back().off;
+            free_list.pop_back();
+        }
+    }
+};
+
+// a node is replayed per slice when it depends on a cut index; without cuts the whole tree is "the slice"
+inline bool per_slice(const qb200_tnplan* P, int id) { return P->sliced.empty() || !P->nodes[id].invariant; }
+
+int32_t launch_node(qb200_ctx* ctx, qb200_tnplan* P, int id) {
+    const int nl = P->nleaves;
+    const TNNode& n = P->nodes[id];
+    TNStep& st = P->steps[id - nl];
+    const bool last = (id == (int)P->nodes.size() - 1);
+    GemmArgs g = st.args;
+    g.A = st.spec.swapped ? P->node_ptr[n.right] : P->node_ptr[n.left];
+    g.B = st.spec.swapped ? P->node_ptr[n.left] : P->node_ptr[n.right];
+    g.C = last ? P->acc : P->node_ptr[id];  // the rank-0 result of every slice is accumulated on the device (beta = 1)
+    g.conjA = g.conjB = 0;
+    g.alpha = make_double2(1.0, 0.0);
+    g.beta = last ? make_double2(1.0, 0.0) : make_double2(0.0, 0.0);
+    g.beta_zero = last ? 0 : 1;
+    PhaseTimer pt(ctx, QB_PH_TN_GEMM, 8.0 * g.M * (double)g.N * g.K * g.batch);
+    return launch_gemm(ctx, g);
+}
+
+// one slice: gather the leaf slices at cursor[0], replay the per-slice part of the tree, advance the cursor
+int32_t emit_slice(qb200_ctx* ctx, qb200_tnplan* P) {
+    if (P->nleaf_desc > 0) {
+        const unsigned chunks = (unsigned)std::min<int64_t>(std::max<int64_t>((P->max_leaf_out + 255) / 256, 1), 1024);
+        tn_slice_leaves_kernel<<<dim3((unsigned)P->nleaf_desc, chunks), 256, 0, ctx->stream>>>(P->leaf_desc, P->cursor,
+                                                                                              P->cut_meta, P->leaf_arena);
+        QB_LAUNCH_CHECK(ctx);
+    }
+    for (int id = P->nleaves; id < (int)P->nodes.size(); ++id)
+        if (per_slice(P, id)) QB_TRY(launch_node(ctx, P, id));
+    tn_advance_cursor_kernel<<<1, 1, 0, ctx->stream>>>(P->cursor);
+    QB_LAUNCH_CHECK(ctx);
+    return QB200_OK;
+}
+
+// QB200_TN_GRAPH=0 replays with plain launches (A/B and debugging); so do the phase profiler and QB200_SYNC_DEBUG
+bool want_graph(qb200_ctx* ctx) {
+    static const bool use_graph = [] {
+        const char* e = getenv("QB200_TN_GRAPH");
+        return !(e && e[0] == '0');
+    }();
+    return use_graph && !qb_sync_debug() && !ctx->prof_on;
+}
+
+// tables, arenas, leaf-slice descriptors and the slice graph for the given leaf buffers
+int32_t build_executor(qb200_ctx* ctx, qb200_tnplan* P, qb200_tensor* const* leaves) {
+    release_executor(ctx, P);
+    const int nl = P->nleaves, nn = (int)P->nodes.size();
+    std::set<int32_t> cut(P->sliced.begin(), P->sliced.end());
+    auto sliced_elems = [&](const TNNode& n) {
+        int64_t e = 1;
+        for (size_t i = 0; i < n.modes.size(); ++i)
+            if (!cut.count(n.modes[i])) e *= n.ext[i];
+        return e;
+    };
+    P->node_ptr.assign(nn, nullptr);
+    P->bound_leaves.assign(nl, nullptr);
+    // leaves: invariant ones are read in place, the others are gathered per slice into the leaf arena
+    std::vector<qb200_tnplan::LeafSlice> desc;
+    std::vector<int> desc_leaf;
+    size_t leaf_bytes = 0;
+    P->max_leaf_out = 0;
+    for (int t = 0; t < nl; ++t) {
+        const TNNode& n = P->nodes[t];
+        P->bound_leaves[t] = leaves[t]->data;
+        if (n.invariant) {
+            P->node_ptr[t] = (c128*)leaves[t]->data;
+            continue;
+        }
+        qb200_tnplan::LeafSlice d;
+        memset(&d, 0, sizeof(d));
+        d.src = (const c128*)leaves[t]->data;
+        d.dst_off = (int64_t)(leaf_bytes / sizeof(c128));
+        d.nout = 1;
+        int64_t stride = 1;
+        for (size_t i = 0; i < n.modes.size(); ++i) {
+            auto it = std::find(P->sliced.begin(), P->sliced.end(), n.modes[i]);
+            if (it != P->sliced.end()) {
+                d.cut_id[d.ncut] = (int32_t)(it - P->sliced.begin());
+                d.cut_stride[d.ncut++] = stride;
+            } else {
+                d.ext_out[d.rank_out] = n.ext[i];
+                d.stride_out[d.rank_out++] = stride;
+                d.nout *= n.ext[i];
+            }
+            stride *= n.ext[i];
+        }
+        leaf_bytes += align_up((size_t)d.nout * sizeof(c128));
+        P->max_leaf_out = std::max(P->max_leaf_out, d.nout);
+        desc.push_back(d);
+        desc_leaf.push_back(t);
+    }
+    P->nleaf_desc = (int)desc.size();
+    // intermediates: slice-invariant nodes keep their own buffers, per-slice nodes share one arena by lifetime
+    ArenaPlan ap;
+    std::vector<size_t> off(nn, 0);
+    size_t inv_bytes = 0;
+    for (int id = nl; id < nn; ++id) {
+        const TNNode& n = P->nodes[id];
+        const size_t bytes = (size_t)sliced_elems(n) * sizeof(c128);
+        if (id == nn - 1) continue;  // the root lands in the accumulator
+        if (!per_slice(P, id)) {
+            off[id] = inv_bytes;
+            inv_bytes += align_up(std::max<size_t>(bytes, 16));
+            continue;
+        }
+        off[id] = ap.alloc(bytes);
+        for (int ch : {n.left, n.right})
+            if (ch >= nl && per_slice(P, ch)) ap.release(off[ch], (size_t)sliced_elems(P->nodes[ch]) * sizeof(c128));
+    }
+    P->arena_bytes = ap.peak;
+    P->inv_bytes = inv_bytes;
+    auto dev_alloc = [&](size_t bytes) -> void* {
+        void* p = nullptr;
+        if (cudaMallocAsync(&p, std::max<size_t>(bytes, 256), ctx->stream) != cudaSuccess) return nullptr;
+        return p;
+    };
+    P->arena = (c128*)dev_alloc(ap.peak);
+    P->inv_arena = (c128*)dev_alloc(inv_bytes);
+    P->leaf_arena = (c128*)dev_alloc(leaf_bytes);
+    P->leaf_desc = (qb200_tnplan::LeafSlice*)dev_alloc(desc.size() * sizeof(qb200_tnplan::LeafSlice));
+    P->cut_meta = (int64_t*)dev_alloc(2 * sizeof(int64_t) * std::max<size_t>(P->sliced.size(), 1));
+    P->cursor = (int64_t*)dev_alloc(2 * sizeof(int64_t));
+    P->acc = (c128*)dev_alloc(sizeof(c128));
+    if (!P->arena || !P->inv_arena || !P->leaf_arena || !P->leaf_desc || !P->cut_meta || !P->cursor || !P->acc) {
+        release_executor(ctx, P);
+        QB_FAIL(ctx, QB200_E_CUDA, "tn_contract_sliced: out of device memory (arena %zu + %zu bytes)", ap.peak, inv_bytes);
+    }
+    for (size_t i = 0; i < desc.size(); ++i) P->node_ptr[desc_leaf[i]] = P->leaf_arena + desc[i].dst_off;
+    for (int id = nl; id < nn - 1; ++id)
+        P->node_ptr[id] = per_slice(P, id) ? (c128*)((char*)P->arena + off[id]) : (c128*)((char*)P->inv_arena + off[id]);
+    std::vector<int64_t> meta(2 * std::max<size_t>(P->sliced.size(), 1), 1);
+    {
+        int64_t div = 1;
+        for (size_t i = 0; i < P->sliced.size(); ++i) {
+            meta[2 * i] = div;
+            meta[2 * i + 1] = P->sliced_ext[i];
+            div *= P->sliced_ext[i];
+        }
+    }
+    if (!desc.empty())
+        QB_CUDA(ctx, cudaMemcpyAsync(P->leaf_desc, desc.data(), desc.size() * sizeof(qb200_tnplan::LeafSlice),
+                                     cudaMemcpyHostToDevice, ctx->stream));
+    QB_CUDA(ctx, cudaMemcpyAsync(P->cut_meta, meta.data(), meta.size() * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // desc / meta are host temporaries
+    // offset tables of every step (device-built, kept for the life of the executor)
+    for (int id = nl; id < nn; ++id) {
+        TNStep& st = P->steps[id - nl];
+        int64_t nent = contract_table_entries(st.spec);
+        if (nent > 0) {
+            st.tables = (int64_t*)dev_alloc(sizeof(int64_t) * nent);
+            if (!st.tables) {
+                release_executor(ctx, P);
+                QB_FAIL(ctx, QB200_E_CUDA, "tn_contract_sliced: out of device memory (offset tables)");
+            }
+        }
+        memset(&st.args, 0, sizeof(st.args));
+        QB_TRY(materialize_contract(ctx, st.spec, st.tables, &st.args));
+        st.ready = true;
+    }
+    // the slice as a CUDA graph: (1 + #per-slice nodes + 1) launches become one graph launch per slice
+    P->exec_graph_mode = want_graph(ctx);
+    if (P->exec_graph_mode) {
+        const int64_t l0 = ctx->launches;
+        QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        QB_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        int32_t r = emit_slice(ctx, P);
+        cudaGraph_t g = nullptr;
+        cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+        P->launches_per_slice = ctx->launches - l0;
+        ctx->launches = l0;  // nothing ran yet
+        if (r != QB200_OK || e != cudaSuccess || !g) {
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+            release_executor(ctx, P);
+            if (r != QB200_OK) return r;
+            QB_FAIL(ctx, QB200_E_CUDA, "tn_contract_sliced: graph capture failed: %s", cudaGetErrorString(e));
+        }
+        P->graph = g;
+        e = cudaGraphInstantiate(&P->graph_exec, g, 0);
+        if (e != cudaSuccess) {
+            release_executor(ctx, P);
+            QB_FAIL(ctx, QB200_E_CUDA, "tn_contract_sliced: cudaGraphInstantiate: %s", cudaGetErrorString(e));
+        }
+    }
+    P->exec_ready = true;
+    return QB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
 int32_t qb200_tn_contract_sliced(qb200_ctx* ctx, qb200_tnplan* P, qb200_tensor* const* leaves, int64_t first_slice,
                                  int64_t stride, double acc[2]) {
     if (!ctx || !P || !leaves || !acc || stride < 1 || first_slice < 0) QB_FAIL(ctx, QB200_E_INVALID, "tn_contract_sliced: bad argument");
@@ -253,159 +559,29 @@ int32_t qb200_tn_contract_sliced(qb200_ctx* ctx, qb200_tnplan* P, qb200_tensor* 
         for (int i = 0; i < L->rank; ++i)
             if (L->ext[i] != P->nodes[t].ext[i]) QB_FAIL(ctx, QB200_E_INVALID, "tn_contract_sliced: leaf %d extent mismatch", t);
     }
-    Workspace ws(ctx);
-    c128* accd = ws.get<c128>(1);
-    if (!accd) QB_FAIL(ctx, QB200_E_CUDA, "tn_contract_sliced: workspace allocation failed");
-    QB_CUDA(ctx, cudaMemsetAsync(accd, 0, sizeof(c128), ctx->stream));
-    if (nn == nl) {
-        QB_FAIL(ctx, QB200_E_UNSUPPORTED, "tn_contract_sliced: network with a single tensor");
-    }
-    std::set<int32_t> cut(P->sliced.begin(), P->sliced.end());
-    // slice-invariant sub-trees are contracted once PER CALL: `leaves` belong to the caller and may hold other data
-    // the next time (a cache that outlived the call returned stale sub-trees)
-    auto drop_cache = [&]() {
-        for (auto& p : P->cached)
-            if (p) {
-                cudaFreeAsync(p, ctx->stream);
-                p = nullptr;
-            }
-    };
-    drop_cache();
-    std::vector<c128*> buf(nn, nullptr);
-    std::vector<bool> owned(nn, false);
-    const c128 ONE = {1.0, 0.0}, ZERO = {0.0, 0.0};
-
+    if (nn == nl) QB_FAIL(ctx, QB200_E_UNSUPPORTED, "tn_contract_sliced: network with a single tensor");
+    bool rebuild = !P->exec_ready || P->exec_graph_mode != want_graph(ctx);
+    for (int t = 0; t < nl && !rebuild; ++t) rebuild = (P->bound_leaves[t] != leaves[t]->data);
+    if (rebuild) QB_TRY(build_executor(ctx, P, leaves));
+    QB_CUDA(ctx, cudaMemsetAsync(P->acc, 0, sizeof(c128), ctx->stream));
+    // slice-invariant sub-trees: once PER CALL (the leaf contents belong to the caller and may have changed)
+    if (!P->sliced.empty())
+        for (int id = nl; id < nn; ++id)
+            if (P->nodes[id].invariant) QB_TRY(launch_node(ctx, P, id));
+    int64_t* cur = reinterpret_cast<int64_t*>(ctx->scratch_host);
+    cur[0] = first_slice;
+    cur[1] = stride;
+    QB_CUDA(ctx, cudaMemcpyAsync(P->cursor, cur, 2 * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
     for (int64_t s = first_slice; s < P->nslices; s += stride) {
-        // cut index values, first cut index fastest (Iterators.product order, examples/distributed.jl:47,69)
-        std::map<int32_t, int64_t> value;
-        {
-            int64_t rem = s;
-            for (size_t i = 0; i < P->sliced.size(); ++i) {
-                value[P->sliced[i]] = rem % P->sliced_ext[i];
-                rem /= P->sliced_ext[i];
-            }
-        }
-        // leaves restricted to this slice
-        for (int t = 0; t < nl; ++t) {
-            const TNNode& n = P->nodes[t];
-            if (n.invariant) {
-                buf[t] = (c128*)leaves[t]->data;
-                owned[t] = false;
-                continue;
-            }
-            qb200_tensor cur = *leaves[t];
-            cur.owned = false;
-            std::vector<int32_t> m = n.modes;
-            c128* held = nullptr;
-            for (size_t i = 0; i < m.size();) {
-                if (!cut.count(m[i])) {
-                    ++i;
-                    continue;
-                }
-                qb200_tensor nxt = cur;
-                nxt.rank = cur.rank - 1;
-                int64_t cnt = 1;
-                for (int j = 0, k2 = 0; j < cur.rank; ++j)
-                    if (j != (int)i) {
-                        nxt.ext[k2++] = cur.ext[j];
-                        cnt *= cur.ext[j];
-                    }
-                void* p = nullptr;
-                QB_CUDA(ctx, cudaMallocAsync(&p, sizeof(c128) * std::max<int64_t>(cnt, 1), ctx->stream));
-                nxt.data = p;
-                int32_t r = qb200_select_mode(ctx, &cur, (int32_t)i, value[m[i]], &nxt);
-                if (held) cudaFreeAsync(held, ctx->stream);
-                held = (c128*)p;
-                if (r != QB200_OK) {
-                    cudaFreeAsync(held, ctx->stream);
-                    return r;
-                }
-                cur = nxt;
-                m.erase(m.begin() + i);
-            }
-            buf[t] = (c128*)cur.data;
-            owned[t] = true;
-        }
-        // replay the tree
-        for (int id = nl; id < nn; ++id) {
-            TNNode& n = P->nodes[id];
-            TNStep& st = P->steps[id - nl];
-            const bool last = (id == nn - 1);
-            if (n.invariant && P->cached[id]) {
-                buf[id] = P->cached[id];
-                owned[id] = false;
-                continue;
-            }
-            if (!st.ready) {
-                int64_t nent = contract_table_entries(st.spec);
-                if (nent > 0) {
-                    void* p = nullptr;
-                    QB_CUDA(ctx, cudaMallocAsync(&p, sizeof(int64_t) * nent, ctx->stream));
-                    st.tables = (int64_t*)p;
-                }
-                memset(&st.args, 0, sizeof(st.args));
-                QB_TRY(materialize_contract(ctx, st.spec, st.tables, &st.args));
-                st.ready = true;
-            }
-            int64_t osize = 1;
-            for (size_t i = 0; i < n.modes.size(); ++i)
-                if (!cut.count(n.modes[i])) osize *= n.ext[i];
-            c128* outp;
-            if (last) {
-                outp = accd;  // rank-0 result accumulated on the device
-            } else {
-                void* p = nullptr;
-                cudaError_t e = cudaMallocAsync(&p, sizeof(c128) * osize, ctx->stream);
-                if (e != cudaSuccess) QB_FAIL(ctx, QB200_E_CUDA, "tn_contract_sliced: out of device memory (%lld elements)", (long long)osize);
-                outp = (c128*)p;
-            }
-            GemmArgs g = st.args;
-            g.A = st.spec.swapped ? buf[n.right] : buf[n.left];
-            g.B = st.spec.swapped ? buf[n.left] : buf[n.right];
-            g.C = outp;
-            g.conjA = g.conjB = 0;
-            g.alpha = ONE;
-            g.beta = last ? ONE : ZERO;
-            g.beta_zero = last ? 0 : 1;
-            if (getenv("QB200_DEBUG_TN") && s == first_slice) {
-                cudaEvent_t e0, e1;
-                cudaEventCreate(&e0);
-                cudaEventCreate(&e1);
-                cudaEventRecord(e0, ctx->stream);
-                QB_TRY(launch_gemm(ctx, g));
-                cudaEventRecord(e1, ctx->stream);
-                cudaEventSynchronize(e1);
-                float msf = 0;
-                cudaEventElapsedTime(&msf, e0, e1);
-                double fl = 8.0 * g.M * (double)g.N * g.K * g.batch;
-                fprintf(stderr, "[tn] step %d M %d N %d K %d batch %d akfast %d bkfast %d tabs %d%d%d%d%d%d  %.3f ms %.2f TF/s inv %d\n",
-                        id - nl, g.M, g.N, g.K, g.batch, g.a_kfast, g.b_kfast, g.am.tab != nullptr, g.ak.tab != nullptr,
-                        g.bk.tab != nullptr, g.bn.tab != nullptr, g.cm.tab != nullptr, g.cn.tab != nullptr, msf,
-                        fl / msf / 1e9, (int)n.invariant);
-                cudaEventDestroy(e0);
-                cudaEventDestroy(e1);
-            } else
-                QB_TRY(launch_gemm(ctx, g));
-            // children are consumed exactly once in a tree
-            for (int ch : {n.left, n.right}) {
-                if (owned[ch] && buf[ch]) cudaFreeAsync(buf[ch], ctx->stream);
-                buf[ch] = nullptr;
-                owned[ch] = false;
-            }
-            if (last) {
-                buf[id] = nullptr;
-            } else if (n.invariant) {
-                P->cached[id] = outp;  // reused by every later slice of this call
-                buf[id] = outp;
-                owned[id] = false;
-            } else {
-                buf[id] = outp;
-                owned[id] = true;
-            }
+        if (P->graph_exec) {
+            QB_CUDA(ctx, cudaGraphLaunch(P->graph_exec, ctx->stream));
+            ctx->launches += P->launches_per_slice;
+        } else {
+            QB_TRY(emit_slice(ctx, P));
         }
     }
-    drop_cache();
-    QB_CUDA(ctx, cudaMemcpyAsync(ctx->scratch_host, accd, sizeof(c128), cudaMemcpyDeviceToHost, ctx->stream));
+    QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // also: scratch_host (cursor) is free again
+    QB_CUDA(ctx, cudaMemcpyAsync(ctx->scratch_host, P->acc, sizeof(c128), cudaMemcpyDeviceToHost, ctx->stream));
     QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     acc[0] += ctx->scratch_host[0];
     acc[1] += ctx->scratch_host[1];

@@ -176,3 +176,27 @@ def test_oracle_restarts_from_device_state(qb, ctx):
     o.evolve(oc.gate(U, [4, 5]), iscanonical=True, maxdim=8, renormalize=True)
     g.evolve(np.reshape(U, (2, 2, 2, 2), order="F"), [4, 5], iscanonical=True, maxdim=8, renormalize=True)
     assert_lams(g.lambdas(), o.lambdas())
+
+
+def test_circuit_front_end_drives_the_chain(qb, ctx):
+    """`evolve!(::Ansatz, ::Gate)` (ext/QrochetQuacExt.jl:15) and a gate list read from the text format: a nearest-
+    neighbour circuit on |0..0> as a chain, against the state vector (threshold 1e-14 keeps the bonds at their rank)."""
+    from qrochet_b200 import gates as G
+    n = 6
+    text = "qubits 6\nh 1\ncx 1 2\ncx 2 3\nrz 3 0.4\nfsim 3 4 0.3 0.9\nh 6\ncx 6 5\nrzz 4 5 0.7\nswap 2 3\nu3 2 0.1 0.2 0.3\ncz 2 1\n"
+    nq, circ = G.loads(text)
+    assert nq == n
+    e0 = np.array([1.0, 0.0])
+    psi = qb.B200MPS.from_product(ctx, [e0] * n)
+    ref = sv.zero_state(n)
+    for g in circ:
+        G.evolve_gate(psi, g, threshold=1e-14)
+        ref = sv.apply_gate(ref, g.matrix(), list(g.lanes), n)
+    assert np.allclose(gpu_dense(psi), ref, atol=1e-12)
+    # the same circuit as ONE dependency-scheduled gate list per run of two-lane gates
+    psi2 = qb.B200MPS.from_product(ctx, [e0] * n)
+    G.evolve_gates(psi2, circ, threshold=1e-14)
+    assert np.allclose(gpu_dense(psi2), ref, atol=1e-12)
+    assert max(psi2.bond_dims()) <= 4
+    with pytest.raises(ValueError):
+        G.evolve_gate(psi, G.Gate("cx", (1, 3)))          # "Gate lanes must be contiguous" (Chain.jl:574)
