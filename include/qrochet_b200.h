@@ -17,7 +17,8 @@
  *     float2 storage; qb200_contract runs on tcgen05 (TF32, 3xTF32 split, TMEM accumulators: FP32-level accuracy), the
  *     HBM-bound helpers run natively, qb200_qr / qb200_svd factorise in FP64 and narrow the factors).  The operands
  *     of one call must share the complex type.  QB200_F64 holds Schmidt vectors; QB200_F32 vectors are accepted and
- *     held widened to FP64 (upload / download convert).  The fused qb200_mps_* / qb200_tn_* paths are ComplexF64.
+ *     held widened to FP64 (upload / download convert).  The fused qb200_mps_* chains store ComplexF64 or ComplexF32 sites
+ *     (qb200_mps_create_typed) and compute in FP64; qb200_tn_* is ComplexF64.
  *   - one context = one device + one stream; calls on a context are serialised by the caller.
  *     Kernels are asynchronous on that stream; only *_download, scalar-returning calls and calls
  *     with `kept` outputs synchronise.
@@ -141,13 +142,25 @@ int32_t qb200_svd_totals(qb200_ctx* ctx, int64_t* calls, int64_t* sweeps);
  * A qb200_mps owns n site tensors in the private layout (l, o, r) column-major plus the Schmidt
  * vectors (device + host mirror).  form: 0 = plain (no Λ), 1 = Vidal Γ/Λ (after canonize!). */
 int32_t qb200_mps_create(qb200_ctx* ctx, int32_t nsites, qb200_mps** out);
+/* the same with the storage type of the site tensors chosen: QB200_C128, or QB200_C64 = ComplexF32 sites in HBM (half
+ * the footprint; `rand(...; eltype = ComplexF32)`, Chain.jl:226-227).  The fused chains compute in FP64 by explicit
+ * choice (the Jacobi SVD is 95 % of the work and needs FP64 for its 1e-12 bar): a ComplexF32 chain is widened for the
+ * duration of a call and its results are rounded to ComplexF32 once, at the end (parity bar 1e-5, north star). */
+int32_t qb200_mps_create_typed(qb200_ctx* ctx, int32_t nsites, int32_t dtype, qb200_mps** out);
+int32_t qb200_mps_dtype(const qb200_mps* mps);
 int32_t qb200_mps_free(qb200_ctx* ctx, qb200_mps* mps);
 int32_t qb200_mps_copy(qb200_ctx* ctx, const qb200_mps* src, qb200_mps** out);
 /* site (0-based) from a host array with extents (chi_l, p, chi_r) column-major */
 int32_t qb200_mps_set_site(qb200_ctx* ctx, qb200_mps* mps, int32_t site, int64_t chil, int64_t p, int64_t chir,
                            const void* host_c128);
+/* the same from host data of any element type of the reference's `eltype` keyword: QB200_C128 / C64 / F64 / F32 (real
+ * chains -- the reference's default eltype is Float64 -- are accepted and held as complex); converted on the device */
+int32_t qb200_mps_set_site_typed(qb200_ctx* ctx, qb200_mps* mps, int32_t site, int32_t host_dtype, int64_t chil,
+                                 int64_t p, int64_t chir, const void* host);
 int32_t qb200_mps_site_dims(const qb200_mps* mps, int32_t site, int64_t dims[3]);
 int32_t qb200_mps_get_site(qb200_ctx* ctx, const qb200_mps* mps, int32_t site, void* host_c128);
+/* host_dtype = QB200_C128 or QB200_C64, whatever the storage type */
+int32_t qb200_mps_get_site_typed(qb200_ctx* ctx, const qb200_mps* mps, int32_t site, int32_t host_dtype, void* host);
 int32_t qb200_mps_set_lambda(qb200_ctx* ctx, qb200_mps* mps, int32_t bond, int64_t n, const double* host);
 /* returns length; host may be NULL to query; -1 (as length 0 + QB200_E_NOSPECTRUM) if absent */
 int32_t qb200_mps_get_lambda(qb200_ctx* ctx, const qb200_mps* mps, int32_t bond, double* host, int64_t* n);

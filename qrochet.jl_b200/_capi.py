@@ -71,6 +71,10 @@ _protos = {
     "qb200_svd_last_sweeps": (_i32, [_p]),
     "qb200_svd_totals": (_i32, [_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "qb200_mps_create": (_i32, [_p, _i32, C.POINTER(_p)]),
+    "qb200_mps_create_typed": (_i32, [_p, _i32, _i32, C.POINTER(_p)]),
+    "qb200_mps_dtype": (_i32, [_p]),
+    "qb200_mps_set_site_typed": (_i32, [_p, _p, _i32, _i32, _i64, _i64, _i64, _p]),
+    "qb200_mps_get_site_typed": (_i32, [_p, _p, _i32, _i32, _p]),
     "qb200_mps_free": (_i32, [_p, _p]),
     "qb200_mps_copy": (_i32, [_p, _p, C.POINTER(_p)]),
     "qb200_mps_set_site": (_i32, [_p, _p, _i32, _i64, _i64, _i64, _p]),

@@ -227,8 +227,10 @@ int32_t qb_svd_emit(qb200_ctx* ctx, SvdState* st, int64_t kept, c128* U, int64_t
 void qb_svd_release(qb200_ctx* ctx, SvdState* st);
 
 // Cholesky-QR step on a 64-column panel with the Jacobi gram / update kernels (svd_jacobi.cu), used by K4
+// before2_dev (may be null): squared norms the 64 columns had at the start of the Gram-Schmidt pass; a column whose
+// squared norm is now below dep_tol^2 times that raises *fail_dev (numerically dependent column, see qr.cu)
 int32_t qb_cholqr_panel_step(qb200_ctx* ctx, c128* P, int64_t ld, int64_t m, c128* R, int64_t ldr, c128* Gpart,
-                             c128* Wbuf, int* flags_dev, int* fail_dev);
+                             c128* Wbuf, int* flags_dev, int* fail_dev, const double* before2_dev, double dep_tol);
 size_t qb_cholqr_gpart_elems(qb200_ctx* ctx);
 
 // (left | right) matricisation of a tensor: returns a column-major rows x cols matrix (a permuted copy in

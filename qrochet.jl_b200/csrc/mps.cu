@@ -22,7 +22,13 @@
 struct qb200_mps {
     int n = 0;
     int form = 0;  // 0 plain, 1 Vidal (after canonize!), 2 mixed
-    std::vector<c128*> site;
+    // Storage type of the site tensors in HBM: QB200_C128, or QB200_C64 (float2: half the footprint).  The fused chains
+    // compute in FP64 by explicit choice -- 95 % of the work is the Jacobi SVD, whose rotations need FP64 to deliver the
+    // Schmidt values to 1e-12 -- so a ComplexF32 chain is widened for the duration of a call (WideScope) and its
+    // results are rounded back to ComplexF32 once, at the end (parity bar: 1e-5, north star).
+    int dtype = QB200_C128;
+    bool wide = false;  // a C64 chain whose site pointers currently hold the widened (ComplexF64) copies
+    std::vector<c128*> site;  // float2* in disguise while dtype == C64 && !wide
     std::vector<int64_t> chil, p, chir;
     std::vector<double*> lam;  // device, null when absent
     std::vector<std::vector<double>> lam_host;
@@ -250,6 +256,90 @@ int32_t absorb_lambdas(qb200_ctx* ctx, qb200_mps* m) {
     return QB200_OK;
 }
 
+// real (Float64 / Float32) host data -> ComplexF64 on the device (`rand(...; eltype = Float64)` is the reference's
+// default, Chain.jl:226-227: real chains are accepted at the boundary and computed in complex arithmetic)
+template <typename T>
+__global__ void widen_real_kernel(const T* __restrict__ src, c128* __restrict__ dst, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = make_double2((double)src[i], 0.0);
+}
+
+inline int64_t site_elems(const qb200_mps* m, int s) { return m->chil[s] * m->p[s] * m->chir[s]; }
+inline size_t site_esz(const qb200_mps* m) { return (m->dtype == QB200_C64 && !m->wide) ? sizeof(float2) : sizeof(c128); }
+
+// For the duration of one public call a ComplexF32 chain holds ComplexF64 copies of its sites (every kernel of the fused
+// path is FP64); on exit the (possibly new) sites are rounded back to float2 storage.  No-op for ComplexF64 chains and
+// for nested scopes.  `writeback = false` for calls that only read the chain: the float2 originals are kept aside and
+// put back, nothing is rounded.
+struct WideScope {
+    qb200_ctx* ctx;
+    qb200_mps* m;
+    bool active = false, writeback;
+    std::vector<c128*> kept;  // float2 originals (read-only scopes)
+    int32_t status = QB200_OK;
+    WideScope(qb200_ctx* c, const qb200_mps* mc, bool wb) : ctx(c), m(const_cast<qb200_mps*>(mc)), writeback(wb) {
+        if (!m || m->dtype != QB200_C64 || m->wide) return;
+        active = true;
+        kept.assign(m->n, nullptr);
+        for (int s = 0; s < m->n; ++s) {
+            if (!m->site[s]) continue;
+            const int64_t cnt = site_elems(m, s);
+            c128* w = dev_alloc(ctx, cnt);
+            if (!w || qb_widen_c64(ctx, m->site[s], w, cnt) != QB200_OK) {
+                status = QB200_E_CUDA;
+                ctx->err = "mps: out of device memory while widening a ComplexF32 chain";
+                if (w) cudaFreeAsync(w, ctx->stream);
+                continue;  // the site stays narrow; the caller sees `status` and backs out
+            }
+            kept[s] = m->site[s];
+            m->site[s] = w;
+        }
+        m->wide = (status == QB200_OK);
+        if (status != QB200_OK) {
+            restore_failed();
+        } else if (writeback) {  // the float2 originals are dead from here on: the call will produce the new ones
+            for (auto& p : kept)
+                if (p) {
+                    cudaFreeAsync(p, ctx->stream);
+                    p = nullptr;
+                }
+        }
+    }
+    void restore_failed() {  // partial widening: put every site back to float2
+        for (int s = 0; s < m->n; ++s)
+            if (kept.size() > (size_t)s && kept[s]) {
+                cudaFreeAsync(m->site[s], ctx->stream);
+                m->site[s] = kept[s];
+                kept[s] = nullptr;
+            }
+        active = false;
+    }
+    ~WideScope() {
+        if (!active) return;
+        for (int s = 0; s < m->n; ++s) {
+            if (!m->site[s]) continue;
+            if (!writeback) {
+                cudaFreeAsync(m->site[s], ctx->stream);
+                m->site[s] = kept[s];
+                continue;
+            }
+            const int64_t cnt = site_elems(m, s);
+            void* nar = nullptr;
+            if (cudaMallocAsync(&nar, sizeof(float2) * (size_t)std::max<int64_t>(cnt, 1), ctx->stream) == cudaSuccess &&
+                qb_narrow_c128(ctx, m->site[s], nar, cnt) == QB200_OK) {
+                cudaFreeAsync(m->site[s], ctx->stream);
+                m->site[s] = (c128*)nar;
+            } else {  // cannot round back: keep the chain usable by switching its storage type
+                m->dtype = QB200_C128;
+            }
+        }
+        m->wide = false;
+    }
+};
+#define QB_WIDE(ctx, m, writeback)      \
+    WideScope _wide_##m(ctx, m, writeback); \
+    if (_wide_##m.status != QB200_OK) return _wide_##m.status
+
 int32_t check_site(qb200_ctx* ctx, const qb200_mps* m, int s) {
     if (!m || s < 0 || s >= m->n) QB_FAIL(ctx, QB200_E_INVALID, "mps: site %d out of range", s);
     if (!m->site[s]) QB_FAIL(ctx, QB200_E_INVALID, "mps: site %d not set", s);
@@ -284,6 +374,16 @@ int32_t qb200_mps_create(qb200_ctx* ctx, int32_t nsites, qb200_mps** out) {
     return QB200_OK;
 }
 
+// storage type chosen at creation: QB200_C128 or QB200_C64 (ComplexF32 sites in HBM, FP64 arithmetic inside the calls)
+int32_t qb200_mps_create_typed(qb200_ctx* ctx, int32_t nsites, int32_t dtype, qb200_mps** out) {
+    if (dtype != QB200_C128 && dtype != QB200_C64)
+        QB_FAIL(ctx, QB200_E_UNSUPPORTED, "mps_create: storage type must be ComplexF64 or ComplexF32 (real data is widened at set_site)");
+    QB_TRY(qb200_mps_create(ctx, nsites, out));
+    (*out)->dtype = dtype;
+    return QB200_OK;
+}
+int32_t qb200_mps_dtype(const qb200_mps* m) { return m ? m->dtype : -1; }
+
 int32_t qb200_mps_free(qb200_ctx* ctx, qb200_mps* m) {
     if (!m) return QB200_OK;
     for (auto p : m->site)
@@ -299,15 +399,18 @@ int32_t qb200_mps_copy(qb200_ctx* ctx, const qb200_mps* src, qb200_mps** out) {
     qb200_mps* m = nullptr;
     QB_TRY(qb200_mps_create(ctx, src->n, &m));
     m->form = src->form;
+    m->dtype = src->dtype;
+    m->wide = src->wide;  // a copy taken inside a WideScope is a ComplexF64 scratch chain (never rounded back)
+    const size_t esz = site_esz(src);
     for (int s = 0; s < src->n; ++s) {
         if (!src->site[s]) continue;
         int64_t cnt = src->chil[s] * src->p[s] * src->chir[s];
-        c128* d = dev_alloc(ctx, cnt);
+        c128* d = dev_alloc(ctx, (int64_t)((cnt * esz + sizeof(c128) - 1) / sizeof(c128)));
         if (!d) {
             qb200_mps_free(ctx, m);
             QB_FAIL(ctx, QB200_E_CUDA, "mps_copy: out of device memory");
         }
-        cudaMemcpyAsync(d, src->site[s], sizeof(c128) * cnt, cudaMemcpyDeviceToDevice, ctx->stream);
+        cudaMemcpyAsync(d, src->site[s], esz * cnt, cudaMemcpyDeviceToDevice, ctx->stream);
         set_site_dev(ctx, m, s, d, src->chil[s], src->p[s], src->chir[s]);
     }
     for (int b = 0; b < src->n - 1; ++b) {
@@ -323,16 +426,59 @@ int32_t qb200_mps_copy(qb200_ctx* ctx, const qb200_mps* src, qb200_mps** out) {
     return QB200_OK;
 }
 
-int32_t qb200_mps_set_site(qb200_ctx* ctx, qb200_mps* m, int32_t s, int64_t chil, int64_t p, int64_t chir,
-                           const void* host) {
+// site (0-based) from a host array with extents (chi_l, p, chi_r) column-major of element type host_dtype
+// (QB200_C128 / C64 / F64 / F32); converted on the device to the chain's storage type
+int32_t qb200_mps_set_site_typed(qb200_ctx* ctx, qb200_mps* m, int32_t s, int32_t host_dtype, int64_t chil, int64_t p,
+                                 int64_t chir, const void* host) {
     if (!m || s < 0 || s >= m->n || !host || chil < 1 || p < 1 || chir < 1)
         QB_FAIL(ctx, QB200_E_INVALID, "mps_set_site: bad argument");
-    int64_t cnt = chil * p * chir;
-    c128* d = dev_alloc(ctx, cnt);
-    if (!d) QB_FAIL(ctx, QB200_E_CUDA, "mps_set_site: out of device memory");
-    QB_CUDA(ctx, cudaMemcpyAsync(d, host, sizeof(c128) * cnt, cudaMemcpyHostToDevice, ctx->stream));
-    QB_CUDA(ctx, qb_stream_sync(ctx));
-    return set_site_dev(ctx, m, s, d, chil, p, chir);
+    if (host_dtype < QB200_C128 || host_dtype > QB200_F32) QB_FAIL(ctx, QB200_E_UNSUPPORTED, "mps_set_site: unknown element type");
+    if (m->wide) QB_FAIL(ctx, QB200_E_INVALID, "mps_set_site: chain is in use");
+    const int64_t cnt = chil * p * chir;
+    const size_t hsz = dtype_size(host_dtype);
+    Workspace ws(ctx);
+    void* raw = ws.get<char>((size_t)cnt * hsz);
+    if (!raw) QB_FAIL(ctx, QB200_E_CUDA, "mps_set_site: out of device memory");
+    QB_CUDA(ctx, cudaMemcpyAsync(raw, host, hsz * cnt, cudaMemcpyHostToDevice, ctx->stream));
+    const size_t ssz = (m->dtype == QB200_C64) ? sizeof(float2) : sizeof(c128);
+    void* dst = nullptr;
+    QB_CUDA(ctx, cudaMallocAsync(&dst, ssz * (size_t)cnt, ctx->stream));
+    int32_t r = QB200_OK;
+    if (host_dtype == m->dtype) {
+        if (cudaMemcpyAsync(dst, raw, ssz * cnt, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess) r = QB200_E_CUDA;
+    } else {
+        // through ComplexF64: real -> complex, ComplexF32 -> ComplexF64, then (for a ComplexF32 chain) one rounding
+        c128* wide = (m->dtype == QB200_C128) ? (c128*)dst : ws.get<c128>((size_t)cnt);
+        if (!wide) r = QB200_E_CUDA;
+        const unsigned blocks = (unsigned)std::min<int64_t>((cnt + 255) / 256, 4096);
+        if (r == QB200_OK) {
+            if (host_dtype == QB200_C128) {
+                if (wide != raw && cudaMemcpyAsync(wide, raw, sizeof(c128) * cnt, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess)
+                    r = QB200_E_CUDA;
+            } else if (host_dtype == QB200_C64) {
+                r = qb_widen_c64(ctx, raw, wide, cnt);
+            } else if (host_dtype == QB200_F64) {
+                widen_real_kernel<double><<<blocks, 256, 0, ctx->stream>>>((const double*)raw, wide, cnt);
+                ctx->launches++;
+            } else {
+                widen_real_kernel<float><<<blocks, 256, 0, ctx->stream>>>((const float*)raw, wide, cnt);
+                ctx->launches++;
+            }
+        }
+        if (r == QB200_OK && m->dtype == QB200_C64) r = qb_narrow_c128(ctx, wide, dst, cnt);
+    }
+    if (r == QB200_OK && qb_stream_sync(ctx) != cudaSuccess) r = QB200_E_CUDA;  // the host buffer is only borrowed
+    if (r != QB200_OK) {
+        cudaFreeAsync(dst, ctx->stream);
+        if (ctx->err.empty()) ctx->err = "mps_set_site: conversion failed";
+        return r;
+    }
+    return set_site_dev(ctx, m, s, (c128*)dst, chil, p, chir);
+}
+
+int32_t qb200_mps_set_site(qb200_ctx* ctx, qb200_mps* m, int32_t s, int64_t chil, int64_t p, int64_t chir,
+                           const void* host) {
+    return qb200_mps_set_site_typed(ctx, m, s, QB200_C128, chil, p, chir, host);
 }
 
 int32_t qb200_mps_site_dims(const qb200_mps* m, int32_t s, int64_t dims[3]) {
@@ -343,12 +489,34 @@ int32_t qb200_mps_site_dims(const qb200_mps* m, int32_t s, int64_t dims[3]) {
     return QB200_OK;
 }
 
-int32_t qb200_mps_get_site(qb200_ctx* ctx, const qb200_mps* m, int32_t s, void* host) {
+// site to the host as ComplexF64 (host_dtype = QB200_C128) or ComplexF32 (QB200_C64), whatever the storage type
+int32_t qb200_mps_get_site_typed(qb200_ctx* ctx, const qb200_mps* m, int32_t s, int32_t host_dtype, void* host) {
     QB_TRY(check_site(ctx, m, s));
-    int64_t cnt = m->chil[s] * m->p[s] * m->chir[s];
-    QB_CUDA(ctx, cudaMemcpyAsync(host, m->site[s], sizeof(c128) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!host || (host_dtype != QB200_C128 && host_dtype != QB200_C64)) QB_FAIL(ctx, QB200_E_INVALID, "mps_get_site: bad argument");
+    const int64_t cnt = site_elems(m, s);
+    const int have = (m->dtype == QB200_C64 && !m->wide) ? QB200_C64 : QB200_C128;
+    Workspace ws(ctx);
+    const void* src = m->site[s];
+    if (have != host_dtype) {
+        if (host_dtype == QB200_C128) {
+            c128* w = ws.get<c128>((size_t)cnt);
+            if (!w) QB_FAIL(ctx, QB200_E_CUDA, "mps_get_site: out of device memory");
+            QB_TRY(qb_widen_c64(ctx, m->site[s], w, cnt));
+            src = w;
+        } else {
+            float2* nar = ws.get<float2>((size_t)cnt);
+            if (!nar) QB_FAIL(ctx, QB200_E_CUDA, "mps_get_site: out of device memory");
+            QB_TRY(qb_narrow_c128(ctx, m->site[s], nar, cnt));
+            src = nar;
+        }
+    }
+    QB_CUDA(ctx, cudaMemcpyAsync(host, src, dtype_size(host_dtype) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
     QB_CUDA(ctx, qb_stream_sync(ctx));
     return QB200_OK;
+}
+
+int32_t qb200_mps_get_site(qb200_ctx* ctx, const qb200_mps* m, int32_t s, void* host) {
+    return qb200_mps_get_site_typed(ctx, m, s, QB200_C128, host);
 }
 
 int32_t qb200_mps_set_lambda(qb200_ctx* ctx, qb200_mps* m, int32_t b, int64_t n, const double* host) {
@@ -377,6 +545,7 @@ int32_t qb200_mps_set_form(qb200_mps* m, int32_t form) {
 // canonize! (Chain.jl:469-497)
 int32_t qb200_mps_canonize(qb200_ctx* ctx, qb200_mps* m) {
     QB_TRY(check_complete(ctx, m));
+    QB_WIDE(ctx, m, true);
     // Schmidt vectors already sitting on bonds are absorbed by the QR sweep's contract!(tn, virtualind) (Chain.jl:372)
     QB_TRY(absorb_lambdas(ctx, m));
     for (int s = m->n - 1; s >= 1; --s) QB_TRY(right_canonize_qr(ctx, m, s));
@@ -398,6 +567,7 @@ int32_t qb200_mps_canonize(qb200_ctx* ctx, qb200_mps* m) {
 // mixed_canonize! (Chain.jl:509-524)
 int32_t qb200_mps_mixed_canonize(qb200_ctx* ctx, qb200_mps* m, int32_t center) {
     QB_TRY(check_complete(ctx, m));
+    QB_WIDE(ctx, m, true);
     if (center < 1 || center >= m->n)
         QB_FAIL(ctx, QB200_E_INVALID, "Cannot right-canonize left-most tensor (center must be in 2..n)");
     // absorb any Schmidt vector into the site on its right: the chain becomes plain
@@ -413,6 +583,7 @@ int32_t qb200_mps_mixed_canonize(qb200_ctx* ctx, qb200_mps* m, int32_t center) {
 int32_t qb200_mps_truncate(qb200_ctx* ctx, qb200_mps* m, int32_t b, int64_t maxdim, double threshold,
                            int64_t* kept_out) {
     QB_TRY(check_complete(ctx, m));
+    QB_WIDE(ctx, m, true);
     if (b < 0 || b >= m->n - 1) QB_FAIL(ctx, QB200_E_INVALID, "Invalid bond %d", b);
     if (!m->lam[b]) QB_FAIL(ctx, QB200_E_NOSPECTRUM, "Can't access the spectrum on bond (%d, %d)", b + 1, b + 2);
     if (maxdim <= 0 && threshold < 0.0) threshold = 1e-16;
@@ -439,6 +610,7 @@ int32_t qb200_mps_truncate(qb200_ctx* ctx, qb200_mps* m, int32_t b, int64_t maxd
 
 int32_t qb200_mps_evolve1(qb200_ctx* ctx, qb200_mps* m, int32_t s, const void* gate) {
     QB_TRY(check_site(ctx, m, s));
+    QB_WIDE(ctx, m, true);
     if (!gate) QB_FAIL(ctx, QB200_E_INVALID, "evolve1: null gate");
     int64_t p = m->p[s];
     if (p > QB200_MAX_PHYS) QB_FAIL(ctx, QB200_E_UNSUPPORTED, "evolve1: physical dimension %lld > %d", (long long)p, QB200_MAX_PHYS);
@@ -606,6 +778,7 @@ extern "C" {
 int32_t qb200_mps_evolve2(qb200_ctx* ctx, qb200_mps* m, int32_t b, const void* gate, int64_t maxdim, double threshold,
                           int32_t renormalize, int32_t iscanonical, int64_t* kept_out, double* discarded_weight) {
     if (!ctx || !m) QB_FAIL(ctx, QB200_E_INVALID, "evolve2: null argument");
+    QB_WIDE(ctx, m, true);
     return evolve2_core(ctx, m, b, gate, maxdim, threshold, renormalize, iscanonical, kept_out, discarded_weight, true);
 }
 
@@ -733,6 +906,7 @@ int32_t qb200_mps_evolve2_layer(qb200_ctx* ctx, qb200_mps* m, int32_t nb, const 
                                 int64_t maxdim, double threshold, int32_t renormalize, int32_t iscanonical,
                                 int64_t* kept_out, double* discarded_weight) {
     QB_TRY(check_complete(ctx, m));
+    QB_WIDE(ctx, m, true);
     if (nb < 0 || (nb > 0 && (!bonds || !gates))) QB_FAIL(ctx, QB200_E_INVALID, "evolve2_layer: bad argument");
     std::vector<int> sorted(bonds, bonds + nb);
     std::sort(sorted.begin(), sorted.end());
@@ -754,6 +928,7 @@ int32_t qb200_mps_evolve2_circuit(qb200_ctx* ctx, qb200_mps* m, int32_t nops, co
                                   int64_t maxdim, double threshold, int32_t renormalize, int32_t iscanonical,
                                   int64_t* kept_out, double* discarded_weight) {
     QB_TRY(check_complete(ctx, m));
+    QB_WIDE(ctx, m, true);
     if (nops < 0 || (nops > 0 && (!bonds || !gates))) QB_FAIL(ctx, QB200_E_INVALID, "evolve2_circuit: bad argument");
     for (int i = 0; i < nops; ++i)
         if (bonds[i] < 0 || bonds[i] >= m->n - 1) QB_FAIL(ctx, QB200_E_INVALID, "evolve2_circuit: bond out of range");
@@ -767,6 +942,7 @@ int32_t qb200_mps_evolve2_circuit(qb200_ctx* ctx, qb200_mps* m, int32_t nops, co
 // plain canonize!.
 int32_t qb200_mps_compress(qb200_ctx* ctx, qb200_mps* m, int64_t maxdim, double threshold) {
     QB_TRY(check_complete(ctx, m));
+    QB_WIDE(ctx, m, true);
     QB_TRY(absorb_lambdas(ctx, m));  // the sweeps below start from a plain chain
     for (int s = m->n - 1; s >= 1; --s) QB_TRY(right_canonize_qr(ctx, m, s));
     for (int s = 0; s < m->n - 1; ++s) {
@@ -812,6 +988,7 @@ int32_t upload_mpo(qb200_ctx* ctx, const qb200_mps* m, const int64_t* dl, const 
 // Schmidt vectors are absorbed first; the result is a plain chain with bonds chi*D -- call qb200_mps_compress.
 int32_t qb200_mps_apply_mpo(qb200_ctx* ctx, qb200_mps* m, const int64_t* dl, const int64_t* dr, const void* sites) {
     QB_TRY(check_complete(ctx, m));
+    QB_WIDE(ctx, m, true);
     if (!dl || !dr || !sites) QB_FAIL(ctx, QB200_E_INVALID, "apply_mpo: null argument");
     Workspace ws(ctx);
     std::vector<c128*> W;
@@ -841,6 +1018,7 @@ int32_t qb200_mps_apply_mpo(qb200_ctx* ctx, qb200_mps* m, const int64_t* dl, con
 int32_t qb200_mps_expect_mpo(qb200_ctx* ctx, const qb200_mps* m, const int64_t* dl, const int64_t* dr,
                              const void* sites, double result[2]) {
     QB_TRY(check_complete(ctx, m));
+    QB_WIDE(ctx, m, false);
     if (!dl || !dr || !sites || !result) QB_FAIL(ctx, QB200_E_INVALID, "expect_mpo: null argument");
     Workspace ws(ctx);
     std::vector<c128*> W;
@@ -893,6 +1071,8 @@ int32_t qb200_mps_expect_mpo(qb200_ctx* ctx, const qb200_mps* m, const int64_t* 
 int32_t qb200_mps_overlap(qb200_ctx* ctx, const qb200_mps* a, const qb200_mps* b, double result[2]) {
     QB_TRY(check_complete(ctx, a));
     QB_TRY(check_complete(ctx, b));
+    QB_WIDE(ctx, a, false);
+    QB_WIDE(ctx, b, false);
     if (a->n != b->n) QB_FAIL(ctx, QB200_E_INVALID, "Ansatzes must have the same sites");
     int64_t maxa = 1, maxb = 1, maxp = 1;
     for (int s = 0; s < a->n; ++s) {
@@ -929,6 +1109,7 @@ int32_t qb200_mps_overlap(qb200_ctx* ctx, const qb200_mps* a, const qb200_mps* b
 int32_t qb200_mps_expect1_batch(qb200_ctx* ctx, const qb200_mps* m, int32_t nobs, const int32_t* sites,
                                 const void* ops, double* results) {
     QB_TRY(check_complete(ctx, m));
+    QB_WIDE(ctx, m, false);
     if (nobs < 0 || (nobs > 0 && (!sites || !ops || !results))) QB_FAIL(ctx, QB200_E_INVALID, "expect: bad argument");
     if (nobs == 0) return QB200_OK;
     const int n = m->n;
@@ -1026,6 +1207,7 @@ int32_t qb200_mps_broadcast(qb200_ctx* ctx, qb200_mps** inout, int32_t root) {
     if (sender && !*inout) QB_FAIL(ctx, QB200_E_INVALID, "mps_broadcast: the root rank must pass its chain");
     if (!sender && *inout) QB_FAIL(ctx, QB200_E_INVALID, "mps_broadcast: receiving ranks must pass NULL");
     if (sender) QB_TRY(check_complete(ctx, *inout));
+    if (sender && (*inout)->wide) QB_FAIL(ctx, QB200_E_INVALID, "mps_broadcast: chain is in use");
     Workspace ws(ctx);
     constexpr int MAXN = 2000;  // header: n, form, then (chil, p, chir, lambda length) per site; fits the pinned page
     int64_t* hdr_dev = ws.get<int64_t>(2 + 4 * MAXN);
@@ -1037,7 +1219,7 @@ int32_t qb200_mps_broadcast(qb200_ctx* ctx, qb200_mps** inout, int32_t root) {
         if (m->n > MAXN) QB_FAIL(ctx, QB200_E_UNSUPPORTED, "mps_broadcast: more than %d sites", MAXN);
         memset(hdr, 0, hbytes);
         hdr[0] = m->n;
-        hdr[1] = m->form;
+        hdr[1] = m->form + 16 * m->dtype;
         for (int s = 0; s < m->n; ++s) {
             hdr[2 + 4 * s] = m->chil[s];
             hdr[3 + 4 * s] = m->p[s];
@@ -1052,10 +1234,11 @@ int32_t qb200_mps_broadcast(qb200_ctx* ctx, qb200_mps** inout, int32_t root) {
     qb200_mps* m = *inout;
     if (!sender) {
         QB_TRY(qb200_mps_create(ctx, (int32_t)hdr[0], &m));
-        m->form = (int)hdr[1];
+        m->form = (int)(hdr[1] % 16);
+        m->dtype = (int)(hdr[1] / 16);
         for (int s = 0; s < m->n; ++s) {
             const int64_t cl = hdr[2 + 4 * s], p = hdr[3 + 4 * s], cr = hdr[4 + 4 * s], ll = hdr[5 + 4 * s];
-            c128* d = dev_alloc(ctx, cl * p * cr);
+            c128* d = dev_alloc(ctx, (int64_t)((cl * p * cr * site_esz(m) + sizeof(c128) - 1) / sizeof(c128)));
             if (!d) {
                 qb200_mps_free(ctx, m);
                 QB_FAIL(ctx, QB200_E_CUDA, "mps_broadcast: out of device memory");
@@ -1074,7 +1257,7 @@ int32_t qb200_mps_broadcast(qb200_ctx* ctx, qb200_mps** inout, int32_t root) {
     }
     int32_t r = QB200_OK;
     for (int s = 0; s < m->n && r == QB200_OK; ++s) {
-        r = qb_comm_broadcast_bytes(ctx, m->site[s], sizeof(c128) * (size_t)(m->chil[s] * m->p[s] * m->chir[s]), root);
+        r = qb_comm_broadcast_bytes(ctx, m->site[s], site_esz(m) * (size_t)(m->chil[s] * m->p[s] * m->chir[s]), root);
         if (r == QB200_OK && s < m->n - 1 && m->lam[s])
             r = qb_comm_broadcast_bytes(ctx, m->lam[s], sizeof(double) * m->lam_host[s].size(), root);
     }
@@ -1096,6 +1279,7 @@ int32_t qb200_mps_broadcast(qb200_ctx* ctx, qb200_mps** inout, int32_t root) {
 int32_t qb200_mps_expect(qb200_ctx* ctx, const qb200_mps* m, int32_t nobs, const int32_t* nlanes, const int32_t* sites,
                          const void* ops, double result[2]) {
     QB_TRY(check_complete(ctx, m));
+    QB_WIDE(ctx, m, false);
     if (nobs < 0 || !result || (nobs > 0 && (!nlanes || !sites || !ops))) QB_FAIL(ctx, QB200_E_INVALID, "expect: bad argument");
     qb200_mps* phi = nullptr;
     QB_TRY(qb200_mps_copy(ctx, m, &phi));

@@ -184,6 +184,34 @@ __global__ void __launch_bounds__(QR_THREADS)
     }
 }
 
+// squared column norms, one warp per column
+__global__ void colnorm2_kernel(const c128* __restrict__ A, int64_t ld, int64_t m, int64_t ncols, double* __restrict__ out) {
+    const int64_t col = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (col >= ncols) return;
+    const int lane = threadIdx.x & 31;
+    const c128* x = A + col * ld;
+    double acc = 0.0;
+    for (int64_t r = lane; r < m; r += 32) {
+        c128 v = x[r];
+        acc += v.x * v.x + v.y * v.y;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[col] = acc;
+}
+
+// a reproducible pseudo-random column (entries in (-1, 1)): the replacement of a numerically dependent column
+__global__ void random_column_kernel(c128* __restrict__ x, int64_t m, uint64_t seed) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(2 * i + 1);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        const double re = (double)(z >> 40) * (1.0 / 8388608.0) - 1.0;
+        const double im = (double)((z >> 16) & 0xFFFFFF) * (1.0 / 8388608.0) - 1.0;
+        x[i] = make_double2(re, im);
+    }
+}
+
 __global__ void zero_kernel(c128* x, int64_t rows, int64_t cols, int64_t ld) {
     int64_t total = rows * cols;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
@@ -229,11 +257,82 @@ static int32_t tsqr_panel(qb200_ctx* ctx, int64_t m, int w, c128* P, int64_t ld,
     return QB200_OK;
 }
 
+// Relative size below which what is left of a column after the projection against the earlier columns is rounding noise:
+// the projection subtracts ~j0 terms, each carrying eps of the column's norm.
+static inline double dep_tol(int64_t j0, int w) { return 16.0 * 1.1102230246251565e-16 * std::sqrt((double)(j0 + w)); }
+
+// Panel factorisation that is safe for rank-deficient input.  A column that is numerically dependent on the earlier
+// columns is pure rounding noise once those have been projected out; normalising it (what any Gram-Schmidt or
+// Householder panel step does) yields a "completion" vector that still lies in the span of the earlier columns -- for
+// structurally rank-deficient tensors (an MPO-applied state: exact zeros, exact repetitions) entirely so -- and a second
+// Gram-Schmidt pass cannot repair that: Q comes out with non-orthogonal columns and every later column that was
+// projected on it is damaged (measured on B200: |Q^H Q - I| = 0.23 on a 5120 x 2560 matrix of rank 1536, and
+// canonize! of H|psi> changed the norm of the state by 23 %).  So: factor, look at diag(R); every column whose
+// diagonal entry is below dep_tol x (its norm at the start of the pass) is replaced by a pseudo-random vector made
+// orthogonal (twice) to ALL earlier columns, the panel is factored again, and the column of R is zeroed (the dependent
+// column has no component along its completion vector).  This is what LAPACK's Householder QR delivers implicitly:
+// orthonormal Q whatever the rank.  `save` holds the panel as it was before the factorisation (m x w, ld = m) and is
+// updated with the replacements; Qall / ldq / j0: the columns [0, j0) of Q are the earlier, final columns.
+static int32_t robust_panel(qb200_ctx* ctx, int64_t m, int w, c128* P, int64_t ld, c128* Rpp, int64_t ldr, const c128* Qall,
+                            int64_t ldq, int64_t j0, const double* before2_dev, c128* save) {
+    const c128 one = make_double2(1.0, 0.0), zero = make_double2(0.0, 0.0), mone = make_double2(-1.0, 0.0);
+    std::vector<char> replaced(w, 0);
+    Workspace ws(ctx);
+    c128* coef = nullptr;
+    c128* orig = nullptr;  // the dependent columns as they were (their components along the panel's other columns go to R)
+    const double tol = dep_tol(j0, w);
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        QB_TRY(tsqr_panel(ctx, m, w, P, ld, Rpp, ldr));
+        // diag(R) of the panel and the squared norms the columns had at the start of the pass -> host (one sync)
+        double* host = ctx->scratch_host;
+        QB_CUDA(ctx, cudaMemcpy2DAsync(host, sizeof(c128), Rpp, (size_t)(ldr + 1) * sizeof(c128), sizeof(c128), (size_t)w,
+                                       cudaMemcpyDeviceToHost, ctx->stream));
+        QB_CUDA(ctx, cudaMemcpyAsync(host + 2 * w, before2_dev, sizeof(double) * w, cudaMemcpyDeviceToHost, ctx->stream));
+        QB_CUDA(ctx, qb_stream_sync(ctx));
+        std::vector<int> dep;
+        for (int c = 0; c < w; ++c) {
+            if (replaced[c]) continue;
+            const double d2 = host[2 * c] * host[2 * c] + host[2 * c + 1] * host[2 * c + 1];
+            if (d2 <= tol * tol * host[2 * w + c]) dep.push_back(c);
+        }
+        if (dep.empty()) break;
+        if (attempt == 3) QB_FAIL(ctx, QB200_E_NOCONVERGE, "qr: could not complete a rank-deficient panel");
+        if (!orig) orig = ws.get<c128>((size_t)(m * w));
+        if (!orig) QB_FAIL(ctx, QB200_E_CUDA, "qr: workspace allocation failed");
+        for (int c : dep) {
+            c128* x = save + (int64_t)c * m;
+            QB_CUDA(ctx, cudaMemcpyAsync(orig + (int64_t)c * m, x, sizeof(c128) * (size_t)m, cudaMemcpyDeviceToDevice, ctx->stream));
+            random_column_kernel<<<(unsigned)std::min<int64_t>((m + 255) / 256, 1024), 256, 0, ctx->stream>>>(
+                x, m, 0x5EEDull + 1315423911ull * (uint64_t)(j0 + c));
+            QB_LAUNCH_CHECK(ctx);
+            if (j0 > 0) {
+                if (!coef) coef = ws.get<c128>((size_t)j0);
+                if (!coef) QB_FAIL(ctx, QB200_E_CUDA, "qr: workspace allocation failed");
+                for (int rep = 0; rep < 2; ++rep) {
+                    QB_TRY(qb_gemm(ctx, 2, 0, j0, 1, m, one, Qall, ldq, x, m, zero, coef, j0));
+                    QB_TRY(qb_gemm(ctx, 0, 0, m, 1, j0, mone, Qall, ldq, coef, j0, one, x, m));
+                }
+            }
+            replaced[c] = 1;
+        }
+        QB_TRY(qb_copy_matrix(ctx, m, w, save, m, P, ld, 0));
+    }
+    // column c of the panel's R block: the components of the ORIGINAL column along the panel's earlier columns (a
+    // dependency inside the panel), nothing on or below the diagonal (no component along its completion vector)
+    for (int c = 0; c < w; ++c)
+        if (replaced[c]) {
+            QB_TRY(qb_gemm(ctx, 2, 0, w, 1, m, one, P, ld, orig + (int64_t)c * m, m, zero, Rpp + (int64_t)c * ldr, ldr));
+            QB_CUDA(ctx, cudaMemsetAsync(Rpp + (int64_t)c * ldr + c, 0, sizeof(c128) * (size_t)(w - c), ctx->stream));
+        }
+    return QB200_OK;
+}
+
 // one right-looking block Gram-Schmidt pass: Q (m x k, in place) = Q' R, R k x k upper triangular (zeroed first).
 // Panels of 64 columns.  Fast path (m % 64 == 0, full panels): Cholesky-QR2 on the panel with the Jacobi gram /
 // update kernels (Gram 64 x 64 -> scaled Cholesky in shared memory -> P <- P R^-1, twice); when a scaled pivot says
-// the panel is too ill conditioned for a Gram-based step, the saved panel is restored and factorised by the
-// Householder TSQR instead.  Trailing updates: C = Q_p^H T (split-K GEMM), T -= Q_p C.
+// the panel is too ill conditioned for a Gram-based step, or a column has lost (numerically) all of its norm to the
+// earlier columns, the saved panel is restored and factorised by robust_panel (Householder TSQR + completion of
+// dependent columns) instead.  Trailing updates: C = Q_p^H T (split-K GEMM), T -= Q_p C.
 static int32_t bgs_pass(qb200_ctx* ctx, int64_t m, int64_t k, c128* Q, int64_t ldq, c128* R, int64_t ldr) {
     const c128 one = make_double2(1.0, 0.0), zero = make_double2(0.0, 0.0), mone = make_double2(-1.0, 0.0);
     zero_kernel<<<(unsigned)std::min<int64_t>((k * k + 255) / 256, 4096), 256, 0, ctx->stream>>>(R, k, k, ldr);
@@ -241,16 +340,20 @@ static int32_t bgs_pass(qb200_ctx* ctx, int64_t m, int64_t k, c128* Q, int64_t l
     const int PW = 64;
     const bool fast_ok = (m % 64 == 0) && m >= 64 && !getenv("QB200_NO_CHOLQR");
     Workspace ws(ctx);
-    c128 *Gpart = nullptr, *Wbuf = nullptr, *save = nullptr, *R1 = nullptr, *R2 = nullptr;
+    c128 *Gpart = nullptr, *Wbuf = nullptr, *R1 = nullptr, *R2 = nullptr;
     int* flags = nullptr;
+    c128* save = ws.get<c128>((size_t)(m * PW));
+    double* before2 = ws.get<double>((size_t)k);  // squared column norms at the start of the pass
+    if (!save || !before2) QB_FAIL(ctx, QB200_E_CUDA, "qr: workspace allocation failed");
+    colnorm2_kernel<<<(unsigned)((k + 7) / 8), 256, 0, ctx->stream>>>(Q, ldq, m, k, before2);
+    QB_LAUNCH_CHECK(ctx);
     if (fast_ok) {
         Gpart = ws.get<c128>(qb_cholqr_gpart_elems(ctx));
         Wbuf = ws.get<c128>(64 * 64);
-        save = ws.get<c128>((size_t)(m * PW));
         R1 = ws.get<c128>(64 * 64);
         R2 = ws.get<c128>(64 * 64);
         flags = ws.get<int>(2);
-        if (!Gpart || !Wbuf || !save || !R1 || !R2 || !flags) QB_FAIL(ctx, QB200_E_CUDA, "qr: workspace allocation failed");
+        if (!Gpart || !Wbuf || !R1 || !R2 || !flags) QB_FAIL(ctx, QB200_E_CUDA, "qr: workspace allocation failed");
     }
     // super-panels of 128 columns = two Cholesky-QR sub-panels of 64; the trailing matrix is updated once per
     // super-panel (K = 128 GEMMs: half the launches, twice the depth)
@@ -262,11 +365,12 @@ static int32_t bgs_pass(qb200_ctx* ctx, int64_t m, int64_t k, c128* Q, int64_t l
             c128* P = Q + j0 * ldq;
             c128* Rpp = R + j0 + j0 * ldr;
             bool done = false;
+            QB_TRY(qb_copy_matrix(ctx, m, w, P, ldq, save, m, 0));
             if (fast_ok && w == PW) {
-                QB_TRY(qb_copy_matrix(ctx, m, PW, P, ldq, save, m, 0));
                 QB_CUDA(ctx, cudaMemsetAsync(flags, 0, 2 * sizeof(int), ctx->stream));
-                QB_TRY(qb_cholqr_panel_step(ctx, P, ldq, m, R1, 64, Gpart, Wbuf, flags, flags + 1));
-                QB_TRY(qb_cholqr_panel_step(ctx, P, ldq, m, R2, 64, Gpart, Wbuf, flags, flags + 1));
+                QB_TRY(qb_cholqr_panel_step(ctx, P, ldq, m, R1, 64, Gpart, Wbuf, flags, flags + 1, before2 + j0,
+                                            dep_tol(j0, w)));
+                QB_TRY(qb_cholqr_panel_step(ctx, P, ldq, m, R2, 64, Gpart, Wbuf, flags, flags + 1, nullptr, 0.0));
                 QB_CUDA(ctx, cudaMemcpyAsync(ctx->scratch_host, flags + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
                 QB_CUDA(ctx, qb_stream_sync(ctx));
                 int failed = *reinterpret_cast<int*>(ctx->scratch_host);
@@ -277,7 +381,7 @@ static int32_t bgs_pass(qb200_ctx* ctx, int64_t m, int64_t k, c128* Q, int64_t l
                     QB_TRY(qb_copy_matrix(ctx, m, PW, save, m, P, ldq, 0));
                 }
             }
-            if (!done) QB_TRY(tsqr_panel(ctx, m, w, P, ldq, Rpp, ldr));
+            if (!done) QB_TRY(robust_panel(ctx, m, w, P, ldq, Rpp, ldr, Q, ldq, j0, before2 + j0, save));
             int64_t nin = s0 + sw - j0 - w;  // rest of the super-panel
             if (nin > 0) {
                 c128* T = Q + (j0 + w) * ldq;

@@ -822,6 +822,143 @@ __global__ void __launch_bounds__(UPD_THREADS, 2)
 }
 
 // ---------------------------------------------------------------------------------------------
+// update kernel with a sum plane: the 3M product needs Ar + Ai for every element of the chunk, and
+// in jacobi_update_kernel<1> each of the 8 warps forms it for all 2048 elements it consumes (64 FP64 adds per lane and
+// chunk on the pipe the DMMAs run on: DADD was 35 % of the stall samples).  Here the PRODUCER writes S = re + im next to
+// X (one add per element it stores: 8 per lane and chunk) and the consumer streams S through the same cp.async ring
+// (8 more bytes per element, L2 resident) -- bit-identical results, since S is the very sum the consumer used to form.
+// Ring: 2 stages of (64 x 34 ComplexF64 + 64 x 40 Float64) = 110.6 KB, still 2 CTAs per SM.
+constexpr int US_NST = 2, US_SP = 40;  // S pitch = 8 mod 16 doubles: a warp's 8-byte fragment loads take the minimal 2 wavefronts
+constexpr size_t UPDS_STAGE = (size_t)JP * U_ZP * sizeof(c128) + (size_t)JP * US_SP * sizeof(double);
+constexpr size_t UPDS_SMEM = US_NST * UPDS_STAGE;
+
+__global__ void __launch_bounds__(UPD_THREADS, 2)
+    jacobi_update_splane_kernel(c128* __restrict__ Z, double* __restrict__ Zs, int64_t ldz, int nb, int step,
+                                const c128* __restrict__ Wg, const int* __restrict__ flags, int npairs, int nchunk) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int total = npairs * nchunk;
+    int lo, hi;
+    gram_item_range(blockIdx.x, gridDim.x, total, lo, hi);
+    const int p0 = (lo < hi) ? lo / nchunk : 0;
+    unsigned amask;
+    {
+        const int p = p0 + lane;
+        const int f = (lo < hi && p < npairs) ? flags[p] : 0;
+        amask = __ballot_sync(0xffffffffu, f != 0);
+    }
+    struct Cursor {
+        int item, pair, chunk, I, J;
+    };
+    auto pair_active = [&](int pair) {
+        const int d = pair - p0;
+        return d < 32 ? ((amask >> d) & 1u) != 0 : flags[pair] != 0;
+    };
+    auto settle = [&](Cursor& c) {
+        while (c.item < hi && !pair_active(c.pair)) {
+            c.item += nchunk - c.chunk;
+            c.chunk = 0;
+            ++c.pair;
+        }
+        if (c.item < hi) rr_pair(nb, step, c.pair, c.I, c.J);
+    };
+    auto advance = [&](Cursor& c) {
+        ++c.item;
+        if (++c.chunk == nchunk) {
+            c.chunk = 0;
+            ++c.pair;
+            settle(c);
+        }
+    };
+    const int l_row = tid & 31, l_col0 = tid >> 5;    // X: one 16-byte element per cp.async
+    const int s_rp = tid & 15, s_col0 = tid >> 4;     // S: two rows (16 bytes) per cp.async
+    auto load_chunk = [&](const Cursor& c, int st) {
+        c128* zs = reinterpret_cast<c128*>(smem_raw + (size_t)st * UPDS_STAGE);
+        double* ss = reinterpret_cast<double*>(zs + JP * U_ZP);
+        const c128* src = Z + (int64_t)c.chunk * U_ROWS + l_row;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int col = l_col0 + 8 * i;
+            cp_async16(zs + col * U_ZP + l_row, src + panel_col(c.I, c.J, col) * ldz, true);
+        }
+        const double* srs = Zs + (int64_t)c.chunk * U_ROWS + 2 * s_rp;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int col = s_col0 + 16 * i;
+            cp_async16(ss + col * US_SP + 2 * s_rp, srs + panel_col(c.I, c.J, col) * ldz, true);
+        }
+    };
+    Cursor cur{lo, p0, lo - p0 * nchunk, 0, 1};
+    settle(cur);
+    Cursor pf = cur;
+    if (pf.item < hi) {
+        load_chunk(pf, 0);
+        advance(pf);
+    }
+    cp_async_commit();
+    int cur_pair = -1, stage = 0;
+    c128 breg[JP / 4];
+    while (cur.item < hi) {
+        if (cur.pair != cur_pair) {
+            const c128* wsrc = Wg + (size_t)cur.pair * (JP * JP) + (warp * 8 + g) * JP + t;
+#pragma unroll
+            for (int kk = 0; kk < JP / 4; ++kk) breg[kk] = wsrc[kk * 4];
+            cur_pair = cur.pair;
+        }
+        cp_async_wait<0>();
+        __syncthreads();  // the landed chunk is visible; every warp has left the other buffer
+        if (pf.item < hi) {
+            load_chunk(pf, stage ^ 1);
+            advance(pf);
+        }
+        cp_async_commit();
+        const c128* za = reinterpret_cast<const c128*>(smem_raw + (size_t)stage * UPDS_STAGE) + g;
+        const double* sa = reinterpret_cast<const double*>(smem_raw + (size_t)stage * UPDS_STAGE + (size_t)JP * U_ZP * sizeof(c128)) + g;
+        const int64_t r0 = (int64_t)cur.chunk * U_ROWS + g;
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+            double pp[2][2], qq[2][2], ss[2][2];
+#pragma unroll
+            for (int a = 0; a < 2; ++a) pp[a][0] = pp[a][1] = qq[a][0] = qq[a][1] = ss[a][0] = ss[a][1] = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < JP / 4; ++kk) {
+                const double br = breg[kk].x, bi = breg[kk].y, bs = br + bi;
+#pragma unroll
+                for (int a = 0; a < 2; ++a) {
+                    const c128 v = za[(kk * 4 + t) * U_ZP + (hh * 2 + a) * 8];
+                    const double sv = sa[(kk * 4 + t) * US_SP + (hh * 2 + a) * 8];
+                    dmma884(pp[a], v.x, br);
+                    dmma884(qq[a], v.y, bi);
+                    dmma884(ss[a], sv, bs);
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int64_t zo = r0 + panel_col(cur.I, cur.J, warp * 8 + 2 * t + h) * ldz;
+#pragma unroll
+                for (int a = 0; a < 2; ++a) {
+                    const double re = pp[a][h] - qq[a][h], im = ss[a][h] - pp[a][h] - qq[a][h];
+                    Z[zo + (hh * 2 + a) * 8] = make_double2(re, im);
+                    Zs[zo + (hh * 2 + a) * 8] = re + im;
+                }
+            }
+        }
+        stage ^= 1;
+        advance(cur);
+    }
+    cp_async_wait<0>();
+}
+
+// S = re + im of every element of X (the sum plane the kernel above consumes), once before the first sweep
+__global__ void splane_init_kernel(const c128* __restrict__ Z, double* __restrict__ Zs, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const c128 v = Z[i];
+        Zs[i] = v.x + v.y;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Cholesky-QR step of a 64-column panel (used by K4): sums the partial Grams, factors the diagonally scaled
 // G = R^H R in shared memory, writes R (upper triangular) and W = R^-1, which the update kernel applies (P <- P W).
 // `fail` is raised when a scaled pivot drops below `piv_tol` (panel numerically rank deficient for a Gram-based
@@ -829,7 +966,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 2)
 __global__ void __launch_bounds__(256, 1)
     panel_chol_kernel(const c128* __restrict__ Gpart, int gram_ctas, int nchunk, c128* __restrict__ Wout,
                       c128* __restrict__ Rout, int64_t ldr, int* __restrict__ flags, int* __restrict__ fail,
-                      double piv_tol) {
+                      double piv_tol, const double* __restrict__ before2, double dep_tol2) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     c128* G = reinterpret_cast<c128*>(smem_raw);
     c128* Wm = G + JP * GLD;
@@ -867,6 +1004,9 @@ __global__ void __launch_bounds__(256, 1)
             bad = 1;
             g = 1.0;
         }
+        // a column that lost (numerically) all of its norm to the earlier columns is rounding noise: the caller must
+        // complete it with a genuinely new direction (qr.cu: robust_panel), not normalise the noise
+        if (before2 && !(g > dep_tol2 * before2[tid])) bad = 1;
         d[tid] = sqrt(g);
     }
     __syncthreads();
@@ -1090,6 +1230,7 @@ struct SvdState {
     c128* Z = nullptr;  // X (mp x np); the rotations are NOT accumulated (see qb_svd_emit)
     c128* B0 = nullptr;  // rb x k: B with its columns sorted by norm (B0 = Q R; Q itself is never needed)
     float2* Z32 = nullptr;  // FP32 shadow of X for the low-precision Gram of the early sweeps (null: not used)
+    double* Zs = nullptr;   // sum plane re + im of X for jacobi_update_splane_kernel (null: not used)
     std::vector<double> sigma_sorted;
     double* sigma_dev = nullptr;
     int* perm_dev = nullptr;     // sigma order (descending) -> column of Z
@@ -1102,6 +1243,15 @@ static bool update_3m() {
     static const bool on = [] {
         const char* e = getenv("QB200_UPDATE_3M");
         return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
+// QB200_UPDATE_SPLANE=1: the update kernel with a producer-written sum plane (jacobi_update_splane_kernel)
+static bool update_splane() {
+    static const bool on = [] {
+        const char* e = getenv("QB200_UPDATE_SPLANE");
+        return e && e[0] == '1';
     }();
     return on;
 }
@@ -1128,6 +1278,7 @@ void qb_svd_release(qb200_ctx* ctx, SvdState* st) {
     if (st->Z) cudaFreeAsync(st->Z, ctx->stream);
     if (st->B0) cudaFreeAsync(st->B0, ctx->stream);
     if (st->Z32) cudaFreeAsync(st->Z32, ctx->stream);
+    if (st->Zs) cudaFreeAsync(st->Zs, ctx->stream);
     if (st->sigma_dev) cudaFreeAsync(st->sigma_dev, ctx->stream);
     if (st->perm_dev) cudaFreeAsync(st->perm_dev, ctx->stream);
     if (st->colperm_dev) cudaFreeAsync(st->colperm_dev, ctx->stream);
@@ -1162,6 +1313,7 @@ int32_t qb_svd_init(qb200_ctx* ctx) {
     QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_gram32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRAM32_SMEM));
     QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_update_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM));
     QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_update_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM));
+    QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_update_splane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPDS_SMEM));
     QB_CUDA(ctx, cudaFuncSetAttribute(panel_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)((size_t)2 * JP * GLD * sizeof(c128))));
     return QB200_OK;
@@ -1281,6 +1433,15 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
         int32_t r = qb_narrow_c128(ctx, st->Z, st->Z32, st->ldz * st->np);
         if (r != QB200_OK) return fail(r);
     }
+    const bool splane = update_splane() && update_3m() && nb > 2 && !shadow;
+    if (splane) {
+        if (cudaMallocAsync(&st->Zs, sizeof(double) * st->ldz * st->np, ctx->stream) != cudaSuccess) {
+            ctx->err = "svd: out of device memory";
+            return fail(QB200_E_CUDA);
+        }
+        splane_init_kernel<<<grid_cap(ctx, st->ldz * st->np, 256), 256, 0, ctx->stream>>>(st->Z, st->Zs, st->ldz * st->np);
+        ctx->launches++;
+    }
     const int max_sweeps = 40;
     int sweep = 0;
     bool converged = false;
@@ -1312,8 +1473,12 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
             }
             {
                 PhaseTimer pt(ctx, QB_PH_JUPDATE, 8.0 * npairs * (double)st->ldz * JP * JP);  // ldz = rows of X
-                (update_3m() ? jacobi_update_kernel<1> : jacobi_update_kernel<0>)<<<upd_ctas, UPD_THREADS, UPD_SMEM, ctx->stream>>>(
-                    st->Z, st->ldz, nb, step, Wg, flags, npairs, u_nchunk, shadow ? st->Z32 : nullptr);
+                if (splane)
+                    jacobi_update_splane_kernel<<<upd_ctas, UPD_THREADS, UPDS_SMEM, ctx->stream>>>(st->Z, st->Zs, st->ldz, nb, step, Wg,
+                                                                                                 flags, npairs, u_nchunk);
+                else
+                    (update_3m() ? jacobi_update_kernel<1> : jacobi_update_kernel<0>)<<<upd_ctas, UPD_THREADS, UPD_SMEM, ctx->stream>>>(
+                        st->Z, st->ldz, nb, step, Wg, flags, npairs, u_nchunk, shadow ? st->Z32 : nullptr);
             }
         }
         cudaMemcpyAsync(scale, scale + 1, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
@@ -1593,13 +1758,14 @@ constexpr size_t CHOL_SMEM = (size_t)2 * JP * GLD * sizeof(c128);
 // One Cholesky-QR step on the 64-column panel P (m x 64, ld, m % 64 == 0): P <- P R^-1, R (64 x 64, ldr) written.
 // Raises *fail_dev when the panel is too ill conditioned for a Gram-based step (caller falls back to TSQR).
 int32_t qb_cholqr_panel_step(qb200_ctx* ctx, c128* P, int64_t ld, int64_t m, c128* R, int64_t ldr, c128* Gpart,
-                             c128* Wbuf, int* flags_dev, int* fail_dev) {
+                             c128* Wbuf, int* flags_dev, int* fail_dev, const double* before2_dev, double dep_tol) {
     const int mp = (int)m, nchunk = mp / G_BKR;
     // few, fat CTAs: the single-CTA Cholesky kernel has to sum every partial Gram
     const int gram_ctas = std::max(1, std::min(16, nchunk));
     jacobi_gram_kernel<0><<<gram_ctas, 256, GRAM_SMEM, ctx->stream>>>(P, ld, mp, 2, -1, 1, Gpart);
     QB_LAUNCH_CHECK(ctx);
-    panel_chol_kernel<<<1, 256, CHOL_SMEM, ctx->stream>>>(Gpart, gram_ctas, nchunk, Wbuf, R, ldr, flags_dev, fail_dev, 1e-11);
+    panel_chol_kernel<<<1, 256, CHOL_SMEM, ctx->stream>>>(Gpart, gram_ctas, nchunk, Wbuf, R, ldr, flags_dev, fail_dev, 1e-11,
+                                                          before2_dev, dep_tol * dep_tol);
     QB_LAUNCH_CHECK(ctx);
     const int u_nchunk = mp / U_ROWS;
     const int upd_ctas = std::max(1, std::min(2 * ctx->sm_count, u_nchunk));

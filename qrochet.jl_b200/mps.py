@@ -13,18 +13,45 @@ from ._capi import check, lib
 from .device import Context
 
 
+_HOST_CODES = {np.dtype(np.complex128): capi.C128, np.dtype(np.complex64): capi.C64,
+               np.dtype(np.float64): capi.F64, np.dtype(np.float32): capi.F32}
+
+
+def _host_code(a: np.ndarray):
+    """(array, element-type code) for the boundary: the four `eltype`s of `rand` (Chain.jl:226-227) cross as they are,
+    anything else (integers, bool: `zeros(Product, n)`) is converted to ComplexF64 on the host."""
+    if a.dtype not in _HOST_CODES:
+        a = a.astype(np.complex128)
+    return a, _HOST_CODES[a.dtype]
+
+
+def _storage(arrays, dtype):
+    """Storage type of the chain: ComplexF32 only when asked for, or when every site array is single precision."""
+    if dtype is not None:
+        dt = np.dtype(dtype)
+        if dt not in (np.dtype(np.complex128), np.dtype(np.complex64)):
+            raise ValueError("storage type must be complex128 or complex64 (real data is held as complex)")
+        return capi.C64 if dt == np.dtype(np.complex64) else capi.C128
+    single = all(np.asarray(a).dtype in (np.dtype(np.complex64), np.dtype(np.float32)) for a in arrays)
+    return capi.C64 if single and len(arrays) else capi.C128
+
+
 class B200MPS:
-    def __init__(self, ctx: Context, arrays=None, order=("o", "l", "r"), _handle=None):
+    def __init__(self, ctx: Context, arrays=None, order=("o", "l", "r"), dtype=None, _handle=None):
+        """`arrays`: site arrays in the reference's `order` (default (o, l, r), Chain.jl:33) of any of the reference's
+        element types (ComplexF64, ComplexF32, Float64, Float32; real chains are held as complex).  `dtype`: storage
+        type in HBM, complex128 or complex64 (default: complex64 only if every array is single precision); the fused
+        chains compute in FP64 either way."""
         self.ctx = ctx
         if _handle is not None:
             self.h = _handle
             return
         n = len(arrays)
         h = C.c_void_p()
-        check(ctx.h, lib.qb200_mps_create(ctx.h, n, C.byref(h)))
+        check(ctx.h, lib.qb200_mps_create_typed(ctx.h, n, _storage(arrays, dtype), C.byref(h)))
         self.h = h
         for k, a in enumerate(arrays):
-            a = np.asarray(a, dtype=np.complex128)
+            a, code = _host_code(np.asarray(a))
             labels = [c for c in order if not ((c == "l" and k == 0) or (c == "r" and k == n - 1))]
             assert a.ndim == len(labels), (k, a.shape, labels)
             # -> (l, o, r) with size-1 edge bonds
@@ -36,21 +63,23 @@ class B200MPS:
             if k == n - 1:
                 a = a[..., None]
             buf = np.asfortranarray(a)
-            check(ctx.h, lib.qb200_mps_set_site(ctx.h, self.h, k, buf.shape[0], buf.shape[1], buf.shape[2],
-                                                buf.ctypes.data_as(C.c_void_p)))
+            check(ctx.h, lib.qb200_mps_set_site_typed(ctx.h, self.h, k, code, buf.shape[0], buf.shape[1], buf.shape[2],
+                                                      buf.ctypes.data_as(C.c_void_p)))
 
     @classmethod
-    def from_sites(cls, ctx: Context, sites, lambdas=None, form: int = 0) -> "B200MPS":
+    def from_sites(cls, ctx: Context, sites, lambdas=None, form: int = 0, dtype=None) -> "B200MPS":
         """Adapt an MPS given in the private layout: `sites[k]` has extents (chi_l, p, chi_r) (Fortran order,
         ideally pinned host memory), `lambdas[b]` the Schmidt vector on bond b or None."""
         n = len(sites)
         h = C.c_void_p()
-        check(ctx.h, lib.qb200_mps_create(ctx.h, n, C.byref(h)))
+        check(ctx.h, lib.qb200_mps_create_typed(ctx.h, n, _storage(sites, dtype), C.byref(h)))
         self = cls(ctx, _handle=h)
         for k, a in enumerate(sites):
-            assert a.dtype == np.complex128 and a.ndim == 3 and a.flags.f_contiguous
-            check(ctx.h, lib.qb200_mps_set_site(ctx.h, h, k, a.shape[0], a.shape[1], a.shape[2],
-                                                a.ctypes.data_as(C.c_void_p)))
+            a, code = _host_code(a)
+            assert a.ndim == 3
+            a = np.asfortranarray(a)
+            check(ctx.h, lib.qb200_mps_set_site_typed(ctx.h, h, k, code, a.shape[0], a.shape[1], a.shape[2],
+                                                      a.ctypes.data_as(C.c_void_p)))
         for b, lam in enumerate(lambdas or []):
             if lam is not None:
                 lam = np.ascontiguousarray(lam, dtype=np.float64)
@@ -58,6 +87,11 @@ class B200MPS:
                                                       lam.ctypes.data_as(C.POINTER(C.c_double))))
         check(ctx.h, lib.qb200_mps_set_form(h, form))
         return self
+
+    @property
+    def dtype(self):
+        """Storage type of the site tensors in HBM."""
+        return np.dtype(np.complex64) if lib.qb200_mps_dtype(self.h) == capi.C64 else np.dtype(np.complex128)
 
     @classmethod
     def from_product(cls, ctx: Context, vectors) -> "B200MPS":
@@ -108,11 +142,13 @@ class B200MPS:
     def bond_dims(self):
         return [self.site_dims(s)[2] for s in range(self.nsites - 1)]
 
-    def site(self, s: int) -> np.ndarray:
-        """Host copy of site s (0-based) with extents (chi_l, p, chi_r)."""
+    def site(self, s: int, dtype=np.complex128) -> np.ndarray:
+        """Host copy of site s (0-based) with extents (chi_l, p, chi_r), as complex128 (default) or complex64."""
         d = self.site_dims(s)
-        out = np.empty(d, dtype=np.complex128, order="F")
-        check(self.ctx.h, lib.qb200_mps_get_site(self.ctx.h, self.h, s, out.ctypes.data_as(C.c_void_p)))
+        dt = np.dtype(dtype)
+        out = np.empty(d, dtype=dt, order="F")
+        check(self.ctx.h, lib.qb200_mps_get_site_typed(self.ctx.h, self.h, s, _HOST_CODES[dt],
+                                                       out.ctypes.data_as(C.c_void_p)))
         return out
 
     def arrays(self):

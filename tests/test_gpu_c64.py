@@ -187,3 +187,78 @@ def test_label_driven_chain_in_complexf32(qb, ctx):
     kk = min(len(lam), len(lam_ref))
     assert np.abs(lam[:kk] - lam_ref[:kk]).max() <= TOL * lam_ref[0]
     assert all(t.data.dtype in (1, 3) for t in q.tn.tensors)
+
+
+# ---- the fused chains (qb200_mps_*) with ComplexF32 storage and real element types (VERDICT r1 "missing" 4) ------------
+def _mps_dense(g):
+    lams, n = g.lambdas(), g.nsites
+    psi = np.ones((1, 1), dtype=complex)
+    for s in range(n):
+        a = g.site(s)
+        if s < n - 1 and lams[s] is not None:
+            a = a * lams[s][None, None, :]
+        psi = np.tensordot(psi, a, axes=(1, 0)).reshape(-1, a.shape[2], order="F")
+    return psi[:, 0]
+
+
+def test_fused_chain_with_complexf32_storage(qb, ctx):
+    """`rand(Chain, Open, State; eltype = ComplexF32)` (Chain.jl:226-227) through canonize! / evolve! / truncate! / overlap /
+    expect on the fused path: sites live in HBM as float2 (half the footprint), the kernels run in FP64, results are
+    rounded to ComplexF32 once per call.  Parity bar of the north star for ComplexF32: 1e-5."""
+    from oracle import chain as oc
+    n, chi = 10, 16
+    arrays = [a.astype(np.complex64) for a in oc.rand_mps_arrays(np.random.default_rng(501), n, chi)]
+    o = oc.Chain([a.astype(np.complex128) for a in arrays])
+    g = qb.B200MPS(ctx, arrays)
+    assert g.dtype == np.complex64 and g.site(3, dtype=np.complex64).dtype == np.complex64
+    assert np.array_equal(g.site(3, dtype=np.complex64), np.transpose(arrays[3], (1, 0, 2)))     # stored as given, bit for bit
+    assert abs(g.norm() - o.norm()) <= TOL
+    o.canonize()
+    g.canonize()
+    assert g.form == 1 and g.dtype == np.complex64
+    for x, y in zip(g.lambdas(), o.lambdas()):
+        assert len(x) == len(y) and np.abs(x - y).max() <= TOL * y[0]
+    rng = np.random.default_rng(502)
+    for bond in (5, 4, 6, 5):
+        U = oc.haar_unitary(rng)
+        o.evolve(oc.gate(U, [bond, bond + 1]), iscanonical=True, maxdim=12, renormalize=True)
+        kept, _ = g.evolve(np.reshape(U, (2, 2, 2, 2), order="F"), [bond, bond + 1], iscanonical=True, maxdim=12,
+                           renormalize=True)
+        assert kept == len(o.lambdas()[bond - 1])                                  # truncation decisions: bit-exact
+    for x, y in zip(g.lambdas(), o.lambdas()):
+        assert np.abs(x - y).max() <= TOL * y[0]
+    assert np.abs(_mps_dense(g) - o.to_dense()).max() <= 10 * TOL
+    Z = np.diag([1.0, -1.0]).astype(complex)
+    assert abs(g.expect([Z], [4])[0] - o.expect([oc.gate(Z, [4])])) <= TOL
+    other = [a.astype(np.complex64) for a in oc.rand_mps_arrays(np.random.default_rng(503), n, 8)]
+    want = o.overlap(oc.Chain([a.astype(np.complex128) for a in other]))
+    assert abs(g.overlap(qb.B200MPS(ctx, other)) - want) <= TOL
+    assert abs(g.overlap(qb.B200MPS(ctx, other, dtype=np.complex128)) - want) <= TOL     # mixed storage types
+    # a gate list on worker streams and a copy keep the storage type
+    gates = [np.reshape(oc.haar_unitary(rng), (2, 2, 2, 2), order="F") for _ in range(4)]
+    c = g.copy()
+    assert c.dtype == np.complex64
+    c.evolve_circuit(gates, [2, 7, 3, 6], iscanonical=True, maxdim=12, renormalize=True)
+    for gt, b in zip(gates, [2, 7, 3, 6]):
+        o.evolve(oc.Dense(gt, [oc.site(b), oc.site(b + 1), oc.site(b, True), oc.site(b + 1, True)]), iscanonical=True,
+                 maxdim=12, renormalize=True)
+    for x, y in zip(c.lambdas(), o.lambdas()):
+        assert len(x) == len(y) and np.abs(x - y).max() <= TOL * y[0]
+
+
+def test_real_element_types_are_accepted_at_the_boundary(qb, ctx):
+    """The reference's DEFAULT `eltype` of `rand` is Float64 (Chain.jl:226): real site arrays cross the boundary as they
+    are and are held as complex."""
+    from oracle import chain as oc
+    n, chi = 8, 8
+    for dt, tol in ((np.float64, 1e-10), (np.float32, TOL)):
+        arrays = [a.astype(dt) for a in oc.rand_mps_arrays(np.random.default_rng(511), n, chi, dtype=np.float64)]
+        o = oc.Chain([a.astype(np.complex128) for a in arrays])
+        g = qb.B200MPS(ctx, arrays)
+        assert g.dtype == (np.complex64 if dt == np.float32 else np.complex128)
+        assert abs(g.norm() - o.norm()) <= tol
+        o.canonize()
+        g.canonize()
+        for x, y in zip(g.lambdas(), o.lambdas()):
+            assert np.abs(x - y).max() <= max(tol, 1e-12) * y[0]
+        assert np.abs(np.abs(np.vdot(_mps_dense(g), o.to_dense())) - 1.0) <= 10 * tol
