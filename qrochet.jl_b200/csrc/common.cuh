@@ -37,6 +37,7 @@ struct qb200_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int sm_count = 148;
     int last_svd_sweeps = 0;
+    int qr_last_dependent = 0;  // numerically dependent columns the last qb_qr_matrix on this context had to complete
     int64_t svd_calls = 0, svd_sweeps = 0;  // totals since creation (this context only; workers are summed by the getter)
     void* nccl_comm = nullptr;
     int comm_rank = 0, comm_nranks = 1;  // set by qb200_comm_init

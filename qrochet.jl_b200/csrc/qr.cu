@@ -321,6 +321,7 @@ static int32_t robust_panel(qb200_ctx* ctx, int64_t m, int w, c128* P, int64_t l
     // dependency inside the panel), nothing on or below the diagonal (no component along its completion vector)
     for (int c = 0; c < w; ++c)
         if (replaced[c]) {
+            ctx->qr_last_dependent++;
             QB_TRY(qb_gemm(ctx, 2, 0, w, 1, m, one, P, ld, orig + (int64_t)c * m, m, zero, Rpp + (int64_t)c * ldr, ldr));
             QB_CUDA(ctx, cudaMemsetAsync(Rpp + (int64_t)c * ldr + c, 0, sizeof(c128) * (size_t)(w - c), ctx->stream));
         }
@@ -413,6 +414,7 @@ int32_t qb_qr_matrix(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64_
     if (m > INT32_MAX / 2) QB_FAIL(ctx, QB200_E_UNSUPPORTED, "qr: too many rows");
     const int64_t k = std::min(m, n);
     const c128 one = make_double2(1.0, 0.0), zero = make_double2(0.0, 0.0);
+    ctx->qr_last_dependent = 0;
     QB_TRY(qb_copy_matrix(ctx, m, k, A, lda, Q, ldq, 0));
     Workspace ws(ctx);
     c128* R1 = ws.get<c128>((size_t)k * k);

@@ -471,7 +471,8 @@ __global__ void __launch_bounds__(EVD_THREADS, 1)
     // the first is the usual relative criterion, the second the accuracy a GEMM-applied rotation can deliver at
     // all (every column of an updated panel carries an absolute error ~ eps * sigma_1); without it columns whose
     // norm is at the rounding level of sigma_1 would be rotated for ever.
-    const double abs_tol = abs_c * scale_in[0];
+    // abs_c < 0: the factor lives in scale_in[2] (set by the host between sweeps without re-capturing the sweep graph)
+    const double abs_tol = (abs_c < 0.0 ? scale_in[2] : abs_c) * scale_in[0];
     const double rt2 = rot_tol * rot_tol, at2 = abs_tol * abs_tol;
     double mx = 0.0, gmax = 0.0;
     for (int e = tid; e < JP * JP; e += EVD_THREADS) {
@@ -822,143 +823,6 @@ __global__ void __launch_bounds__(UPD_THREADS, 2)
 }
 
 // ---------------------------------------------------------------------------------------------
-// update kernel with a sum plane: the 3M product needs Ar + Ai for every element of the chunk, and
-// in jacobi_update_kernel<1> each of the 8 warps forms it for all 2048 elements it consumes (64 FP64 adds per lane and
-// chunk on the pipe the DMMAs run on: DADD was 35 % of the stall samples).  Here the PRODUCER writes S = re + im next to
-// X (one add per element it stores: 8 per lane and chunk) and the consumer streams S through the same cp.async ring
-// (8 more bytes per element, L2 resident) -- bit-identical results, since S is the very sum the consumer used to form.
-// Ring: 2 stages of (64 x 34 ComplexF64 + 64 x 40 Float64) = 110.6 KB, still 2 CTAs per SM.
-constexpr int US_NST = 2, US_SP = 40;  // S pitch = 8 mod 16 doubles: a warp's 8-byte fragment loads take the minimal 2 wavefronts
-constexpr size_t UPDS_STAGE = (size_t)JP * U_ZP * sizeof(c128) + (size_t)JP * US_SP * sizeof(double);
-constexpr size_t UPDS_SMEM = US_NST * UPDS_STAGE;
-
-__global__ void __launch_bounds__(UPD_THREADS, 2)
-    jacobi_update_splane_kernel(c128* __restrict__ Z, double* __restrict__ Zs, int64_t ldz, int nb, int step,
-                                const c128* __restrict__ Wg, const int* __restrict__ flags, int npairs, int nchunk) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int g = lane >> 2, t = lane & 3;
-    const int total = npairs * nchunk;
-    int lo, hi;
-    gram_item_range(blockIdx.x, gridDim.x, total, lo, hi);
-    const int p0 = (lo < hi) ? lo / nchunk : 0;
-    unsigned amask;
-    {
-        const int p = p0 + lane;
-        const int f = (lo < hi && p < npairs) ? flags[p] : 0;
-        amask = __ballot_sync(0xffffffffu, f != 0);
-    }
-    struct Cursor {
-        int item, pair, chunk, I, J;
-    };
-    auto pair_active = [&](int pair) {
-        const int d = pair - p0;
-        return d < 32 ? ((amask >> d) & 1u) != 0 : flags[pair] != 0;
-    };
-    auto settle = [&](Cursor& c) {
-        while (c.item < hi && !pair_active(c.pair)) {
-            c.item += nchunk - c.chunk;
-            c.chunk = 0;
-            ++c.pair;
-        }
-        if (c.item < hi) rr_pair(nb, step, c.pair, c.I, c.J);
-    };
-    auto advance = [&](Cursor& c) {
-        ++c.item;
-        if (++c.chunk == nchunk) {
-            c.chunk = 0;
-            ++c.pair;
-            settle(c);
-        }
-    };
-    const int l_row = tid & 31, l_col0 = tid >> 5;    // X: one 16-byte element per cp.async
-    const int s_rp = tid & 15, s_col0 = tid >> 4;     // S: two rows (16 bytes) per cp.async
-    auto load_chunk = [&](const Cursor& c, int st) {
-        c128* zs = reinterpret_cast<c128*>(smem_raw + (size_t)st * UPDS_STAGE);
-        double* ss = reinterpret_cast<double*>(zs + JP * U_ZP);
-        const c128* src = Z + (int64_t)c.chunk * U_ROWS + l_row;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            int col = l_col0 + 8 * i;
-            cp_async16(zs + col * U_ZP + l_row, src + panel_col(c.I, c.J, col) * ldz, true);
-        }
-        const double* srs = Zs + (int64_t)c.chunk * U_ROWS + 2 * s_rp;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            int col = s_col0 + 16 * i;
-            cp_async16(ss + col * US_SP + 2 * s_rp, srs + panel_col(c.I, c.J, col) * ldz, true);
-        }
-    };
-    Cursor cur{lo, p0, lo - p0 * nchunk, 0, 1};
-    settle(cur);
-    Cursor pf = cur;
-    if (pf.item < hi) {
-        load_chunk(pf, 0);
-        advance(pf);
-    }
-    cp_async_commit();
-    int cur_pair = -1, stage = 0;
-    c128 breg[JP / 4];
-    while (cur.item < hi) {
-        if (cur.pair != cur_pair) {
-            const c128* wsrc = Wg + (size_t)cur.pair * (JP * JP) + (warp * 8 + g) * JP + t;
-#pragma unroll
-            for (int kk = 0; kk < JP / 4; ++kk) breg[kk] = wsrc[kk * 4];
-            cur_pair = cur.pair;
-        }
-        cp_async_wait<0>();
-        __syncthreads();  // the landed chunk is visible; every warp has left the other buffer
-        if (pf.item < hi) {
-            load_chunk(pf, stage ^ 1);
-            advance(pf);
-        }
-        cp_async_commit();
-        const c128* za = reinterpret_cast<const c128*>(smem_raw + (size_t)stage * UPDS_STAGE) + g;
-        const double* sa = reinterpret_cast<const double*>(smem_raw + (size_t)stage * UPDS_STAGE + (size_t)JP * U_ZP * sizeof(c128)) + g;
-        const int64_t r0 = (int64_t)cur.chunk * U_ROWS + g;
-#pragma unroll 1
-        for (int hh = 0; hh < 2; ++hh) {
-            double pp[2][2], qq[2][2], ss[2][2];
-#pragma unroll
-            for (int a = 0; a < 2; ++a) pp[a][0] = pp[a][1] = qq[a][0] = qq[a][1] = ss[a][0] = ss[a][1] = 0.0;
-#pragma unroll
-            for (int kk = 0; kk < JP / 4; ++kk) {
-                const double br = breg[kk].x, bi = breg[kk].y, bs = br + bi;
-#pragma unroll
-                for (int a = 0; a < 2; ++a) {
-                    const c128 v = za[(kk * 4 + t) * U_ZP + (hh * 2 + a) * 8];
-                    const double sv = sa[(kk * 4 + t) * US_SP + (hh * 2 + a) * 8];
-                    dmma884(pp[a], v.x, br);
-                    dmma884(qq[a], v.y, bi);
-                    dmma884(ss[a], sv, bs);
-                }
-            }
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int64_t zo = r0 + panel_col(cur.I, cur.J, warp * 8 + 2 * t + h) * ldz;
-#pragma unroll
-                for (int a = 0; a < 2; ++a) {
-                    const double re = pp[a][h] - qq[a][h], im = ss[a][h] - pp[a][h] - qq[a][h];
-                    Z[zo + (hh * 2 + a) * 8] = make_double2(re, im);
-                    Zs[zo + (hh * 2 + a) * 8] = re + im;
-                }
-            }
-        }
-        stage ^= 1;
-        advance(cur);
-    }
-    cp_async_wait<0>();
-}
-
-// S = re + im of every element of X (the sum plane the kernel above consumes), once before the first sweep
-__global__ void splane_init_kernel(const c128* __restrict__ Z, double* __restrict__ Zs, int64_t n) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const c128 v = Z[i];
-        Zs[i] = v.x + v.y;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
 // Cholesky-QR step of a 64-column panel (used by K4): sums the partial Grams, factors the diagonally scaled
 // G = R^H R in shared memory, writes R (upper triangular) and W = R^-1, which the update kernel applies (P <- P W).
 // `fail` is raised when a scaled pivot drops below `piv_tol` (panel numerically rank deficient for a Gram-based
@@ -1153,6 +1017,8 @@ __global__ void col_norm_kernel(const c128* __restrict__ Z, int64_t ldz, int mp,
 }
 
 // scale[0] = scale[1] = max_j sigma[j] (bit pattern of a non-negative double orders like an integer)
+__global__ void set_double_kernel(double* p, double v) { *p = v; }
+
 __global__ void max_reduce_kernel(const double* __restrict__ sigma, int n, double* __restrict__ scale) {
     __shared__ double sh[32];
     double mx = 0.0;
@@ -1165,6 +1031,7 @@ __global__ void max_reduce_kernel(const double* __restrict__ sigma, int n, doubl
         for (int i = 1; i < (int)(blockDim.x >> 5); ++i) mx = fmax(mx, sh[i]);
         scale[0] = mx;
         scale[1] = mx;
+        scale[2] = 0.0;  // absolute floor of the orthogonality test: off (pure relative criterion)
     }
 }
 
@@ -1230,7 +1097,6 @@ struct SvdState {
     c128* Z = nullptr;  // X (mp x np); the rotations are NOT accumulated (see qb_svd_emit)
     c128* B0 = nullptr;  // rb x k: B with its columns sorted by norm (B0 = Q R; Q itself is never needed)
     float2* Z32 = nullptr;  // FP32 shadow of X for the low-precision Gram of the early sweeps (null: not used)
-    double* Zs = nullptr;   // sum plane re + im of X for jacobi_update_splane_kernel (null: not used)
     std::vector<double> sigma_sorted;
     double* sigma_dev = nullptr;
     int* perm_dev = nullptr;     // sigma order (descending) -> column of Z
@@ -1243,15 +1109,6 @@ static bool update_3m() {
     static const bool on = [] {
         const char* e = getenv("QB200_UPDATE_3M");
         return !(e && e[0] == '0');
-    }();
-    return on;
-}
-
-// QB200_UPDATE_SPLANE=1: the update kernel with a producer-written sum plane (jacobi_update_splane_kernel)
-static bool update_splane() {
-    static const bool on = [] {
-        const char* e = getenv("QB200_UPDATE_SPLANE");
-        return e && e[0] == '1';
     }();
     return on;
 }
@@ -1278,7 +1135,6 @@ void qb_svd_release(qb200_ctx* ctx, SvdState* st) {
     if (st->Z) cudaFreeAsync(st->Z, ctx->stream);
     if (st->B0) cudaFreeAsync(st->B0, ctx->stream);
     if (st->Z32) cudaFreeAsync(st->Z32, ctx->stream);
-    if (st->Zs) cudaFreeAsync(st->Zs, ctx->stream);
     if (st->sigma_dev) cudaFreeAsync(st->sigma_dev, ctx->stream);
     if (st->perm_dev) cudaFreeAsync(st->perm_dev, ctx->stream);
     if (st->colperm_dev) cudaFreeAsync(st->colperm_dev, ctx->stream);
@@ -1313,7 +1169,6 @@ int32_t qb_svd_init(qb200_ctx* ctx) {
     QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_gram32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRAM32_SMEM));
     QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_update_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM));
     QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_update_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM));
-    QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_update_splane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPDS_SMEM));
     QB_CUDA(ctx, cudaFuncSetAttribute(panel_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)((size_t)2 * JP * GLD * sizeof(c128))));
     return QB200_OK;
@@ -1404,7 +1259,7 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
     c128* Wg = ws.get<c128>((size_t)npairs * JP * JP);
     int* flags = ws.get<int>(npairs);
     unsigned long long* stat = ws.get<unsigned long long>(1);
-    double* scale = ws.get<double>(2);  // [0] largest column norm seen in the previous sweep, [1] running max
+    double* scale = ws.get<double>(3);  // [0] largest column norm seen in the previous sweep, [1] running max, [2] absolute floor factor
     c128* Dstore = (nb > 2) ? ws.get<c128>((size_t)nb * JB * JB) : nullptr;  // carried diagonal Gram blocks
     if (!Gpart || !Wg || !flags || !stat || !scale || (nb > 2 && !Dstore)) {
         ctx->err = "svd: workspace allocation failed";
@@ -1414,12 +1269,26 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
     const double eps = 1.1102230246251565e-16;
     const double rot_tol = std::sqrt((double)st->mp) * eps;
     const double conv_tol = 1e-7;  // quadratic convergence: what is left after such a sweep is <~ 40 worst^2
-    const double abs_c = 0.0;  // pure relative criterion: R^H is column graded, so one-sided Jacobi keeps relative accuracy (no noise floor)
+    // Orthogonality test of a column pair: |g_ij| <= rot_tol |x_i||x_j| (pure relative: R^H is column graded, so one-sided
+    // Jacobi keeps relative accuracy and there is no noise floor) -- unless the matrix is numerically RANK DEFICIENT.  Then
+    // some columns of X are rounding noise (norm ~ eps sigma_1 sqrt(updates)), every GEMM-applied rotation regenerates
+    // their O(1) relative couplings and the relative test never passes (measured: 40 sweeps without convergence on the
+    // 5120 x 2560, rank-1536 site matrix of an MPO-applied state).  For such inputs -- the QR preconditioner reports
+    // dependent columns, or the iteration is still running after 14 sweeps -- pairs also count as orthogonal when
+    // |g_ij| <= ABS_FLOOR sigma_1 max(|x_i|, |x_j|): columns below the floor are left alone.  Singular values keep their
+    // absolute accuracy eps sigma_1 (the bar is 1e-12 sigma_1); only values below 1e-13 sigma_1 lose relative digits.
+    const double abs_c = -1.0;  // read from scale[2]
+    const double ABS_FLOOR = 1024.0 * 1.1102230246251565e-16;
+    bool floor_on = ctx->qr_last_dependent > 0;
     const int inner_sweeps = (nb == 2) ? 12 : 1;
     const int nact = (nb == 2) ? (int)std::min<int64_t>(64, (k + 1) / 2 * 2) : 64;
     col_norm_kernel<<<(st->np + 7) / 8, 256, 0, ctx->stream>>>(st->Z, st->ldz, st->mp, st->np, st->sigma_dev);
     max_reduce_kernel<<<1, 256, 0, ctx->stream>>>(st->sigma_dev, st->np, scale);
     ctx->launches += 2;
+    if (floor_on) {
+        set_double_kernel<<<1, 1, 0, ctx->stream>>>(scale + 2, ABS_FLOOR);
+        ctx->launches++;
+    }
     // mixed-precision Gram (see jacobi_gram32_kernel): sweep 0 runs in FP64 and measures the couplings; while the
     // largest coupling of the previous sweep is above LOWP_TOL the cross Grams come from the FP32 shadow of X, which
     // the update kernel keeps in step.  Once below, the iteration is FP64 only for good.
@@ -1432,15 +1301,6 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
         }
         int32_t r = qb_narrow_c128(ctx, st->Z, st->Z32, st->ldz * st->np);
         if (r != QB200_OK) return fail(r);
-    }
-    const bool splane = update_splane() && update_3m() && nb > 2 && !shadow;
-    if (splane) {
-        if (cudaMallocAsync(&st->Zs, sizeof(double) * st->ldz * st->np, ctx->stream) != cudaSuccess) {
-            ctx->err = "svd: out of device memory";
-            return fail(QB200_E_CUDA);
-        }
-        splane_init_kernel<<<grid_cap(ctx, st->ldz * st->np, 256), 256, 0, ctx->stream>>>(st->Z, st->Zs, st->ldz * st->np);
-        ctx->launches++;
     }
     const int max_sweeps = 40;
     int sweep = 0;
@@ -1473,12 +1333,8 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
             }
             {
                 PhaseTimer pt(ctx, QB_PH_JUPDATE, 8.0 * npairs * (double)st->ldz * JP * JP);  // ldz = rows of X
-                if (splane)
-                    jacobi_update_splane_kernel<<<upd_ctas, UPD_THREADS, UPDS_SMEM, ctx->stream>>>(st->Z, st->Zs, st->ldz, nb, step, Wg,
-                                                                                                 flags, npairs, u_nchunk);
-                else
-                    (update_3m() ? jacobi_update_kernel<1> : jacobi_update_kernel<0>)<<<upd_ctas, UPD_THREADS, UPD_SMEM, ctx->stream>>>(
-                        st->Z, st->ldz, nb, step, Wg, flags, npairs, u_nchunk, shadow ? st->Z32 : nullptr);
+                (update_3m() ? jacobi_update_kernel<1> : jacobi_update_kernel<0>)<<<upd_ctas, UPD_THREADS, UPD_SMEM, ctx->stream>>>(
+                    st->Z, st->ldz, nb, step, Wg, flags, npairs, u_nchunk, shadow ? st->Z32 : nullptr);
             }
         }
         cudaMemcpyAsync(scale, scale + 1, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
@@ -1516,6 +1372,11 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
             fprintf(stderr, "[qb200 svd] %lld x %lld (jacobi on %lld^2, nb %d) sweep %d%s worst %.3e\n", (long long)m,
                     (long long)n, (long long)k, nb, sweep, lowp ? " (tf32 gram)" : "", worst);
         if (!(worst > conv_tol)) converged = true;
+        if (!converged && !floor_on && sweep >= 13) {  // numerically rank deficient after all: switch the floor on
+            floor_on = true;
+            set_double_kernel<<<1, 1, 0, ctx->stream>>>(scale + 2, ABS_FLOOR);
+            ctx->launches++;
+        }
         if (shadow) {
             lowp = worst > LOWP_TOL;
             if (!lowp) shadow = false;  // quadratic phase ahead: FP64 Gram from here on, the shadow is no longer kept
@@ -1564,6 +1425,34 @@ int32_t qb_svd_emit(qb200_ctx* ctx, SvdState* st, int64_t kept, c128* U, int64_t
     const c128* X = st->Z;
     const c128 ONE = make_double2(1.0, 0.0), ZERO = make_double2(0.0, 0.0);
     Workspace ws(ctx);
+    // Exactly zero singular values (zero columns of X: trailing dependent columns, zero input): their X-side vectors are
+    // zero columns, not unit vectors.  Complete them to an orthonormal set with K4 (robust_panel replaces dependent
+    // columns by new orthogonal directions) and emit from the completed factor instead of X.
+    const c128* Xsrc = X;
+    int64_t xld = st->ldz;
+    const int* xperm = st->perm_dev;
+    int xnorm = 1;
+    if (st->sigma_sorted[kept - 1] == 0.0) {
+        c128* Xn = ws.get<c128>((size_t)(k * kept));
+        c128* Qx = ws.get<c128>((size_t)(k * kept));
+        c128* Rx = ws.get<c128>((size_t)(kept * kept));
+        int* ident = ws.get<int>((size_t)kept);
+        if (!Xn || !Qx || !Rx || !ident) QB_FAIL(ctx, QB200_E_CUDA, "svd: workspace allocation failed");
+        svd_emit_kernel<<<grid_cap(ctx, k * kept, 256), 256, 0, ctx->stream>>>(X, st->ldz, k, kept, st->perm_dev, st->sigma_dev,
+                                                                               1, 0, 0, nullptr, Xn, k, nullptr, 0, 1);
+        QB_LAUNCH_CHECK(ctx);
+        QB_TRY(qb_qr_matrix(ctx, k, kept, Xn, k, Qx, k, Rx, kept, 2));
+        fix_phase_kernel<<<grid_cap(ctx, k * kept, 256), 256, 0, ctx->stream>>>(Qx, k, kept, Rx, kept, Xn);
+        QB_LAUNCH_CHECK(ctx);
+        std::vector<int> id((size_t)kept);
+        std::iota(id.begin(), id.end(), 0);
+        QB_CUDA(ctx, cudaMemcpyAsync(ident, id.data(), sizeof(int) * kept, cudaMemcpyHostToDevice, ctx->stream));
+        QB_CUDA(ctx, qb_stream_sync(ctx));
+        Xsrc = Xn;
+        xld = k;
+        xperm = ident;
+        xnorm = 0;
+    }
     // Neither the rotations nor Q were kept.  With B0 = B P = Q R and R^H = Xn S Vs^H (Xn orthonormal):
     // B0 Xn = Q R Xn = Q Vs S, so the "Q side" factor is Y = B0 Xn S^-1 -- ONE GEMM with the (sorted) input matrix.
     // Column j of Y carries a relative error ~ eps sigma_1 / sigma_j: harmless (norm-wise backward stable), but it
@@ -1574,7 +1463,7 @@ int32_t qb_svd_emit(qb200_ctx* ctx, SvdState* st, int64_t kept, c128* U, int64_t
         double* isg = ws.get<double>((size_t)kept);
         if (!Xsel || !isg) QB_FAIL(ctx, QB200_E_CUDA, "svd: workspace allocation failed");
         svd_emit_kernel<<<grid_cap(ctx, k * kept, 256), 256, 0, ctx->stream>>>(
-            X, st->ldz, k, kept, st->perm_dev, st->sigma_dev, 1, 0, 0, nullptr, Xsel, k, nullptr, 0, 1);
+            Xsrc, xld, k, kept, xperm, st->sigma_dev, xnorm, 0, 0, nullptr, Xsel, k, nullptr, 0, 1);
         QB_LAUNCH_CHECK(ctx);
         svd_emit_sigma_kernel<<<(unsigned)((kept + 255) / 256), 256, 0, ctx->stream>>>(st->sigma_dev, st->perm_dev, kept,
                                                                                       -1.0, isg);
@@ -1608,7 +1497,7 @@ int32_t qb_svd_emit(qb200_ctx* ctx, SvdState* st, int64_t kept, c128* U, int64_t
         } else {  // U = P Xn
             if (ldu != st->m && uinv) QB_FAIL(ctx, QB200_E_UNSUPPORTED, "svd: strided U with fused scaling");
             svd_emit_kernel<<<grid_cap(ctx, st->m * kept, 256), 256, 0, ctx->stream>>>(
-                X, st->ldz, st->m, kept, st->perm_dev, st->sigma_dev, 1, 0, 0, st->colperm_dev, U, ldu, uinv, uinv_len,
+                Xsrc, xld, st->m, kept, xperm, st->sigma_dev, xnorm, 0, 0, st->colperm_dev, U, ldu, uinv, uinv_len,
                 1);
             QB_LAUNCH_CHECK(ctx);
         }
@@ -1630,7 +1519,7 @@ int32_t qb_svd_emit(qb200_ctx* ctx, SvdState* st, int64_t kept, c128* U, int64_t
             }
         } else {  // V = P Xn
             svd_emit_kernel<<<grid_cap(ctx, st->n * kept, 256), 256, 0, ctx->stream>>>(
-                X, st->ldz, st->n, kept, st->perm_dev, st->sigma_dev, 1, 1, vmode, st->colperm_dev, V, ldv, vinv, 0,
+                Xsrc, xld, st->n, kept, xperm, st->sigma_dev, xnorm, 1, vmode, st->colperm_dev, V, ldv, vinv, 0,
                 vinv ? vinv_div : 1);
             QB_LAUNCH_CHECK(ctx);
         }

@@ -337,3 +337,61 @@ def test_tcgen05_tf32_building_block_is_exact(qb, ctx):
     err, tf128, tf256 = ctx.tcgen05_tf32_probe()
     assert err == 0.0
     assert tf128 > 500.0 and tf256 > 500.0, (tf128, tf256)
+
+
+def _structured_rank_deficient(rng, m, n, r):
+    """Rank r with EXACT zeros and exact repetitions (the structure of an MPO-applied site tensor): what is left of a
+    dependent column after projecting out the others is rounding noise that lies INSIDE the span already covered --
+    the case in which normalising the noise (Gram-Schmidt, round 1) gave Q columns that were not orthogonal."""
+    a = np.zeros((m, n), dtype=complex)
+    half = m // 2
+    base = crand(rng, half, r)
+    a[:half, :r] = base
+    for j in range(r, n):                      # every further column: an exact copy or an exact combination, rows below `half` all zero
+        a[:half, j] = base[:, j % r] if j % 3 else base[:, j % r] + 2.0 * base[:, (j + 1) % r]
+    return a
+
+
+@pytest.mark.parametrize("m,n,r", [(1280, 640, 200), (640, 640, 256), (200, 120, 30), (2560, 1280, 700)])
+def test_qr_of_structured_rank_deficient_input_is_orthonormal(qb, ctx, m, n, r):
+    rng = np.random.default_rng(21)
+    a = _structured_rank_deficient(rng, m, n, r)
+    q, rr = qb.qr(ctx.array(np.asfortranarray(a)), (0, 1), 1)
+    q, rr = q.to_host(), rr.to_host()
+    k = min(m, n)
+    assert np.abs(q.conj().T @ q - np.eye(k)).max() < 1e-12          # orthonormal whatever the rank, as LAPACK's Q
+    assert np.linalg.norm(q @ rr - a) <= 1e-12 * np.linalg.norm(a)
+    assert np.abs(np.tril(rr[:, :k], -1)).max() < 1e-12 * np.abs(a).max()
+
+
+@pytest.mark.parametrize("m,n,r", [(1280, 640, 200), (640, 1280, 256), (200, 120, 30)])
+def test_svd_of_structured_rank_deficient_input(qb, ctx, m, n, r):
+    rng = np.random.default_rng(22)
+    a = _structured_rank_deficient(rng, max(m, n), min(m, n), r)
+    if m < n:
+        a = a.conj().T.copy()
+    u, s, vc, kept, dw = qb.svd(ctx.array(np.asfortranarray(a)), (0, 1), 1)
+    u, s, vc = u.to_host(), s.to_host(), vc.to_host()
+    k = min(m, n)
+    s_ref = sla.svd(a, compute_uv=False, lapack_driver="gesdd")
+    assert kept == k and np.abs(s - s_ref).max() <= 1e-12 * s_ref[0]
+    assert np.abs(u.conj().T @ u - np.eye(k)).max() < 1e-11          # null-space columns included
+    assert np.abs(vc.T @ vc.conj() - np.eye(k)).max() < 1e-11
+    assert np.linalg.norm((u * s) @ vc.T - a) <= 1e-12 * np.linalg.norm(a)
+    # with the truncate! rule's absolute threshold the kept count is the rank
+    _, s2, _, kept2, _ = qb.svd(ctx.array(np.asfortranarray(a)), (0, 1), 1, threshold=1e-10 * s_ref[0])
+    assert kept2 == r
+
+
+def test_canonize_of_an_mpo_applied_state_keeps_the_state(qb, ctx):
+    """H|psi> has structurally rank-deficient site tensors (bond chi*D, rank < chi*D): canonize! must leave the state and
+    its norm alone (it changed the norm by 23 % at n = 20, chi = 512 before the QR completed dependent columns)."""
+    n, chi = 14, 128
+    arrays = qb.rand_mps_arrays(np.random.default_rng(1003), n, chi)
+    g = qb.B200MPS(ctx, arrays).apply_mpo(qb.heisenberg_mpo_arrays(n))
+    n0 = g.norm()
+    c = g.copy().canonize()
+    assert abs(c.norm() - n0) <= 1e-10 * n0
+    assert abs(c.overlap(g) - n0 ** 2) <= 1e-10 * n0 ** 2
+    for lam in c.lambdas():
+        assert abs(np.sum(lam ** 2) - n0 ** 2) <= 1e-10 * n0 ** 2
