@@ -257,22 +257,29 @@ static int32_t tsqr_panel(qb200_ctx* ctx, int64_t m, int w, c128* P, int64_t ld,
     return QB200_OK;
 }
 
-// Relative size below which what is left of a column after the projection against the earlier columns is rounding noise:
-// the projection subtracts ~j0 terms, each carrying eps of the column's norm.
+// Relative size below which what is left of a column after the projection against the earlier columns is certainly
+// rounding noise (the projection subtracts ~j0 terms, each carrying eps of the column's norm).  Used for the first panel
+// (nothing to re-project against) and as a backstop; the decisive test is the re-projection below.
 static inline double dep_tol(int64_t j0, int w) { return 16.0 * 1.1102230246251565e-16 * std::sqrt((double)(j0 + w)); }
+// A column that lost more than this fraction of its norm in the projection sends its panel to robust_panel
+constexpr double CAREFUL_LOSS = 1e-6;
 
 // Panel factorisation that is safe for rank-deficient input.  A column that is numerically dependent on the earlier
-// columns is pure rounding noise once those have been projected out; normalising it (what any Gram-Schmidt or
-// Householder panel step does) yields a "completion" vector that still lies in the span of the earlier columns -- for
-// structurally rank-deficient tensors (an MPO-applied state: exact zeros, exact repetitions) entirely so -- and a second
-// Gram-Schmidt pass cannot repair that: Q comes out with non-orthogonal columns and every later column that was
-// projected on it is damaged (measured on B200: |Q^H Q - I| = 0.23 on a 5120 x 2560 matrix of rank 1536, and
-// canonize! of H|psi> changed the norm of the state by 23 %).  So: factor, look at diag(R); every column whose
-// diagonal entry is below dep_tol x (its norm at the start of the pass) is replaced by a pseudo-random vector made
-// orthogonal (twice) to ALL earlier columns, the panel is factored again, and the column of R is zeroed (the dependent
-// column has no component along its completion vector).  This is what LAPACK's Householder QR delivers implicitly:
-// orthonormal Q whatever the rank.  `save` holds the panel as it was before the factorisation (m x w, ld = m) and is
-// updated with the replacements; Qall / ldq / j0: the columns [0, j0) of Q are the earlier, final columns.
+// columns is rounding noise once those have been projected out; normalising it (what any Gram-Schmidt or Householder
+// panel step does) yields a "completion" vector that still lies in the span of the earlier columns -- for structurally
+// rank-deficient tensors (an MPO-applied state: exact zeros, exact repetitions) entirely so -- and a second Gram-Schmidt
+// pass cannot repair that: Q comes out with non-orthogonal columns and every later column projected on it is damaged
+// (measured on B200: |Q^H Q - I| = 0.23 on a 5120 x 2560 matrix of rank 1536; canonize! of H|psi> changed the norm of
+// the state by 23 %).  The test for "this Q column is garbage" must not depend on an eps-sized threshold (the input of a
+// sweep carries the rounding of the previous sites, so what is left of a dependent column is not just projection noise):
+// it is Kahan's "twice is enough" criterion.  Factor the panel, project its Q once more on the earlier columns and look at
+// what survives: a healthy column keeps its unit norm, a garbage column collapses.  Columns whose norm falls below 1/2
+// are replaced by a pseudo-random vector made orthogonal (twice) to ALL earlier columns and the panel is factored again;
+// their column of R keeps only the components of the original column along the panel's other columns (nothing along
+// the completion vector).  When no column collapses the re-projection is folded into R (R[0:j0, panel] += C2 Rpp) and
+// the panel is re-orthonormalised -- a block Gram-Schmidt step with immediate re-orthogonalisation.  This is what
+// LAPACK's Householder QR delivers implicitly: orthonormal Q whatever the rank.  `save` holds the panel as it was before
+// the factorisation (m x w, ld = m) and is updated with the replacements; Rtop = R(0, j0): the rows of R above the panel.
 static int32_t robust_panel(qb200_ctx* ctx, int64_t m, int w, c128* P, int64_t ld, c128* Rpp, int64_t ldr, const c128* Qall,
                             int64_t ldq, int64_t j0, const double* before2_dev, c128* save) {
     const c128 one = make_double2(1.0, 0.0), zero = make_double2(0.0, 0.0), mone = make_double2(-1.0, 0.0);
@@ -280,60 +287,117 @@ static int32_t robust_panel(qb200_ctx* ctx, int64_t m, int w, c128* P, int64_t l
     Workspace ws(ctx);
     c128* coef = nullptr;
     c128* orig = nullptr;  // the dependent columns as they were (their components along the panel's other columns go to R)
+    c128* xd = nullptr;    // their replacements, gathered (m x #dependent)
+    c128* C2 = (j0 > 0) ? ws.get<c128>((size_t)(j0 * w)) : nullptr;
+    c128* R2 = ws.get<c128>((size_t)(w * w));
+    c128* Rt = ws.get<c128>((size_t)(w * w));
+    double* nu2 = ws.get<double>((size_t)w);
+    if ((j0 > 0 && !C2) || !R2 || !Rt || !nu2) QB_FAIL(ctx, QB200_E_CUDA, "qr: workspace allocation failed");
+    c128* Rtop = Rpp - j0;  // same columns of R, rows 0 .. j0-1
     const double tol = dep_tol(j0, w);
-    for (int attempt = 0; attempt < 4; ++attempt) {
+    // every attempt that does not succeed enlarges the set of replaced columns, so w + 1 attempts always suffice
+    for (int attempt = 0; attempt <= w; ++attempt) {
         QB_TRY(tsqr_panel(ctx, m, w, P, ld, Rpp, ldr));
-        // diag(R) of the panel and the squared norms the columns had at the start of the pass -> host (one sync)
+        for (int c = 0; c < w; ++c)  // a completion vector carries nothing of the original column
+            if (replaced[c]) QB_CUDA(ctx, cudaMemsetAsync(Rpp + (int64_t)c * ldr, 0, sizeof(c128) * w, ctx->stream));
         double* host = ctx->scratch_host;
+        if (attempt == 0) {  // the common case: no column lost more than CAREFUL_LOSS of its norm -> the panel is healthy
+            QB_CUDA(ctx, cudaMemcpy2DAsync(host, sizeof(c128), Rpp, (size_t)(ldr + 1) * sizeof(c128), sizeof(c128), (size_t)w,
+                                           cudaMemcpyDeviceToHost, ctx->stream));
+            QB_CUDA(ctx, cudaMemcpyAsync(host + 2 * w, before2_dev, sizeof(double) * w, cudaMemcpyDeviceToHost, ctx->stream));
+            QB_CUDA(ctx, qb_stream_sync(ctx));
+            bool healthy = true;
+            for (int c = 0; c < w; ++c) {
+                const double d2 = host[2 * c] * host[2 * c] + host[2 * c + 1] * host[2 * c + 1];
+                if (!(d2 > CAREFUL_LOSS * CAREFUL_LOSS * host[2 * w + c])) healthy = false;
+            }
+            if (healthy) return QB200_OK;
+        }
+        if (j0 > 0) {  // what survives of the panel's Q when the earlier columns are projected out once more
+            QB_TRY(qb_gemm(ctx, 2, 0, j0, w, m, one, Qall, ldq, P, ld, zero, C2, j0));
+            QB_TRY(qb_gemm(ctx, 0, 0, m, w, j0, mone, Qall, ldq, C2, j0, one, P, ld));
+            colnorm2_kernel<<<(unsigned)((w + 7) / 8), 256, 0, ctx->stream>>>(P, ld, m, w, nu2);
+            QB_LAUNCH_CHECK(ctx);
+        }
+        // diag(R) of the panel, the squared norms at the start of the pass and the survival norms -> host (one sync)
         QB_CUDA(ctx, cudaMemcpy2DAsync(host, sizeof(c128), Rpp, (size_t)(ldr + 1) * sizeof(c128), sizeof(c128), (size_t)w,
                                        cudaMemcpyDeviceToHost, ctx->stream));
         QB_CUDA(ctx, cudaMemcpyAsync(host + 2 * w, before2_dev, sizeof(double) * w, cudaMemcpyDeviceToHost, ctx->stream));
+        if (j0 > 0) QB_CUDA(ctx, cudaMemcpyAsync(host + 3 * w, nu2, sizeof(double) * w, cudaMemcpyDeviceToHost, ctx->stream));
         QB_CUDA(ctx, qb_stream_sync(ctx));
         std::vector<int> dep;
         for (int c = 0; c < w; ++c) {
             if (replaced[c]) continue;
             const double d2 = host[2 * c] * host[2 * c] + host[2 * c + 1] * host[2 * c + 1];
-            if (d2 <= tol * tol * host[2 * w + c]) dep.push_back(c);
+            const bool noise = d2 <= tol * tol * host[2 * w + c];
+            const bool collapsed = j0 > 0 && host[3 * w + c] < 0.25;
+            if (noise || collapsed) dep.push_back(c);
         }
-        if (dep.empty()) break;
-        if (attempt == 3) QB_FAIL(ctx, QB200_E_NOCONVERGE, "qr: could not complete a rank-deficient panel");
+        if (dep.empty()) {
+            if (j0 > 0) {  // fold the re-projection into R and re-orthonormalise the panel: Q_p = Q' R2, Rpp <- R2 Rpp
+                QB_TRY(qb_gemm(ctx, 0, 0, j0, w, w, one, C2, j0, Rpp, ldr, one, Rtop, ldr));
+                QB_CUDA(ctx, cudaMemsetAsync(R2, 0, sizeof(c128) * (size_t)(w * w), ctx->stream));  // tsqr_panel writes the upper blocks only
+                QB_TRY(tsqr_panel(ctx, m, w, P, ld, R2, w));
+                QB_TRY(qb_gemm(ctx, 0, 0, w, w, w, one, R2, w, Rpp, ldr, zero, Rt, w));
+                QB_TRY(qb_copy_matrix(ctx, w, w, Rt, w, Rpp, ldr, 0));
+            }
+            break;
+        }
+        if (attempt == w) QB_FAIL(ctx, QB200_E_NOCONVERGE, "qr: could not complete a rank-deficient panel");
         if (!orig) orig = ws.get<c128>((size_t)(m * w));
         if (!orig) QB_FAIL(ctx, QB200_E_CUDA, "qr: workspace allocation failed");
-        for (int c : dep) {
-            c128* x = save + (int64_t)c * m;
-            QB_CUDA(ctx, cudaMemcpyAsync(orig + (int64_t)c * m, x, sizeof(c128) * (size_t)m, cudaMemcpyDeviceToDevice, ctx->stream));
+        // all dependent columns of the panel at once: random vectors, projected twice on the earlier columns (two GEMM
+        // pairs per attempt, not per column)
+        if (!xd) xd = ws.get<c128>((size_t)(m * w));
+        if (!xd) QB_FAIL(ctx, QB200_E_CUDA, "qr: workspace allocation failed");
+        const int nd = (int)dep.size();
+        for (int i = 0; i < nd; ++i) {
+            const int c = dep[i];
+            QB_CUDA(ctx, cudaMemcpyAsync(orig + (int64_t)c * m, save + (int64_t)c * m, sizeof(c128) * (size_t)m,
+                                         cudaMemcpyDeviceToDevice, ctx->stream));
             random_column_kernel<<<(unsigned)std::min<int64_t>((m + 255) / 256, 1024), 256, 0, ctx->stream>>>(
-                x, m, 0x5EEDull + 1315423911ull * (uint64_t)(j0 + c));
+                xd + (int64_t)i * m, m, 0x5EEDull + 1315423911ull * (uint64_t)(j0 + c));
             QB_LAUNCH_CHECK(ctx);
-            if (j0 > 0) {
-                if (!coef) coef = ws.get<c128>((size_t)j0);
-                if (!coef) QB_FAIL(ctx, QB200_E_CUDA, "qr: workspace allocation failed");
-                for (int rep = 0; rep < 2; ++rep) {
-                    QB_TRY(qb_gemm(ctx, 2, 0, j0, 1, m, one, Qall, ldq, x, m, zero, coef, j0));
-                    QB_TRY(qb_gemm(ctx, 0, 0, m, 1, j0, mone, Qall, ldq, coef, j0, one, x, m));
-                }
-            }
             replaced[c] = 1;
         }
+        if (j0 > 0) {
+            if (!coef) coef = ws.get<c128>((size_t)(j0 * w));
+            if (!coef) QB_FAIL(ctx, QB200_E_CUDA, "qr: workspace allocation failed");
+            for (int rep = 0; rep < 2; ++rep) {
+                QB_TRY(qb_gemm(ctx, 2, 0, j0, nd, m, one, Qall, ldq, xd, m, zero, coef, j0));
+                QB_TRY(qb_gemm(ctx, 0, 0, m, nd, j0, mone, Qall, ldq, coef, j0, one, xd, m));
+            }
+        }
+        for (int i = 0; i < nd; ++i)
+            QB_CUDA(ctx, cudaMemcpyAsync(save + (int64_t)dep[i] * m, xd + (int64_t)i * m, sizeof(c128) * (size_t)m,
+                                         cudaMemcpyDeviceToDevice, ctx->stream));
         QB_TRY(qb_copy_matrix(ctx, m, w, save, m, P, ld, 0));
     }
     // column c of the panel's R block: the components of the ORIGINAL column along the panel's earlier columns (a
     // dependency inside the panel), nothing on or below the diagonal (no component along its completion vector)
-    for (int c = 0; c < w; ++c)
-        if (replaced[c]) {
-            ctx->qr_last_dependent++;
-            QB_TRY(qb_gemm(ctx, 2, 0, w, 1, m, one, P, ld, orig + (int64_t)c * m, m, zero, Rpp + (int64_t)c * ldr, ldr));
-            QB_CUDA(ctx, cudaMemsetAsync(Rpp + (int64_t)c * ldr + c, 0, sizeof(c128) * (size_t)(w - c), ctx->stream));
-        }
+    bool any = false;
+    for (int c = 0; c < w; ++c) any = any || replaced[c];
+    if (any) {
+        // one GEMM for all of them (columns of `orig` that were never saved hold junk; their results are not used)
+        QB_TRY(qb_gemm(ctx, 2, 0, w, w, m, one, P, ld, orig, m, zero, Rt, w));
+        for (int c = 0; c < w; ++c)
+            if (replaced[c]) {
+                ctx->qr_last_dependent++;
+                QB_CUDA(ctx, cudaMemsetAsync(Rpp + (int64_t)c * ldr, 0, sizeof(c128) * (size_t)w, ctx->stream));
+                if (c > 0)
+                    QB_CUDA(ctx, cudaMemcpyAsync(Rpp + (int64_t)c * ldr, Rt + (int64_t)c * w, sizeof(c128) * (size_t)c,
+                                                 cudaMemcpyDeviceToDevice, ctx->stream));
+            }
+    }
     return QB200_OK;
 }
 
 // one right-looking block Gram-Schmidt pass: Q (m x k, in place) = Q' R, R k x k upper triangular (zeroed first).
 // Panels of 64 columns.  Fast path (m % 64 == 0, full panels): Cholesky-QR2 on the panel with the Jacobi gram /
 // update kernels (Gram 64 x 64 -> scaled Cholesky in shared memory -> P <- P R^-1, twice); when a scaled pivot says
-// the panel is too ill conditioned for a Gram-based step, or a column has lost (numerically) all of its norm to the
-// earlier columns, the saved panel is restored and factorised by robust_panel (Householder TSQR + completion of
-// dependent columns) instead.  Trailing updates: C = Q_p^H T (split-K GEMM), T -= Q_p C.
+// the panel is too ill conditioned for a Gram-based step, or a column has lost more than CAREFUL_LOSS of its norm to the
+// earlier columns, the saved panel is restored and factorised by robust_panel (Householder TSQR, re-projection,
+// completion of dependent columns) instead.  Trailing updates: C = Q_p^H T (split-K GEMM), T -= Q_p C.
 static int32_t bgs_pass(qb200_ctx* ctx, int64_t m, int64_t k, c128* Q, int64_t ldq, c128* R, int64_t ldr) {
     const c128 one = make_double2(1.0, 0.0), zero = make_double2(0.0, 0.0), mone = make_double2(-1.0, 0.0);
     zero_kernel<<<(unsigned)std::min<int64_t>((k * k + 255) / 256, 4096), 256, 0, ctx->stream>>>(R, k, k, ldr);
@@ -370,7 +434,7 @@ static int32_t bgs_pass(qb200_ctx* ctx, int64_t m, int64_t k, c128* Q, int64_t l
             if (fast_ok && w == PW) {
                 QB_CUDA(ctx, cudaMemsetAsync(flags, 0, 2 * sizeof(int), ctx->stream));
                 QB_TRY(qb_cholqr_panel_step(ctx, P, ldq, m, R1, 64, Gpart, Wbuf, flags, flags + 1, before2 + j0,
-                                            dep_tol(j0, w)));
+                                            CAREFUL_LOSS));
                 QB_TRY(qb_cholqr_panel_step(ctx, P, ldq, m, R2, 64, Gpart, Wbuf, flags, flags + 1, nullptr, 0.0));
                 QB_CUDA(ctx, cudaMemcpyAsync(ctx->scratch_host, flags + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
                 QB_CUDA(ctx, qb_stream_sync(ctx));
