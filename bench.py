@@ -33,6 +33,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "TEBD sweeps/s (n=64, chi=1024, ComplexF64)"
 SIG_TOL = 1e-12
+POOL_DMMA_PEAK_TFLOPS = 37.06   # best FP64 DMMA issue rate measured on this pool's B200s (profiles/r1b_peaks.txt)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -351,8 +352,11 @@ def run_b200(args):
     ms_per_step = ms / args.steps
     value = world * 1e3 / ms_per_step
     peak_after, peak_after_runs = median_peak(ctx)
-    peak_tf = max(peak_before, peak_after)
-    peak_stable = abs(peak_before - peak_after) <= 0.05 * peak_tf
+    # The micro-benchmark under-reads on some boxes of the pool (29.7 against 37.0 TFLOP/s at identical clocks, while the
+    # sweep itself runs at the same speed: BENCH_r01 vs SCALE_r01, gpurun_out/r2multi): the denominator is never taken
+    # below the pool's best measured value, so that a slow reading cannot inflate the fraction.
+    peak_tf = max(peak_before, peak_after, POOL_DMMA_PEAK_TFLOPS)
+    peak_stable = abs(peak_before - peak_after) <= 0.05 * max(peak_before, peak_after)
     if not peak_stable:
         print(f"[bench] WARNING: DMMA peak micro-benchmark unstable: {peak_before:.2f} before vs {peak_after:.2f} "
               f"TFLOP/s after the timed region", file=sys.stderr, flush=True)
@@ -433,7 +437,9 @@ def run_b200(args):
                              "per bond on the true bond profile = %.2f TFLOP) / measured ms_per_step of the timed region; "
                              "independent of the Jacobi sweep count actually executed" % alg_tf,
             "peak_source": "FP64 DMMA m8n8k4 issue-bound micro-benchmark of libqrochet_b200_diag.so, median of 5 runs "
-                           "before and after the timed region, larger of the two (MEASURED_PEAKS.json has no FP64 figure)",
+                           "before and after the timed region; the larger of the two and of the pool's best measured value "
+                           "(37.06 TFLOP/s, profiles/r1b_peaks.txt) so that a slow reading cannot inflate the fraction "
+                           "(MEASURED_PEAKS.json has no FP64 figure)",
             "peak_before_after": [peak_before, peak_after], "peak_runs": [peak_before_runs, peak_after_runs],
             "peak_stable": bool(peak_stable),
             "traffic": (traffic or {}).get("jacobi_update_kernel", {}).get("dram_bytes_per_launch") if traffic else None,
@@ -498,6 +504,9 @@ def run_b200(args):
                 line["sliced_contraction_round1_planner"], _ = run_sliced(ctx, qb, rank, world, peak_tf, barrier,
                                                                           max_over_ranks, reps=1, optimizer=0,
                                                                           check_against=amp_ref)
+                line["sliced_contraction_time_model_planner"], _ = run_sliced(ctx, qb, rank, world, peak_tf, barrier,
+                                                                              max_over_ranks, optimizer=2,
+                                                                              check_against=amp_ref)
         except Exception as e:  # never lose the headline line to the extra measurement
             line["sliced_contraction"] = {"error": str(e)[:300]}
     if not args.no_expect:
@@ -560,8 +569,10 @@ def run_sliced(ctx, qb, rank, world, peak_tf, barrier, max_over_ranks, qubits=40
            "ms": best, "time_to_amplitude_ms": best, "scaling": "strong",
            "config": {"workload": f"{qubits}-qubit depth-{depth} random FSim circuit amplitude <b|U|0..0>, random product "
                                   f"bra (seed 4000), slice target 2^{int(np.log2(target))} elements (BASELINE configs[4])",
-                      "planner": "round 2: ContractSimplification + multi-start greedy + sub-tree reconfiguration"
-                                 if optimizer else "round 1: one greedy tree",
+                      "planner": {0: "round 1: one greedy tree",
+                                  1: "round 2: ContractSimplification + multi-start greedy + sub-tree reconfiguration "
+                                     "(objective: flops)",
+                                  2: "round 2, objective = time model max(macs, 10 x elements moved) per node"}[optimizer],
                       "plan_s": plan_s, "nslices": sc.nslices, "cut_indices": len(sc.sliced_modes),
                       "flops_per_slice": sc.flops_per_slice, "flops_slice_invariant": sc.flops_invariant,
                       "total_flops": sc.nslices * sc.flops_per_slice + sc.flops_invariant,

@@ -161,6 +161,15 @@ class _Net:
         return self.size(inv, cut)
 
 
+def _node_cost(objective, macs, elems):
+    """0: complex multiply-adds; 1: the executor's time model on B200 in multiply-add units, max(macs, 10 x elements
+    moved) (tn_plan.cu: node_cost)."""
+    if objective == 0:
+        return macs
+    bw = (1 << 110) if elems > (1 << 110) // 10 else elems * 10
+    return max(macs, bw)
+
+
 def _connected(a, b):
     return any(x in b["modes"] for x in a["modes"])
 
@@ -211,7 +220,7 @@ def _greedy(net, nodes, live, alpha2):
         live.append(len(nodes) - 1)
 
 
-def _reconfigure_at(net, nodes, i):
+def _reconfigure_at(net, nodes, i, objective=0):
     """One sub-tree reconfiguration at internal node i; True when the sub-tree was replaced by a cheaper one."""
     fr = [nodes[i]["left"], nodes[i]["right"]]
     while len(fr) < PLAN_K:
@@ -233,7 +242,9 @@ def _reconfigure_at(net, nodes, i):
         j = stack.pop()
         if j in frontier:
             continue
-        old_fl += net.flops(nodes, j)
+        old_fl += _node_cost(objective, net.flops(nodes, j),
+                             net.size(nodes[nodes[j]["left"]]["modes"]) + net.size(nodes[nodes[j]["right"]]["modes"])
+                             + net.size(nodes[j]["modes"]))
         old_mx = max(old_mx, net.size(nodes[j]["modes"]))
         stack += [nodes[j]["left"], nodes[j]["right"]]
     full = (1 << K) - 1
@@ -257,7 +268,8 @@ def _reconfigure_at(net, nodes, i):
         while sub:
             if sub & low:
                 o = m ^ sub
-                fl = best[sub][0] + best[o][0] + net.size(modes[sub] | modes[o])
+                fl = best[sub][0] + best[o][0] + _node_cost(objective, net.size(modes[sub] | modes[o]),
+                                                            size[sub] + size[o] + size[m])
                 mx = max(best[sub][1], best[o][1], size[m])
                 if choice is None or (fl, mx) < (choice[0], choice[1]):
                     choice = (fl, mx, (sub, o))
@@ -283,7 +295,7 @@ def _reconfigure_at(net, nodes, i):
     return True
 
 
-def _reconfigure(net, nodes, root):
+def _reconfigure(net, nodes, root, objective=0):
     for _ in range(PLAN_ROUNDS):
         improved = False
         stack = [root]
@@ -291,7 +303,7 @@ def _reconfigure(net, nodes, root):
             i = stack.pop()
             if nodes[i]["left"] < 0:
                 continue
-            if _reconfigure_at(net, nodes, i):
+            if _reconfigure_at(net, nodes, i, objective):
                 improved = True
             stack += [nodes[i]["right"], nodes[i]["left"]]  # left sub-tree first
         if not improved:
@@ -347,27 +359,33 @@ def _findslices(net, nodes, max_elements):
     return cut
 
 
-def _sliced_cost(net, nodes, cut):
-    """(complex MACs per slice of the nodes that depend on a cut index, MACs of the slice-invariant nodes, #slices)."""
+def _sliced_cost(net, nodes, cut, objective=0):
+    """(complex MACs per slice of the nodes that depend on a cut index, MACs of the slice-invariant nodes, #slices,
+    objective cost per slice, objective cost of the invariant nodes)."""
     nleaves = len(net.leaf_modes)
     inv = [not any(x in cut for x in net.leaf_modes[i]) for i in range(nleaves)]
-    per_slice = once = 0
+    per_slice = once = obj_ps = obj_once = 0
     for i in range(nleaves, len(nodes)):
         inv.append(inv[nodes[i]["left"]] and inv[nodes[i]["right"]])
         f = net.flops(nodes, i, cut)
+        c = _node_cost(objective, f, net.size(nodes[nodes[i]["left"]]["modes"], cut)
+                       + net.size(nodes[nodes[i]["right"]]["modes"], cut) + net.size(nodes[i]["modes"], cut))
         if inv[i]:
             once += f
+            obj_once += c
         else:
             per_slice += f
+            obj_ps += c
     nsl = 1
     for x in cut:
         nsl = min(nsl * net.ext[x], 1 << 62)
-    return per_slice, once, nsl
+    return per_slice, once, nsl, obj_ps, obj_once
 
 
 def plan(modes, extents, max_elements, optimizer=1):
     """modes: list of tuples; extents: dict mode -> size.  optimizer 0: the round-1 rule (one greedy tree, α = 1, no
-    simplification, no local search); 1: the full planner above.  Returns dict(path, sliced, nodes, macs_per_slice,
+    simplification, no local search); 1: the full planner above minimising flops; 2: the same minimising the executor's
+    time model (_node_cost).  Returns dict(path, sliced, nodes, macs_per_slice,
     macs_invariant, nslices)."""
     net = _Net(modes, extents)
     nleaves = len(net.leaf_modes)
@@ -380,12 +398,13 @@ def plan(modes, extents, max_elements, optimizer=1):
                 _simplify(net, nodes, live)
             _greedy(net, nodes, live, alpha2)
             root = live[0]
+            objective = 1 if optimizer >= 2 else 0
             if optimizer:
-                _reconfigure(net, nodes, root)
+                _reconfigure(net, nodes, root, objective)
             tree, path = _compact(net, nodes, root)
             cut = _findslices(net, tree, max_elements)
-            per_slice, once, nsl = _sliced_cost(net, tree, cut)
-            total = min(per_slice * nsl + once, PLAN_CAP_TOTAL)
+            per_slice, once, nsl, obj_ps, obj_once = _sliced_cost(net, tree, cut, objective)
+            total = min(obj_ps * nsl + obj_once, PLAN_CAP_TOTAL)
             if best is None or total < best[0]:
                 best = (total, tree, path, cut, per_slice, once, nsl)
     _, tree, path, cut, per_slice, once, nsl = best

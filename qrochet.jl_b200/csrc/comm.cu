@@ -22,6 +22,8 @@ struct NcclApi {
     ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 
@@ -42,6 +44,8 @@ NcclApi* nccl() {
             api.Broadcast = (decltype(api.Broadcast))dlsym(api.lib, "ncclBroadcast");
             api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
             api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.lib, "ncclGetErrorString");
+            api.GroupStart = (decltype(api.GroupStart))dlsym(api.lib, "ncclGroupStart");
+            api.GroupEnd = (decltype(api.GroupEnd))dlsym(api.lib, "ncclGroupEnd");
         }
     }
     if (!api.lib || !api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy) return nullptr;
@@ -57,6 +61,15 @@ int32_t qb_comm_broadcast_bytes(qb200_ctx* ctx, void* dev, size_t bytes, int roo
     if (!dev) QB_FAIL(ctx, QB200_E_INVALID, "broadcast: null buffer");
     ncclResult_t r = a->Broadcast(dev, dev, bytes, ncclUint8, root, (ncclComm_t)ctx->nccl_comm, ctx->stream);
     if (r != 0) QB_FAIL(ctx, QB200_E_COMM, "ncclBroadcast: %s", a->GetErrorString ? a->GetErrorString(r) : "error");
+    return QB200_OK;
+}
+
+// ncclGroupStart / ncclGroupEnd around a series of broadcasts: one fused launch instead of one per tensor
+int32_t qb_comm_group(qb200_ctx* ctx, bool begin) {
+    NcclApi* a = nccl();
+    if (!a || !a->GroupStart || !a->GroupEnd) return QB200_OK;  // not available: the calls simply run one by one
+    ncclResult_t r = begin ? a->GroupStart() : a->GroupEnd();
+    if (r != 0) QB_FAIL(ctx, QB200_E_COMM, "ncclGroup%s: %s", begin ? "Start" : "End", a->GetErrorString ? a->GetErrorString(r) : "error");
     return QB200_OK;
 }
 

@@ -203,7 +203,9 @@ int32_t qb_gemm(qb200_ctx* ctx, int opA, int opB, int64_t M, int64_t N, int64_t 
 
 // thin QR of a column-major m x n matrix (ld = lda); Q: m x k (ldq), R: k x n (ldr), k = min(m,n).
 // A is not modified.
-// passes = 2: Q orthonormal to machine precision; passes = 1: only R is trustworthy (SVD preconditioner)
+// passes = 2: Q orthonormal to machine precision; passes = 1: only R is trustworthy; passes = QB_QR_R_ONLY: the caller
+// uses R alone (SVD preconditioner) -- R to machine precision, Q as the first pass left it when the refinement applies
+constexpr int QB_QR_R_ONLY = -1;
 int32_t qb_qr_matrix(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64_t lda, c128* Q, int64_t ldq,
                      c128* R, int64_t ldr, int passes = 2);
 
@@ -241,6 +243,7 @@ int32_t qb_matricize(qb200_ctx* ctx, const qb200_tensor* A, const int32_t* order
 
 // NCCL broadcast of raw device bytes from `root` (comm.cu); the communicator must have been set up by qb200_comm_init
 int32_t qb_comm_broadcast_bytes(qb200_ctx* ctx, void* dev, size_t bytes, int root);
+int32_t qb_comm_group(qb200_ctx* ctx, bool begin);  // ncclGroupStart / ncclGroupEnd
 
 // elementwise helpers (elementwise.cu)
 int32_t qb_scale_mode_raw(qb200_ctx* ctx, const c128* in, c128* out, int64_t inner, int64_t d, int64_t outer,

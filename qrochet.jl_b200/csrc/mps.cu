@@ -1255,11 +1255,15 @@ int32_t qb200_mps_broadcast(qb200_ctx* ctx, qb200_mps** inout, int32_t root) {
             }
         }
     }
-    int32_t r = QB200_OK;
+    int32_t r = qb_comm_group(ctx, true);  // all tensors of the chain in ONE fused NCCL launch
     for (int s = 0; s < m->n && r == QB200_OK; ++s) {
         r = qb_comm_broadcast_bytes(ctx, m->site[s], site_esz(m) * (size_t)(m->chil[s] * m->p[s] * m->chir[s]), root);
         if (r == QB200_OK && s < m->n - 1 && m->lam[s])
             r = qb_comm_broadcast_bytes(ctx, m->lam[s], sizeof(double) * m->lam_host[s].size(), root);
+    }
+    {
+        int32_t r2 = qb_comm_group(ctx, false);
+        if (r == QB200_OK) r = r2;
     }
     if (r == QB200_OK && !sender)  // host mirrors of the Schmidt vectors (truncate! reads them element-wise on the host)
         for (int s = 0; s < m->n - 1 && r == QB200_OK; ++s)

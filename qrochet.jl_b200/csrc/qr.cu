@@ -212,6 +212,27 @@ __global__ void random_column_kernel(c128* __restrict__ x, int64_t m, uint64_t s
     }
 }
 
+// R2 = I + triu(D, 1) + diag(D) / 2 with D = E - I, E = Q1^H Q1 (in place in E): the Cholesky factor of I + D to first
+// order in D.  The largest |D_ij| goes to *dmax (bit pattern of a non-negative double orders like an integer).
+__global__ void refine_r2_kernel(c128* __restrict__ E, int64_t k, unsigned long long* __restrict__ dmax) {
+    double mx = 0.0;
+    const int64_t total = k * k;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = idx % k, j = idx / k;
+        c128 v = E[idx];
+        if (i == j) {
+            mx = fmax(mx, fabs(v.x - 1.0));
+            E[idx] = make_double2(0.5 * (1.0 + v.x), 0.0);
+        } else {
+            mx = fmax(mx, fmax(fabs(v.x), fabs(v.y)));
+            if (i > j) E[idx] = make_double2(0.0, 0.0);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0 && mx > 0.0) atomicMax(dmax, (unsigned long long)__double_as_longlong(mx));
+}
+
 __global__ void zero_kernel(c128* x, int64_t rows, int64_t cols, int64_t ld) {
     int64_t total = rows * cols;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
@@ -484,7 +505,35 @@ int32_t qb_qr_matrix(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64_
     c128* R1 = ws.get<c128>((size_t)k * k);
     c128* R2 = ws.get<c128>((size_t)k * k);
     if (!R1 || !R2) QB_FAIL(ctx, QB200_E_CUDA, "qr: workspace allocation failed");
-    if (passes <= 1) {
+    static const bool refine_enabled = [] {
+        const char* e = getenv("QB200_QR_REFINE");
+        return !(e && e[0] == '0');
+    }();
+    bool refined = false;
+    if (passes == QB_QR_R_ONLY && refine_enabled) {
+        // Only R is wanted (the SVD preconditioner): the second Gram-Schmidt pass exists to remove the loss of
+        // orthogonality D = Q1^H Q1 - I ~ kappa eps of the first from R.  To first order the Cholesky factor of I + D
+        // is R2 = I + triu(D, 1) + diag(D)/2, so R = R2 R1 costs two GEMMs (k x k x m and k^3) instead of a second
+        // latency-bound pass over 2k/64 panels; the neglected term is O(|D|^2), so the shortcut is taken only when
+        // max |D_ij| <= 1e-9 (and the first pass met no dependent column); otherwise the full second pass runs.
+        QB_TRY(bgs_pass(ctx, m, k, Q, ldq, R1, k));
+        if (ctx->qr_last_dependent == 0) {
+            unsigned long long* dmax = ws.get<unsigned long long>(1);
+            if (!dmax) QB_FAIL(ctx, QB200_E_CUDA, "qr: workspace allocation failed");
+            QB_CUDA(ctx, cudaMemsetAsync(dmax, 0, sizeof(unsigned long long), ctx->stream));
+            QB_TRY(qb_gemm(ctx, 2, 0, k, k, m, one, Q, ldq, Q, ldq, zero, R2, k));
+            refine_r2_kernel<<<(unsigned)std::min<int64_t>((k * k + 255) / 256, 2048), 256, 0, ctx->stream>>>(R2, k, dmax);
+            QB_LAUNCH_CHECK(ctx);
+            QB_TRY(qb_gemm(ctx, 0, 0, k, k, k, one, R2, k, R1, k, zero, R, ldr));
+            QB_CUDA(ctx, cudaMemcpyAsync(ctx->scratch_host, dmax, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            QB_CUDA(ctx, qb_stream_sync(ctx));
+            refined = ctx->scratch_host[0] <= 1e-9;
+        }
+        if (!refined) {
+            QB_TRY(bgs_pass(ctx, m, k, Q, ldq, R2, k));
+            QB_TRY(qb_gemm(ctx, 0, 0, k, k, k, one, R2, k, R1, k, zero, R, ldr));
+        }
+    } else if (passes <= 1 && passes != QB_QR_R_ONLY) {
         // one pass: R is backward stable (as for modified Gram-Schmidt), Q is orthonormal only to kappa(A) eps
         QB_TRY(bgs_pass(ctx, m, k, Q, ldq, R1, k));
         QB_TRY(qb_copy_matrix(ctx, k, k, R1, k, R, ldr, 0));

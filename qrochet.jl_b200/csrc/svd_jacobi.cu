@@ -1241,7 +1241,7 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
             // only R is used afterwards (U S = A V, see qb_svd_emit).  Both Gram-Schmidt passes are still needed:
             // with one pass the singular values of R deviate from those of A by the loss of orthogonality of Q,
             // ~ kappa(A) eps (measured 1e-10 sigma_1 on a 1e10-graded matrix), R = R2 R1 restores eps sigma_1.
-            int32_t r = qb_qr_matrix(ctx, rb, k, B0, rb, Qtmp, rb, R, k, 2);
+            int32_t r = qb_qr_matrix(ctx, rb, k, B0, rb, Qtmp, rb, R, k, QB_QR_R_ONLY);
             if (r != QB200_OK) return fail(r);
         }
         // Z = R^H zero-padded

@@ -29,6 +29,16 @@ constexpr int PLAN_K = 8;
 constexpr int PLAN_ROUNDS = 32;
 const int PLAN_ALPHAS[2] = {2, 4};
 
+// Objective of the local search and of the candidate choice.  0: complex multiply-adds (EinExprs `flops`).  1: a time
+// model of this executor on B200 in multiply-add units: a node costs max(macs, 10 x elements moved) -- the FP64 DMMA
+// GEMM sustains ~4.1e12 complex MAC/s, HBM ~4.1e11 ComplexF64 elements/s, so a node with fewer than 10 MACs per element
+// moved is bandwidth-bound.  Exact integers in both implementations.
+inline u128 node_cost(int objective, u128 macs, u128 elems) {
+    if (objective == 0) return macs;
+    const u128 bw = elems > (((u128)1 << 110) / 10) ? ((u128)1 << 110) : elems * 10;
+    return macs > bw ? macs : bw;
+}
+
 inline u128 sat_mul(u128 a, u128 b) {
     if (a == 0 || b == 0) return 0;
     if (a > CAP / b) return CAP;
@@ -166,7 +176,7 @@ void greedy(Net& net, std::vector<PlanNode>& nodes, std::vector<int>& live, int 
 }
 
 // One sub-tree reconfiguration at internal node i; true when the sub-tree was replaced by a cheaper one.
-bool reconfigure_at(Net& net, std::vector<PlanNode>& nodes, int i) {
+bool reconfigure_at(Net& net, std::vector<PlanNode>& nodes, int i, int objective) {
     std::vector<int> fr = {nodes[i].left, nodes[i].right};
     while ((int)fr.size() < PLAN_K) {
         int pick = -1;
@@ -196,7 +206,8 @@ bool reconfigure_at(Net& net, std::vector<PlanNode>& nodes, int i) {
             int j = stack.back();
             stack.pop_back();
             if (std::find(fr.begin(), fr.end(), j) != fr.end()) continue;
-            old_fl += net.flops(nodes, j);
+            old_fl += node_cost(objective, net.flops(nodes, j),
+                                net.size(nodes[nodes[j].left].modes) + net.size(nodes[nodes[j].right].modes) + net.size(nodes[j].modes));
             old_mx = std::max(old_mx, net.size(nodes[j].modes));
             stack.push_back(nodes[j].left);
             stack.push_back(nodes[j].right);
@@ -253,7 +264,7 @@ bool reconfigure_at(Net& net, std::vector<PlanNode>& nodes, int i) {
             if (!(sub & low)) continue;
             const int o = m ^ sub;
             for (int w = 0; w < W; ++w) un[w] = bits[(size_t)sub * W + w] | bits[(size_t)o * W + w];
-            const u128 fl = best[sub].fl + best[o].fl + set_size(un.data());
+            const u128 fl = best[sub].fl + best[o].fl + node_cost(objective, set_size(un.data()), size[sub] + size[o] + size[m]);
             const u128 mx = std::max(std::max(best[sub].mx, best[o].mx), size[m]);
             if (!have || fl < ch.fl || (fl == ch.fl && mx < ch.mx)) {
                 have = true;
@@ -289,7 +300,7 @@ bool reconfigure_at(Net& net, std::vector<PlanNode>& nodes, int i) {
     return true;
 }
 
-void reconfigure(Net& net, std::vector<PlanNode>& nodes, int root) {
+void reconfigure(Net& net, std::vector<PlanNode>& nodes, int root, int objective) {
     for (int round = 0; round < PLAN_ROUNDS; ++round) {
         bool improved = false;
         std::vector<int> stack = {root};
@@ -297,7 +308,7 @@ void reconfigure(Net& net, std::vector<PlanNode>& nodes, int root) {
             int i = stack.back();
             stack.pop_back();
             if (nodes[i].left < 0) continue;
-            if (reconfigure_at(net, nodes, i)) improved = true;
+            if (reconfigure_at(net, nodes, i, objective)) improved = true;
             stack.push_back(nodes[i].right);  // left sub-tree first
             stack.push_back(nodes[i].left);
         }
@@ -364,7 +375,7 @@ void findslices(Net& net, const std::vector<PlanNode>& nodes, int64_t max_elemen
 }
 
 void sliced_cost(Net& net, const std::vector<PlanNode>& nodes, const std::vector<int>& cut, u128* per_slice, u128* once,
-                 int64_t* nsl) {
+                 int64_t* nsl, int objective, u128* obj_per_slice, u128* obj_once) {
     const int nleaves = (int)net.leaf_modes.size();
     std::vector<char> is_cut(net.nm, 0);
     for (int x : cut) is_cut[x] = 1;
@@ -372,15 +383,19 @@ void sliced_cost(Net& net, const std::vector<PlanNode>& nodes, const std::vector
     for (int i = 0; i < nleaves; ++i)
         for (int x : net.leaf_modes[i])
             if (is_cut[x]) inv[i] = 0;
-    *per_slice = 0;
-    *once = 0;
+    *per_slice = *once = *obj_per_slice = *obj_once = 0;
     for (size_t i = nleaves; i < nodes.size(); ++i) {
         inv[i] = inv[nodes[i].left] && inv[nodes[i].right];
         const u128 f = net.flops(nodes, (int)i, &is_cut);
-        if (inv[i])
+        const u128 c = node_cost(objective, f, net.size(nodes[nodes[i].left].modes, &is_cut) +
+                                                  net.size(nodes[nodes[i].right].modes, &is_cut) + net.size(nodes[i].modes, &is_cut));
+        if (inv[i]) {
             *once += f;
-        else
+            *obj_once += c;
+        } else {
             *per_slice += f;
+            *obj_per_slice += c;
+        }
     }
     int64_t n = 1;
     for (int x : cut) n = (n > ((int64_t)1 << 62) / net.ext[x]) ? ((int64_t)1 << 62) : n * net.ext[x];
@@ -412,16 +427,18 @@ PlanResult plan_network(const std::vector<std::vector<int>>& leaf_modes, const s
             if (simp) simplify(net, nodes, live);
             greedy(net, nodes, live, optimizer ? PLAN_ALPHAS[ai] : 2);
             const int root = live[0];
-            if (optimizer) reconfigure(net, nodes, root);
+            const int objective = optimizer >= 2 ? 1 : 0;
+            if (optimizer) reconfigure(net, nodes, root, objective);
             PlanResult r;
             compact(net, nodes, root, &r.nodes, &r.path);
             findslices(net, r.nodes, max_elements, &r.cut);
-            sliced_cost(net, r.nodes, r.cut, &r.macs_per_slice, &r.macs_invariant, &r.nslices);
+            u128 obj_ps = 0, obj_once = 0;
+            sliced_cost(net, r.nodes, r.cut, &r.macs_per_slice, &r.macs_invariant, &r.nslices, objective, &obj_ps, &obj_once);
             u128 total;
-            if (r.macs_per_slice != 0 && (u128)r.nslices > (CAP_TOTAL - std::min(CAP_TOTAL, r.macs_invariant)) / r.macs_per_slice)
+            if (obj_ps != 0 && (u128)r.nslices > (CAP_TOTAL - std::min(CAP_TOTAL, obj_once)) / obj_ps)
                 total = CAP_TOTAL;
             else
-                total = std::min(CAP_TOTAL, r.macs_per_slice * (u128)r.nslices + r.macs_invariant);
+                total = std::min(CAP_TOTAL, obj_ps * (u128)r.nslices + obj_once);
             if (!have || total < best_total) {
                 have = true;
                 best_total = total;

@@ -27,6 +27,7 @@ struct PlanResult {
 };
 
 // leaf_modes: dense ids 0 .. nmodes-1; ext[mode]; optimizer 0 = one greedy tree (the round-1 rule), 1 = full planner
+// minimising flops, 2 = full planner minimising the executor's time model (max(macs, 10 x elements moved) per node)
 PlanResult plan_network(const std::vector<std::vector<int>>& leaf_modes, const std::vector<int64_t>& ext,
                         int64_t max_elements, int optimizer);
 
