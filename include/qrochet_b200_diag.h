@@ -32,6 +32,8 @@ int32_t qb200_bench_dual_pipe(qb200_ctx* ctx, double* tflops3);
 /* DMMA issue-pattern micro-benchmark: TFLOP/s for {independent accumulators, complex-multiply pattern with register
  * operands, the same with A fragments re-loaded from shared memory} x {8, 16, 32 warps per SM}; row-major [3][3] */
 int32_t qb200_bench_dmma_patterns(qb200_ctx* ctx, double* tflops9);
+/* 3M complex-product DMMA stream: operand sum by DADD / from a shared-memory plane / absent, at 8 and 16 warps per SM */
+int32_t qb200_bench_dmma_3m(qb200_ctx* ctx, double* tflops6);
 
 #ifdef __cplusplus
 }

@@ -184,6 +184,80 @@ extern "C" int32_t qb200_bench_dmma_patterns(qb200_ctx* ctx, double* tflops9) {
     return QB200_OK;
 }
 
+// Experiment (round 2): what do the operand sums of the 3M complex product cost next to the DMMA stream?  The loop of
+// jacobi_update_kernel<1> (per k-step and row tile: one LDS.128, 3 DMMA) with MODE 0: the sum ar + ai formed by a DADD
+// per fragment (what the kernel does), 1: the sum read from a shared-memory plane (LDS.64, no DADD), 2: no third operand
+// at all (ar reused: the DMMA stream alone with its LDS.128).  3 accumulator sets x 2 row tiles, B from registers.
+template <int MODE>
+__global__ void __launch_bounds__(256, 2) dmma_3m_kernel(double* out, int iters) {
+    __shared__ __align__(16) double2 zs[64 * 18];
+    __shared__ __align__(16) double ss_plane[64 * 20];
+    for (int i = threadIdx.x; i < 64 * 18; i += 256) zs[i] = make_double2(1.0 + i * 1e-9, 1.0 - i * 1e-9);
+    for (int i = threadIdx.x; i < 64 * 20; i += 256) ss_plane[i] = 2.0 + i * 1e-9;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+    double pp[2][2], qq[2][2], sm[2][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) pp[i][0] = pp[i][1] = qq[i][0] = qq[i][1] = sm[i][0] = sm[i][1] = 0.0;
+    double2 breg[16];
+    double bsum[16];
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+        breg[kk] = make_double2(a + kk, b - kk);
+        bsum[kk] = breg[kk].x + breg[kk].y;
+    }
+    const double2* za = zs + g;
+    const double* sa = ss_plane + g;
+    for (int it = 0; it < iters; it += 16) {
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {
+                double2 v = za[(kk * 4 + t) * 18 + x * 8];
+                double s3;
+                if (MODE == 0) s3 = v.x + v.y;
+                else if (MODE == 1) s3 = sa[(kk * 4 + t) * 20 + x * 8];
+                else s3 = v.x;
+                dmma884(pp[x], v.x, breg[kk].x);
+                dmma884(qq[x], v.y, breg[kk].y);
+                dmma884(sm[x], s3, bsum[kk]);
+            }
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) s += pp[i][0] + pp[i][1] + qq[i][0] + qq[i][1] + sm[i][0] + sm[i][1];
+    if (s == 123.456) out[0] = s;
+}
+
+// tflops[3 modes][2 occupancies: 8, 16 warps per SM] of EXECUTED DMMA flops
+extern "C" int32_t qb200_bench_dmma_3m(qb200_ctx* ctx, double* tflops6) {
+    if (!ctx || !tflops6) return QB200_E_INVALID;
+    Workspace ws(ctx);
+    double* out = ws.get<double>(1);
+    const int iters = 4096;
+    for (int mode = 0; mode < 3; ++mode)
+        for (int occ = 0; occ < 2; ++occ) {
+            const int blocks = ctx->sm_count * (1 << occ);
+            auto launch = [&](int n) {
+                if (mode == 0) dmma_3m_kernel<0><<<blocks, 256, 0, ctx->stream>>>(out, n);
+                if (mode == 1) dmma_3m_kernel<1><<<blocks, 256, 0, ctx->stream>>>(out, n);
+                if (mode == 2) dmma_3m_kernel<2><<<blocks, 256, 0, ctx->stream>>>(out, n);
+            };
+            launch(64);
+            QB_LAUNCH_CHECK(ctx);
+            QB_TRY(qb200_timer_begin(ctx));
+            launch(iters);
+            QB_LAUNCH_CHECK(ctx);
+            double ms = 0.0;
+            QB_TRY(qb200_timer_end(ctx, &ms));
+            double flops = (double)blocks * 8 * iters * 6.0 * 512.0;
+            tflops6[mode * 2 + occ] = flops / (ms * 1e-3) / 1e12;
+        }
+    return QB200_OK;
+}
+
 // Legacy warp-level tensor path (mma.sync, SASS HMMA) peak for the ComplexF32 kernels: TF32 m16n8k8 and BF16 m16n8k16
 // with FP32 accumulation, issue-bound, 8 independent accumulator tiles per warp.
 __device__ __forceinline__ void mma_tf32_1688(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
