@@ -69,7 +69,8 @@ int32_t qb200_timer_end(qb200_ctx* ctx, double* ms);
 
 /* phase profiler (CUDA events around the library's internal phases, used by bench.py for the roofline):
  * phases: 0 theta GEMM, 1 gate, 2 SVD (whole), 3 Jacobi gram, 4 Jacobi evd, 5 Jacobi update, 6 SVD emit,
- * 7 mode scale, 8 QR, 9 sliced-TN GEMM.  read() synchronises, returns per-phase launch count, summed
+ * 7 mode scale, 8 QR, 9 sliced-TN GEMM, 10 / 11 / 12 low-precision stage of the mixed-precision Jacobi SVD (Gram, update,
+ * FP64 orthonormalisation + application of the accumulated rotations).  read() synchronises, returns per-phase launch count, summed
  * milliseconds and summed algorithmic work (flops, or bytes for HBM-bound phases), and resets. */
 int32_t qb200_prof_enable(qb200_ctx* ctx, int32_t on);
 int32_t qb200_prof_read(qb200_ctx* ctx, int32_t nphases, int64_t* counts, double* ms, double* work);

@@ -34,6 +34,9 @@ int32_t qb200_bench_dual_pipe(qb200_ctx* ctx, double* tflops3);
 int32_t qb200_bench_dmma_patterns(qb200_ctx* ctx, double* tflops9);
 /* 3M complex-product DMMA stream: operand sum by DADD / from a shared-memory plane / absent, at 8 and 16 warps per SM */
 int32_t qb200_bench_dmma_3m(qb200_ctx* ctx, double* tflops6);
+/* Jacobi update kernel (k x k matrix, microseconds per launch) against diagnostic variants that drop one ingredient each:
+ * {production 3M, no operand-sum DADDs, no global stores, no cp.async refill, all three, all three and no barrier, 4M} */
+int32_t qb200_bench_update_variants(qb200_ctx* ctx, int32_t k, int32_t steps, double* us7);
 
 #ifdef __cplusplus
 }

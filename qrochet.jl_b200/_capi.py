@@ -125,6 +125,7 @@ _diag_protos = {
     "qb200_bench_dual_pipe": (_i32, [_p, _pdbl]),
     "qb200_bench_dmma_patterns": (_i32, [_p, _pdbl]),
     "qb200_bench_dmma_3m": (_i32, [_p, _pdbl]),
+    "qb200_bench_update_variants": (_i32, [_p, _i32, _i32, _pdbl]),
 }
 DIAG_EXPORTS = sorted(_diag_protos)
 _diag = None

@@ -99,7 +99,10 @@ enum QbPhase {
     QB_PH_SCALE = 7,
     QB_PH_QR = 8,
     QB_PH_TN_GEMM = 9,
-    QB_PH_COUNT = 10
+    QB_PH_LP_GRAM = 10,    // low-precision (FP32 / TF32) stage of the mixed-precision Jacobi SVD: Gram
+    QB_PH_LP_UPDATE = 11,  // ... update of the FP32 shadow [X; V]
+    QB_PH_LP_GLUE = 12,    // ... V orthonormalised in FP64 and applied: X <- X0 V
+    QB_PH_COUNT = 13
 };
 
 // RAII phase timer: records two events on the stream when profiling is enabled, otherwise free
@@ -235,6 +238,10 @@ void qb_svd_release(qb200_ctx* ctx, SvdState* st);
 int32_t qb_cholqr_panel_step(qb200_ctx* ctx, c128* P, int64_t ld, int64_t m, c128* R, int64_t ldr, c128* Gpart,
                              c128* Wbuf, int* flags_dev, int* fail_dev, const double* before2_dev, double dep_tol);
 size_t qb_cholqr_gpart_elems(qb200_ctx* ctx);
+namespace qb {
+// timing harness of the Jacobi update kernel and its diagnostic variants (svd_jacobi.cu), used by the diagnostics library
+int32_t qb_update_bench(qb200_ctx* ctx, int k, int steps, double* us_out, int nvar);
+}
 
 // (left | right) matricisation of a tensor: returns a column-major rows x cols matrix (a permuted copy in
 // `ws` unless `order` is the identity)

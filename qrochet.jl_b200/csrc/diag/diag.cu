@@ -258,6 +258,14 @@ extern "C" int32_t qb200_bench_dmma_3m(qb200_ctx* ctx, double* tflops6) {
     return QB200_OK;
 }
 
+// Jacobi update kernel against its own diagnostic variants (what bounds it?): us per launch at k x k for
+// {production 3M, no operand-sum DADDs, no global stores, no cp.async after the prologue, all three, all three and no
+// barrier, 4M production}
+extern "C" int32_t qb200_bench_update_variants(qb200_ctx* ctx, int32_t k, int32_t steps, double* us7) {
+    if (!ctx || !us7) return QB200_E_INVALID;
+    return qb::qb_update_bench(ctx, k, steps, us7, 7);
+}
+
 // Legacy warp-level tensor path (mma.sync, SASS HMMA) peak for the ComplexF32 kernels: TF32 m16n8k8 and BF16 m16n8k16
 // with FP32 accumulation, issue-bound, 8 independent accumulator tiles per warp.
 __device__ __forceinline__ void mma_tf32_1688(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {

@@ -363,6 +363,128 @@ __global__ void __launch_bounds__(256, 2)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Mixed-precision Jacobi, low-precision stage ("stage A", see qb_svd_factor): the iteration runs on an FP32 shadow
+// S = [X32; V32] (2 mp x np, column-major float2, lds = 2 mp: the image of X on top, the accumulated rotations below).
+// Rotations still come from jacobi_evd_kernel (exact plane rotations in FP64 from whatever Gram it is given).
+
+// S <- [narrow(X); I]
+__global__ void lp_init_kernel(const c128* __restrict__ Z, int64_t ldz, int mp, int np, float2* __restrict__ S,
+                               int64_t lds) {
+    const int64_t total = (int64_t)2 * mp * np;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = idx % (2 * mp), c = idx / (2 * mp);
+        float2 v;
+        if (r < mp) {
+            const c128 z = Z[r + c * ldz];
+            v = make_float2((float)z.x, (float)z.y);
+        } else {
+            v = make_float2((r - mp) == c ? 1.f : 0.f, 0.f);
+        }
+        S[r + c * lds] = v;
+    }
+}
+
+// V (np x np, ld = np, ComplexF64) <- lower half of S
+__global__ void lp_extract_v_kernel(const float2* __restrict__ S, int64_t lds, int mp, int np, c128* __restrict__ V) {
+    const int64_t total = (int64_t)np * np;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = idx % np, c = idx / np;
+        const float2 v = S[mp + r + c * lds];
+        V[idx] = make_double2((double)v.x, (double)v.y);
+    }
+}
+
+__global__ void add_diag_kernel(c128* __restrict__ T, int n, double v) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) T[(int64_t)i * n + i].x += v;
+}
+
+// Full 64 x 64 Gram of every pair of a step (step 0 of a sweep) from X32, FP32 FMA.  grid (nsplit, npairs):
+// CTA (s, p) sums the rows [s rows_per, (s + 1) rows_per) of the panel of pair p and writes partial slot
+// 2 (p nsplit + s) -- what jacobi_evd_kernel expects from gram_ctas = npairs nsplit CTAs with nchunk = nsplit.
+// Thread (ti, tj) of the 16 x 16 grid owns the 4 x 4 block G[4 ti .. , 4 tj ..].
+__global__ void __launch_bounds__(256) lp_gram_full_kernel(const float2* __restrict__ S, int64_t lds, int rows_per, int nb,
+                                                           int step, c128* __restrict__ Gpart) {
+    __shared__ float2 Xs[32][JP + 1];
+    const int tid = threadIdx.x, ti = tid & 15, tj = tid >> 4;
+    const int pair = blockIdx.y, split = blockIdx.x, nsplit = gridDim.x;
+    int I, J;
+    rr_pair(nb, step, pair, I, J);
+    const float2* src = S + (int64_t)split * rows_per;
+    float gr[4][4], gi[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) gr[a][b] = gi[a][b] = 0.f;
+    for (int r0 = 0; r0 < rows_per; r0 += 32) {
+        __syncthreads();
+        for (int e = tid; e < 32 * JP; e += 256) {
+            const int r = e & 31, c = e >> 5;
+            Xs[r][c] = src[r0 + r + panel_col(I, J, c) * lds];
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+            float2 a[4], b[4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                a[x] = Xs[r][4 * ti + x];
+                b[x] = Xs[r][4 * tj + x];
+            }
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {  // conj(a) b
+                    gr[x][y] += a[x].x * b[y].x + a[x].y * b[y].y;
+                    gi[x][y] += a[x].x * b[y].y - a[x].y * b[y].x;
+                }
+        }
+    }
+    c128* out = Gpart + (size_t)2 * (pair * nsplit + split) * (JP * JP);
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) out[(4 * ti + x) + JP * (4 * tj + y)] = make_double2((double)gr[x][y], (double)gi[x][y]);
+}
+
+// Reference update of the shadow, FP32 FMA: S_p <- S_p W_p on all 2 mp rows.  grid (rows / 32, npairs).  Slow (CUDA
+// cores); kept as the specification the tcgen05 kernel is tested against (QB200_LP_UPDATE=simple).
+__global__ void __launch_bounds__(256) lp_update_simple_kernel(float2* __restrict__ S, int64_t lds, int nb, int step,
+                                                               const c128* __restrict__ Wg, const int* __restrict__ flags) {
+    __shared__ float2 Ws[JP * JP];   // [k][n]
+    __shared__ float2 Xs[JP * 32];   // [k][row]
+    const int pair = blockIdx.y;
+    if (!flags[pair]) return;
+    int I, J;
+    rr_pair(nb, step, pair, I, J);
+    const int tid = threadIdx.x, r = tid & 31, cg = tid >> 5;
+    const int64_t row0 = (int64_t)blockIdx.x * 32;
+    for (int e = tid; e < JP * JP; e += 256) {
+        const int k = e & 63, n = e >> 6;
+        const c128 w = Wg[(size_t)pair * (JP * JP) + n * JP + k];
+        Ws[k * JP + n] = make_float2((float)w.x, (float)w.y);
+    }
+    for (int e = tid; e < JP * 32; e += 256) {
+        const int rr = e & 31, k = e >> 5;
+        Xs[k * 32 + rr] = S[row0 + rr + panel_col(I, J, k) * lds];
+    }
+    __syncthreads();
+    float2 acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = make_float2(0.f, 0.f);
+    for (int k = 0; k < JP; ++k) {
+        const float2 x = Xs[k * 32 + r];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float2 w = Ws[k * JP + cg * 8 + j];
+            acc[j].x += x.x * w.x - x.y * w.y;
+            acc[j].y += x.x * w.y + x.y * w.x;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) S[row0 + r + panel_col(I, J, cg * 8 + j) * lds] = acc[j];
+}
+
+// ---------------------------------------------------------------------------------------------
 // evd kernel: two-sided Jacobi on the 64 x 64 Hermitian Gram matrix of one block pair.
 //
 // Each parallel step applies 32 disjoint plane rotations J = prod_k J_k:
@@ -662,7 +784,9 @@ constexpr int U_ROWS = 32, U_ZP = 34, U_NST = 3;  // pitch = 2 mod 8 (in c128): 
 constexpr size_t UPD_SMEM = (size_t)U_NST * JP * U_ZP * sizeof(c128);
 constexpr int UPD_THREADS = 256;
 
-template <int M3>
+// VAR != 0: timing variants for qb_update_bench only (wrong results): bit 0 no operand-sum DADDs, bit 1 no global
+// stores, bit 2 no cp.async after the prologue, bit 3 no barrier
+template <int M3, int VAR = 0>
 __global__ void __launch_bounds__(UPD_THREADS, 2)
     jacobi_update_kernel(c128* __restrict__ Z, int64_t ldz, int nb, int step, const c128* __restrict__ Wg,
                          const int* __restrict__ flags, int npairs, int nchunk, float2* __restrict__ Z32) {
@@ -741,9 +865,9 @@ __global__ void __launch_bounds__(UPD_THREADS, 2)
         // ONE barrier per chunk: it publishes the landed chunk AND says every warp has left the previous chunk,
         // whose buffer the prefetch below overwrites
         cp_async_wait<U_NST - 2>();
-        __syncthreads();
+        if (!(VAR & 8)) __syncthreads();
         if (pf.item < hi) {
-            load_chunk(pf, (stage + U_NST - 1) % U_NST);
+            if (!(VAR & 4)) load_chunk(pf, (stage + U_NST - 1) % U_NST);
             advance(pf);
         }
         cp_async_commit();
@@ -761,13 +885,13 @@ __global__ void __launch_bounds__(UPD_THREADS, 2)
                 for (int a = 0; a < 2; ++a) pp[a][0] = pp[a][1] = qq[a][0] = qq[a][1] = ss[a][0] = ss[a][1] = 0.0;
 #pragma unroll
                 for (int kk = 0; kk < JP / 4; ++kk) {
-                    const double br = breg[kk].x, bi = breg[kk].y, bs = br + bi;
+                    const double br = breg[kk].x, bi = breg[kk].y, bs = (VAR & 1) ? br : br + bi;
 #pragma unroll
                     for (int a = 0; a < 2; ++a) {
                         c128 v = za[(kk * 4 + t) * U_ZP + (hh * 2 + a) * 8];
                         dmma884(pp[a], v.x, br);
                         dmma884(qq[a], v.y, bi);
-                        dmma884(ss[a], v.x + v.y, bs);
+                        dmma884(ss[a], (VAR & 1) ? v.x : v.x + v.y, bs);
                     }
                 }
 #pragma unroll
@@ -776,6 +900,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 2)
 #pragma unroll
                     for (int a = 0; a < 2; ++a) {
                         const double re = pp[a][h] - qq[a][h], im = ss[a][h] - pp[a][h] - qq[a][h];
+                        if ((VAR & 2) && re != 1.2345e300) continue;
                         Z[zo + (hh * 2 + a) * 8] = make_double2(re, im);
                         if (Z32) Z32[zo + (hh * 2 + a) * 8] = make_float2((float)re, (float)im);  // FP32 shadow (gram32)
                     }
@@ -1113,6 +1238,15 @@ static bool update_3m() {
     return on;
 }
 
+// QB200_SVD_MIXED=1: mixed-precision Jacobi (FP32 stage A + FP64 stage B, see qb_svd_factor)
+static bool mixed_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("QB200_SVD_MIXED");
+        return e && e[0] == '1';
+    }();
+    return on;
+}
+
 // QB200_GRAM_LOWP=1 switches the mixed-precision Gram on (TF32 Gram while couplings > LOWP_TOL).  Default OFF:
 // measured on B200 at k = 2048 (profiles/r1b_lowp_gram.txt) the Gram phase drops 19.5 -> 15.0 ms per bond (the
 // per-launch cost is ramp / flush / tail, not DMMA) while the FP32 shadow stores cost the update kernel 3.3 ms:
@@ -1302,6 +1436,102 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
         int32_t r = qb_narrow_c128(ctx, st->Z, st->Z32, st->ldz * st->np);
         if (r != QB200_OK) return fail(r);
     }
+    // ---- mixed precision: the linear phase of the iteration on an FP32 shadow ("stage A") ----
+    // The first ~8 of ~11 sweeps only steer: their rotations need no FP64 accuracy, but X <- X W_p applied in FP64 is
+    // 80 % of the SVD's tensor-pipe time.  Stage A runs the same block iteration on S = [X32; V32] (FP32 image of X
+    // and the accumulated rotations) -- cross Grams on the TF32 path, rotations by the same evd kernel, updates on the
+    // FP32 / TF32 tensor path -- until the couplings reach the FP32 noise level.  Then V32 is widened, orthonormalised
+    // in FP64 (two Newton-Schulz steps: its unitarity defect ~1e-6 -> 1e-12 -> 1e-24), X <- X0 V is ONE FP64 GEMM, and
+    // the FP64 iteration ("stage B", the loop below, unchanged) starts from nearly orthogonal columns: 2-3 sweeps.
+    // The result is an exact unitary image of X0 whatever stage A did; only the sweep count depends on it.
+    int sweeps_a = 0;
+    if (mixed_enabled() && nb >= 16 && !floor_on && !shadow) {
+        Workspace wsa(ctx);
+        const int64_t lds = (int64_t)2 * st->mp;
+        const int np = st->np, mp = st->mp;
+        float2* S = wsa.get<float2>((size_t)lds * np);
+        int nsplit = 1;  // largest divisor of mp / 32 that is <= 8: every split sums a whole number of 32-row tiles
+        for (int d = 2; d <= 8; ++d)
+            if ((mp / 32) % d == 0) nsplit = d;
+        c128* GpartA = wsa.get<c128>((size_t)2 * std::max(gram_ctas, npairs * nsplit) * JP * JP);
+        if (!S || !GpartA) {
+            ctx->err = "svd: workspace allocation failed";
+            return fail(QB200_E_CUDA);
+        }
+        lp_init_kernel<<<grid_cap(ctx, lds * np, 256), 256, 0, ctx->stream>>>(st->Z, st->ldz, mp, np, S, lds);
+        ctx->launches++;
+        const double rot_tol_a = 2e-6, tol_a = 3e-4;
+        const int max_a = 14;
+        double prev = 1e300;
+        for (; sweeps_a < max_a; ) {
+            cudaMemsetAsync(stat, 0, sizeof(unsigned long long), ctx->stream);
+            for (int step = 0; step < nsteps; ++step) {
+                const int mode = (step == 0) ? 1 : 2;
+                {
+                    PhaseTimer pt(ctx, QB_PH_LP_GRAM, 8.0 * npairs * (double)mp * JP * JP);
+                    if (mode == 1)
+                        lp_gram_full_kernel<<<dim3(nsplit, npairs), 256, 0, ctx->stream>>>(S, lds, mp / nsplit, nb, step, GpartA);
+                    else
+                        jacobi_gram32_kernel<<<gram_ctas, 256, GRAM32_SMEM, ctx->stream>>>(S, lds, mp, nb, step, npairs, GpartA);
+                }
+                {
+                    PhaseTimer pt(ctx, QB_PH_JEVD, 0.0);
+                    jacobi_evd_kernel<<<npairs, EVD_THREADS, EVD_SMEM, ctx->stream>>>(
+                        GpartA, mode == 1 ? npairs * nsplit : gram_ctas, mode == 1 ? nsplit : g_nchunk, npairs, Wg, flags, stat,
+                        rot_tol_a, inner_sweeps, scale, (unsigned long long*)(scale + 1), abs_c, nact, mode, Dstore, nb, step);
+                }
+                {
+                    PhaseTimer pt(ctx, QB_PH_LP_UPDATE, 8.0 * npairs * (double)lds * JP * JP);
+                    lp_update_simple_kernel<<<dim3((unsigned)(lds / 32), npairs), 256, 0, ctx->stream>>>(S, lds, nb, step, Wg, flags);
+                }
+            }
+            cudaMemcpyAsync(scale, scale + 1, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
+            ctx->launches += 3 * (int64_t)nsteps;
+            ++sweeps_a;
+            cudaError_t e = cudaMemcpyAsync(ctx->scratch_host, stat, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = qb_stream_sync(ctx);
+            if (e == cudaSuccess) e = cudaGetLastError();
+            if (e != cudaSuccess) return cuda_fail(e);
+            const double worst = ctx->scratch_host[0];
+            if (getenv("QB200_DEBUG"))
+                fprintf(stderr, "[qb200 svd] stage A (fp32 shadow) sweep %d worst %.3e\n", sweeps_a - 1, worst);
+            if (!(worst > tol_a)) break;
+            if (prev < 1e-2 && worst > 0.3 * prev) break;  // at the noise floor of the shadow
+            prev = worst;
+        }
+        {
+            PhaseTimer pt(ctx, QB_PH_LP_GLUE, 8.0 * (5.0 * np * (double)np * np));
+            c128* Va = wsa.get<c128>((size_t)np * np);
+            c128* Vb = wsa.get<c128>((size_t)np * np);
+            c128* T = wsa.get<c128>((size_t)np * np);
+            c128* X1 = nullptr;
+            if (!Va || !Vb || !T || cudaMallocAsync(&X1, sizeof(c128) * st->ldz * st->np, ctx->stream) != cudaSuccess) {
+                ctx->err = "svd: out of device memory";
+                return fail(QB200_E_CUDA);
+            }
+            lp_extract_v_kernel<<<grid_cap(ctx, (int64_t)np * np, 256), 256, 0, ctx->stream>>>(S, lds, mp, np, Va);
+            ctx->launches++;
+            const c128 one = make_double2(1.0, 0.0), zero = make_double2(0.0, 0.0), mhalf = make_double2(-0.5, 0.0);
+            int32_t r = QB200_OK;
+            for (int it = 0; it < 2 && r == QB200_OK; ++it) {  // V <- V (3/2 I - 1/2 V^H V)
+                r = qb_gemm(ctx, 2, 0, np, np, np, mhalf, Va, np, Va, np, zero, T, np);
+                if (r == QB200_OK) {
+                    add_diag_kernel<<<(np + 255) / 256, 256, 0, ctx->stream>>>(T, np, 1.5);
+                    ctx->launches++;
+                    r = qb_gemm(ctx, 0, 0, np, np, np, one, Va, np, T, np, zero, Vb, np);
+                }
+                std::swap(Va, Vb);
+            }
+            if (r == QB200_OK) r = qb_gemm(ctx, 0, 0, mp, np, np, one, st->Z, st->ldz, Va, np, zero, X1, st->ldz);
+            if (r != QB200_OK) {
+                cudaFreeAsync(X1, ctx->stream);
+                return fail(r);
+            }
+            cudaFreeAsync(st->Z, ctx->stream);
+            st->Z = X1;
+        }
+    }
+
     const int max_sweeps = 40;
     int sweep = 0;
     bool converged = false;
@@ -1383,9 +1613,9 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
         }
     }
     if (sweep_graph) cudaGraphExecDestroy(sweep_graph);
-    ctx->last_svd_sweeps = sweep;
+    ctx->last_svd_sweeps = sweep + sweeps_a;
     ctx->svd_calls++;
-    ctx->svd_sweeps += sweep;
+    ctx->svd_sweeps += sweep + sweeps_a;
     if (!converged) {
         ctx->err = "svd: Jacobi did not converge within the sweep limit";
         return fail(QB200_E_NOCONVERGE);
@@ -1663,3 +1893,58 @@ int32_t qb_cholqr_panel_step(qb200_ctx* ctx, c128* P, int64_t ld, int64_t m, c12
     return QB200_OK;
 }
 size_t qb_cholqr_gpart_elems(qb200_ctx* ctx) { return (size_t)2 * 2 * ctx->sm_count * JP * JP; }
+
+// Timing harness for the diagnostics library (qb200_bench_update_variants): `steps` launches of the Jacobi update kernel
+// on a k x k matrix with W = I for every pair, per variant (see the VAR template parameter); ms_out[v] = mean
+// microseconds per launch.  Variant 0 is the production kernel.
+namespace qb {
+int32_t qb_update_bench(qb200_ctx* ctx, int k, int steps, double* us_out, int nvar) {
+    const int np = (k + 63) / 64 * 64, nb = np / JB, npairs = nb / 2;
+    Workspace ws(ctx);
+    c128* Z = ws.get<c128>((size_t)np * np);
+    c128* Wg = ws.get<c128>((size_t)npairs * JP * JP);
+    int* flags = ws.get<int>(npairs);
+    if (!Z || !Wg || !flags) QB_FAIL(ctx, QB200_E_CUDA, "update bench: allocation failed");
+    svd_init_kernel<<<grid_cap(ctx, (int64_t)np * np, 256), 256, 0, ctx->stream>>>(Z, np, np, np, 0, 0, nullptr, 1, 0);
+    std::vector<c128> w((size_t)npairs * JP * JP, make_double2(0.0, 0.0));
+    for (int p = 0; p < npairs; ++p)
+        for (int i = 0; i < JP; ++i) w[(size_t)p * JP * JP + i * JP + i] = make_double2(1.0, 0.0);
+    std::vector<int> f(npairs, 1);
+    QB_CUDA(ctx, cudaMemcpyAsync(Wg, w.data(), sizeof(c128) * w.size(), cudaMemcpyHostToDevice, ctx->stream));
+    QB_CUDA(ctx, cudaMemcpyAsync(flags, f.data(), sizeof(int) * npairs, cudaMemcpyHostToDevice, ctx->stream));
+    QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int u_nchunk = np / U_ROWS;
+    const int upd_ctas = std::max(1, std::min(2 * ctx->sm_count, npairs * u_nchunk));
+    auto launch = [&](int v, int step) {
+        switch (v) {
+            case 0: jacobi_update_kernel<1, 0><<<upd_ctas, UPD_THREADS, UPD_SMEM, ctx->stream>>>(Z, np, nb, step, Wg, flags, npairs, u_nchunk, nullptr); break;
+            case 1: jacobi_update_kernel<1, 1><<<upd_ctas, UPD_THREADS, UPD_SMEM, ctx->stream>>>(Z, np, nb, step, Wg, flags, npairs, u_nchunk, nullptr); break;
+            case 2: jacobi_update_kernel<1, 2><<<upd_ctas, UPD_THREADS, UPD_SMEM, ctx->stream>>>(Z, np, nb, step, Wg, flags, npairs, u_nchunk, nullptr); break;
+            case 3: jacobi_update_kernel<1, 4><<<upd_ctas, UPD_THREADS, UPD_SMEM, ctx->stream>>>(Z, np, nb, step, Wg, flags, npairs, u_nchunk, nullptr); break;
+            case 4: jacobi_update_kernel<1, 7><<<upd_ctas, UPD_THREADS, UPD_SMEM, ctx->stream>>>(Z, np, nb, step, Wg, flags, npairs, u_nchunk, nullptr); break;
+            case 5: jacobi_update_kernel<1, 15><<<upd_ctas, UPD_THREADS, UPD_SMEM, ctx->stream>>>(Z, np, nb, step, Wg, flags, npairs, u_nchunk, nullptr); break;
+            default: jacobi_update_kernel<0, 0><<<upd_ctas, UPD_THREADS, UPD_SMEM, ctx->stream>>>(Z, np, nb, step, Wg, flags, npairs, u_nchunk, nullptr); break;
+        }
+    };
+    for (int v = 0; v < nvar && v < 7; ++v) {
+        if (v >= 1 && v <= 5) {
+            cudaError_t e = cudaSuccess;
+            if (v == 1) e = cudaFuncSetAttribute(jacobi_update_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM);
+            if (v == 2) e = cudaFuncSetAttribute(jacobi_update_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM);
+            if (v == 3) e = cudaFuncSetAttribute(jacobi_update_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM);
+            if (v == 4) e = cudaFuncSetAttribute(jacobi_update_kernel<1, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM);
+            if (v == 5) e = cudaFuncSetAttribute(jacobi_update_kernel<1, 15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM);
+            QB_CUDA(ctx, e);
+        }
+        for (int i = 0; i < 5; ++i) launch(v, i % (nb - 1));
+        QB_LAUNCH_CHECK(ctx);
+        QB_TRY(qb200_timer_begin(ctx));
+        for (int i = 0; i < steps; ++i) launch(v, i % (nb - 1));
+        QB_LAUNCH_CHECK(ctx);
+        double ms = 0.0;
+        QB_TRY(qb200_timer_end(ctx, &ms));
+        us_out[v] = ms * 1e3 / steps;
+    }
+    return QB200_OK;
+}
+}  // namespace qb

@@ -44,7 +44,7 @@ class Context:
         return ms.value
 
     PHASES = ("theta_gemm", "gate", "svd", "jacobi_gram", "jacobi_evd", "jacobi_update", "svd_emit", "mode_scale",
-              "qr", "tn_gemm")
+              "qr", "tn_gemm", "lowp_gram", "lowp_update", "lowp_glue")
 
     def profile(self, on: bool):
         check(self.h, lib.qb200_prof_enable(self.h, int(on)))

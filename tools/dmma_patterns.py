@@ -19,3 +19,10 @@ names = ["3M: sum by DADD per fragment", "3M: sum from a shared plane (LDS.64)",
 print("executed DMMA TFLOP/s at 8 / 16 warps per SM")
 for m in range(3):
     print(f"{names[m]:40s}", " ".join(f"{out6[m * 2 + o]:7.2f}" for o in range(2)))
+us = (C.c_double * 7)()
+capi.check(ctx.h, d.qb200_bench_update_variants(ctx.h, 2048, 63, us))
+names = ["production (3M)", "no operand-sum DADDs", "no global stores", "no cp.async refill", "none of the three",
+         "none of the three, no barrier", "4M product"]
+print("jacobi_update_kernel at 2048 x 2048, microseconds per launch (ideal DMMA time at 37.1 TFLOP/s: 3M 43.4, 4M 57.9)")
+for n, v in zip(names, us):
+    print(f"{n:40s} {v:8.2f}")
