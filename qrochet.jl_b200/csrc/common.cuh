@@ -241,6 +241,10 @@ size_t qb_cholqr_gpart_elems(qb200_ctx* ctx);
 namespace qb {
 // timing harness of the Jacobi update kernel and its diagnostic variants (svd_jacobi.cu), used by the diagnostics library
 int32_t qb_update_bench(qb200_ctx* ctx, int k, int steps, double* us_out, int nvar);
+// mixed-precision Jacobi, stage A (jacobi_lp_tc5.cu): S_p <- S_p W_p on the FP32 shadow, tcgen05 3xTF32
+int32_t init_lp_update_tc5(qb200_ctx* ctx);
+int32_t launch_lp_update_tc5(qb200_ctx* ctx, float2* S, int64_t lds, int64_t rows, int nb, int step, const c128* Wg,
+                             const int* flags, int npairs);
 }
 
 // (left | right) matricisation of a tensor: returns a column-major rows x cols matrix (a permuted copy in

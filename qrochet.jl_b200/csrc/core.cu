@@ -38,6 +38,7 @@ int32_t qb200_create(int32_t device, qb200_ctx** out) {
     int32_t r = qb::init_gemm(ctx);
     if (r == QB200_OK) r = qb::init_gemm_c64(ctx);
     if (r == QB200_OK) r = qb::init_gemm_c64_tc5(ctx);
+    if (r == QB200_OK) r = qb::init_lp_update_tc5(ctx);
     if (r == QB200_OK) r = qb_qr_init(ctx);
     if (r == QB200_OK) r = qb_svd_init(ctx);
     if (r != QB200_OK) {

@@ -26,40 +26,13 @@
 
 #include "common.cuh"
 #include "mma.cuh"
+#include "jacobi_rr.cuh"
 
 using namespace qb;
 
 namespace {
 
-constexpr int JB = 32;   // column block width
-constexpr int JP = 64;   // panel width (two blocks)
 constexpr int GLD = 65;  // shared-memory pitch of the 64 x 64 matrices in the evd kernel
-
-// circle-method round robin: n (even) players, round `step` in [0, n-1), pair k in [0, n/2)
-__device__ __forceinline__ void rr_pair(int n, int step, int k, int& p, int& q) {
-    if (step < 0) {  // consecutive blocks (2k, 2k+1): a 64-column panel addressed directly (QR panels)
-        p = 2 * k;
-        q = 2 * k + 1;
-        return;
-    }
-    if (n == 2) {
-        p = 0;
-        q = 1;
-        return;
-    }
-    int a, b;
-    if (k == 0) {
-        a = n - 1;
-        b = step;
-    } else {
-        a = (step + k) % (n - 1);
-        b = (step - k + (n - 1)) % (n - 1);
-    }
-    p = min(a, b);
-    q = max(a, b);
-}
-
-__device__ __forceinline__ int64_t panel_col(int I, int J, int c) { return (c < JB) ? (I * JB + c) : (J * JB + c - JB); }
 
 // ---------------------------------------------------------------------------------------------
 // gram kernel: G_p = P_p^H P_p for every pair of the step.
@@ -446,6 +419,17 @@ __global__ void __launch_bounds__(256) lp_gram_full_kernel(const float2* __restr
         for (int y = 0; y < 4; ++y) out[(4 * ti + x) + JP * (4 * tj + y)] = make_double2((double)gr[x][y], (double)gi[x][y]);
 }
 
+// max |a - b| and max |b| (as float bit patterns: non-negative floats order like unsigned integers)
+__global__ void lp_maxdiff_kernel(const float2* __restrict__ a, const float2* __restrict__ b, int64_t n, unsigned* __restrict__ out) {
+    float d = 0.f, m = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        d = fmaxf(d, fmaxf(fabsf(a[i].x - b[i].x), fabsf(a[i].y - b[i].y)));
+        m = fmaxf(m, fmaxf(fabsf(b[i].x), fabsf(b[i].y)));
+    }
+    atomicMax(out, __float_as_uint(d));
+    atomicMax(out + 1, __float_as_uint(m));
+}
+
 // Reference update of the shadow, FP32 FMA: S_p <- S_p W_p on all 2 mp rows.  grid (rows / 32, npairs).  Slow (CUDA
 // cores); kept as the specification the tcgen05 kernel is tested against (QB200_LP_UPDATE=simple).
 __global__ void __launch_bounds__(256) lp_update_simple_kernel(float2* __restrict__ S, int64_t lds, int nb, int step,
@@ -503,9 +487,18 @@ __global__ void __launch_bounds__(256) lp_update_simple_kernel(float2* __restric
 constexpr int EVD_THREADS = 544;
 constexpr int EVD_LOADERS = 512;  // threads that assemble G (8 elements each)
 constexpr int EVD_NBLK = 32 * 33 / 2;
-constexpr size_t EVD_SMEM = (size_t)2 * JP * GLD * sizeof(c128) + 32 * sizeof(double) + 32 * sizeof(c128) +
-                            64 * sizeof(int) + 64 * sizeof(double) + EVD_NBLK * sizeof(short);
+constexpr size_t EVD_SMEM_TAIL = 32 * sizeof(double) + 32 * sizeof(c128) + 64 * sizeof(int) + 64 * sizeof(double) +
+                                 EVD_NBLK * sizeof(short);
+constexpr size_t EVD_SMEM = (size_t)2 * JP * GLD * sizeof(c128) + EVD_SMEM_TAIL;
+constexpr size_t EVD_SMEM_WREG = (size_t)JP * GLD * sizeof(c128) + EVD_SMEM_TAIL;  // W in registers: G only
 
+// WREG = 1 (mode 2 only: 32 cross rotations (i, 32 + (i + t) mod 32) per step, one inner sweep): W never touches shared
+// memory.  Warp w of the 16 apply-warps owns rows 4w .. 4w+3; lane i keeps, for each of them, W[r][i] and the entry of
+// the column currently paired with i, W[r][32 + (i + t) mod 32]: the rotation of lane i acts on exactly these two, and
+// the partner column of the next step is the one lane i+1 holds now -- one warp shuffle per step passes it on.  After
+// the 32 steps every lane is back at column 32 + i.  Shared memory drops to the 65 KB of G (the kernel then shares an SM
+// with an update / Gram CTA of another stream) and the W phase to register arithmetic.
+template <int WREG>
 __global__ void __launch_bounds__(EVD_THREADS, 1)
     jacobi_evd_kernel(const c128* __restrict__ Gpart, int gram_ctas, int nchunk, int npairs_total,
                       c128* __restrict__ Wout, int* __restrict__ flags,
@@ -514,8 +507,8 @@ __global__ void __launch_bounds__(EVD_THREADS, 1)
                       int nact, int mode, c128* __restrict__ Dstore, int nb, int step) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     c128* G = reinterpret_cast<c128*>(smem_raw);
-    c128* W = G + JP * GLD;
-    double* rcs = reinterpret_cast<double*>(W + JP * GLD);   // rotation cosines, buffer 0
+    c128* W = G + JP * GLD;                                   // WREG: not allocated, never touched
+    double* rcs = reinterpret_cast<double*>(WREG ? W : W + JP * GLD);   // rotation cosines, buffer 0
     double* red = rcs + 32 + 64 + 32;                          // reduction scratch (64 doubles), later cosines buffer 1
     short* tri = reinterpret_cast<short*>(red + 64);
 
@@ -576,7 +569,7 @@ __global__ void __launch_bounds__(EVD_THREADS, 1)
         for (int j = 0; j < PER; ++j) {
             const int e = tid + EVD_LOADERS * j, r = e & 63, c = e >> 6;
             G[c * GLD + r] = make_double2(sx[j], sy[j]);
-            W[c * GLD + r] = make_double2(r == c ? 1.0 : 0.0, 0.0);
+            if constexpr (!WREG) W[c * GLD + r] = make_double2(r == c ? 1.0 : 0.0, 0.0);
         }
     }
     for (int e = tid; e < EVD_NBLK; e += EVD_THREADS) {
@@ -695,6 +688,15 @@ __global__ void __launch_bounds__(EVD_THREADS, 1)
         rpq_buf[buf][2 * tid] = p;
         rpq_buf[buf][2 * tid + 1] = q;
     };
+    c128 wp[4], wq[4];  // WREG: see the kernel comment
+    if constexpr (WREG) {
+        const int lane = tid & 31, r0 = 4 * ((tid >> 5) - 1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            wp[j] = make_double2(r0 + j == lane ? 1.0 : 0.0, 0.0);
+            wq[j] = make_double2(r0 + j == 32 + lane ? 1.0 : 0.0, 0.0);
+        }
+    }
     __syncthreads();
     if (tid < 32) compute_rotations(0, 0);
     __syncthreads();
@@ -746,6 +748,24 @@ __global__ void __launch_bounds__(EVD_THREADS, 1)
         // phase B: warp 0 prepares the next step's rotations, warps 1..15 apply the current ones to W
         if (tid < 32) {
             if (gs + 1 < total_steps) compute_rotations(gs + 1, buf ^ 1);
+        } else if constexpr (WREG) {
+            const int lane = tid & 31;
+            const c128 sn = rs[lane];
+            const double cs = rc[lane];
+            if (sn.x != 0.0 || sn.y != 0.0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const c128 xp = wp[j], xq = wq[j];
+                    wp[j] = csub(cscale(xp, cs), cmul(cconj(sn), xq));
+                    wq[j] = cadd(cmul(sn, xp), cscale(xq, cs));
+                }
+            }
+            const int from = (lane + 1) & 31;  // the column that pairs with this lane's p column at the next step
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                wq[j].x = __shfl_sync(0xffffffffu, wq[j].x, from);
+                wq[j].y = __shfl_sync(0xffffffffu, wq[j].y, from);
+            }
         } else {
             for (int item = tid - 32; item < 32 * JP; item += EVD_THREADS - 32) {
                 int r = item & 63, k = item >> 6;
@@ -762,9 +782,20 @@ __global__ void __launch_bounds__(EVD_THREADS, 1)
         __syncthreads();
     }
     c128* dst = Wout + (size_t)pair * (JP * JP);
-    for (int e = tid; e < JP * JP; e += EVD_THREADS) {
-        int r = e & 63, c = e >> 6;
-        dst[e] = W[c * GLD + r];
+    if constexpr (WREG) {
+        if (tid >= 32) {  // after the 32 steps lane i holds columns i and 32 + i of its 4 rows
+            const int lane = tid & 31, r0 = 4 * ((tid >> 5) - 1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                dst[lane * JP + r0 + j] = wp[j];
+                dst[(32 + lane) * JP + r0 + j] = wq[j];
+            }
+        }
+    } else {
+        for (int e = tid; e < JP * JP; e += EVD_THREADS) {
+            int r = e & 63, c = e >> 6;
+            dst[e] = W[c * GLD + r];
+        }
     }
     if (Dstore)
         for (int e = tid; e < 2 * JB * JB; e += EVD_THREADS) {
@@ -1238,6 +1269,15 @@ static bool update_3m() {
     return on;
 }
 
+// QB200_EVD_WREG=0: the cross-rotation steps keep W in shared memory like the full steps (A/B switch; default: registers)
+static bool evd_wreg() {
+    static const bool on = [] {
+        const char* e = getenv("QB200_EVD_WREG");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
 // QB200_SVD_MIXED=1: mixed-precision Jacobi (FP32 stage A + FP64 stage B, see qb_svd_factor)
 static bool mixed_enabled() {
     static const bool on = [] {
@@ -1299,7 +1339,8 @@ __global__ void svd_gather_cols_kernel(const c128* __restrict__ A, int64_t lda, 
 int32_t qb_svd_init(qb200_ctx* ctx) {
     QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_gram_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRAM_SMEM));
     QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_gram_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRAM_SMEM));
-    QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_evd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EVD_SMEM));
+    QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_evd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EVD_SMEM));
+    QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_evd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EVD_SMEM_WREG));
     QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_gram32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRAM32_SMEM));
     QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_update_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM));
     QB_CUDA(ctx, cudaFuncSetAttribute(jacobi_update_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM));
@@ -1460,10 +1501,15 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
         }
         lp_init_kernel<<<grid_cap(ctx, lds * np, 256), 256, 0, ctx->stream>>>(st->Z, st->ldz, mp, np, S, lds);
         ctx->launches++;
+        static const int lp_mode = [] {  // QB200_LP_UPDATE: (default) tcgen05 kernel, "simple" FP32 FMA kernel, "check" both
+            const char* e = getenv("QB200_LP_UPDATE");
+            return !e ? 0 : (e[0] == 's' ? 1 : (e[0] == 'c' ? 2 : 0));
+        }();
         const double rot_tol_a = 2e-6, tol_a = 3e-4;
         const int max_a = 14;
         double prev = 1e300;
-        for (; sweeps_a < max_a; ) {
+        int32_t emit_rc = QB200_OK;
+        auto emit_sweep_a = [&]() {
             cudaMemsetAsync(stat, 0, sizeof(unsigned long long), ctx->stream);
             for (int step = 0; step < nsteps; ++step) {
                 const int mode = (step == 0) ? 1 : 2;
@@ -1476,22 +1522,77 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
                 }
                 {
                     PhaseTimer pt(ctx, QB_PH_JEVD, 0.0);
-                    jacobi_evd_kernel<<<npairs, EVD_THREADS, EVD_SMEM, ctx->stream>>>(
+                    (mode == 2 && evd_wreg() ? jacobi_evd_kernel<1> : jacobi_evd_kernel<0>)<<<npairs, EVD_THREADS, mode == 2 && evd_wreg() ? EVD_SMEM_WREG : EVD_SMEM, ctx->stream>>>(
                         GpartA, mode == 1 ? npairs * nsplit : gram_ctas, mode == 1 ? nsplit : g_nchunk, npairs, Wg, flags, stat,
                         rot_tol_a, inner_sweeps, scale, (unsigned long long*)(scale + 1), abs_c, nact, mode, Dstore, nb, step);
                 }
-                {
+                if (lp_mode == 2 && sweeps_a == 0 && step < 2) {  // QB200_LP_UPDATE=check: tcgen05 kernel against the FP32 FMA one
+                    float2* T = nullptr;
+                    unsigned* dmax = nullptr;
+                    cudaMallocAsync(&T, sizeof(float2) * lds * np, ctx->stream);
+                    cudaMallocAsync(&dmax, 2 * sizeof(unsigned), ctx->stream);
+                    cudaMemsetAsync(dmax, 0, 2 * sizeof(unsigned), ctx->stream);
+                    cudaMemcpyAsync(T, S, sizeof(float2) * lds * np, cudaMemcpyDeviceToDevice, ctx->stream);
+                    lp_update_simple_kernel<<<dim3((unsigned)(lds / 32), npairs), 256, 0, ctx->stream>>>(T, lds, nb, step, Wg, flags);
+                    int32_t r = launch_lp_update_tc5(ctx, S, lds, lds, nb, step, Wg, flags, npairs);
+                    if (r != QB200_OK) emit_rc = r;
+                    lp_maxdiff_kernel<<<grid_cap(ctx, lds * np, 256), 256, 0, ctx->stream>>>(S, T, lds * np, dmax);
+                    unsigned h[2];
+                    cudaMemcpyAsync(h, dmax, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
+                    cudaStreamSynchronize(ctx->stream);
+                    float fd, fm;
+                    memcpy(&fd, &h[0], 4);
+                    memcpy(&fm, &h[1], 4);
+                    fprintf(stderr, "[qb200 svd] lp update check step %d: max |tc5 - fma| = %.3e, max |fma| = %.3e\n", step, fd, fm);
+                    cudaFreeAsync(T, ctx->stream);
+                    cudaFreeAsync(dmax, ctx->stream);
+                } else {
                     PhaseTimer pt(ctx, QB_PH_LP_UPDATE, 8.0 * npairs * (double)lds * JP * JP);
-                    lp_update_simple_kernel<<<dim3((unsigned)(lds / 32), npairs), 256, 0, ctx->stream>>>(S, lds, nb, step, Wg, flags);
+                    if (lp_mode == 1) {
+                        lp_update_simple_kernel<<<dim3((unsigned)(lds / 32), npairs), 256, 0, ctx->stream>>>(S, lds, nb, step, Wg, flags);
+                    } else {
+                        int32_t r = launch_lp_update_tc5(ctx, S, lds, lds, nb, step, Wg, flags, npairs);
+                        if (r != QB200_OK) emit_rc = r;
+                    }
                 }
             }
             cudaMemcpyAsync(scale, scale + 1, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
+        };
+        // one stage-A sweep = 3 (nb - 1) launches with sweep-independent arguments: captured once, replayed
+        cudaGraphExec_t graph_a = nullptr;
+        static const bool graph_a_enabled = [] {
+            const char* e = getenv("QB200_SVD_GRAPH");
+            return !(e && e[0] == '0');
+        }();
+        if (graph_a_enabled && lp_mode == 0 && !ctx->prof_on && !qb_sync_debug()) {
+            cudaGraph_t g = nullptr;
+            if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                emit_sweep_a();
+                cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
+                if (ce == cudaSuccess && g && emit_rc == QB200_OK && cudaGraphInstantiate(&graph_a, g, 0) != cudaSuccess) graph_a = nullptr;
+                if (g) cudaGraphDestroy(g);
+                if (!graph_a) cudaGetLastError();  // fall back to plain launches
+                emit_rc = QB200_OK;
+            }
+        }
+        for (; sweeps_a < max_a; ) {
+            if (graph_a)
+                cudaGraphLaunch(graph_a, ctx->stream);
+            else
+                emit_sweep_a();
+            if (emit_rc != QB200_OK) {
+                if (graph_a) cudaGraphExecDestroy(graph_a);
+                return fail(emit_rc);
+            }
             ctx->launches += 3 * (int64_t)nsteps;
             ++sweeps_a;
             cudaError_t e = cudaMemcpyAsync(ctx->scratch_host, stat, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
             if (e == cudaSuccess) e = qb_stream_sync(ctx);
             if (e == cudaSuccess) e = cudaGetLastError();
-            if (e != cudaSuccess) return cuda_fail(e);
+            if (e != cudaSuccess) {
+                if (graph_a) cudaGraphExecDestroy(graph_a);
+                return cuda_fail(e);
+            }
             const double worst = ctx->scratch_host[0];
             if (getenv("QB200_DEBUG"))
                 fprintf(stderr, "[qb200 svd] stage A (fp32 shadow) sweep %d worst %.3e\n", sweeps_a - 1, worst);
@@ -1499,6 +1600,7 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
             if (prev < 1e-2 && worst > 0.3 * prev) break;  // at the noise floor of the shadow
             prev = worst;
         }
+        if (graph_a) cudaGraphExecDestroy(graph_a);
         {
             PhaseTimer pt(ctx, QB_PH_LP_GLUE, 8.0 * (5.0 * np * (double)np * np));
             c128* Va = wsa.get<c128>((size_t)np * np);
@@ -1557,7 +1659,7 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
             }
             {
                 PhaseTimer pt(ctx, QB_PH_JEVD, 0.0);
-                jacobi_evd_kernel<<<npairs, EVD_THREADS, EVD_SMEM, ctx->stream>>>(
+                (mode == 2 && evd_wreg() ? jacobi_evd_kernel<1> : jacobi_evd_kernel<0>)<<<npairs, EVD_THREADS, mode == 2 && evd_wreg() ? EVD_SMEM_WREG : EVD_SMEM, ctx->stream>>>(
                     Gpart, gram_ctas, g_nchunk, npairs, Wg, flags, stat, rot_tol, inner_sweeps, scale,
                     (unsigned long long*)(scale + 1), abs_c, nact, mode, Dstore, nb, step);
             }
