@@ -262,6 +262,204 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_c128_kernel(const GemmAr
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Thin variant for the shapes a sliced circuit network is made of: a huge free dimension against a gate-sized operand
+// (N <= 16 after orientation, K of 4 .. 128).  These contractions are HBM-bound streams (16 .. 64 flop per byte of the big
+// operand), and the 128 x 64 tile kernel above runs them latency-bound: one 512-thread CTA per SM (128 registers), each
+// with three dependent global round trips (offset table -> operand -> offset table -> store) and a tile that is 7/8
+// padding.  Here a CTA is 128 threads on a 128 x (8 NT) tile with 2 cp.async stages (35 KB): a dozen CTAs per SM keep
+// the memory system busy.  Same GemmArgs contract, fragment layout and (4M) complex product; no split-K.
+constexpr int TH_THREADS = 128, TH_STAGES = 2;
+template <int NT>
+struct ThinCfg {
+    static constexpr int BNT = 8 * NT, PBT = BNT + 2;
+    static constexpr size_t SMEM = (size_t)TH_STAGES * BK * (PA + PBT) * sizeof(c128);
+};
+
+template <int NT>
+__global__ void __launch_bounds__(TH_THREADS, NT == 1 ? 4 : 3) gemm_c128_thin_kernel(const GemmArgs p) {
+    constexpr int BNT = ThinCfg<NT>::BNT, PBT = ThinCfg<NT>::PBT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    c128* As = reinterpret_cast<c128*>(smem_raw);      // [TH_STAGES][BK][PA]
+    c128* Bs = As + (size_t)TH_STAGES * BK * PA;       // [TH_STAGES][BK][PBT]
+    const int tid = threadIdx.x, lane = tid & 31, wm = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BNT, z = blockIdx.z;
+    const c128* __restrict__ A = p.A + p.ab.at(z);
+    const c128* __restrict__ B = p.B + p.bb.at(z);
+    c128* __restrict__ C = p.C + p.cb.at(z);
+
+    constexpr int A_PER = BM * BK / TH_THREADS;  // 8
+    int a_ml[A_PER], a_kl[A_PER];
+    int64_t a_moff[A_PER];
+    bool a_ok[A_PER];
+#pragma unroll
+    for (int i = 0; i < A_PER; ++i) {
+        const int e = tid + TH_THREADS * i;
+        if (p.a_kfast) {
+            a_kl[i] = e % BK;
+            a_ml[i] = e / BK;
+        } else {
+            a_ml[i] = e % BM;
+            a_kl[i] = e / BM;
+        }
+        a_ok[i] = (m0 + a_ml[i]) < p.M;
+        a_moff[i] = a_ok[i] ? p.am.at(m0 + a_ml[i]) : 0;
+    }
+    // B tile: BK x BNT <= 128 elements, at most one per thread
+    const bool b_item = tid < BK * BNT;
+    const int b_kl = p.b_kfast ? tid % BK : tid / BNT, b_nl = p.b_kfast ? tid / BK : tid % BNT;
+    const bool b_ok = b_item && (n0 + b_nl) < p.N;
+    const int64_t b_noff = b_ok ? p.bn.at(n0 + b_nl) : 0;
+
+    const int KT = (p.K + BK - 1) / BK;
+    auto load_tile = [&](int kt, int s) {
+        c128* as = As + (size_t)s * BK * PA;
+        c128* bs = Bs + (size_t)s * BK * PBT;
+#pragma unroll
+        for (int i = 0; i < A_PER; ++i) {
+            const int kg = kt * BK + a_kl[i];
+            const bool ok = a_ok[i] && kg < p.K;
+            cp_async16(as + a_kl[i] * PA + a_ml[i], ok ? (A + a_moff[i] + p.ak.at(kg)) : p.A, ok);
+        }
+        if (b_item) {
+            const int kg = kt * BK + b_kl;
+            const bool ok = b_ok && kg < p.K;
+            cp_async16(bs + b_kl * PBT + b_nl, ok ? (B + b_noff + p.bk.at(kg)) : p.B, ok);
+        }
+    };
+    double accr[4][NT][2], acci[4][NT][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) accr[i][j][0] = accr[i][j][1] = acci[i][j][0] = acci[i][j][1] = 0.0;
+
+    load_tile(0, 0);
+    cp_async_commit();
+    const int sgnA = p.conjA ? 0x80000000 : 0, sgnB = p.conjB ? 0x80000000 : 0;
+    for (int kt = 0; kt < KT; ++kt) {
+        if (kt + 1 < KT) load_tile(kt + 1, (kt + 1) & 1);  // the other stage was released by the barrier that ended tile kt-1
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const c128* as = As + (size_t)(kt & 1) * BK * PA + wm * 32 + g;
+        const c128* bs = Bs + (size_t)(kt & 1) * BK * PBT + g;
+#pragma unroll
+        for (int kk = 0; kk < BK / 4; ++kk) {
+            double br[NT], bi[NT];
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                const c128 v = bs[(kk * 4 + t) * PBT + j * 8];
+                br[j] = v.x;
+                bi[j] = flip_sign(v.y, sgnB);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const c128 v = as[(kk * 4 + t) * PA + i * 8];
+                const double ar = v.x, ai = flip_sign(v.y, sgnA), nai = flip_sign(ai, 0x80000000);
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    dmma884(accr[i][j], ar, br[j]);
+                    dmma884(acci[i][j], ar, bi[j]);
+                    dmma884(accr[i][j], nai, bi[j]);
+                    dmma884(acci[i][j], ai, br[j]);
+                }
+            }
+        }
+        __syncthreads();  // every warp has left stage kt & 1 before the prefetch of tile kt + 2 overwrites it
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + wm * 32 + i * 8 + g;
+        if (m >= p.M) continue;
+        const int64_t mo = p.cm.at(m);
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int n = n0 + j * 8 + 2 * t + h;
+                if (n >= p.N) continue;
+                c128* dst = C + mo + p.cn.at(n);
+                const double vr = accr[i][j][h], vi = acci[i][j][h];
+                c128 o;
+                o.x = p.alpha.x * vr - p.alpha.y * vi;
+                o.y = p.alpha.x * vi + p.alpha.y * vr;
+                if (!p.beta_zero) {
+                    const c128 old = *dst;
+                    o.x += p.beta.x * old.x - p.beta.y * old.y;
+                    o.y += p.beta.x * old.y + p.beta.y * old.x;
+                }
+                *dst = o;
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Dot-product variant: at most 4 x 4 outputs over a long summed dimension (the closing contractions of a circuit
+// network: two big tensors sharing almost all their modes).  On the tile kernel every k tile costs a dependent
+// offset-table fetch for 1/32 of a tile of useful data; here consecutive threads walk k, keep the <= 16 complex sums
+// in registers and a fixed-order block reduction (shuffle tree, then warps in order) leaves one partial per CTA for
+// splitk_reduce_kernel -- deterministic, HBM-bound.
+constexpr int DOT_THREADS = 256;
+__global__ void __launch_bounds__(DOT_THREADS) gemm_c128_dot_kernel(const GemmArgs p) {
+    __shared__ double red[DOT_THREADS / 32][32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const c128* __restrict__ A = p.A + p.ab.at(0);
+    const c128* __restrict__ B = p.B + p.bb.at(0);
+    int64_t amo[4], bno[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        amo[i] = i < p.M ? p.am.at(i) : 0;
+        bno[i] = i < p.N ? p.bn.at(i) : 0;
+    }
+    double ar[4][4], ai[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ar[i][j] = ai[i][j] = 0.0;
+    const double sa = p.conjA ? -1.0 : 1.0, sb = p.conjB ? -1.0 : 1.0;
+    for (int64_t k = (int64_t)blockIdx.x * DOT_THREADS + tid; k < p.K; k += (int64_t)gridDim.x * DOT_THREADS) {
+        const int64_t ako = p.ak.at(k), bko = p.bk.at(k);
+        c128 a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            a[i] = i < p.M ? A[amo[i] + ako] : make_double2(0.0, 0.0);
+            b[i] = i < p.N ? B[bko + bno[i]] : make_double2(0.0, 0.0);
+            a[i].y *= sa;
+            b[i].y *= sb;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                ar[i][j] += a[i].x * b[j].x - a[i].y * b[j].y;
+                ai[i][j] += a[i].x * b[j].y + a[i].y * b[j].x;
+            }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double vr = warp_sum(ar[i][j]), vi = warp_sum(ai[i][j]);
+            if (lane == 0) {
+                red[warp][2 * (i + 4 * j)] = vr;
+                red[warp][2 * (i + 4 * j) + 1] = vi;
+            }
+        }
+    __syncthreads();
+    if (tid < 16) {
+        const int i = tid & 3, j = tid >> 2;
+        if (i < p.M && j < p.N) {
+            double vr = 0.0, vi = 0.0;
+            for (int w = 0; w < DOT_THREADS / 32; ++w) {
+                vr += red[w][2 * tid];
+                vi += red[w][2 * tid + 1];
+            }
+            p.partial[(size_t)blockIdx.x * p.M * p.N + i + (size_t)p.M * j] = make_double2(vr, vi);
+        }
+    }
+}
+
 // sums the split-K partials in a fixed order (deterministic) and applies alpha / beta
 __global__ void splitk_reduce_kernel(const GemmArgs p) {
     int64_t total = (int64_t)p.M * p.N;
@@ -311,6 +509,8 @@ int32_t build_offsets(qb200_ctx* ctx, const ModeList& ml, int64_t total, int64_t
 int32_t init_gemm(qb200_ctx* ctx) {
     QB_CUDA(ctx, cudaFuncSetAttribute(gemm_c128_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
     QB_CUDA(ctx, cudaFuncSetAttribute(gemm_c128_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+    QB_CUDA(ctx, cudaFuncSetAttribute(gemm_c128_thin_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ThinCfg<1>::SMEM));
+    QB_CUDA(ctx, cudaFuncSetAttribute(gemm_c128_thin_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ThinCfg<2>::SMEM));
     return QB200_OK;
 }
 
@@ -332,18 +532,47 @@ int32_t launch_gemm(qb200_ctx* ctx, const GemmArgs& args_in) {
     args.partial = nullptr;
     args.acc_init = 0;
     Workspace ws(ctx);
+    if (args.M <= 4 && args.batch == 1 && args.K >= 4096) {  // (N <= M after the orientation) long dot products
+        const int nsplit = (int)std::min<int64_t>(2 * ctx->sm_count, (args.K + DOT_THREADS - 1) / DOT_THREADS);
+        args.partial = ws.get<c128>((size_t)nsplit * args.M * args.N);
+        if (!args.partial) QB_FAIL(ctx, QB200_E_CUDA, "gemm: split-K workspace allocation failed");
+        args.ksplit = nsplit;
+        gemm_c128_dot_kernel<<<nsplit, DOT_THREADS, 0, ctx->stream>>>(args);
+        QB_LAUNCH_CHECK(ctx);
+        splitk_reduce_kernel<<<1, 32, 0, ctx->stream>>>(args);
+        QB_LAUNCH_CHECK(ctx);
+        return QB200_OK;
+    }
     {
         // split-K when the output has too few tiles to fill the machine and K is long
         int64_t tiles = (int64_t)((args.M + BM - 1) / BM) * ((args.N + BN - 1) / BN);
         int KT = (args.K + BK - 1) / BK;
         if (args.batch == 1 && tiles * 2 <= ctx->sm_count && KT >= 64) {
-            int want = (int)std::min<int64_t>(ctx->sm_count / tiles, KT / 16);
+            // long dot products (a handful of output tiles): up to 4 CTAs per SM, each k tile costs a dependent
+            // offset-table fetch, so short K ranges per CTA matter more than the (tiny) partial buffers
+            int want = (int)std::min<int64_t>((tiles * 8 <= ctx->sm_count ? 4 : 1) * (int64_t)ctx->sm_count / tiles, KT / 16);
             if (want > 1) {
                 args.partial = ws.get<c128>((size_t)want * args.M * args.N);
                 if (!args.partial) QB_FAIL(ctx, QB200_E_CUDA, "gemm: split-K workspace allocation failed");
                 args.ksplit = want;
             }
         }
+    }
+    // gate-sized operand against a long free dimension: the thin kernel (QB200_GEMM_THIN=0: A/B switch)
+    static const bool thin_on = [] {
+        const char* e = getenv("QB200_GEMM_THIN");
+        return !(e && e[0] == '0');
+    }();
+    if (thin_on && args.ksplit == 1 && args.N <= 16 && args.M >= 2048) {
+        const int nt = args.N <= 8 ? 1 : 2;
+        dim3 grid((args.M + BM - 1) / BM, (args.N + 8 * nt - 1) / (8 * nt), args.batch);
+        if (grid.z > 65535) QB_FAIL(ctx, QB200_E_UNSUPPORTED, "gemm grid too large");
+        if (nt == 1)
+            gemm_c128_thin_kernel<1><<<grid, TH_THREADS, ThinCfg<1>::SMEM, ctx->stream>>>(args);
+        else
+            gemm_c128_thin_kernel<2><<<grid, TH_THREADS, ThinCfg<2>::SMEM, ctx->stream>>>(args);
+        QB_LAUNCH_CHECK(ctx);
+        return QB200_OK;
     }
     // beta = 1 with alpha = +-1 and no split-K: fold C into the accumulators
     if (args.ksplit == 1 && !args.beta_zero && args.beta.x == 1.0 && args.beta.y == 0.0 && args.alpha.y == 0.0 &&

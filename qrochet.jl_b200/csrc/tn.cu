@@ -383,8 +383,25 @@ int32_t emit_slice(qb200_ctx* ctx, qb200_tnplan* P) {
                                                                                               P->cut_meta, P->leaf_arena);
         QB_LAUNCH_CHECK(ctx);
     }
-    for (int id = P->nleaves; id < (int)P->nodes.size(); ++id)
-        if (per_slice(P, id)) QB_TRY(launch_node(ctx, P, id));
+    static const bool debug_tn = getenv("QB200_DEBUG_TN") != nullptr;  // per-node timing (plain launches, one sync per node)
+    for (int id = P->nleaves; id < (int)P->nodes.size(); ++id) {
+        if (!per_slice(P, id)) continue;
+        if (debug_tn) {
+            double ms = 0.0;
+            QB_TRY(qb200_timer_begin(ctx));
+            QB_TRY(launch_node(ctx, P, id));
+            QB_TRY(qb200_timer_end(ctx, &ms));
+            const GemmArgs& g = P->steps[id - P->nleaves].args;
+            const double macs = (double)g.M * g.N * g.K * g.batch;
+            const double bytes = 16.0 * ((double)g.M * g.K + (double)g.K * g.N + (double)g.M * g.N) * g.batch;
+            fprintf(stderr, "[qb200 tn] node %4d M %8d N %8d K %6d batch %5d tab(am ak bk bn cm cn) %d%d%d%d%d%d kfast %d%d  %8.1f us  %6.2f TF/s  %7.1f GB/s\n",
+                    id, g.M, g.N, g.K, g.batch, g.am.tab != nullptr, g.ak.tab != nullptr, g.bk.tab != nullptr,
+                    g.bn.tab != nullptr, g.cm.tab != nullptr, g.cn.tab != nullptr, g.a_kfast, g.b_kfast, ms * 1e3,
+                    8.0 * macs / (ms * 1e9), bytes / (ms * 1e6));
+        } else {
+            QB_TRY(launch_node(ctx, P, id));
+        }
+    }
     tn_advance_cursor_kernel<<<1, 1, 0, ctx->stream>>>(P->cursor);
     QB_LAUNCH_CHECK(ctx);
     return QB200_OK;
@@ -396,7 +413,7 @@ bool want_graph(qb200_ctx* ctx) {
         const char* e = getenv("QB200_TN_GRAPH");
         return !(e && e[0] == '0');
     }();
-    return use_graph && !qb_sync_debug() && !ctx->prof_on;
+    return use_graph && !qb_sync_debug() && !ctx->prof_on && !getenv("QB200_DEBUG_TN");
 }
 
 // tables, arenas, leaf-slice descriptors and the slice graph for the given leaf buffers

@@ -46,6 +46,17 @@ CONTRACT_CASES = [
     ((1, 300000), (0, 1), (300000,), (1,), (0,)),                  # long K: split-K path
     ((300, 20), (0, 1), (20, 200), (1, 2), (0, 2)),                # M > N
     ((20, 200), (1, 0), (20, 300), (1, 2), (0, 2)),                # N > M -> swapped operands
+    # gate-sized operand against a long free dimension: the thin kernel (N <= 16, M >= 2048 after orientation)
+    ((4100, 8), (0, 1), (8, 8), (1, 2), (0, 2)),                   # N = 8, K = 8, ragged M
+    ((8, 4100), (1, 0), (5, 8), (2, 1), (2, 0)),                   # transposed operands and result, N = 5
+    ((2,) * 13, tuple(range(13)), (2,) * 6, (1, 5, 9, 20, 21, 22),
+     (0, 20, 2, 3, 4, 21, 6, 7, 8, 22, 10, 11, 12)),               # circuit-like: 3-qubit gate on a 13-qubit state
+    ((2,) * 14, tuple(range(14)), (4, 4, 2, 2), (30, 31, 3, 11),
+     (0, 1, 2, 30, 4, 5, 6, 7, 8, 9, 10, 31, 12, 13)),             # N = 16 (two 8-column tiles), K = 4
+    ((16, 130, 3), (0, 1, 2), (130, 12), (1, 5), (5, 0, 2)),        # K = 130 (17 k tiles), batchless, N = 12
+    ((2100, 3, 20), (0, 1, 2), (20, 3, 7), (2, 1, 5), (1, 0, 5)),   # kept shared mode = batch of thin products
+    ((3, 5000, 2), (0, 1, 2), (4, 2, 5000), (3, 2, 1), (3, 0)),     # <= 4 x 4 outputs over K = 10000: the dot kernel
+    ((2,) * 14, tuple(range(14)), (2,) * 14, (0, 20, 2, 3, 4, 5, 6, 7, 21, 9, 10, 11, 12, 13), (8, 1, 20, 21)),  # closing contraction
 ]
 
 
