@@ -11,14 +11,19 @@ namespace qb {
 // Cr = P - Q, Ci = S - P - Q at the end: 3 DMMA + operand sums (DADD) instead of 4 DMMA.  The component-wise error
 // bound becomes eps (|Ar| + |Ai|)(|Br| + |Bi|) -- norm-wise the same class as the 4M product.  accr/acci/accs hold
 // P/Q/S in that mode.
-template <int M3>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_c128_kernel(const GemmArgs p) {
+// HALF = 1: 64-row tile, 256 threads (8 warps as 2 x 4), 68 KB: TWO CTAs per SM.  For short K (a few k tiles per CTA) the
+// prologue (offset tables -> operands) and the epilogue (offset tables -> stores) of one CTA overlap the DMMA stream of
+// the other; with the 128-row tile's single resident CTA they are exposed (measured on the N = 64, K = 64 node of the
+// sliced benchmark network: 21 TFLOP/s).
+template <int M3, int HALF>
+__global__ void __launch_bounds__(HALF ? 256 : GEMM_THREADS, HALF ? 2 : 1) gemm_c128_kernel(const GemmArgs p) {
+    constexpr int TBM = HALF ? 64 : BM, TPA = TBM + 2, TTHREADS = TBM * 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    c128* As = reinterpret_cast<c128*>(smem_raw);  // [STAGES][BK][PA]
-    c128* Bs = As + (size_t)STAGES * BK * PA;      // [STAGES][BK][PB]
+    c128* As = reinterpret_cast<c128*>(smem_raw);  // [STAGES][BK][TPA]
+    c128* Bs = As + (size_t)STAGES * BK * TPA;      // [STAGES][BK][PB]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp & 3, wn = warp >> 2;  // wn in 0..3: 16 columns each
+    const int wm = warp % (TBM / 32), wn = warp / (TBM / 32);  // wn in 0..3: 16 columns each
     const int g = lane >> 2, t = lane & 3;
     // grouped rasterisation: consecutive CTAs walk 8 M-tiles x all N-tiles, so the tiles resident at any time share
     // A and B panels that fit in L2 (a plain M-fastest order streams all of A from HBM once per wave)
@@ -32,7 +37,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_c128_kernel(const GemmAr
         tile_m = first_m + (id % per_group) % gsz;
         tile_n = (id % per_group) / gsz;
     }
-    const int m0 = tile_m * BM, n0 = tile_n * BN;
+    const int m0 = tile_m * TBM, n0 = tile_n * BN;
     // blockIdx.z is the batch entry, or the K split when split-K is on (batch == 1 then)
     const int z = (p.ksplit > 1) ? 0 : blockIdx.z;
     const int split = (p.ksplit > 1) ? blockIdx.z : 0;
@@ -42,19 +47,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_c128_kernel(const GemmAr
     c128* __restrict__ C = p.C + p.cb.at(z);
 
     // ---- loader coordinates (fixed for the whole K loop) ----
-    constexpr int A_PER = BM * BK / GEMM_THREADS, B_PER = BN * BK / GEMM_THREADS;
+    constexpr int A_PER = TBM * BK / TTHREADS, B_PER = BN * BK / TTHREADS;
     int a_ml[A_PER], a_kl[A_PER];
     int64_t a_moff[A_PER];
     bool a_ok[A_PER];
 #pragma unroll
     for (int i = 0; i < A_PER; ++i) {
-        int e = tid + GEMM_THREADS * i;
+        int e = tid + TTHREADS * i;
         if (p.a_kfast) {
             a_kl[i] = e % BK;
             a_ml[i] = e / BK;
         } else {
-            a_ml[i] = e % BM;
-            a_kl[i] = e / BM;
+            a_ml[i] = e % TBM;
+            a_kl[i] = e / TBM;
         }
         a_ok[i] = (m0 + a_ml[i]) < p.M;
         a_moff[i] = a_ok[i] ? p.am.at(m0 + a_ml[i]) : 0;
@@ -64,7 +69,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_c128_kernel(const GemmAr
     bool b_ok[B_PER];
 #pragma unroll
     for (int i = 0; i < B_PER; ++i) {
-        int e = tid + GEMM_THREADS * i;
+        int e = tid + TTHREADS * i;
         if (p.b_kfast) {
             b_kl[i] = e % BK;
             b_nl[i] = e / BK;
@@ -82,14 +87,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_c128_kernel(const GemmAr
     const int KT = max(0, min(KT_all, kt0 + kt_per) - kt0);  // k tiles handled by this CTA
 
     auto load_tile = [&](int kt, int s) {
-        c128* as = As + (size_t)s * BK * PA;
+        c128* as = As + (size_t)s * BK * TPA;
         c128* bs = Bs + (size_t)s * BK * PB;
 #pragma unroll
         for (int i = 0; i < A_PER; ++i) {
             int kg = (kt0 + kt) * BK + a_kl[i];
             bool ok = a_ok[i] && kg < p.K;
             const c128* src = ok ? (A + a_moff[i] + p.ak.at(kg)) : p.A;
-            cp_async16(as + a_kl[i] * PA + a_ml[i], src, ok);
+            cp_async16(as + a_kl[i] * TPA + a_ml[i], src, ok);
         }
 #pragma unroll
         for (int i = 0; i < B_PER; ++i) {
@@ -152,7 +157,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_c128_kernel(const GemmAr
             if (nk < KT) load_tile(nk, nk % STAGES);
             cp_async_commit();
         }
-        const c128* as = As + (size_t)(kt % STAGES) * BK * PA + wm * 32 + g;
+        const c128* as = As + (size_t)(kt % STAGES) * BK * TPA + wm * 32 + g;
         const c128* bs = Bs + (size_t)(kt % STAGES) * BK * PB + wn * 16 + g;
 #pragma unroll
         for (int kk = 0; kk < BK / 4; ++kk) {
@@ -167,7 +172,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_c128_kernel(const GemmAr
                 }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    c128 v = as[(kk * 4 + t) * PA + i * 8];
+                    c128 v = as[(kk * 4 + t) * TPA + i * 8];
                     const double ar = v.x, ai = flip_sign(v.y, sgnA), asum = ar + ai;
 #pragma unroll
                     for (int j = 0; j < NJ; ++j) {
@@ -180,7 +185,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_c128_kernel(const GemmAr
             double ar[4], ai[4], nai[4], br[NJ], bi[NJ];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                c128 v = as[(kk * 4 + t) * PA + i * 8];
+                c128 v = as[(kk * 4 + t) * TPA + i * 8];
                 ar[i] = v.x;
                 ai[i] = flip_sign(v.y, sgnA);
                 nai[i] = flip_sign(ai[i], 0x80000000);
@@ -277,14 +282,15 @@ struct ThinCfg {
 };
 
 template <int NT>
-__global__ void __launch_bounds__(TH_THREADS, NT == 1 ? 4 : 3) gemm_c128_thin_kernel(const GemmArgs p) {
+__global__ void __launch_bounds__(TH_THREADS, NT == 1 ? 4 : 3) gemm_c128_thin_kernel(const GemmArgs p, int ntiles) {
     constexpr int BNT = ThinCfg<NT>::BNT, PBT = ThinCfg<NT>::PBT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     c128* As = reinterpret_cast<c128*>(smem_raw);      // [TH_STAGES][BK][PA]
     c128* Bs = As + (size_t)TH_STAGES * BK * PA;       // [TH_STAGES][BK][PBT]
     const int tid = threadIdx.x, lane = tid & 31, wm = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BNT, z = blockIdx.z;
+    // N tiles fastest: the CTAs that share an A tile are resident together (A comes from HBM once, from L2 afterwards)
+    const int m0 = (blockIdx.x / ntiles) * BM, n0 = (blockIdx.x % ntiles) * BNT, z = blockIdx.z;
     const c128* __restrict__ A = p.A + p.ab.at(z);
     const c128* __restrict__ B = p.B + p.bb.at(z);
     c128* __restrict__ C = p.C + p.cb.at(z);
@@ -507,8 +513,10 @@ int32_t build_offsets(qb200_ctx* ctx, const ModeList& ml, int64_t total, int64_t
 }
 
 int32_t init_gemm(qb200_ctx* ctx) {
-    QB_CUDA(ctx, cudaFuncSetAttribute(gemm_c128_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-    QB_CUDA(ctx, cudaFuncSetAttribute(gemm_c128_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+    QB_CUDA(ctx, cudaFuncSetAttribute(gemm_c128_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+    QB_CUDA(ctx, cudaFuncSetAttribute(gemm_c128_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+    QB_CUDA(ctx, cudaFuncSetAttribute(gemm_c128_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_HALF));
+    QB_CUDA(ctx, cudaFuncSetAttribute(gemm_c128_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_HALF));
     QB_CUDA(ctx, cudaFuncSetAttribute(gemm_c128_thin_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ThinCfg<1>::SMEM));
     QB_CUDA(ctx, cudaFuncSetAttribute(gemm_c128_thin_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ThinCfg<2>::SMEM));
     return QB200_OK;
@@ -563,14 +571,17 @@ int32_t launch_gemm(qb200_ctx* ctx, const GemmArgs& args_in) {
         const char* e = getenv("QB200_GEMM_THIN");
         return !(e && e[0] == '0');
     }();
-    if (thin_on && args.ksplit == 1 && args.N <= 16 && args.M >= 2048) {
+    // N <= 16: always; N <= 64 while K <= 16 (HBM-bound: the 4M product and the A tile re-read from L2 by the N tiles cost
+    // less than the tile kernel's single resident CTA per SM; with longer K that kernel's 3M product wins)
+    if (thin_on && args.ksplit == 1 && args.M >= 2048 && (args.N <= 16 || (args.N <= 64 && args.K <= 16))) {
         const int nt = args.N <= 8 ? 1 : 2;
-        dim3 grid((args.M + BM - 1) / BM, (args.N + 8 * nt - 1) / (8 * nt), args.batch);
+        const int ntiles = (args.N + 8 * nt - 1) / (8 * nt);
+        dim3 grid((unsigned)((args.M + BM - 1) / BM) * ntiles, 1, args.batch);
         if (grid.z > 65535) QB_FAIL(ctx, QB200_E_UNSUPPORTED, "gemm grid too large");
         if (nt == 1)
-            gemm_c128_thin_kernel<1><<<grid, TH_THREADS, ThinCfg<1>::SMEM, ctx->stream>>>(args);
+            gemm_c128_thin_kernel<1><<<grid, TH_THREADS, ThinCfg<1>::SMEM, ctx->stream>>>(args, ntiles);
         else
-            gemm_c128_thin_kernel<2><<<grid, TH_THREADS, ThinCfg<2>::SMEM, ctx->stream>>>(args);
+            gemm_c128_thin_kernel<2><<<grid, TH_THREADS, ThinCfg<2>::SMEM, ctx->stream>>>(args, ntiles);
         QB_LAUNCH_CHECK(ctx);
         return QB200_OK;
     }
@@ -578,13 +589,23 @@ int32_t launch_gemm(qb200_ctx* ctx, const GemmArgs& args_in) {
     if (args.ksplit == 1 && !args.beta_zero && args.beta.x == 1.0 && args.beta.y == 0.0 && args.alpha.y == 0.0 &&
         (args.alpha.x == 1.0 || args.alpha.x == -1.0))
         args.acc_init = 1;
-    dim3 grid((args.M + BM - 1) / BM, (args.N + BN - 1) / BN, args.ksplit > 1 ? args.ksplit : args.batch);
+    // short K, many tiles: the 64-row tile with two CTAs per SM (QB200_GEMM_HALF=0: A/B switch)
+    static const bool half_on = [] {
+        const char* e = getenv("QB200_GEMM_HALF");
+        return !(e && e[0] == '0');
+    }();
+    const bool half = half_on && args.ksplit == 1 && args.K <= 128 && (int64_t)((args.M + 63) / 64) * ((args.N + BN - 1) / BN) * args.batch >= 4 * ctx->sm_count;
+    const int tbm = half ? 64 : BM;
+    dim3 grid((args.M + tbm - 1) / tbm, (args.N + BN - 1) / BN, args.ksplit > 1 ? args.ksplit : args.batch);
     if (grid.y > 65535 || grid.z > 65535) QB_FAIL(ctx, QB200_E_UNSUPPORTED, "gemm grid too large");
     static const bool gemm_3m = [] {  // QB200_GEMM_3M=0 selects the 4-DMMA complex product
         const char* e = getenv("QB200_GEMM_3M");
         return !(e && e[0] == '0');
     }();
-    (gemm_3m ? gemm_c128_kernel<1> : gemm_c128_kernel<0>)<<<grid, GEMM_THREADS, GEMM_SMEM, ctx->stream>>>(args);
+    if (half)
+        (gemm_3m ? gemm_c128_kernel<1, 1> : gemm_c128_kernel<0, 1>)<<<grid, 256, GEMM_SMEM_HALF, ctx->stream>>>(args);
+    else
+        (gemm_3m ? gemm_c128_kernel<1, 0> : gemm_c128_kernel<0, 0>)<<<grid, GEMM_THREADS, GEMM_SMEM, ctx->stream>>>(args);
     QB_LAUNCH_CHECK(ctx);
     if (args.ksplit > 1) {
         int64_t total = (int64_t)args.M * args.N;

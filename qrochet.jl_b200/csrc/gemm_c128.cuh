@@ -21,6 +21,7 @@ constexpr int BM = 128, BN = 64, BK = 8, STAGES = 4;
 constexpr int PA = BM + 2, PB = BN + 2;
 constexpr int GEMM_THREADS = 512;  // 16 warps as 4(M) x 4(N), warp tile 32 x 16: 4 warps per SMSP hide LDS / barrier stalls
 constexpr size_t GEMM_SMEM = (size_t)STAGES * BK * (PA + PB) * sizeof(c128);
+constexpr size_t GEMM_SMEM_HALF = (size_t)STAGES * BK * (64 + 2 + PB) * sizeof(c128);  // 64-row tile variant
 
 struct Operand {
     const int64_t* tab;  // offset table or null

@@ -159,21 +159,40 @@ int32_t qb200_tn_plan_opt(qb200_ctx* ctx, int32_t ntensors, const int32_t* ranks
         }
     }
     PlanResult pr = plan_network(leaf_modes, dext, max_elements, optimizer);
-    for (size_t id = ntensors; id < pr.nodes.size(); ++id) {
-        TNNode n;
-        n.left = pr.nodes[id].left;
-        n.right = pr.nodes[id].right;
-        for (int x : pr.nodes[id].modes) {
-            n.modes.push_back(label[x]);
-            n.ext.push_back(dext[x]);
-        }
-        P->nodes.push_back(n);
-    }
     std::set<int32_t> cut;
     for (int x : pr.cut) {
         cut.insert(label[x]);
         P->sliced.push_back(label[x]);
         P->sliced_ext.push_back(dext[x]);
+    }
+    // Storage order of an intermediate (free to choose: only the path and the cuts are part of the plan's contract):
+    // the kept modes of the LARGER child first, in that child's order, then those of the smaller one.  The larger child
+    // becomes the M side of the GEMM, whose rows enumerate its free modes in its own order, so both the reads of that
+    // operand and the stores of the result walk memory contiguously (a gate-sized left child would otherwise put ITS
+    // modes fastest and every 16-byte store of the big result would land in a sector of its own: measured 4x the
+    // algorithmic L2 write traffic).
+    auto sliced_size = [&](const TNNode& n) {
+        double s = 1.0;
+        for (size_t i = 0; i < n.modes.size(); ++i)
+            if (!cut.count(n.modes[i])) s *= (double)n.ext[i];
+        return s;
+    };
+    for (size_t id = ntensors; id < pr.nodes.size(); ++id) {
+        TNNode n;
+        n.left = pr.nodes[id].left;
+        n.right = pr.nodes[id].right;
+        std::set<int32_t> kept;
+        for (int x : pr.nodes[id].modes) kept.insert(label[x]);
+        const TNNode &L = P->nodes[n.left], &R = P->nodes[n.right];
+        const bool right_first = sliced_size(R) > sliced_size(L);
+        for (const TNNode* c : {right_first ? &R : &L, right_first ? &L : &R})
+            for (size_t i = 0; i < c->modes.size(); ++i)
+                if (kept.count(c->modes[i])) {
+                    n.modes.push_back(c->modes[i]);
+                    n.ext.push_back(c->ext[i]);
+                    kept.erase(c->modes[i]);  // a kept shared (batch) mode is stored once, at its first position
+                }
+        P->nodes.push_back(n);
     }
     P->nslices = pr.nslices;
     auto node_size = [&](const TNNode& n) {

@@ -55,6 +55,8 @@ CONTRACT_CASES = [
      (0, 1, 2, 30, 4, 5, 6, 7, 8, 9, 10, 31, 12, 13)),             # N = 16 (two 8-column tiles), K = 4
     ((16, 130, 3), (0, 1, 2), (130, 12), (1, 5), (5, 0, 2)),        # K = 130 (17 k tiles), batchless, N = 12
     ((2100, 3, 20), (0, 1, 2), (20, 3, 7), (2, 1, 5), (1, 0, 5)),   # kept shared mode = batch of thin products
+    ((2,) * 14, tuple(range(14)), (2,) * 9, (2, 6, 10, 20, 21, 22, 23, 24, 25),
+     (0, 1, 20, 3, 4, 5, 21, 7, 8, 9, 22, 11, 12, 13, 23, 24, 25)),  # N = 64 in four 16-column tiles, K = 8
     ((3, 5000, 2), (0, 1, 2), (4, 2, 5000), (3, 2, 1), (3, 0)),     # <= 4 x 4 outputs over K = 10000: the dot kernel
     ((2,) * 14, tuple(range(14)), (2,) * 14, (0, 20, 2, 3, 4, 5, 6, 7, 21, 9, 10, 11, 12, 13), (8, 1, 20, 21)),  # closing contraction
 ]

@@ -8,3 +8,5 @@ grep -A400 "rep 1" $out/nodes.err | sort -k22 -n -r | head -8
 python tools/time_sliced.py 40 6 24 > $out/sliced_thin.log 2>&1; cat $out/sliced_thin.log
 QB200_GEMM_THIN=0 python tools/time_sliced.py 40 6 24 > $out/sliced_nothin.log 2>&1; tail -1 $out/sliced_nothin.log
 python tools/time_sliced.py 40 7 24 64 > $out/sliced_d7.log 2>&1; cat $out/sliced_d7.log
+QB200_GEMM_HALF=0 python tools/time_sliced.py 40 6 24 > $out/sliced_nohalf.log 2>&1; tail -1 $out/sliced_nohalf.log
+python tools/time_gemm.py > $out/time_gemm.log 2>&1; tail -12 $out/time_gemm.log
