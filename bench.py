@@ -442,7 +442,8 @@ def run_b200(args):
                            "(MEASURED_PEAKS.json has no FP64 figure)",
             "peak_before_after": [peak_before, peak_after], "peak_runs": [peak_before_runs, peak_after_runs],
             "peak_stable": bool(peak_stable),
-            "traffic": (traffic or {}).get("jacobi_update_kernel", {}).get("dram_bytes_per_launch") if traffic else None,
+            "traffic": next((v.get("dram_bytes_per_launch") for k, v in (traffic or {}).items()
+                             if k.startswith("jacobi_update_kernel")), None),
             "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch of jacobi_update_kernel from the "
                             "committed ncu --set full capture (profiles/r2_ncu_traffic.json, written by "
                             "tools/ncu_traffic.py); algorithmic: 2 x 32 MiB of X + 2 MiB of W per launch",
@@ -509,6 +510,20 @@ def run_b200(args):
                                                                               check_against=amp_ref)
         except Exception as e:  # never lose the headline line to the extra measurement
             line["sliced_contraction"] = {"error": str(e)[:300]}
+        try:
+            # one layer deeper: 57x the work of the depth-6 network with the round-2 planner (1024 slices at the 2^24
+            # target), i.e. enough slices per GPU for the 1 -> 8 GPU curve to mean something; checked against the same
+            # amplitude from the 64-slice plan of the 2^28 target
+            big7, amp7 = run_sliced(ctx, qb, 0, world=1, peak_tf=peak_tf, barrier=lambda: ctx.synchronize(),
+                                    max_over_ranks=lambda x: x, depth=7, target=2 ** 28, reps=1)
+            line["sliced_contraction_depth7"], _ = run_sliced(ctx, qb, rank, world, peak_tf, barrier, max_over_ranks,
+                                                              depth=7, reps=2, check_against=amp7)
+            line["sliced_contraction_depth7"]["amplitude_check"]["against"] = (
+                "the same amplitude from the 64-slice plan of the 2^28 slice target, contracted on one GPU")
+            if world == 1:
+                line["sliced_contraction_depth7_large_target"] = big7
+        except Exception as e:
+            line["sliced_contraction_depth7"] = {"error": str(e)[:300]}
     if not args.no_expect:
         try:
             line["expect_batch"] = run_expect_batch(ctx, qb, rank, world, n, chi, barrier, max_over_ranks)
