@@ -401,6 +401,185 @@ __global__ void __launch_bounds__(TH_THREADS, NT == 1 ? 4 : 3) gemm_c128_thin_ke
 }
 
 // ---------------------------------------------------------------------------------------------
+// Streaming variant of the thin kernel for a single N tile (N <= 16, K <= 128): persistent CTAs, the gate-sized operand
+// parked in shared memory once, and ONE software pipeline over the flattened (M tile, k tile) sequence -- a 3-stage
+// cp.async ring that runs on into the next M tile while the current one is computed and stored.  What made the
+// per-tile kernel latency-bound is taken off the critical path: the row-offset tables (am for the loads, cm for the
+// stores) are fetched one tile ahead into registers, the k- and n-offset tables live in shared memory.
+constexpr int ST_STAGES = 3, ST_MAXK = 128;
+template <int NT>
+struct StreamCfg {
+    static constexpr int BNT = 8 * NT, PBT = BNT + 2;
+    static size_t smem(int K) {
+        const int kp = (K + BK - 1) / BK * BK;
+        return (size_t)ST_STAGES * BK * PA * sizeof(c128) + (size_t)kp * PBT * sizeof(c128) + (size_t)(kp + BNT) * sizeof(int64_t);
+    }
+};
+
+template <int NT>
+__global__ void __launch_bounds__(TH_THREADS, NT == 1 ? 4 : 3) gemm_c128_stream_kernel(const GemmArgs p, int mtiles) {
+    constexpr int BNT = StreamCfg<NT>::BNT, PBT = StreamCfg<NT>::PBT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int KT = (p.K + BK - 1) / BK, KP = KT * BK;
+    c128* As = reinterpret_cast<c128*>(smem_raw);             // [ST_STAGES][BK][PA]
+    c128* Bs = As + (size_t)ST_STAGES * BK * PA;              // [KP][PBT], zero padded
+    int64_t* aks = reinterpret_cast<int64_t*>(Bs + (size_t)KP * PBT);  // ak offsets [KP]
+    int64_t* cns = aks + KP;                                  // cn offsets [BNT]
+    const int tid = threadIdx.x, lane = tid & 31, wm = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int z = blockIdx.z;
+    const c128* __restrict__ A = p.A + p.ab.at(z);
+    const c128* __restrict__ B = p.B + p.bb.at(z);
+    c128* __restrict__ C = p.C + p.cb.at(z);
+
+    for (int k = tid; k < KP; k += TH_THREADS) aks[k] = k < p.K ? p.ak.at(k) : 0;
+    if (tid < BNT) cns[tid] = tid < p.N ? p.cn.at(tid) : 0;
+    for (int e = tid; e < KP * BNT; e += TH_THREADS) {
+        const int k = p.b_kfast ? e % KP : e / BNT, n = p.b_kfast ? e / KP : e % BNT;
+        const bool ok = k < p.K && n < p.N;
+        cp_async16(Bs + k * PBT + n, ok ? (B + p.bn.at(n) + p.bk.at(k)) : p.B, ok);
+    }
+    cp_async_commit();  // the oldest group: complete at the first wait below
+
+    constexpr int A_PER = BM * BK / TH_THREADS;  // 8
+    int a_ml[A_PER], a_kl[A_PER];
+#pragma unroll
+    for (int i = 0; i < A_PER; ++i) {
+        const int e = tid + TH_THREADS * i;
+        if (p.a_kfast) {
+            a_kl[i] = e % BK;
+            a_ml[i] = e / BK;
+        } else {
+            a_ml[i] = e % BM;
+            a_kl[i] = e / BM;
+        }
+    }
+    const int ntl = (mtiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // M tiles of this CTA
+    const int total = ntl * KT;
+    auto tile_m0 = [&](int j) { return ((int)blockIdx.x + j * (int)gridDim.x) * BM; };
+    // row offsets of the loads (8 per thread) and of the stores (4 per thread), one tile ahead
+    int64_t am_iss[A_PER], am_nxt[A_PER], cm_cur[4], cm_nxt[4];
+    unsigned ok_iss = 0, ok_nxt = 0;
+    auto fetch_am = [&](int j, int64_t (&dst)[A_PER], unsigned& okm) {
+        okm = 0;
+        if (j >= ntl) return;
+        const int m0 = tile_m0(j);
+#pragma unroll
+        for (int i = 0; i < A_PER; ++i) {
+            const bool ok = (m0 + a_ml[i]) < p.M;
+            dst[i] = ok ? p.am.at(m0 + a_ml[i]) : 0;
+            okm |= (ok ? 1u : 0u) << i;
+        }
+    };
+    auto fetch_cm = [&](int j, int64_t (&dst)[4]) {
+        if (j >= ntl) return;
+        const int m0 = tile_m0(j);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int m = m0 + wm * 32 + i * 8 + g;
+            dst[i] = m < p.M ? p.cm.at(m) : -1;
+        }
+    };
+    fetch_am(0, am_iss, ok_iss);
+    fetch_am(1, am_nxt, ok_nxt);
+    fetch_cm(0, cm_cur);
+    fetch_cm(1, cm_nxt);
+    __syncthreads();  // aks / cns visible
+
+    int qi = 0, ji = 0, kti = 0;
+    auto issue = [&]() {
+        if (qi < total) {
+            c128* as = As + (size_t)(qi % ST_STAGES) * BK * PA;
+#pragma unroll
+            for (int i = 0; i < A_PER; ++i) {
+                const int kg = kti * BK + a_kl[i];
+                const bool ok = ((ok_iss >> i) & 1u) && kg < p.K;
+                cp_async16(as + a_kl[i] * PA + a_ml[i], ok ? (A + am_iss[i] + aks[kg]) : p.A, ok);
+            }
+            if (++kti == KT) {
+                kti = 0;
+                ++ji;
+#pragma unroll
+                for (int i = 0; i < A_PER; ++i) am_iss[i] = am_nxt[i];
+                ok_iss = ok_nxt;
+                fetch_am(ji + 1, am_nxt, ok_nxt);
+            }
+        }
+        cp_async_commit();
+        ++qi;
+    };
+    double accr[4][NT][2], acci[4][NT][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) accr[i][j][0] = accr[i][j][1] = acci[i][j][0] = acci[i][j][1] = 0.0;
+#pragma unroll
+    for (int s = 0; s < ST_STAGES - 1; ++s) issue();
+    const int sgnA = p.conjA ? 0x80000000 : 0, sgnB = p.conjB ? 0x80000000 : 0;
+    int jc = 0, kt = 0;
+    for (int qc = 0; qc < total; ++qc) {
+        cp_async_wait<ST_STAGES - 2>();
+        __syncthreads();  // stage qc landed for everyone; everyone has left stage qc - 1, which the next issue overwrites
+        issue();
+        const c128* as = As + (size_t)(qc % ST_STAGES) * BK * PA + wm * 32 + g;
+        const c128* bs = Bs + (size_t)kt * BK * PBT + g;
+#pragma unroll
+        for (int kk = 0; kk < BK / 4; ++kk) {
+            double br[NT], bi[NT];
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                const c128 v = bs[(kk * 4 + t) * PBT + j * 8];
+                br[j] = v.x;
+                bi[j] = flip_sign(v.y, sgnB);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const c128 v = as[(kk * 4 + t) * PA + i * 8];
+                const double ar = v.x, ai = flip_sign(v.y, sgnA), nai = flip_sign(ai, 0x80000000);
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    dmma884(accr[i][j], ar, br[j]);
+                    dmma884(acci[i][j], ar, bi[j]);
+                    dmma884(accr[i][j], nai, bi[j]);
+                    dmma884(acci[i][j], ai, br[j]);
+                }
+            }
+        }
+        if (++kt == KT) {  // the tile is complete: store it, start the next one
+            kt = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int64_t mo = cm_cur[i];
+#pragma unroll
+                for (int j = 0; j < NT; ++j)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int n = j * 8 + 2 * t + h;
+                        const double vr = accr[i][j][h], vi = acci[i][j][h];
+                        accr[i][j][h] = acci[i][j][h] = 0.0;
+                        if (mo < 0 || n >= p.N) continue;
+                        c128* dst = C + mo + cns[n];
+                        c128 o;
+                        o.x = p.alpha.x * vr - p.alpha.y * vi;
+                        o.y = p.alpha.x * vi + p.alpha.y * vr;
+                        if (!p.beta_zero) {
+                            const c128 old = *dst;
+                            o.x += p.beta.x * old.x - p.beta.y * old.y;
+                            o.y += p.beta.x * old.y + p.beta.y * old.x;
+                        }
+                        *dst = o;
+                    }
+            }
+            ++jc;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cm_cur[i] = cm_nxt[i];
+            fetch_cm(jc + 1, cm_nxt);
+        }
+    }
+    cp_async_wait<0>();
+}
+
+// ---------------------------------------------------------------------------------------------
 // Dot-product variant: at most 4 x 4 outputs over a long summed dimension (the closing contractions of a circuit
 // network: two big tensors sharing almost all their modes).  On the tile kernel every k tile costs a dependent
 // offset-table fetch for 1/32 of a tile of useful data; here consecutive threads walk k, keep the <= 16 complex sums
@@ -519,6 +698,8 @@ int32_t init_gemm(qb200_ctx* ctx) {
     QB_CUDA(ctx, cudaFuncSetAttribute(gemm_c128_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_HALF));
     QB_CUDA(ctx, cudaFuncSetAttribute(gemm_c128_thin_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ThinCfg<1>::SMEM));
     QB_CUDA(ctx, cudaFuncSetAttribute(gemm_c128_thin_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ThinCfg<2>::SMEM));
+    QB_CUDA(ctx, cudaFuncSetAttribute(gemm_c128_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StreamCfg<1>::smem(ST_MAXK)));
+    QB_CUDA(ctx, cudaFuncSetAttribute(gemm_c128_stream_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StreamCfg<2>::smem(ST_MAXK)));
     return QB200_OK;
 }
 
@@ -578,6 +759,20 @@ int32_t launch_gemm(qb200_ctx* ctx, const GemmArgs& args_in) {
         const int ntiles = (args.N + 8 * nt - 1) / (8 * nt);
         dim3 grid((unsigned)((args.M + BM - 1) / BM) * ntiles, 1, args.batch);
         if (grid.z > 65535) QB_FAIL(ctx, QB200_E_UNSUPPORTED, "gemm grid too large");
+        static const bool stream_on = [] {  // QB200_GEMM_STREAM=0: per-tile thin kernel only (A/B switch)
+            const char* e = getenv("QB200_GEMM_STREAM");
+            return !(e && e[0] == '0');
+        }();
+        if (stream_on && ntiles == 1 && args.K <= 32) {  // longer K: the per-tile kernel's 4 CTAs per SM win (K = 128: 91 vs 112 us)
+            const int mtiles = (args.M + BM - 1) / BM;
+            dim3 sgrid((unsigned)std::min(mtiles, (nt == 1 ? 4 : 3) * ctx->sm_count), 1, args.batch);
+            if (nt == 1)
+                gemm_c128_stream_kernel<1><<<sgrid, TH_THREADS, StreamCfg<1>::smem(args.K), ctx->stream>>>(args, mtiles);
+            else
+                gemm_c128_stream_kernel<2><<<sgrid, TH_THREADS, StreamCfg<2>::smem(args.K), ctx->stream>>>(args, mtiles);
+            QB_LAUNCH_CHECK(ctx);
+            return QB200_OK;
+        }
         if (nt == 1)
             gemm_c128_thin_kernel<1><<<grid, TH_THREADS, ThinCfg<1>::SMEM, ctx->stream>>>(args, ntiles);
         else
