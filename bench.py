@@ -112,11 +112,15 @@ class ClockSampler:
         self.device = device
         self.proc = None
         self.lines = []
+        # sampling period; QB200_BENCH_CLOCK_MS overrides (0: no sampling), see the note where the sampler is started
+        self.period_ms = int(os.environ.get("QB200_BENCH_CLOCK_MS", "500"))
 
     def start(self):
+        if self.period_ms <= 0:
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "500"],
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()

@@ -419,12 +419,20 @@ static int32_t robust_panel(qb200_ctx* ctx, int64_t m, int w, c128* P, int64_t l
 // the panel is too ill conditioned for a Gram-based step, or a column has lost more than CAREFUL_LOSS of its norm to the
 // earlier columns, the saved panel is restored and factorised by robust_panel (Householder TSQR, re-projection,
 // completion of dependent columns) instead.  Trailing updates: C = Q_p^H T (split-K GEMM), T -= Q_p C.
-static int32_t bgs_pass(qb200_ctx* ctx, int64_t m, int64_t k, c128* Q, int64_t ldq, c128* R, int64_t ldr) {
+// optimistic != nullptr: every panel takes the Cholesky-QR fast path WITHOUT the per-panel read-back of its failure flag
+// (one host round trip per 64 columns: 32 per bulk TEBD bond, each a sleep / wake-up of the worker thread -- what made
+// the sweep time depend on how busy the host's cores are).  The flag accumulates on the device and is read ONCE at the
+// end; *optimistic = true means "some panel failed, the contents of Q and R are garbage": the caller restores its input
+// and runs the careful pass.  Only possible when every panel is a full fast-path panel.
+static int32_t bgs_pass(qb200_ctx* ctx, int64_t m, int64_t k, c128* Q, int64_t ldq, c128* R, int64_t ldr,
+                        bool* optimistic = nullptr) {
     const c128 one = make_double2(1.0, 0.0), zero = make_double2(0.0, 0.0), mone = make_double2(-1.0, 0.0);
     zero_kernel<<<(unsigned)std::min<int64_t>((k * k + 255) / 256, 4096), 256, 0, ctx->stream>>>(R, k, k, ldr);
     QB_LAUNCH_CHECK(ctx);
     const int PW = 64;
     const bool fast_ok = (m % 64 == 0) && m >= 64 && !getenv("QB200_NO_CHOLQR");
+    const bool opt = optimistic && fast_ok && (k % 64 == 0);
+    if (optimistic) *optimistic = false;
     Workspace ws(ctx);
     c128 *Gpart = nullptr, *Wbuf = nullptr, *R1 = nullptr, *R2 = nullptr;
     int* flags = nullptr;
@@ -440,6 +448,7 @@ static int32_t bgs_pass(qb200_ctx* ctx, int64_t m, int64_t k, c128* Q, int64_t l
         R2 = ws.get<c128>(64 * 64);
         flags = ws.get<int>(2);
         if (!Gpart || !Wbuf || !R1 || !R2 || !flags) QB_FAIL(ctx, QB200_E_CUDA, "qr: workspace allocation failed");
+        if (opt) QB_CUDA(ctx, cudaMemsetAsync(flags, 0, 2 * sizeof(int), ctx->stream));
     }
     // super-panels of 128 columns = two Cholesky-QR sub-panels of 64; the trailing matrix is updated once per
     // super-panel (K = 128 GEMMs: half the launches, twice the depth)
@@ -451,8 +460,17 @@ static int32_t bgs_pass(qb200_ctx* ctx, int64_t m, int64_t k, c128* Q, int64_t l
             c128* P = Q + j0 * ldq;
             c128* Rpp = R + j0 + j0 * ldr;
             bool done = false;
-            QB_TRY(qb_copy_matrix(ctx, m, w, P, ldq, save, m, 0));
-            if (fast_ok && w == PW) {
+            if (opt) {
+                QB_CUDA(ctx, cudaMemsetAsync(flags, 0, sizeof(int), ctx->stream));  // flags[1] (failure) accumulates
+                QB_TRY(qb_cholqr_panel_step(ctx, P, ldq, m, R1, 64, Gpart, Wbuf, flags, flags + 1, before2 + j0,
+                                            CAREFUL_LOSS));
+                QB_TRY(qb_cholqr_panel_step(ctx, P, ldq, m, R2, 64, Gpart, Wbuf, flags, flags + 1, nullptr, 0.0));
+                QB_TRY(qb_gemm(ctx, 0, 0, PW, PW, PW, one, R2, 64, R1, 64, zero, Rpp, ldr));
+                done = true;
+            } else {
+                QB_TRY(qb_copy_matrix(ctx, m, w, P, ldq, save, m, 0));
+            }
+            if (!opt && fast_ok && w == PW) {
                 QB_CUDA(ctx, cudaMemsetAsync(flags, 0, 2 * sizeof(int), ctx->stream));
                 QB_TRY(qb_cholqr_panel_step(ctx, P, ldq, m, R1, 64, Gpart, Wbuf, flags, flags + 1, before2 + j0,
                                             CAREFUL_LOSS));
@@ -485,7 +503,28 @@ static int32_t bgs_pass(qb200_ctx* ctx, int64_t m, int64_t k, c128* Q, int64_t l
             QB_TRY(qb_gemm(ctx, 0, 0, m, nt, sw, mone, P, ldq, C, ldr, one, T, ldq));   // T -= P C
         }
     }
+    if (opt) {
+        QB_CUDA(ctx, cudaMemcpyAsync(ctx->scratch_host, flags + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        QB_CUDA(ctx, qb_stream_sync(ctx));
+        *optimistic = *reinterpret_cast<int*>(ctx->scratch_host) != 0;
+    }
     return QB200_OK;
+}
+
+// first pass over a fresh copy of A: optimistic, with the careful pass as the fallback
+static int32_t first_pass(qb200_ctx* ctx, int64_t m, int64_t k, const c128* A, int64_t lda, c128* Q, int64_t ldq, c128* R,
+                          int64_t ldr) {
+    static const bool optimistic_on = [] {  // QB200_QR_OPTIMISTIC=0: per-panel read-back as before (A/B switch)
+        const char* e = getenv("QB200_QR_OPTIMISTIC");
+        return !(e && e[0] == '0');
+    }();
+    if (optimistic_on) {
+        bool failed = false;
+        QB_TRY(bgs_pass(ctx, m, k, Q, ldq, R, ldr, &failed));
+        if (!failed) return QB200_OK;
+        QB_TRY(qb_copy_matrix(ctx, m, k, A, lda, Q, ldq, 0));
+    }
+    return bgs_pass(ctx, m, k, Q, ldq, R, ldr);
 }
 
 int32_t qb_qr_init(qb200_ctx* ctx) {
@@ -516,7 +555,7 @@ int32_t qb_qr_matrix(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64_
         // is R2 = I + triu(D, 1) + diag(D)/2, so R = R2 R1 costs two GEMMs (k x k x m and k^3) instead of a second
         // latency-bound pass over 2k/64 panels; the neglected term is O(|D|^2), so the shortcut is taken only when
         // max |D_ij| <= 1e-9 (and the first pass met no dependent column); otherwise the full second pass runs.
-        QB_TRY(bgs_pass(ctx, m, k, Q, ldq, R1, k));
+        QB_TRY(first_pass(ctx, m, k, A, lda, Q, ldq, R1, k));
         if (ctx->qr_last_dependent == 0) {
             unsigned long long* dmax = ws.get<unsigned long long>(1);
             if (!dmax) QB_FAIL(ctx, QB200_E_CUDA, "qr: workspace allocation failed");
@@ -535,10 +574,10 @@ int32_t qb_qr_matrix(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64_
         }
     } else if (passes <= 1 && passes != QB_QR_R_ONLY) {
         // one pass: R is backward stable (as for modified Gram-Schmidt), Q is orthonormal only to kappa(A) eps
-        QB_TRY(bgs_pass(ctx, m, k, Q, ldq, R1, k));
+        QB_TRY(first_pass(ctx, m, k, A, lda, Q, ldq, R1, k));
         QB_TRY(qb_copy_matrix(ctx, k, k, R1, k, R, ldr, 0));
     } else {
-        QB_TRY(bgs_pass(ctx, m, k, Q, ldq, R1, k));
+        QB_TRY(first_pass(ctx, m, k, A, lda, Q, ldq, R1, k));
         QB_TRY(bgs_pass(ctx, m, k, Q, ldq, R2, k));
         QB_TRY(qb_gemm(ctx, 0, 0, k, k, k, one, R2, k, R1, k, zero, R, ldr));
     }
