@@ -1278,6 +1278,46 @@ static bool evd_wreg() {
     return on;
 }
 
+// Device-side sweep control of the Jacobi iteration (round 2): the whole iteration is ONE launch of a CUDA graph whose
+// only node is a WHILE conditional; its body is the captured sweep followed by this one-thread kernel, which does what
+// the host does between two sweeps -- read the largest coupling of the sweep, decide convergence, switch the absolute
+// floor on for numerically rank-deficient input, carry the column-norm scale over -- and tells the graph whether to run
+// the body again: no host round trip per sweep (11 per bulk TEBD bond otherwise).
+struct SweepCtl {
+    int sweeps, converged, floor_on, pad;
+    double worst[48];
+};
+__global__ void jacobi_sweep_ctl_kernel(cudaGraphConditionalHandle handle, unsigned long long* __restrict__ stat,
+                                        double* __restrict__ scale, SweepCtl* __restrict__ ctl, double conv_tol,
+                                        int max_sweeps, int floor_after, double abs_floor) {
+    const double worst = __longlong_as_double((long long)*stat);
+    const int s = ctl->sweeps;  // index of the sweep that just ran
+    if (s < 48) ctl->worst[s] = worst;
+    ctl->sweeps = s + 1;
+    *stat = 0ull;
+    scale[0] = scale[1];
+    const bool conv = !(worst > conv_tol);
+    if (conv) {
+        ctl->converged = 1;
+    } else if (!ctl->floor_on && s >= floor_after) {
+        ctl->floor_on = 1;
+        scale[2] = abs_floor;
+    }
+    cudaGraphSetConditional(handle, (!conv && s + 1 < max_sweeps) ? 1u : 0u);
+}
+
+// QB200_SVD_WHILE=1 selects it.  Default OFF: measured on B200 (gpurun_out/r3i, same box, back to back) the sweep is not
+// faster -- 3.19 s against 3.05 s per TEBD sweep for the best steps, identical sweep counts and results: with 12 bonds in
+// flight the per-sweep read-back of one bond is hidden behind the kernels of the others, while the conditional graph
+// costs more to instantiate per SVD.  Kept as the host-free form of the iteration (single-stream latency paths).
+static bool while_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("QB200_SVD_WHILE");
+        return e && e[0] == '1';
+    }();
+    return on;
+}
+
 // QB200_SVD_MIXED=1: mixed-precision Jacobi (FP32 stage A + FP64 stage B, see qb_svd_factor)
 static bool mixed_enabled() {
     static const bool on = [] {
@@ -1641,8 +1681,9 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
     // ONCE per SVD as a CUDA graph and replayed (189 launches -> 1 graph launch per sweep at k = 2048; the host thread of
     // a worker stream issues ~10x fewer driver calls per SVD).  Plain launches with the phase profiler, the
     // mixed-precision Gram experiment, QB200_SYNC_DEBUG, QB200_SVD_GRAPH=0 and for single-pair problems.
-    auto emit_sweep = [&](bool lowp_now) {
-        cudaMemsetAsync(stat, 0, sizeof(unsigned long long), ctx->stream);
+    auto emit_sweep = [&](bool lowp_now, bool kernels_only = false) {  // kernels_only: the WHILE body (its control kernel
+                                                                       // resets stat and carries the scale over)
+        if (!kernels_only) cudaMemsetAsync(stat, 0, sizeof(unsigned long long), ctx->stream);
         for (int step = 0; step < nsteps; ++step) {
             const int mode = (nb == 2) ? 0 : (step == 0 ? 1 : 2);
             {
@@ -1669,14 +1710,72 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
                     st->Z, st->ldz, nb, step, Wg, flags, npairs, u_nchunk, shadow ? st->Z32 : nullptr);
             }
         }
-        cudaMemcpyAsync(scale, scale + 1, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
+        if (!kernels_only) cudaMemcpyAsync(scale, scale + 1, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
     };
     static const bool graph_enabled = [] {
         const char* e = getenv("QB200_SVD_GRAPH");
         return !(e && e[0] == '0');
     }();
+    const bool graph_ok = graph_enabled && nb > 2 && !ctx->prof_on && !shadow && !qb_sync_debug();
+    // ---- the whole iteration as one WHILE graph (device-side convergence) ----
+    bool while_done = false;
+    if (graph_ok && while_enabled()) {
+        SweepCtl* ctl = ws.get<SweepCtl>(1);
+        cudaGraph_t g = nullptr;
+        cudaGraphExec_t gx = nullptr;
+        bool built = false;
+        if (ctl && cudaGraphCreate(&g, 0) == cudaSuccess) {
+            cudaGraphConditionalHandle handle;
+            cudaGraphNodeParams np_ = {};
+            np_.type = cudaGraphNodeTypeConditional;
+            cudaGraphNode_t node;
+            if (cudaGraphConditionalHandleCreate(&handle, g, 1, cudaGraphCondAssignDefault) == cudaSuccess) {
+                np_.conditional.handle = handle;
+                np_.conditional.type = cudaGraphCondTypeWhile;
+                np_.conditional.size = 1;
+                if (cudaGraphAddNode(&node, g, nullptr, 0, &np_) == cudaSuccess &&
+                    cudaStreamBeginCaptureToGraph(ctx->stream, np_.conditional.phGraph_out[0], nullptr, nullptr, 0,
+                                                  cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                    emit_sweep(false, true);
+                    jacobi_sweep_ctl_kernel<<<1, 1, 0, ctx->stream>>>(handle, stat, scale, ctl, conv_tol, max_sweeps, 13,
+                                                                      ABS_FLOOR);
+                    built = cudaStreamEndCapture(ctx->stream, nullptr) == cudaSuccess &&
+                            cudaGraphInstantiate(&gx, g, 0) == cudaSuccess;
+                }
+            }
+        }
+        if (built) {
+            SweepCtl init;
+            memset(&init, 0, sizeof(init));
+            init.floor_on = floor_on ? 1 : 0;
+            SweepCtl* hctl = reinterpret_cast<SweepCtl*>(ctx->scratch_host + 16);  // pinned page; [0 .. 15] is used elsewhere
+            *hctl = init;
+            cudaError_t e = cudaMemcpyAsync(ctl, hctl, sizeof(SweepCtl), cudaMemcpyHostToDevice, ctx->stream);
+            if (e == cudaSuccess) e = cudaMemsetAsync(stat, 0, sizeof(unsigned long long), ctx->stream);
+            if (e == cudaSuccess) e = cudaGraphLaunch(gx, ctx->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(hctl, ctl, sizeof(SweepCtl), cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = qb_stream_sync(ctx);
+            if (e == cudaSuccess) e = cudaGetLastError();
+            cudaGraphExecDestroy(gx);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) return cuda_fail(e);
+            sweep = hctl->sweeps;
+            converged = hctl->converged != 0;
+            floor_on = hctl->floor_on != 0;
+            ctx->launches += (3 * (int64_t)nsteps + 1) * sweep;
+            if (getenv("QB200_DEBUG"))
+                for (int i = 0; i < sweep && i < 48; ++i)
+                    fprintf(stderr, "[qb200 svd] %lld x %lld (jacobi on %lld^2, nb %d) sweep %d worst %.3e\n", (long long)m,
+                            (long long)n, (long long)k, nb, i, hctl->worst[i]);
+            while_done = true;
+        } else {
+            if (gx) cudaGraphExecDestroy(gx);
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();  // fall back to one graph launch per sweep
+        }
+    }
     cudaGraphExec_t sweep_graph = nullptr;
-    if (graph_enabled && nb > 2 && !ctx->prof_on && !shadow && !qb_sync_debug()) {
+    if (graph_ok && !while_done) {
         cudaGraph_t g = nullptr;
         if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
             emit_sweep(false);
@@ -1686,7 +1785,7 @@ int32_t qb_svd_factor(qb200_ctx* ctx, int64_t m, int64_t n, const c128* A, int64
             if (!sweep_graph) cudaGetLastError();  // fall back to plain launches
         }
     }
-    for (; sweep < max_sweeps && !converged; ++sweep) {
+    for (; !while_done && sweep < max_sweeps && !converged; ++sweep) {
         if (sweep_graph)
             cudaGraphLaunch(sweep_graph, ctx->stream);
         else
