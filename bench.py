@@ -5,8 +5,9 @@ One "step" = one TEBD sweep: 32 odd-bond + 31 even-bond `evolve!(psi, G; maxdim=
 renormalize=true)` calls on a Vidal-form MPS (BASELINE.json configs[3]).  The sweep is sequential along
 the chain, so at N > 1 GPUs the TEBD line is N independent replicas ("replicas only"); the two paths
 that genuinely shard -- the sliced circuit-TN contraction with one NCCL sum, and batched independent expectation values
-on an MPS replicated by ncclBroadcast -- are reported in the same JSON line under "sliced_contraction" and
-"expect_batch".
+on an MPS replicated by ncclBroadcast -- are reported in the same JSON line under "sliced_contraction" (40 qubits, depth
+6: the round-1 workload), "sliced_contraction_depth7" (one layer deeper: 1024 slices, the workload whose 1 -> 8 GPU curve
+is meaningful) and "expect_batch", each with its own in-run check.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--sites 64] [--bond-dim 1024]
 
