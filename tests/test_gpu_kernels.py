@@ -83,6 +83,22 @@ def test_contract_alpha_beta(qb, ctx):
     assert np.allclose(out.to_host(), (2 - 1j) * a @ b + 0.5j * c, atol=1e-11)
 
 
+@pytest.mark.parametrize("shape", [(4100, 8, 8), (2300, 12, 40), (2100, 7, 130), (3, 4, 6000), (2500, 64, 16), (2500, 64, 64)])
+def test_contract_alpha_beta_on_the_shape_specialised_kernels(qb, ctx, shape):
+    """alpha / beta epilogues of the streaming (N <= 16, K <= 32), thin (N <= 16 longer K; N <= 64 at K <= 16), dot (<= 4 x 4
+    outputs, long K) and 64-row tile kernels."""
+    m, n, k = shape
+    rng = np.random.default_rng(sum(shape))
+    a, b, c = crand(rng, m, k), crand(rng, k, n), crand(rng, m, n)
+    out = ctx.array(c)
+    qb.contract(ctx.array(a), (0, 1), ctx.array(b), (1, 2), (0, 2), out=out, alpha=1.5 - 0.5j, beta=-0.25 + 2j)
+    want = (1.5 - 0.5j) * a @ b + (-0.25 + 2j) * c
+    assert np.abs(out.to_host() - want).max() <= 1e-12 * np.abs(want).max() * max(1.0, k ** 0.5)
+    out1 = ctx.array(c)
+    qb.contract(ctx.array(a), (0, 1), ctx.array(b), (1, 2), (0, 2), out=out1, alpha=1.0, beta=1.0)
+    assert np.abs(out1.to_host() - (a @ b + c)).max() <= 1e-12 * np.abs(want).max() * max(1.0, k ** 0.5)
+
+
 @pytest.mark.parametrize("alpha", [1.0, -1.0])
 def test_contract_accumulate_in_place(qb, ctx, alpha):
     """C += (+-1) A B (beta = 1): the accumulators start from +-C (the QR trailing update T -= P C)."""
